@@ -1,0 +1,214 @@
+/*
+ * rho_b200.h -- C ABI of librho_b200.so: the B200 (sm_100a) implementation of the
+ * rho-tts audio post-processing + validation front end.
+ *
+ * The reference (rhofield/rho-tts) is pure Python and has no FFI for this path; its
+ * extension point is "subclass BaseTTS, register with TTSFactory"
+ * (src/rho_tts/factory.py:110-122).  The Python shim in rho_tts_b200/ keeps those
+ * signatures and calls the entry points below through ctypes.  Each entry point
+ * names the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - Plain C types only.  `stream` is a cudaStream_t passed as void*.
+ *   - Unless a function says HOST, every data pointer is a DEVICE pointer owned by
+ *     the caller; kernels are enqueued on `stream` and the call returns without
+ *     synchronising.  No allocation happens inside those calls: scratch comes from
+ *     the caller-provided workspace (size it with rho_b200_workspace_bytes).
+ *   - Ragged batches: `x` is one fp32 buffer, clip/segment s occupies
+ *     x[off[s] .. off[s]+len[s]).  Every off[s] must be a multiple of 4 (16-byte
+ *     aligned) so 128-bit loads are legal.
+ *   - Return value: 0 on success, negative rho_status on failure; text via
+ *     rho_b200_last_error().  There is no CPU fallback anywhere.
+ */
+#ifndef RHO_B200_H
+#define RHO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RHO_B200_ABI_VERSION 1
+
+typedef struct rho_handle rho_handle;
+
+typedef enum {
+  RHO_OK = 0,
+  RHO_ERR_INVALID = -1,   /* bad argument */
+  RHO_ERR_CUDA = -2,      /* CUDA runtime error */
+  RHO_ERR_NOGPU = -3,     /* no sm_100 device */
+  RHO_ERR_WORKSPACE = -4, /* workspace too small */
+  RHO_ERR_LAYOUT = -5     /* misaligned offsets / inconsistent ragged layout */
+} rho_status;
+
+/* Call-time configuration.  Mirrors the BaseTTS attributes read at call time
+ * (src/rho_tts/base_tts.py:72-81, 366-367, 420, 455, 519). */
+typedef struct {
+  int32_t sr;             /* sample_rate */
+  int32_t trim_enabled;   /* self.trim_silence */
+  double silence_db;      /* self.silence_threshold_db        (-50.0) */
+  double fade_sec;        /* self.fade_duration_sec           (0.02)  */
+  double xfade_sec;       /* self.crossfade_duration_sec      (0.05)  */
+  double pause_sec;       /* self.inter_sentence_pause_sec    (0.1)   */
+  double decay_thr;       /* self.sound_decay_threshold       (0.3)   */
+} rho_params;
+
+/* flags in rho_seg_info.flags / rho_record.flags */
+#define RHO_F_ALL_SILENT 1u /* no frame above threshold: reference returns a 2-D (1, min(window,L)) view */
+#define RHO_F_FALLBACK   2u /* join took the reference's except-branch: plain cat of the ORIGINAL segments */
+#define RHO_F_TWO_D      4u /* result tensor is (1, n) in the reference, not (n,) */
+#define RHO_F_UNTOUCHED  8u /* trimming disabled or empty input */
+
+/* Per-segment trim result (16 B).  base_tts.py:348-399. */
+typedef struct {
+  int32_t start;  /* first kept sample  */
+  int32_t end;    /* one past last kept */
+  float dc;       /* mean over [start,end) that was subtracted */
+  uint32_t flags;
+} rho_seg_info;
+
+/* Per-item score record (48 B): the thing that is all-gathered across GPUs. */
+typedef struct {
+  int32_t start;        /* segment 0 trim start                                   */
+  int32_t end;          /* segment 0 trim end                                     */
+  int32_t out_len;      /* samples written for this item                          */
+  uint32_t flags;
+  float dc;             /* segment 0 DC                                           */
+  float first_rms;      /* base_tts.py:314                                        */
+  float last_rms;       /* base_tts.py:315                                        */
+  float cosine;         /* base_tts.py:341-344 (0 until rho_b200_cosine ran)      */
+  double decay_ratio;   /* last/first in double, 1.0 on the early-outs (:304-318) */
+  int32_t ok;           /* ratio >= decay_thr (:322)                              */
+  int32_t n_segments;
+} rho_record;
+
+/* ------------------------------------------------------------------ lifecycle */
+int rho_b200_abi_version(void);
+/* Creates a handle on CUDA device `device`; builds and uploads the constant tables
+ * (resample taps, Hann window, mel filterbanks 80/128, FFT twiddles). */
+int rho_b200_create(rho_handle** h, int device);
+int rho_b200_destroy(rho_handle* h);
+/* Thread-local message of the last failing call on this thread. */
+const char* rho_b200_last_error(void);
+
+/* HOST-side tables, computable without a GPU (used by the CPU test-suite to compare
+ * the library's constants with torchaudio / transformers):
+ *   kind 0: resample taps 24k->16k, out[2*23]      (torchaudio functional.py:1305-1405)
+ *   kind 1: periodic Hann(400), out[400]           (feature_extraction_whisper.py:141)
+ *   kind 2: mel filterbank, arg = n_mels, out[n_mels*201] row-major [mel][bin]
+ *                                                   (transformers audio_utils.py:453-544)
+ * Returns the number of floats written, or a negative status. */
+int rho_b200_host_table(int kind, int arg, float* out, size_t out_capacity);
+
+/* Bytes of scratch the calls below need for a batch of `n_segments` segments in
+ * `n_items` items whose longest segment has `max_seg_len` samples. */
+size_t rho_b200_workspace_bytes(int n_segments, int n_items, int64_t max_seg_len);
+
+/* ------------------------------------------------- post-process / join (a1-a5) */
+/* Silence-trim bounds only.  Replaces BaseTTS._trim_silence (base_tts.py:348-392).
+ * trim_flags[s]: bit0 = from_start, bit1 = from_end (NULL = both).
+ * Writes info[s] = {start, end, dc over [start,end), flags}. */
+int rho_b200_trim_scan(rho_handle* h, const float* x, const int64_t* off, const int32_t* len,
+                       const uint8_t* trim_flags, int n_segments, int64_t max_seg_len,
+                       const rho_params* p, rho_seg_info* info,
+                       void* workspace, size_t ws_bytes, void* stream);
+
+/* The whole per-item path of BaseTTS._run_pipeline after generation
+ * (base_tts.py:912-926): _smooth_segment_join (:435-536: per-segment trim + DC,
+ * equal-power crossfades, inter-sentence pauses, fallback on mixed ranks, final fades)
+ * followed by _validate_sound_decay (:297-323).  Item i owns segments
+ * [item_first_seg[i], item_first_seg[i+1]).  A one-segment item is the plain
+ * post-process of one clip (trim both ends -> DC -> fades).
+ * y_off[i] (multiple of 4) is where item i is written; the caller reserves
+ * sum(len of its segments) + max(0, n-2)*pause samples for it.
+ * Outputs: y, rec[i], and (optional, may be NULL) seg_info[s]. */
+int rho_b200_join(rho_handle* h, const float* x, const int64_t* seg_off, const int32_t* seg_len,
+                  int n_segments, int64_t max_seg_len,
+                  const int32_t* item_first_seg, int n_items, int64_t max_item_len,
+                  const rho_params* p, float* y, const int64_t* y_off,
+                  rho_record* rec, rho_seg_info* seg_info,
+                  void* workspace, size_t ws_bytes, void* stream);
+
+/* Element-wise pieces exposed one by one for the BaseTTS method shim.  In place on x. */
+/* BaseTTS._remove_dc_offset (base_tts.py:394-399): x -= mean(x).  dc_out (device, 1 float) optional. */
+int rho_b200_remove_dc(rho_handle* h, float* x, int64_t n, float* dc_out,
+                       void* workspace, size_t ws_bytes, void* stream);
+/* BaseTTS._apply_fades (base_tts.py:401-433). */
+int rho_b200_apply_fades(rho_handle* h, float* x, int64_t n, int fade_in, int fade_out,
+                         const rho_params* p, void* stream);
+/* BaseTTS._validate_sound_decay (base_tts.py:297-323) on one clip; rec (device) gets
+ * first_rms/last_rms/decay_ratio/ok. */
+int rho_b200_sound_decay(rho_handle* h, const float* x, int64_t n, const rho_params* p,
+                         rho_record* rec, void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------ resample (a7) */
+/* torchaudio.functional.resample(x, 24000, 16000) (torchaudio functional.py:1405-1432;
+ * reference call sites base_tts.py:632 and the 16 kHz loaders behind :338 / stt_validator).
+ * Clip s has len[s] input samples (device array, may be produced by rho_b200_join:
+ * pass &rec[0].out_len with len_stride = sizeof(rho_record)); writes
+ * ceil(2*len/3) samples at y + y_off[s] and that count to y_len[s]. */
+int rho_b200_resample3to2(rho_handle* h, const float* x, const int64_t* off, const int32_t* len,
+                          int len_stride_bytes, int n, int64_t max_len,
+                          float* y, const int64_t* y_off, int32_t* y_len, void* stream);
+
+/* -------------------------------------------------------------- log-mel (a8) */
+/* WhisperFeatureExtractor (transformers feature_extraction_whisper.py:135-164, 296-303):
+ * STFT(400, hop 160, periodic Hann, centre/reflect) -> |.|^2 -> mel(n_mels in {80,128})
+ * -> log10(clamp 1e-10) -> max(x, clipmax-8) -> (x+4)/4.
+ * pad_frames = 3000: pad/truncate every clip to 30 s, output [n][n_mels][3000].
+ * pad_frames = 0   : unpadded; clip s gets T_s = len16[s]/160 frames written with row
+ *                    stride `mel_stride_frames` at mel + s*n_mels*mel_stride_frames,
+ *                    and n_frames[s] = T_s.
+ * n_frames may be NULL when pad_frames = 3000. */
+int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const int32_t* len16,
+                    int n, int64_t max_len16, int n_mels, int pad_frames,
+                    float* mel, int64_t mel_stride_frames, int32_t* n_frames,
+                    void* workspace, size_t ws_bytes, void* stream);
+
+/* --------------------------------------------------------------- cosine (a6) */
+/* dot(ref, e) / (|ref| * |e|) for n embeddings of dimension dim (base_tts.py:341-344).
+ * out_stride_bytes lets the result land in rho_record.cosine. */
+int rho_b200_cosine(rho_handle* h, const float* emb, const float* ref, int n, int dim,
+                    float* out, int out_stride_bytes, void* stream);
+
+/* ------------------------------------------------ whole validation front end */
+/* join/post-process -> resample 24k->16k -> log-mel -> cosine, device resident.
+ * scratch16 holds the 16 kHz intermediate (same offsets as y, 2/3 the length). */
+int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, const int32_t* seg_len,
+                      int n_segments, int64_t max_seg_len,
+                      const int32_t* item_first_seg, int n_items, int64_t max_item_len,
+                      const rho_params* p, float* y, const int64_t* y_off,
+                      int n_mels, int pad_frames, float* mel, int64_t mel_stride_frames,
+                      const float* emb, const float* ref_emb, int emb_dim,
+                      rho_record* rec, float* scratch16,
+                      void* workspace, size_t ws_bytes, void* stream);
+
+/* HOST entry point: the call a non-torch embedder makes.  All pointers are HOST
+ * buffers (pinned for full speed).  Copies clips in, runs rho_b200_validate in
+ * chunks on internal streams (H2D, compute and D2H overlapped), copies processed
+ * audio, records and (if mel != NULL) features back, and returns after the last
+ * copy finished.  Fixed-length layout: n clips of `clip_len` samples each, every
+ * item is one clip. */
+int rho_b200_validate_host(rho_handle* h, const float* x, int n, int32_t clip_len,
+                           const rho_params* p, float* y /* n*clip_len */, int n_mels, int pad_frames,
+                           float* mel /* n*n_mels*pad_frames or NULL */,
+                           const float* emb, const float* ref_emb, int emb_dim,
+                           rho_record* rec);
+
+/* Number of kernel launches this handle has issued (for bench.py's gpu_launches). */
+int64_t rho_b200_launch_count(rho_handle* h);
+
+/* Per-kernel device time, measured with CUDA events recorded on the launching stream around
+ * every kernel issued between profile_begin and profile_end (profile_end synchronises on them).
+ * ms_per_kernel[id] / launches_per_kernel[id] are indexed by kernel id; rho_b200_kernel_name(id)
+ * names them.  Returns the number of kernel ids, or a negative status.  Not for timed runs. */
+int rho_b200_profile_begin(rho_handle* h);
+int rho_b200_profile_end(rho_handle* h, double* ms_per_kernel, int64_t* launches_per_kernel, int capacity);
+const char* rho_b200_kernel_name(int id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RHO_B200_H */

@@ -1,0 +1,238 @@
+"""Batched host API over librho_b200: what the benchmarks and the BaseTTS shim drive.
+
+Every function takes device-resident torch tensors (PyTorch is the allocator and stream
+provider, nothing more), enqueues the library's kernels on the current CUDA stream and returns
+device tensors; nothing here synchronises or computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import RhoParams, Handle
+from .ragged import RaggedBatch, ALIGN
+
+REC_DTYPE = np.dtype([
+    ("start", "<i4"), ("end", "<i4"), ("out_len", "<i4"), ("flags", "<u4"),
+    ("dc", "<f4"), ("first_rms", "<f4"), ("last_rms", "<f4"), ("cosine", "<f4"),
+    ("decay_ratio", "<f8"), ("ok", "<i4"), ("n_segments", "<i4"),
+])
+SEG_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("dc", "<f4"), ("flags", "<u4")])
+assert REC_DTYPE.itemsize == 48 and SEG_DTYPE.itemsize == 16
+
+
+def make_params(sr: int = 24000, trim_silence: bool = True, silence_threshold_db: float = -50.0,
+                fade_duration_sec: float = 0.02, crossfade_duration_sec: float = 0.05,
+                inter_sentence_pause_sec: float = 0.1, sound_decay_threshold: float = 0.3) -> RhoParams:
+    return RhoParams(int(sr), 1 if trim_silence else 0, float(silence_threshold_db), float(fade_duration_sec),
+                     float(crossfade_duration_sec), float(inter_sentence_pause_sec), float(sound_decay_threshold))
+
+
+def params_from_tts(tts) -> RhoParams:
+    """Read the BaseTTS attributes at call time, as the reference methods do."""
+    return make_params(
+        sr=tts.sample_rate,
+        trim_silence=getattr(tts, "trim_silence", True),
+        silence_threshold_db=getattr(tts, "silence_threshold_db", -50.0),
+        fade_duration_sec=getattr(tts, "fade_duration_sec", 0.02),
+        crossfade_duration_sec=getattr(tts, "crossfade_duration_sec", 0.05),
+        inter_sentence_pause_sec=getattr(tts, "inter_sentence_pause_sec", 0.1),
+        sound_decay_threshold=getattr(tts, "sound_decay_threshold", 0.3),
+    )
+
+
+def _dev_index(t: torch.Tensor) -> int:
+    if not t.is_cuda:
+        raise RuntimeError("rho_tts_b200 runs on CUDA tensors only (no CPU fallback)")
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _stream(dev: int) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _workspace(h: Handle, n_seg: int, n_items: int, max_seg_len: int, device) -> torch.Tensor:
+    nbytes = int(h.lib.rho_b200_workspace_bytes(int(n_seg), int(n_items), int(max_seg_len)))
+    return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+
+
+@dataclass
+class JoinOutput:
+    audio: RaggedBatch          # item i at audio.h_offsets[i]; valid length = records["out_len"][i] (device)
+    records: torch.Tensor       # uint8 [n_items, 48] on the device (rho_record)
+    seg_info: Optional[torch.Tensor]   # uint8 [n_segments, 16] on the device (rho_seg_info)
+
+    def records_host(self) -> np.ndarray:
+        return self.records.cpu().numpy().view(REC_DTYPE).reshape(-1)
+
+    def seg_info_host(self) -> np.ndarray:
+        return self.seg_info.cpu().numpy().view(SEG_DTYPE).reshape(-1)
+
+
+def trim_scan_batch(rb: RaggedBatch, p: RhoParams, trim_flags: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """BaseTTS._trim_silence bounds for every clip (base_tts.py:348-392). Returns uint8 [n,16] rho_seg_info."""
+    dev = _dev_index(rb.data)
+    h = Handle.get(dev)
+    info = torch.empty((rb.n, 16), dtype=torch.uint8, device=rb.device)
+    ws = _workspace(h, rb.n, rb.n, rb.max_len, rb.device)
+    _lib.check(h.lib.rho_b200_trim_scan(h.ptr, _ptr(rb.data), _ptr(rb.offsets), _ptr(rb.lengths), _ptr(trim_flags),
+                                        rb.n, rb.max_len, ctypes.byref(p), _ptr(info), _ptr(ws), ws.numel(),
+                                        _stream(dev)), "trim_scan")
+    return info
+
+
+def join_batch(rb: RaggedBatch, item_first_seg: Sequence[int], p: RhoParams, want_seg_info: bool = True) -> JoinOutput:
+    """BaseTTS._smooth_segment_join + _validate_sound_decay for many items at once
+    (base_tts.py:435-536, 297-323).  item i = segments [item_first_seg[i], item_first_seg[i+1])."""
+    dev = _dev_index(rb.data)
+    h = Handle.get(dev)
+    first = np.asarray(item_first_seg, dtype=np.int32)
+    n_items = len(first) - 1
+    assert n_items >= 0 and first[0] == 0 and first[-1] == rb.n
+    pause = int(p.sr * p.pause_sec) if p.pause_sec > 0 else 0
+    seg_tot = np.concatenate([[0], np.cumsum(rb.h_lengths.astype(np.int64))])
+    cap = (seg_tot[first[1:]] - seg_tot[first[:-1]]) + np.maximum(0, np.diff(first) - 2) * pause
+    out = RaggedBatch.empty_like_lengths(np.maximum(cap, 0).astype(np.int32), rb.device) if n_items else \
+        RaggedBatch.empty_like_lengths(np.zeros(0, np.int32), rb.device)
+    rec = torch.empty((n_items, 48), dtype=torch.uint8, device=rb.device)
+    seg = torch.empty((rb.n, 16), dtype=torch.uint8, device=rb.device) if want_seg_info else None
+    d_first = torch.from_numpy(first).to(rb.device)
+    ws = _workspace(h, rb.n, n_items, rb.max_len, rb.device)
+    _lib.check(h.lib.rho_b200_join(h.ptr, _ptr(rb.data), _ptr(rb.offsets), _ptr(rb.lengths), rb.n, rb.max_len,
+                                   _ptr(d_first), n_items, int(cap.max()) if n_items else 0, ctypes.byref(p),
+                                   _ptr(out.data), _ptr(out.offsets), _ptr(rec), _ptr(seg), _ptr(ws), ws.numel(),
+                                   _stream(dev)), "join")
+    return JoinOutput(out, rec, seg)
+
+
+def post_process_batch(rb: RaggedBatch, p: RhoParams, want_seg_info: bool = False) -> JoinOutput:
+    """Every clip is its own item: trim both ends -> DC -> fades -> decay record
+    (the N == 1 branch of _smooth_segment_join, base_tts.py:447-452)."""
+    return join_batch(rb, np.arange(rb.n + 1, dtype=np.int32), p, want_seg_info)
+
+
+def resample_batch(rb: RaggedBatch, lengths: Optional[torch.Tensor] = None, len_stride: int = 4):
+    """torchaudio.functional.resample(x, 24000, 16000) per clip.  `lengths` (device int32, optional,
+    strided by len_stride bytes) overrides rb.lengths, e.g. the out_len column of the records."""
+    dev = _dev_index(rb.data)
+    h = Handle.get(dev)
+    cap = (2 * rb.h_lengths.astype(np.int64) + 2) // 3
+    out = RaggedBatch.empty_like_lengths(cap.astype(np.int32), rb.device)
+    lens = rb.lengths if lengths is None else lengths
+    _lib.check(h.lib.rho_b200_resample3to2(h.ptr, _ptr(rb.data), _ptr(rb.offsets), _ptr(lens), int(len_stride), rb.n,
+                                           rb.max_len, _ptr(out.data), _ptr(out.offsets), _ptr(out.lengths),
+                                           _stream(dev)), "resample3to2")
+    return out          # out.lengths (device) now holds ceil(2*len/3)
+
+
+def logmel_batch(rb16: RaggedBatch, n_mels: int = 80, pad_to_30s: bool = True,
+                 lengths: Optional[torch.Tensor] = None):
+    """WhisperFeatureExtractor features.  Returns (mel [n, n_mels, T], n_frames int32 [n]) on the device;
+    T = 3000 when padded, else max_len16 // 160 (clip i valid for n_frames[i])."""
+    dev = _dev_index(rb16.data)
+    h = Handle.get(dev)
+    n = rb16.n
+    T = 3000 if pad_to_30s else max(rb16.max_len // 160, 1)
+    mel = torch.empty((n, n_mels, T), dtype=torch.float32, device=rb16.device)
+    n_frames = torch.zeros(n, dtype=torch.int32, device=rb16.device)
+    ws = torch.empty(max(256, 4 * n + 256), dtype=torch.uint8, device=rb16.device)
+    lens = rb16.lengths if lengths is None else lengths
+    _lib.check(h.lib.rho_b200_logmel(h.ptr, _ptr(rb16.data), _ptr(rb16.offsets), _ptr(lens), n, rb16.max_len,
+                                     int(n_mels), 3000 if pad_to_30s else 0, _ptr(mel), T, _ptr(n_frames),
+                                     _ptr(ws), ws.numel(), _stream(dev)), "logmel")
+    return mel, n_frames
+
+
+def cosine_batch(emb: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
+    """dot(ref, e) / (|ref| |e|) per row of emb (base_tts.py:341-344)."""
+    dev = _dev_index(emb)
+    h = Handle.get(dev)
+    emb = emb.contiguous().float()
+    ref = ref.contiguous().float().to(emb.device)
+    out = torch.empty(emb.shape[0], dtype=torch.float32, device=emb.device)
+    _lib.check(h.lib.rho_b200_cosine(h.ptr, _ptr(emb), _ptr(ref), emb.shape[0], emb.shape[1], _ptr(out), 4,
+                                     _stream(dev)), "cosine")
+    return out
+
+
+@dataclass
+class ValidateOutput:
+    audio: RaggedBatch
+    mel: torch.Tensor
+    records: torch.Tensor
+
+    def records_host(self) -> np.ndarray:
+        return self.records.cpu().numpy().view(REC_DTYPE).reshape(-1)
+
+
+class ValidatePlan:
+    """Pre-allocated buffers for repeated rho_b200_validate calls on batches of one shape
+    (the benchmark's steady state: allocation is not part of the hot path)."""
+
+    def __init__(self, rb: RaggedBatch, item_first_seg: Sequence[int], p: RhoParams, n_mels: int = 80,
+                 pad_to_30s: bool = True):
+        self.dev = _dev_index(rb.data)
+        self.h = Handle.get(self.dev)
+        self.p = p
+        self.n_mels = int(n_mels)
+        self.pad_frames = 3000 if pad_to_30s else 0
+        first = np.asarray(item_first_seg, dtype=np.int32)
+        self.n_items = len(first) - 1
+        self.n_seg = rb.n
+        self.max_seg_len = rb.max_len
+        pause = int(p.sr * p.pause_sec) if p.pause_sec > 0 else 0
+        seg_tot = np.concatenate([[0], np.cumsum(rb.h_lengths.astype(np.int64))])
+        cap = (seg_tot[first[1:]] - seg_tot[first[:-1]]) + np.maximum(0, np.diff(first) - 2) * pause
+        self.max_item_len = int(cap.max()) if self.n_items else 0
+        self.out = RaggedBatch.empty_like_lengths(cap.astype(np.int32), rb.device)
+        self.scratch16 = torch.empty_like(self.out.data)
+        self.T = 3000 if pad_to_30s else max(((2 * self.max_item_len + 2) // 3) // 160, 1)
+        self.mel = torch.empty((self.n_items, self.n_mels, self.T), dtype=torch.float32, device=rb.device)
+        self.rec = torch.empty((self.n_items, 48), dtype=torch.uint8, device=rb.device)
+        self.d_first = torch.from_numpy(first).to(rb.device)
+        self.ws = _workspace(self.h, self.n_seg, self.n_items, self.max_seg_len, rb.device)
+
+    def run(self, rb: RaggedBatch, emb: Optional[torch.Tensor], ref: Optional[torch.Tensor]) -> ValidateOutput:
+        h = self.h
+        _lib.check(h.lib.rho_b200_validate(
+            h.ptr, _ptr(rb.data), _ptr(rb.offsets), _ptr(rb.lengths), self.n_seg, self.max_seg_len,
+            _ptr(self.d_first), self.n_items, self.max_item_len, ctypes.byref(self.p),
+            _ptr(self.out.data), _ptr(self.out.offsets), self.n_mels, self.pad_frames, _ptr(self.mel), self.T,
+            _ptr(emb), _ptr(ref), int(emb.shape[1]) if emb is not None else 0, _ptr(self.rec),
+            _ptr(self.scratch16), _ptr(self.ws), self.ws.numel(), _stream(self.dev)), "validate")
+        return ValidateOutput(self.out, self.mel, self.rec)
+
+
+def validate_batch(rb: RaggedBatch, p: RhoParams, emb: Optional[torch.Tensor] = None,
+                   ref: Optional[torch.Tensor] = None, n_mels: int = 80, pad_to_30s: bool = True,
+                   item_first_seg: Optional[Sequence[int]] = None) -> ValidateOutput:
+    """post-process/join -> resample 24k->16k -> log-mel -> cosine, all on the device."""
+    first = np.arange(rb.n + 1, dtype=np.int32) if item_first_seg is None else item_first_seg
+    return ValidatePlan(rb, first, p, n_mels, pad_to_30s).run(rb, emb, ref)
+
+
+def validate_host(x: torch.Tensor, p: RhoParams, emb: Optional[torch.Tensor], ref: Optional[torch.Tensor],
+                  n_mels: int = 80, y: Optional[torch.Tensor] = None, mel: Optional[torch.Tensor] = None,
+                  rec: Optional[torch.Tensor] = None, device: int = 0):
+    """HOST buffers in, HOST buffers out (rho_b200_validate_host): x is a pinned CPU tensor (n, L);
+    the library stages chunks through HBM with copy/compute overlap.  Returns (y, mel, rec) CPU tensors."""
+    assert not x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.is_contiguous()
+    h = Handle.get(device)
+    n, L = x.shape
+    if y is None:
+        y = torch.empty_like(x).pin_memory()
+    if rec is None:
+        rec = torch.empty((n, 48), dtype=torch.uint8).pin_memory()
+    dim = int(emb.shape[1]) if emb is not None else 0
+    _lib.check(h.lib.rho_b200_validate_host(h.ptr, _ptr(x), n, L, ctypes.byref(p), _ptr(y), int(n_mels), 3000,
+                                            _ptr(mel), _ptr(emb), _ptr(ref), dim, _ptr(rec)), "validate_host")
+    return y, mel, rec

@@ -1,0 +1,518 @@
+// C ABI of librho_b200.so (see include/rho_b200.h).  Host-side glue only: argument checks,
+// constants derived the way the reference derives them, workspace carving, launches.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <mutex>
+#include "kernels.h"
+
+namespace rho {
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* where) {
+  return fail(RHO_ERR_CUDA, "%s: %s", where, cudaGetErrorString(e));
+}
+
+// Python: int(sr * 0.01), 10 ** (dB / 20), int(sr * sec) -- all in double, truncation toward zero.
+Derived derive(const rho_params& p) {
+  Derived d;
+  d.window = (int)((double)p.sr * 0.01);
+  d.hop = d.window / 2;
+  d.fade = (int)((double)p.sr * p.fade_sec);
+  d.cf = (int)((double)p.sr * p.xfade_sec);
+  d.pause = (int)((double)p.sr * p.pause_sec);
+  d.pause_on = p.pause_sec > 0.0 ? 1 : 0;
+  if (d.pause < 0) d.pause = 0;
+  d.trim_enabled = p.trim_enabled ? 1 : 0;
+  d.thr = (float)std::pow(10.0, p.silence_db / 20.0);
+  d.decay_thr = p.decay_thr;
+  return d;
+}
+
+}  // namespace rho
+
+using namespace rho;
+
+namespace rho {
+const char* const kKernelNames[KID_COUNT] = {
+  "k_init", "k_scan", "k_finalize_segs", "k_plan_items", "k_gather", "k_finalize_items",
+  "k_resample3to2", "k_logmel_init", "k_logmel_frames", "k_logmel_norm", "k_cosine", "k_single_clip_helpers"};
+}
+
+struct rho_handle {
+  int device;
+  Tables tb;
+  std::vector<void*> allocs;
+  LaunchCtx lc;
+  // arena for the HOST entry point
+  void* arena;
+  size_t arena_bytes;
+  cudaStream_t s_copy_in, s_compute, s_copy_out;
+  bool streams_ok;
+  std::mutex mu;
+};
+
+namespace {
+
+template <typename T>
+cudaError_t dev_upload(rho_handle* h, T** dst, const T* src, size_t n) {
+  cudaError_t e = cudaMalloc((void**)dst, n * sizeof(T));
+  if (e != cudaSuccess) return e;
+  h->allocs.push_back(*dst);
+  return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+struct WsPlan {
+  size_t seg, span, item, block_sum, clip_max, len16, scratch, total;
+  int blocks_per_seg;
+};
+
+WsPlan plan_ws(int n_seg, int n_items, int64_t max_seg_len) {
+  WsPlan w;
+  // hop >= 1; the smallest hop we size for is 40 samples (sr 8 kHz).  blocks = frames upper bound.
+  const int64_t min_hop = 40;
+  w.blocks_per_seg = (int)(max_seg_len / min_hop + 2);
+  size_t o = 0;
+  w.seg = o; o += align_up(sizeof(SegState) * (size_t)(n_seg > 0 ? n_seg : 1), 256);
+  w.span = o; o += align_up(sizeof(SegSpan) * (size_t)(n_seg > 0 ? n_seg : 1), 256);
+  w.item = o; o += align_up(sizeof(ItemState) * (size_t)(n_items > 0 ? n_items : 1), 256);
+  w.clip_max = o; o += align_up(sizeof(int) * (size_t)(n_items > 0 ? n_items : 1), 256);
+  w.len16 = o; o += align_up(sizeof(int32_t) * (size_t)(n_items > 0 ? n_items : 1), 256);
+  w.scratch = o; o += 256;
+  w.block_sum = o; o += align_up(sizeof(float) * (size_t)(n_seg > 0 ? n_seg : 1) * (size_t)w.blocks_per_seg, 256);
+  w.total = o;
+  return w;
+}
+
+// blocks_per_seg actually used by the kernels for this call (depends on the call's hop)
+int blocks_for(const Derived& d, int64_t max_seg_len) {
+  if (max_seg_len <= 0) return 1;
+  return (int)((max_seg_len + 2 * d.hop - d.window) / d.hop + 1);
+}
+
+int carve(void* ws, size_t ws_bytes, int n_seg, int n_items, int64_t max_seg_len, const Derived& d,
+          Workspace* out, double** scratch) {
+  if (d.hop < 40) return fail(RHO_ERR_INVALID, "sample rate too low: hop %d < 40", d.hop);
+  const WsPlan w = plan_ws(n_seg, n_items, max_seg_len);
+  if (ws == nullptr || ws_bytes < w.total)
+    return fail(RHO_ERR_WORKSPACE, "workspace too small: have %zu, need %zu", ws_bytes, w.total);
+  if (((uintptr_t)ws & 255u) != 0) return fail(RHO_ERR_LAYOUT, "workspace must be 256-byte aligned");
+  char* b = (char*)ws;
+  out->seg = (SegState*)(b + w.seg);
+  out->span = (SegSpan*)(b + w.span);
+  out->item = (ItemState*)(b + w.item);
+  out->clip_max = (int*)(b + w.clip_max);
+  out->len16 = (int32_t*)(b + w.len16);
+  out->block_sum = (float*)(b + w.block_sum);
+  out->blocks_per_seg = blocks_for(d, max_seg_len);
+  if (out->blocks_per_seg > w.blocks_per_seg) return fail(RHO_ERR_WORKSPACE, "internal: block_sum sizing");
+  if (scratch) *scratch = (double*)(b + w.scratch);
+  return RHO_OK;
+}
+
+int check_params(const rho_params* p) {
+  if (!p) return fail(RHO_ERR_INVALID, "params is NULL");
+  if (p->sr < 8000 || p->sr > 192000) return fail(RHO_ERR_INVALID, "sample rate %d out of range", p->sr);
+  if (p->fade_sec < 0 || p->xfade_sec < 0) return fail(RHO_ERR_INVALID, "negative fade/crossfade duration");
+  return RHO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rho_b200_abi_version(void) { return RHO_B200_ABI_VERSION; }
+
+const char* rho_b200_last_error(void) { return g_err; }
+
+int rho_b200_host_table(int kind, int arg, float* out, size_t cap) {
+  if (!out) return fail(RHO_ERR_INVALID, "out is NULL");
+  switch (kind) {
+    case 0:
+      if (cap < 2 * RS_TAPS) return fail(RHO_ERR_INVALID, "capacity");
+      host_resample_taps(out); return 2 * RS_TAPS;
+    case 1:
+      if (cap < N_FFT) return fail(RHO_ERR_INVALID, "capacity");
+      host_hann(out); return N_FFT;
+    case 2:
+      if (arg != 80 && arg != 128) return fail(RHO_ERR_INVALID, "n_mels must be 80 or 128");
+      if (cap < (size_t)arg * N_BINS) return fail(RHO_ERR_INVALID, "capacity");
+      host_mel_filterbank(arg, out); return arg * N_BINS;
+    default:
+      return fail(RHO_ERR_INVALID, "unknown table kind %d", kind);
+  }
+}
+
+int rho_b200_create(rho_handle** out, int device) {
+  if (!out) return fail(RHO_ERR_INVALID, "handle out pointer is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return fail(RHO_ERR_NOGPU, "no CUDA device visible (%s); librho_b200 has no CPU fallback",
+                e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(RHO_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return fail(RHO_ERR_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+
+  rho_handle* h = new rho_handle();
+  h->device = device; h->arena = nullptr; h->arena_bytes = 0; h->streams_ok = false;
+  memset(&h->tb, 0, sizeof(h->tb));
+
+  std::vector<float> taps(2 * RS_TAPS), hann(N_FFT), tw(2 * N_FFT);
+  host_resample_taps(taps.data()); host_hann(hann.data()); host_twiddles(tw.data());
+  if ((e = upload_resample_taps(taps.data())) != cudaSuccess) { rho_b200_destroy(h); return cuda_fail(e, "taps"); }
+  if ((e = dev_upload(h, &h->tb.hann, hann.data(), N_FFT)) != cudaSuccess) { rho_b200_destroy(h); return cuda_fail(e, "hann"); }
+  if ((e = dev_upload(h, (float**)&h->tb.twiddle, tw.data(), 2 * N_FFT)) != cudaSuccess) { rho_b200_destroy(h); return cuda_fail(e, "twiddle"); }
+  for (int which = 0; which < 2; ++which) {
+    const int nm = which == 0 ? 80 : 128;
+    std::vector<float> dense((size_t)nm * N_BINS);
+    host_mel_filterbank(nm, dense.data());
+    std::vector<int> lo(nm), cnt(nm), wofs(nm);
+    std::vector<float> w;
+    for (int m = 0; m < nm; ++m) {
+      int a = -1, b = -1;
+      for (int k = 0; k < N_BINS; ++k) if (dense[(size_t)m * N_BINS + k] != 0.f) { if (a < 0) a = k; b = k; }
+      lo[m] = a < 0 ? 0 : a; cnt[m] = a < 0 ? 0 : b - a + 1; wofs[m] = (int)w.size();
+      for (int k = 0; k < cnt[m]; ++k) w.push_back(dense[(size_t)m * N_BINS + lo[m] + k]);
+    }
+    if (w.size() > 416) { rho_b200_destroy(h); return fail(RHO_ERR_INVALID, "mel filterbank nnz %zu > 416", w.size()); }
+    h->tb.mel_nnz[which] = (int)w.size();
+    if ((e = dev_upload(h, &h->tb.mel_lo[which], lo.data(), nm)) != cudaSuccess ||
+        (e = dev_upload(h, &h->tb.mel_cnt[which], cnt.data(), nm)) != cudaSuccess ||
+        (e = dev_upload(h, &h->tb.mel_wofs[which], wofs.data(), nm)) != cudaSuccess ||
+        (e = dev_upload(h, &h->tb.mel_w[which], w.data(), w.size())) != cudaSuccess ||
+        (e = dev_upload(h, &h->tb.mel_dense[which], dense.data(), dense.size())) != cudaSuccess) {
+      rho_b200_destroy(h); return cuda_fail(e, "mel tables");
+    }
+  }
+  *out = h;
+  return RHO_OK;
+}
+
+int rho_b200_destroy(rho_handle* h) {
+  if (!h) return RHO_OK;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->arena) cudaFree(h->arena);
+  if (h->streams_ok) {
+    cudaStreamDestroy(h->s_copy_in); cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy_out);
+  }
+  delete h;
+  return RHO_OK;
+}
+
+int64_t rho_b200_launch_count(rho_handle* h) { return h ? h->lc.launches : 0; }
+
+int rho_b200_profile_begin(rho_handle* h) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  for (auto& sp : h->lc.spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  h->lc.spans.clear();
+  h->lc.profiling = true;
+  return RHO_OK;
+}
+
+int rho_b200_profile_end(rho_handle* h, double* ms_per_kernel, int64_t* launches_per_kernel, int capacity) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  if (capacity < KID_COUNT || !ms_per_kernel || !launches_per_kernel) return fail(RHO_ERR_INVALID, "capacity < %d", (int)KID_COUNT);
+  h->lc.profiling = false;
+  for (int i = 0; i < KID_COUNT; ++i) { ms_per_kernel[i] = 0.0; launches_per_kernel[i] = 0; }
+  int rc = RHO_OK;
+  for (auto& sp : h->lc.spans) {
+    cudaError_t e = cudaEventSynchronize(sp.b);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, sp.a, sp.b);
+    if (e != cudaSuccess) rc = cuda_fail(e, "profile_end");
+    else { ms_per_kernel[sp.id] += ms; launches_per_kernel[sp.id] += 1; }
+    cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+  }
+  h->lc.spans.clear();
+  return rc == RHO_OK ? KID_COUNT : rc;
+}
+
+const char* rho_b200_kernel_name(int id) { return (id >= 0 && id < KID_COUNT) ? kKernelNames[id] : ""; }
+
+size_t rho_b200_workspace_bytes(int n_segments, int n_items, int64_t max_seg_len) {
+  return plan_ws(n_segments, n_items, max_seg_len).total;
+}
+
+int rho_b200_trim_scan(rho_handle* h, const float* x, const int64_t* off, const int32_t* len,
+                       const uint8_t* trim_flags, int n_segments, int64_t max_seg_len,
+                       const rho_params* p, rho_seg_info* info, void* workspace, size_t ws_bytes, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  int rc = check_params(p); if (rc) return rc;
+  if (n_segments < 0 || max_seg_len < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (n_segments == 0) return RHO_OK;
+  if (!x || !off || !len || !info) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  const Derived d = derive(*p);
+  Workspace ws;
+  rc = carve(workspace, ws_bytes, n_segments, n_segments, max_seg_len, d, &ws, nullptr); if (rc) return rc;
+  cudaError_t e = launch_trim_scan(x, off, len, trim_flags, n_segments, max_seg_len, d, ws, info,
+                                   (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "trim_scan");
+}
+
+int rho_b200_join(rho_handle* h, const float* x, const int64_t* seg_off, const int32_t* seg_len,
+                  int n_segments, int64_t max_seg_len, const int32_t* item_first_seg, int n_items,
+                  int64_t max_item_len, const rho_params* p, float* y, const int64_t* y_off,
+                  rho_record* rec, rho_seg_info* seg_info, void* workspace, size_t ws_bytes, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  int rc = check_params(p); if (rc) return rc;
+  if (n_segments < 0 || n_items < 0 || max_seg_len < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (n_items == 0) return RHO_OK;
+  if (!item_first_seg || !y_off || !rec || (n_segments > 0 && (!x || !seg_off || !seg_len || !y)))
+    return fail(RHO_ERR_INVALID, "NULL device pointer");
+  const Derived d = derive(*p);
+  Workspace ws;
+  rc = carve(workspace, ws_bytes, n_segments, n_items, max_seg_len, d, &ws, nullptr); if (rc) return rc;
+  cudaError_t e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len,
+                              d, y, y_off, rec, seg_info, ws, (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "join");
+}
+
+int rho_b200_remove_dc(rho_handle* h, float* x, int64_t n, float* dc_out, void* workspace, size_t ws_bytes, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  if (n < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (n == 0) return RHO_OK;                       // base_tts.py:396-397
+  if (!x) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  if (!workspace || ws_bytes < 256) return fail(RHO_ERR_WORKSPACE, "workspace too small: need 256 bytes");
+  cudaError_t e = launch_remove_dc(x, n, dc_out, (double*)workspace, (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "remove_dc");
+}
+
+int rho_b200_apply_fades(rho_handle* h, float* x, int64_t n, int fade_in, int fade_out, const rho_params* p, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  int rc = check_params(p); if (rc) return rc;
+  if (n < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (n == 0) return RHO_OK;
+  if (!x) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  const Derived d = derive(*p);
+  cudaError_t e = launch_apply_fades(x, n, d.fade, fade_in, fade_out, (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "apply_fades");
+}
+
+int rho_b200_sound_decay(rho_handle* h, const float* x, int64_t n, const rho_params* p, rho_record* rec,
+                         void* workspace, size_t ws_bytes, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  int rc = check_params(p); if (rc) return rc;
+  if (n < 0 || n > INT32_MAX) return fail(RHO_ERR_INVALID, "size out of range");
+  if (!rec || (n > 0 && !x)) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  if (!workspace || ws_bytes < 256) return fail(RHO_ERR_WORKSPACE, "workspace too small: need 256 bytes");
+  cudaError_t e = launch_sound_decay(x, n, p->decay_thr, rec, (double*)workspace, (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "sound_decay");
+}
+
+int rho_b200_resample3to2(rho_handle* h, const float* x, const int64_t* off, const int32_t* len,
+                          int len_stride_bytes, int n, int64_t max_len, float* y, const int64_t* y_off,
+                          int32_t* y_len, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  if (n < 0 || max_len < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (n == 0) return RHO_OK;
+  if (!x || !off || !len || !y || !y_off) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  cudaError_t e = launch_resample3to2(x, off, len, len_stride_bytes, n, max_len, y, y_off, y_len,
+                                      (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "resample3to2");
+}
+
+int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const int32_t* len16, int n,
+                    int64_t max_len16, int n_mels, int pad_frames, float* mel, int64_t mel_stride_frames,
+                    int32_t* n_frames, void* workspace, size_t ws_bytes, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  if (n_mels != 80 && n_mels != 128) return fail(RHO_ERR_INVALID, "n_mels must be 80 or 128, got %d", n_mels);
+  if (pad_frames != 0 && pad_frames != MEL_PAD_FRAMES) return fail(RHO_ERR_INVALID, "pad_frames must be 0 or 3000");
+  if (n < 0 || max_len16 < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (n == 0) return RHO_OK;
+  if (!x16 || !off || !len16 || !mel) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  if (pad_frames == 0 && mel_stride_frames < max_len16 / HOP16) return fail(RHO_ERR_INVALID, "mel_stride_frames too small");
+  if (pad_frames > 0 && mel_stride_frames < pad_frames) return fail(RHO_ERR_INVALID, "mel_stride_frames too small");
+  const size_t need = align_up(sizeof(int) * (size_t)n, 256);
+  if (!workspace || ws_bytes < need) return fail(RHO_ERR_WORKSPACE, "workspace too small: have %zu, need %zu", ws_bytes, need);
+  cudaError_t e = launch_logmel(h->tb, x16, off, len16, n, max_len16, n_mels, pad_frames, mel, mel_stride_frames,
+                                n_frames, (int*)workspace, (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "logmel");
+}
+
+int rho_b200_cosine(rho_handle* h, const float* emb, const float* ref, int n, int dim, float* out,
+                    int out_stride_bytes, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  if (n < 0 || dim <= 0) return fail(RHO_ERR_INVALID, "bad size");
+  if (n == 0) return RHO_OK;
+  if (!emb || !ref || !out) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  cudaError_t e = launch_cosine(emb, ref, n, dim, out, out_stride_bytes, (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "cosine");
+}
+
+int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, const int32_t* seg_len,
+                      int n_segments, int64_t max_seg_len, const int32_t* item_first_seg, int n_items,
+                      int64_t max_item_len, const rho_params* p, float* y, const int64_t* y_off,
+                      int n_mels, int pad_frames, float* mel, int64_t mel_stride_frames,
+                      const float* emb, const float* ref_emb, int emb_dim, rho_record* rec, float* scratch16,
+                      void* workspace, size_t ws_bytes, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  int rc = check_params(p); if (rc) return rc;
+  if (p->sr != 24000) return fail(RHO_ERR_INVALID, "validate needs 24 kHz input (3:2 resampler), got %d", p->sr);
+  if (n_mels != 80 && n_mels != 128) return fail(RHO_ERR_INVALID, "n_mels must be 80 or 128, got %d", n_mels);
+  if (pad_frames != 0 && pad_frames != MEL_PAD_FRAMES) return fail(RHO_ERR_INVALID, "pad_frames must be 0 or 3000");
+  if (n_items <= 0) return n_items == 0 ? RHO_OK : fail(RHO_ERR_INVALID, "negative size");
+  if (!scratch16 || !mel || !rec) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  rc = rho_b200_join(h, x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, p,
+                     y, y_off, rec, nullptr, workspace, ws_bytes, stream);
+  if (rc) return rc;
+  const Derived d = derive(*p);
+  Workspace ws;
+  rc = carve(workspace, ws_bytes, n_segments, n_items, max_seg_len, d, &ws, nullptr); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // 16 kHz intermediate lives at the same offsets as y (it is 2/3 as long)
+  cudaError_t e = launch_resample3to2(y, y_off, &rec[0].out_len, (int)sizeof(rho_record), n_items, max_item_len,
+                                      scratch16, y_off, ws.len16, st, &h->lc);
+  if (e != cudaSuccess) return cuda_fail(e, "resample3to2");
+  const int64_t max16 = (2 * max_item_len + 2) / 3;
+  if (pad_frames == 0 && mel_stride_frames < max16 / HOP16) return fail(RHO_ERR_INVALID, "mel_stride_frames too small");
+  if (pad_frames > 0 && mel_stride_frames < pad_frames) return fail(RHO_ERR_INVALID, "mel_stride_frames too small");
+  e = launch_logmel(h->tb, scratch16, y_off, ws.len16, n_items, max16, n_mels, pad_frames, mel, mel_stride_frames,
+                    nullptr, ws.clip_max, st, &h->lc);
+  if (e != cudaSuccess) return cuda_fail(e, "logmel");
+  if (emb && ref_emb) {
+    e = launch_cosine(emb, ref_emb, n_items, emb_dim, &rec[0].cosine, (int)sizeof(rho_record), st, &h->lc);
+    if (e != cudaSuccess) return cuda_fail(e, "cosine");
+  }
+  return RHO_OK;
+}
+
+// ----------------------------------------------------------------------------- HOST entry point
+int rho_b200_validate_host(rho_handle* h, const float* x, int n, int32_t clip_len, const rho_params* p,
+                           float* y, int n_mels, int pad_frames, float* mel, const float* emb,
+                           const float* ref_emb, int emb_dim, rho_record* rec) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  int rc = check_params(p); if (rc) return rc;
+  if (n < 0 || clip_len <= 0) return fail(RHO_ERR_INVALID, "bad size");
+  if (n == 0) return RHO_OK;
+  if (!x || !y || !rec) return fail(RHO_ERR_INVALID, "NULL host pointer");
+  if (pad_frames != MEL_PAD_FRAMES) return fail(RHO_ERR_INVALID, "host entry point supports pad_frames=3000 only");
+  std::lock_guard<std::mutex> lock(h->mu);
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  if (!h->streams_ok) {
+    if ((e = cudaStreamCreateWithFlags(&h->s_copy_in, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->s_copy_out, cudaStreamNonBlocking)) != cudaSuccess)
+      return cuda_fail(e, "cudaStreamCreate");
+    h->streams_ok = true;
+  }
+  // chunking: CH clips per chunk, 3 chunk slots so copy-in(k+1), compute(k) and copy-out(k-1) overlap
+  const int CH = n < 64 ? n : 64;
+  const int SLOTS = 3;
+  const size_t stride = align_up((size_t)clip_len, 32);                 // samples per clip slot
+  const size_t b_x = align_up(stride * CH * sizeof(float), 256);
+  const size_t b_mel = align_up((size_t)CH * n_mels * pad_frames * sizeof(float), 256);
+  const size_t b_rec = align_up(sizeof(rho_record) * CH, 256);
+  const size_t b_emb = align_up(sizeof(float) * (size_t)CH * (emb_dim > 0 ? emb_dim : 1), 256);
+  const size_t b_meta = align_up((sizeof(int64_t) * 2 + sizeof(int32_t) * 2) * (size_t)(CH + 1), 256);
+  const size_t b_ws = align_up(rho_b200_workspace_bytes(CH, CH, clip_len), 256);
+  const size_t per_slot = 3 * b_x + b_mel + b_rec + b_emb + b_ws;
+  const size_t total = SLOTS * per_slot + b_meta + align_up(sizeof(float) * (emb_dim > 0 ? emb_dim : 1), 256);
+  if (h->arena_bytes < total) {
+    if (h->arena) cudaFree(h->arena);
+    h->arena = nullptr; h->arena_bytes = 0;
+    if ((e = cudaMalloc(&h->arena, total)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(arena)");
+    h->arena_bytes = total;
+  }
+  char* base = (char*)h->arena;
+  // metadata (identical for every chunk): offsets, lengths, item_first_seg
+  std::vector<int64_t> offs(CH + 1);
+  std::vector<int32_t> lens(CH + 1), first(CH + 1);
+  for (int i = 0; i <= CH; ++i) { offs[i] = (int64_t)i * stride; lens[i] = clip_len; first[i] = i; }
+  int64_t* d_off = (int64_t*)base;
+  int32_t* d_len = (int32_t*)(base + sizeof(int64_t) * (CH + 1));
+  int32_t* d_first = (int32_t*)(base + (sizeof(int64_t) + sizeof(int32_t)) * (CH + 1));
+  float* d_ref = (float*)(base + b_meta);
+  cudaStream_t sc = h->s_compute;
+  if ((e = cudaMemcpyAsync(d_off, offs.data(), sizeof(int64_t) * (CH + 1), cudaMemcpyHostToDevice, sc)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(d_len, lens.data(), sizeof(int32_t) * (CH + 1), cudaMemcpyHostToDevice, sc)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(d_first, first.data(), sizeof(int32_t) * (CH + 1), cudaMemcpyHostToDevice, sc)) != cudaSuccess)
+    return cuda_fail(e, "metadata upload");
+  const bool have_emb = emb && ref_emb && emb_dim > 0;
+  if (have_emb && (e = cudaMemcpyAsync(d_ref, ref_emb, sizeof(float) * emb_dim, cudaMemcpyHostToDevice, sc)) != cudaSuccess)
+    return cuda_fail(e, "ref upload");
+  if ((e = cudaStreamSynchronize(sc)) != cudaSuccess) return cuda_fail(e, "metadata sync");  // vectors go out of scope later
+
+  char* slots = base + b_meta + align_up(sizeof(float) * (emb_dim > 0 ? emb_dim : 1), 256);
+  cudaEvent_t ev_in[SLOTS], ev_done[SLOTS], ev_out[SLOTS];
+  for (int s = 0; s < SLOTS; ++s) {
+    cudaEventCreateWithFlags(&ev_in[s], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_done[s], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_out[s], cudaEventDisableTiming);
+  }
+  int status = RHO_OK;
+  const int n_chunks = (n + CH - 1) / CH;
+  for (int k = 0; k < n_chunks && status == RHO_OK; ++k) {
+    const int s = k % SLOTS;
+    const int c0 = k * CH, cn = (n - c0 < CH) ? n - c0 : CH;
+    char* sb = slots + (size_t)s * per_slot;
+    float* d_x = (float*)sb;
+    float* d_y = (float*)(sb + b_x);
+    float* d_16 = (float*)(sb + 2 * b_x);
+    float* d_mel = (float*)(sb + 3 * b_x);
+    rho_record* d_rec = (rho_record*)(sb + 3 * b_x + b_mel);
+    float* d_emb = (float*)(sb + 3 * b_x + b_mel + b_rec);
+    void* d_ws = sb + 3 * b_x + b_mel + b_rec + b_emb;
+    // slot reuse: wait until chunk k-SLOTS has been copied out
+    if (k >= SLOTS) cudaStreamWaitEvent(h->s_copy_in, ev_out[s], 0);
+    if (stride == (size_t)clip_len) {
+      e = cudaMemcpyAsync(d_x, x + (size_t)c0 * clip_len, sizeof(float) * (size_t)cn * clip_len, cudaMemcpyHostToDevice, h->s_copy_in);
+    } else {
+      e = cudaMemcpy2DAsync(d_x, stride * sizeof(float), x + (size_t)c0 * clip_len, (size_t)clip_len * sizeof(float),
+                            (size_t)clip_len * sizeof(float), cn, cudaMemcpyHostToDevice, h->s_copy_in);
+    }
+    if (e == cudaSuccess && have_emb)
+      e = cudaMemcpyAsync(d_emb, emb + (size_t)c0 * emb_dim, sizeof(float) * (size_t)cn * emb_dim, cudaMemcpyHostToDevice, h->s_copy_in);
+    if (e != cudaSuccess) { status = cuda_fail(e, "H2D"); break; }
+    cudaEventRecord(ev_in[s], h->s_copy_in);
+    cudaStreamWaitEvent(sc, ev_in[s], 0);
+    status = rho_b200_validate(h, d_x, d_off, d_len, cn, clip_len, d_first, cn, clip_len, p, d_y, d_off,
+                               n_mels, pad_frames, d_mel, pad_frames, have_emb ? d_emb : nullptr,
+                               have_emb ? d_ref : nullptr, emb_dim, d_rec, d_16, d_ws, b_ws, sc);
+    if (status != RHO_OK) break;
+    cudaEventRecord(ev_done[s], sc);
+    cudaStreamWaitEvent(h->s_copy_out, ev_done[s], 0);
+    if (stride == (size_t)clip_len) {
+      e = cudaMemcpyAsync(y + (size_t)c0 * clip_len, d_y, sizeof(float) * (size_t)cn * clip_len, cudaMemcpyDeviceToHost, h->s_copy_out);
+    } else {
+      e = cudaMemcpy2DAsync(y + (size_t)c0 * clip_len, (size_t)clip_len * sizeof(float), d_y, stride * sizeof(float),
+                            (size_t)clip_len * sizeof(float), cn, cudaMemcpyDeviceToHost, h->s_copy_out);
+    }
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(rec + c0, d_rec, sizeof(rho_record) * cn, cudaMemcpyDeviceToHost, h->s_copy_out);
+    if (e == cudaSuccess && mel)
+      e = cudaMemcpyAsync(mel + (size_t)c0 * n_mels * pad_frames, d_mel, sizeof(float) * (size_t)cn * n_mels * pad_frames,
+                          cudaMemcpyDeviceToHost, h->s_copy_out);
+    if (e != cudaSuccess) { status = cuda_fail(e, "D2H"); break; }
+    cudaEventRecord(ev_out[s], h->s_copy_out);
+  }
+  cudaError_t e1 = cudaStreamSynchronize(h->s_copy_in);
+  cudaError_t e2 = cudaStreamSynchronize(sc);
+  cudaError_t e3 = cudaStreamSynchronize(h->s_copy_out);
+  for (int s = 0; s < SLOTS; ++s) { cudaEventDestroy(ev_in[s]); cudaEventDestroy(ev_done[s]); cudaEventDestroy(ev_out[s]); }
+  if (status != RHO_OK) return status;
+  if (e1 != cudaSuccess) return cuda_fail(e1, "sync copy-in");
+  if (e2 != cudaSuccess) return cuda_fail(e2, "sync compute");
+  if (e3 != cudaSuccess) return cuda_fail(e3, "sync copy-out");
+  return RHO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,563 @@
+// Post-process / join kernels: silence-trim scan, DC, crossfade gather, fades, decay sums.
+//
+// Reference semantics: src/rho_tts/base_tts.py
+//   _trim_silence :348-392, _remove_dc_offset :394-399, _apply_fades :401-433,
+//   _smooth_segment_join :435-536, _validate_sound_decay :297-323.
+//
+// Bit-exactness of the trim decision: torch's CPU avg_pool1d adds the `window`
+// squared samples of a frame strictly left to right in fp32 (zero padding included)
+// and divides by `window`.  k_scan reproduces that chain with __fmul_rn/__fadd_rn
+// (never contracted into an FMA) so `sqrt(sum/window) > thr` is the same predicate.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rho {
+
+// ------------------------------------------------------------------ init
+__global__ void k_init_items(SegState* __restrict__ seg, ItemState* __restrict__ item,
+                             const int32_t* __restrict__ item_first_seg, int n_items) {
+  const int it = blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= n_items) return;
+  ItemState z;
+  z.s_first = 0.0; z.s_last = 0.0; z.out_len = 0; z.flags = 0; z.pad0 = 0; z.pad1 = 0;
+  item[it] = z;
+  const int s0 = item_first_seg[it], s1 = item_first_seg[it + 1];
+  const int n = s1 - s0;
+  for (int s = s0; s < s1; ++s) {
+    const int pos = s - s0;
+    const bool fs = (n == 1) || pos > 0;        // base_tts.py:449, 469-474
+    const bool fe = (n == 1) || pos < n - 1;
+    SegState st;
+    st.first = INT_MAX; st.last = -1; st.start = 0; st.end = 0; st.dc = 0.f;
+    st.flags = (fs ? 0x100u : 0u) | (fe ? 0x200u : 0u);
+    st.item = it; st.pos = pos;
+    seg[s] = st;
+  }
+}
+
+__global__ void k_init_segs(SegState* __restrict__ seg, const uint8_t* __restrict__ trim_flags, int n_seg) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg) return;
+  const unsigned tf = trim_flags ? trim_flags[s] : 3u;
+  SegState st;
+  st.first = INT_MAX; st.last = -1; st.start = 0; st.end = 0; st.dc = 0.f;
+  st.flags = ((tf & 1u) ? 0x100u : 0u) | ((tf & 2u) ? 0x200u : 0u);
+  st.item = s; st.pos = 0;
+  seg[s] = st;
+}
+
+// ------------------------------------------------------------------ scan
+// One thread per energy frame, FR frames per CTA.  The CTA stages the samples its frames
+// cover in shared memory, hop-block by hop-block with a row stride RS chosen so that the
+// per-thread walk (thread t starts at row t) is bank-conflict free:
+//   VEC path  (hop % 4 == 0, window == 2*hop): RS = 4*odd, rows read with 128-bit LDS;
+//   generic   : RS odd, scalar LDS.
+// Thread t of the tile owns frame f = frame0 + t, which covers rows t and t+1 (plus one
+// sample of row t+2 when `window` is odd), and the DC block sum of row t+1 (= global hop
+// block f, samples [f*hop, (f+1)*hop)).
+template <bool VEC>
+__global__ void __launch_bounds__(SCAN_FR)
+k_scan(const float* __restrict__ x, const int64_t* __restrict__ off, const int32_t* __restrict__ len,
+       SegState* __restrict__ seg, float* __restrict__ block_sum, int blocks_per_seg,
+       int window, int hop, int RS, float thr) {
+  extern __shared__ __align__(16) float sm[];
+  const int s = blockIdx.x;
+  const int L = len[s];
+  const int n_frames = (L <= 0) ? 0 : (L + 2 * hop - window) / hop + 1;
+  const int frame0 = blockIdx.y * SCAN_FR;
+  if (frame0 >= n_frames) return;
+  const float* __restrict__ xs = x + off[s];
+  const int rows = SCAN_FR + 2;
+  const long long g0 = (long long)(frame0 - 1) * hop;  // global sample of row 0, col 0 (pad == hop)
+
+  if (VEC) {
+    const int q_per_row = hop >> 2;
+    const int total_q = rows * q_per_row;
+    for (int q = threadIdx.x; q < total_q; q += SCAN_FR) {
+      const int row = q / q_per_row, c4 = (q - row * q_per_row) << 2;
+      const long long g = g0 + (long long)row * hop + c4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g >= 0 && g + 3 < L) {
+        v = ldg_stream4(xs + g);
+      } else if (g + 3 >= 0 && g < L) {
+        if (g + 0 >= 0 && g + 0 < L) v.x = xs[g + 0];
+        if (g + 1 >= 0 && g + 1 < L) v.y = xs[g + 1];
+        if (g + 2 >= 0 && g + 2 < L) v.z = xs[g + 2];
+        if (g + 3 >= 0 && g + 3 < L) v.w = xs[g + 3];
+      }
+      *reinterpret_cast<float4*>(sm + row * RS + c4) = v;
+    }
+  } else {
+    const int total = rows * hop;
+    for (int r = threadIdx.x; r < total; r += SCAN_FR) {
+      const int row = r / hop, c = r - row * hop;
+      const long long g = g0 + r;
+      sm[row * RS + c] = (g >= 0 && g < L) ? xs[g] : 0.f;
+    }
+  }
+  __syncthreads();
+
+  const int t = threadIdx.x;
+  const int f = frame0 + t;
+  bool loud = false;
+  if (f < n_frames) {
+    float acc = 0.f, bs = 0.f;
+    if (VEC) {
+      const float4* p0 = reinterpret_cast<const float4*>(sm + t * RS);
+      const float4* p1 = reinterpret_cast<const float4*>(sm + (t + 1) * RS);
+      const int nq = hop >> 2;
+#pragma unroll 6
+      for (int j = 0; j < nq; ++j) {
+        const float4 v = p0[j];
+        acc = __fadd_rn(acc, __fmul_rn(v.x, v.x));
+        acc = __fadd_rn(acc, __fmul_rn(v.y, v.y));
+        acc = __fadd_rn(acc, __fmul_rn(v.z, v.z));
+        acc = __fadd_rn(acc, __fmul_rn(v.w, v.w));
+      }
+#pragma unroll 6
+      for (int j = 0; j < nq; ++j) {
+        const float4 v = p1[j];
+        acc = __fadd_rn(acc, __fmul_rn(v.x, v.x));
+        acc = __fadd_rn(acc, __fmul_rn(v.y, v.y));
+        acc = __fadd_rn(acc, __fmul_rn(v.z, v.z));
+        acc = __fadd_rn(acc, __fmul_rn(v.w, v.w));
+        bs += (v.x + v.y) + (v.z + v.w);
+      }
+    } else {
+      int left = window;
+      for (int b = 0; left > 0; ++b) {
+        const float* p = sm + (t + b) * RS;
+        const int cnt = left < hop ? left : hop;
+        for (int j = 0; j < cnt; ++j) {
+          const float v = p[j];
+          acc = __fadd_rn(acc, __fmul_rn(v, v));
+        }
+        left -= cnt;
+      }
+      const float* p1 = sm + (t + 1) * RS;
+      for (int j = 0; j < hop; ++j) bs += p1[j];
+    }
+    const float e = __fsqrt_rn(__fdiv_rn(acc, (float)window));
+    loud = e > thr;
+    if (f < blocks_per_seg) block_sum[(size_t)s * blocks_per_seg + f] = bs;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, loud);
+  if (m != 0u && (threadIdx.x & 31) == 0) {
+    const int wbase = frame0 + (threadIdx.x & ~31);
+    atomicMin(&seg[s].first, wbase + (__ffs(m) - 1));
+    atomicMax(&seg[s].last, wbase + (31 - __clz(m)));
+  }
+}
+
+// ------------------------------------------------------------------ per-segment finalize
+// One warp per segment: frames -> [start, end), flags, DC = mean over [start, end).
+__global__ void k_finalize_segs(const float* __restrict__ x, const int64_t* __restrict__ off,
+                                const int32_t* __restrict__ len, SegState* __restrict__ seg,
+                                const float* __restrict__ block_sum, int blocks_per_seg,
+                                int n_seg, int window, int hop, int trim_enabled,
+                                rho_seg_info* __restrict__ info_out) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= n_seg) return;
+  SegState st = seg[s];
+  const int L = len[s];
+  const bool fs = st.flags & 0x100u, fe = st.flags & 0x200u;
+  int start, end;
+  uint32_t flags = 0;
+  if (!trim_enabled || L <= 0) {                       // base_tts.py:360-361
+    start = 0; end = L > 0 ? L : 0; flags = RHO_F_UNTOUCHED;
+  } else if (st.last < 0) {                            // :379-380  audio[:, :window_size] (2-D)
+    start = 0; end = window < L ? window : L; flags = RHO_F_ALL_SILENT;
+  } else {                                             // :386-390
+    const long long a = fs ? ((long long)st.first * window) / 2 : 0;
+    const long long b = fe ? ((long long)(st.last + 2) * window) / 2 : (long long)L;
+    long long sa = a < L ? a : L; if (sa < 0) sa = 0;
+    long long eb = b < L ? b : L; if (eb < sa) eb = sa;
+    start = (int)sa; end = (int)eb;
+  }
+  // DC over [start, end): whole hop blocks from block_sum, ragged edges straight from x.
+  const float* __restrict__ xs = x + off[s];
+  double acc = 0.0;
+  const int n = end - start;
+  if (n > 0) {
+    int kb0 = (start + hop - 1) / hop, kb1 = end / hop;
+    if (kb1 > blocks_per_seg) kb1 = blocks_per_seg;
+    if (kb0 <= kb1) {
+      for (int k = kb0 + lane; k < kb1; k += 32) acc += (double)block_sum[(size_t)s * blocks_per_seg + k];
+      for (int g = start + lane; g < kb0 * hop; g += 32) acc += (double)xs[g];
+      for (int g = kb1 * hop + lane; g < end; g += 32) acc += (double)xs[g];
+    } else {
+      for (int g = start + lane; g < end; g += 32) acc += (double)xs[g];
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    st.start = start; st.end = end;
+    st.dc = n > 0 ? (float)(acc / (double)n) : 0.f;
+    st.flags = (st.flags & 0xffffff00u) | flags;
+    seg[s] = st;
+    if (info_out) {
+      rho_seg_info o; o.start = start; o.end = end; o.dc = st.dc; o.flags = flags;
+      info_out[s] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ per-item plan
+// One thread per item.  Emits, for every segment, the contiguous span of the joined output it
+// produces: [crossfade with previous | body | pause].  Mirrors the emit order of
+// base_tts.py:481-523 and the rank bookkeeping that makes torch.cat throw (-> fallback, :530-533).
+__global__ void k_plan_items(const SegState* __restrict__ seg, const int32_t* __restrict__ seg_len,
+                             SegSpan* __restrict__ span, ItemState* __restrict__ item,
+                             const int32_t* __restrict__ item_first_seg, int n_items,
+                             int cf, int pause, int pause_on) {
+  const int it = blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= n_items) return;
+  const int s0 = item_first_seg[it], s1 = item_first_seg[it + 1];
+  const int n = s1 - s0;
+  if (n <= 0) { item[it].out_len = 0; item[it].flags = 0; return; }
+  SegSpan z; z.dst = 0; z.ov = 0; z.body = 0; z.pause = 0; z.prev_tail = 0; z.pad0 = z.pad1 = z.pad2 = 0;
+  if (n == 1) {                                        // :447-452
+    const SegState st = seg[s0];
+    SegSpan sp = z; sp.body = st.end - st.start;
+    span[s0] = sp;
+    item[it].out_len = sp.body;
+    item[it].flags = (st.flags & RHO_F_ALL_SILENT) ? (RHO_F_ALL_SILENT | RHO_F_TWO_D) : (st.flags & RHO_F_UNTOUCHED);
+    return;
+  }
+  bool has1 = false, has2 = false;
+  auto mark = [&](bool two_d, int cnt) {
+    if (cnt == 0 && !two_d) return;                    // torch.cat skips 1-D empties
+    if (two_d) has2 = true; else has1 = true;
+  };
+  int pos = 0;
+  int Lprev = 0; bool dprev = false;
+  for (int i = 0; i < n; ++i) {
+    const SegState st = seg[s0 + i];
+    const int Li = st.end - st.start;
+    const bool di = (st.flags & RHO_F_ALL_SILENT) != 0;
+    SegSpan sp = z; sp.dst = pos;
+    if (i == 0) {
+      sp.body = (Li > cf) ? Li - cf : Li;              // :484-488
+      mark(di, sp.body);
+    } else {
+      int ov = cf < Lprev ? cf : Lprev; if (Li < ov) ov = Li;   // :491
+      if (ov > 10) {
+        mark(dprev || di, ov);
+        const int rem = (i < n - 1 && Li > ov + cf) ? Li - ov - cf : Li - ov;   // :507-513
+        if (rem > 0) mark(di, rem);
+        const int pz = (pause_on && i < n - 1) ? pause : 0;                      // :518-521
+        if (pause_on && i < n - 1) mark(false, pz);
+        sp.ov = ov; sp.body = rem; sp.pause = pz; sp.prev_tail = Lprev - ov;
+      } else {
+        sp.body = Li;                                  // :523
+        mark(di, Li);
+      }
+    }
+    span[s0 + i] = sp;
+    pos += sp.ov + sp.body + sp.pause;
+    Lprev = Li; dprev = di;
+  }
+  if (has1 && has2) {
+    // fallback: torch.cat(ORIGINAL segments) -- untrimmed, DC kept, no crossfade, no pause.
+    int p = 0;
+    for (int i = 0; i < n; ++i) {
+      SegSpan sp = z; sp.dst = p; sp.body = seg_len[s0 + i];
+      span[s0 + i] = sp; p += sp.body;
+    }
+    item[it].out_len = p; item[it].flags = RHO_F_FALLBACK;
+  } else {
+    item[it].out_len = pos; item[it].flags = has2 ? RHO_F_TWO_D : 0u;
+  }
+}
+
+// ------------------------------------------------------------------ gather
+__device__ __forceinline__ float fade_gain(int o, int out_len, int fade) {
+  // _apply_fades :420-431; skipped entirely when the item is shorter than 2*fade.
+  float g = 1.f;
+  if (fade > 0 && out_len >= 2 * fade) {
+    if (o < fade) g = 0.5f * (1.f - cosf(linspace32(0.f, RHO_PI_F, fade, o)));
+    else if (o >= out_len - fade) g = 0.5f * (1.f + cosf(linspace32(0.f, RHO_PI_F, fade, o - (out_len - fade))));
+  }
+  return g;
+}
+
+// grid (n_seg, tiles); each CTA writes GATHER_TILE consecutive samples of one segment's span.
+__global__ void __launch_bounds__(GATHER_THREADS)
+k_gather(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const SegState* __restrict__ seg,
+         const SegSpan* __restrict__ span, ItemState* __restrict__ item,
+         float* __restrict__ y, const int64_t* __restrict__ y_off, int fade) {
+  const int s = blockIdx.x;
+  const SegSpan sp = span[s];
+  const int span_len = sp.ov + sp.body + sp.pause;
+  const int j0 = blockIdx.y * GATHER_TILE;
+  if (j0 >= span_len) return;
+  const SegState st = seg[s];
+  const ItemState is = item[st.item];
+  const bool fb = (is.flags & RHO_F_FALLBACK) != 0;
+  const int out_len = is.out_len;
+  const int third = out_len / 3;
+  const int src0 = fb ? 0 : st.start;
+  const float dc = fb ? 0.f : st.dc;
+  const float* __restrict__ xc = x + seg_off[s] + src0;
+  float* __restrict__ yo = y + y_off[st.item] + sp.dst;
+  // previous segment (crossfade tail)
+  const float* __restrict__ xp = nullptr; float dcp = 0.f;
+  if (sp.ov > 0) {
+    const SegState pst = seg[s - 1];
+    xp = x + seg_off[s - 1] + pst.start + sp.prev_tail;
+    dcp = pst.dc;
+  }
+  const bool need_fade = fade > 0 && out_len >= 2 * fade;
+  const bool aligned = (((uintptr_t)xc | (uintptr_t)yo) & 15u) == 0;
+
+  float a_first = 0.f, a_last = 0.f;
+  const int jend = min(j0 + GATHER_TILE, span_len);
+  for (int j = j0 + 4 * threadIdx.x; j < jend; j += 4 * GATHER_THREADS) {
+    const int o = sp.dst + j;
+    const bool interior = aligned && j >= sp.ov && j + 3 < sp.ov + sp.body &&
+                          (!need_fade || (o >= fade && o + 3 < out_len - fade));
+    if (interior) {
+      float4 v = ldg_stream4(xc + j);
+      v.x = __fsub_rn(v.x, dc); v.y = __fsub_rn(v.y, dc); v.z = __fsub_rn(v.z, dc); v.w = __fsub_rn(v.w, dc);
+      stg_stream4(yo + j, v);
+      if (o < third || o + 3 >= out_len - third) {
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (o + k < third) a_first += vv[k] * vv[k];
+          if (o + k >= out_len - third) a_last += vv[k] * vv[k];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int jj = j + k;
+        if (jj >= jend) break;
+        float v;
+        if (jj < sp.ov) {               // :497-504 equal-power crossfade
+          const float fo = cosf(linspace32(0.f, RHO_HALF_PI_F, sp.ov, jj));
+          const float fi = cosf(linspace32(RHO_HALF_PI_F, 0.f, sp.ov, jj));
+          const float a = __fmul_rn(__fsub_rn(xp[jj], dcp), fo);
+          const float b = __fmul_rn(__fsub_rn(xc[jj], dc), fi);
+          v = __fadd_rn(a, b);
+        } else if (jj < sp.ov + sp.body) {
+          v = __fsub_rn(xc[jj], dc);
+        } else {
+          v = 0.f;                      // inter-sentence pause
+        }
+        const int oo = o + k;
+        if (need_fade) v = __fmul_rn(v, fade_gain(oo, out_len, fade));
+        yo[jj] = v;
+        if (oo < third) a_first += v * v;
+        if (oo >= out_len - third) a_last += v * v;
+      }
+    }
+  }
+  // block reduction of the two decay sums, one double atomic each per CTA
+  __shared__ double red[2][GATHER_THREADS / 32];
+  double df = warp_sum((double)a_first), dl = warp_sum((double)a_last);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][w] = df; red[1][w] = dl; }
+  __syncthreads();
+  if (w == 0) {
+    df = lane < GATHER_THREADS / 32 ? red[0][lane] : 0.0;
+    dl = lane < GATHER_THREADS / 32 ? red[1][lane] : 0.0;
+    df = warp_sum(df); dl = warp_sum(dl);
+    if (lane == 0) {
+      if (df != 0.0) atomicAdd(&item[st.item].s_first, df);
+      if (dl != 0.0) atomicAdd(&item[st.item].s_last, dl);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ per-item finalize (decay)
+__device__ __forceinline__ void decay_decide(double s_first, double s_last, int n, double thr,
+                                             float* first_rms, float* last_rms, double* ratio, int* ok) {
+  // _validate_sound_decay :304-323
+  *first_rms = 0.f; *last_rms = 0.f; *ratio = 1.0; *ok = 1;
+  const int third = n / 3;
+  if (n <= 0 || third < 1) return;
+  const float fr = __fsqrt_rn((float)(s_first / (double)third));
+  const float lr = __fsqrt_rn((float)(s_last / (double)third));
+  *first_rms = fr; *last_rms = lr;
+  if ((double)fr < 1e-8) return;
+  const double r = (double)lr / (double)fr;
+  *ratio = r; *ok = (r >= thr) ? 1 : 0;
+}
+
+__global__ void k_finalize_items(const SegState* __restrict__ seg, const ItemState* __restrict__ item,
+                                 const int32_t* __restrict__ item_first_seg, int n_items, double decay_thr,
+                                 rho_record* __restrict__ rec) {
+  const int it = blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= n_items) return;
+  const ItemState is = item[it];
+  const int s0 = item_first_seg[it], n = item_first_seg[it + 1] - s0;
+  rho_record r;
+  r.start = 0; r.end = 0; r.dc = 0.f;
+  if (n > 0) { const SegState st = seg[s0]; r.start = st.start; r.end = st.end; r.dc = st.dc; }
+  r.out_len = is.out_len; r.flags = is.flags; r.cosine = 0.f; r.n_segments = n;
+  decay_decide(is.s_first, is.s_last, is.out_len, decay_thr, &r.first_rms, &r.last_rms, &r.decay_ratio, &r.ok);
+  rec[it] = r;
+}
+
+// ------------------------------------------------------------------ single-clip helpers (method shim)
+__global__ void k_sum_single(const float* __restrict__ x, long long n, double* __restrict__ out) {
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += (double)x[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(out, acc);
+}
+__global__ void k_sub_single(float* __restrict__ x, long long n, const double* __restrict__ sum, float* __restrict__ dc_out) {
+  const float dc = (float)(*sum / (double)n);
+  if (dc_out && blockIdx.x == 0 && threadIdx.x == 0) *dc_out = dc;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = __fsub_rn(x[i], dc);
+}
+__global__ void k_fade_single(float* __restrict__ x, long long n, int fade, int fade_in, int fade_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= fade) return;
+  if (fade_in) x[i] = __fmul_rn(x[i], 0.5f * (1.f - cosf(linspace32(0.f, RHO_PI_F, fade, i))));
+  if (fade_out) {
+    const long long o = n - fade + i;
+    x[o] = __fmul_rn(x[o], 0.5f * (1.f + cosf(linspace32(0.f, RHO_PI_F, fade, i))));
+  }
+}
+__global__ void k_decay_sums_single(const float* __restrict__ x, long long n, double* __restrict__ out2) {
+  const long long third = n / 3;
+  double a = 0.0, b = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < third; i += (long long)gridDim.x * blockDim.x) {
+    const float u = x[i], v = x[n - third + i];
+    a += (double)(u * u); b += (double)(v * v);
+  }
+  a = warp_sum(a); b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) { if (a != 0.0) atomicAdd(out2, a); if (b != 0.0) atomicAdd(out2 + 1, b); }
+}
+__global__ void k_decay_final_single(const double* __restrict__ sums, long long n, double thr, rho_record* __restrict__ rec) {
+  rho_record r = *rec;
+  decay_decide(sums[0], sums[1], (int)n, thr, &r.first_rms, &r.last_rms, &r.decay_ratio, &r.ok);
+  r.out_len = (int)n;
+  *rec = r;
+}
+
+// ------------------------------------------------------------------ host launchers
+static inline int scan_row_stride(int hop, bool vec) {
+  if (vec) { int r4 = hop >> 2; if ((r4 & 1) == 0) r4 += 1; return r4 << 2; }
+  return hop | 1;
+}
+
+cudaError_t launch_scan(const float* x, const int64_t* off, const int32_t* len, int n_seg, int64_t max_len,
+                        const Derived& d, const Workspace& ws, cudaStream_t st, LaunchCtx* lc) {
+  if (n_seg <= 0) return cudaSuccess;
+  const bool vec = (d.hop % 4 == 0) && (d.window == 2 * d.hop);
+  const int RS = scan_row_stride(d.hop, vec);
+  const size_t smem = (size_t)(SCAN_FR + 2) * RS * sizeof(float);
+  const int64_t max_frames = max_len <= 0 ? 1 : (max_len + 2 * d.hop - d.window) / d.hop + 1;
+  const unsigned tiles = (unsigned)((max_frames + SCAN_FR - 1) / SCAN_FR);
+  dim3 grid((unsigned)n_seg, tiles ? tiles : 1u);
+  cudaError_t e;
+  if (vec) {
+    e = cudaFuncSetAttribute(k_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    lc->begin(KID_SCAN, st);
+    k_scan<true><<<grid, SCAN_FR, smem, st>>>(x, off, len, ws.seg, ws.block_sum, ws.blocks_per_seg,
+                                             d.window, d.hop, RS, d.thr);
+  } else {
+    e = cudaFuncSetAttribute(k_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    lc->begin(KID_SCAN, st);
+    k_scan<false><<<grid, SCAN_FR, smem, st>>>(x, off, len, ws.seg, ws.block_sum, ws.blocks_per_seg,
+                                              d.window, d.hop, RS, d.thr);
+  }
+  lc->end(st);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_trim_scan(const float* x, const int64_t* off, const int32_t* len, const uint8_t* trim_flags,
+                             int n_seg, int64_t max_len, const Derived& d, const Workspace& ws,
+                             rho_seg_info* info, cudaStream_t st, LaunchCtx* lc) {
+  if (n_seg <= 0) return cudaSuccess;
+  lc->begin(KID_INIT, st);
+  k_init_segs<<<(n_seg + 255) / 256, 256, 0, st>>>(ws.seg, trim_flags, n_seg); lc->end(st);
+  cudaError_t e = launch_scan(x, off, len, n_seg, max_len, d, ws, st, lc);
+  if (e != cudaSuccess) return e;
+  lc->begin(KID_FINALIZE_SEGS, st);
+  k_finalize_segs<<<(n_seg * 32 + 255) / 256, 256, 0, st>>>(x, off, len, ws.seg, ws.block_sum, ws.blocks_per_seg,
+                                                          n_seg, d.window, d.hop, d.trim_enabled, info);
+  lc->end(st);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* seg_len, int n_seg, int64_t max_seg_len,
+                        const int32_t* item_first_seg, int n_items, int64_t max_item_len,
+                        const Derived& d, float* y, const int64_t* y_off, rho_record* rec, rho_seg_info* seg_info,
+                        const Workspace& ws, cudaStream_t st, LaunchCtx* lc) {
+  if (n_items <= 0) return cudaSuccess;
+  lc->begin(KID_INIT, st);
+  k_init_items<<<(n_items + 255) / 256, 256, 0, st>>>(ws.seg, ws.item, item_first_seg, n_items); lc->end(st);
+  cudaError_t e = cudaSuccess;
+  if (n_seg > 0) {
+    e = launch_scan(x, seg_off, seg_len, n_seg, max_seg_len, d, ws, st, lc);
+    if (e != cudaSuccess) return e;
+    lc->begin(KID_FINALIZE_SEGS, st);
+    k_finalize_segs<<<(n_seg * 32 + 255) / 256, 256, 0, st>>>(x, seg_off, seg_len, ws.seg, ws.block_sum,
+                                                            ws.blocks_per_seg, n_seg, d.window, d.hop,
+                                                            d.trim_enabled, seg_info);
+    lc->end(st);
+  }
+  lc->begin(KID_PLAN, st);
+  k_plan_items<<<(n_items + 127) / 128, 128, 0, st>>>(ws.seg, seg_len, ws.span, ws.item, item_first_seg, n_items,
+                                                     d.cf, d.pause, d.pause_on);
+  lc->end(st);
+  if (n_seg > 0) {
+    // a segment's span is at most its own length plus one pause
+    const int64_t max_span = max_seg_len + d.pause;
+    const unsigned tiles = (unsigned)((max_span + GATHER_TILE - 1) / GATHER_TILE);
+    dim3 grid((unsigned)n_seg, tiles ? tiles : 1u);
+    lc->begin(KID_GATHER, st);
+    k_gather<<<grid, GATHER_THREADS, 0, st>>>(x, seg_off, ws.seg, ws.span, ws.item, y, y_off, d.fade);
+    lc->end(st);
+  }
+  (void)max_item_len;
+  lc->begin(KID_FINALIZE_ITEMS, st);
+  k_finalize_items<<<(n_items + 255) / 256, 256, 0, st>>>(ws.seg, ws.item, item_first_seg, n_items, d.decay_thr, rec);
+  lc->end(st);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_remove_dc(float* x, int64_t n, float* dc_out, double* scratch, cudaStream_t st, LaunchCtx* lc) {
+  if (n <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double), st);
+  if (e != cudaSuccess) return e;
+  const int blocks = (int)((n + 4095) / 4096 < 1184 ? (n + 4095) / 4096 : 1184);
+  lc->begin(KID_SINGLE, st);
+  k_sum_single<<<blocks, 256, 0, st>>>(x, n, scratch); lc->end(st);
+  lc->begin(KID_SINGLE, st);
+  k_sub_single<<<blocks, 256, 0, st>>>(x, n, scratch, dc_out); lc->end(st);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_apply_fades(float* x, int64_t n, int fade, int fade_in, int fade_out, cudaStream_t st, LaunchCtx* lc) {
+  if (n <= 0 || fade <= 0 || n < 2 * (int64_t)fade || (!fade_in && !fade_out)) return cudaSuccess;
+  lc->begin(KID_SINGLE, st);
+  k_fade_single<<<(fade + 127) / 128, 128, 0, st>>>(x, n, fade, fade_in, fade_out); lc->end(st);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sound_decay(const float* x, int64_t n, double thr, rho_record* rec, double* scratch,
+                               cudaStream_t st, LaunchCtx* lc) {
+  cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * sizeof(double), st);
+  if (e != cudaSuccess) return e;
+  if (n >= 3) {
+    const int64_t third = n / 3;
+    const int blocks = (int)((third + 2047) / 2048 < 1184 ? (third + 2047) / 2048 : 1184);
+    lc->begin(KID_SINGLE, st);
+    k_decay_sums_single<<<blocks, 256, 0, st>>>(x, n, scratch); lc->end(st);
+  }
+  lc->begin(KID_SINGLE, st);
+  k_decay_final_single<<<1, 1, 0, st>>>(scratch, n, thr, rec); lc->end(st);
+  return cudaGetLastError();
+}
+
+}  // namespace rho

@@ -1,0 +1,95 @@
+// Internal launcher declarations shared by the translation units of librho_b200.
+#pragma once
+#include <vector>
+#include "common.cuh"
+
+namespace rho {
+
+constexpr int SCAN_FR = 128;          // energy frames (= threads) per scan CTA
+constexpr int GATHER_THREADS = 256;
+constexpr int GATHER_TILE = 4096;     // output samples per gather CTA
+
+constexpr int RS_TAPS = 23;           // 24k->16k polyphase kernel length (width 10, orig 3)
+constexpr int N_FFT = 400;
+constexpr int HOP16 = 160;
+constexpr int N_BINS = 201;
+constexpr int MEL_PAD_FRAMES = 3000;
+constexpr int MAX_MELS = 128;
+
+// Device-resident constant tables owned by the handle.
+struct Tables {
+  float* hann;        // [400]
+  float2* twiddle;    // [400]  exp(-2*pi*i*k/400)
+  // sparse mel filterbanks (slaney): for mel m the non-zero bins are [lo[m], lo[m]+cnt[m]) with
+  // weights w[wofs[m] ...]
+  int* mel_lo[2];     // index 0: 80 mels, 1: 128 mels
+  int* mel_cnt[2];
+  int* mel_wofs[2];
+  float* mel_w[2];
+  int mel_nnz[2];
+  float* mel_dense[2];  // [n_mels][201] row-major, fp32 (for the tensor-core path)
+};
+
+// Launch bookkeeping: counts kernel launches and, when profiling is on, brackets every kernel with
+// CUDA events on the launching stream so per-kernel device time can be read back
+// (rho_b200_profile_*; bench.py uses it for the roofline line).
+enum KernelId {
+  KID_INIT = 0, KID_SCAN, KID_FINALIZE_SEGS, KID_PLAN, KID_GATHER, KID_FINALIZE_ITEMS,
+  KID_RESAMPLE, KID_LOGMEL_INIT, KID_LOGMEL_FRAMES, KID_LOGMEL_NORM, KID_COSINE, KID_SINGLE, KID_COUNT
+};
+extern const char* const kKernelNames[KID_COUNT];
+
+struct LaunchCtx {
+  int64_t launches = 0;
+  bool profiling = false;
+  struct Span { int id; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  void begin(int id, cudaStream_t st) {
+    if (!profiling) return;
+    Span sp; sp.id = id;
+    cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
+    cudaEventRecord(sp.a, st);
+    spans.push_back(sp);
+  }
+  void end(cudaStream_t st) {
+    ++launches;
+    if (profiling && !spans.empty()) cudaEventRecord(spans.back().b, st);
+  }
+};
+
+// join.cu
+cudaError_t launch_trim_scan(const float* x, const int64_t* off, const int32_t* len, const uint8_t* trim_flags,
+                             int n_seg, int64_t max_len, const Derived& d, const Workspace& ws,
+                             rho_seg_info* info, cudaStream_t st, LaunchCtx* lc);
+cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* seg_len, int n_seg, int64_t max_seg_len,
+                        const int32_t* item_first_seg, int n_items, int64_t max_item_len,
+                        const Derived& d, float* y, const int64_t* y_off, rho_record* rec, rho_seg_info* seg_info,
+                        const Workspace& ws, cudaStream_t st, LaunchCtx* lc);
+cudaError_t launch_remove_dc(float* x, int64_t n, float* dc_out, double* scratch, cudaStream_t st, LaunchCtx* lc);
+cudaError_t launch_apply_fades(float* x, int64_t n, int fade, int fade_in, int fade_out, cudaStream_t st, LaunchCtx* lc);
+cudaError_t launch_sound_decay(const float* x, int64_t n, double thr, rho_record* rec, double* scratch,
+                               cudaStream_t st, LaunchCtx* lc);
+
+// resample.cu
+cudaError_t upload_resample_taps(const float* taps /* [2][23] */);
+cudaError_t launch_resample3to2(const float* x, const int64_t* off, const int32_t* len, int len_stride_bytes,
+                                int n, int64_t max_len, float* y, const int64_t* y_off, int32_t* y_len,
+                                cudaStream_t st, LaunchCtx* lc);
+
+// logmel.cu
+cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off, const int32_t* len16,
+                          int n, int64_t max_len16, int n_mels, int pad_frames, float* mel,
+                          int64_t mel_stride_frames, int32_t* n_frames, int* clip_max,
+                          cudaStream_t st, LaunchCtx* lc);
+
+// cosine.cu
+cudaError_t launch_cosine(const float* emb, const float* ref, int n, int dim, float* out, int out_stride_bytes,
+                          cudaStream_t st, LaunchCtx* lc);
+
+// tables.cpp (host only, no CUDA)
+void host_resample_taps(float* out /* [2][23] */);
+void host_hann(float* out /* [400] */);
+void host_mel_filterbank(int n_mels, float* out /* [n_mels][201] */);
+void host_twiddles(float* out /* [400][2] */);
+
+}  // namespace rho

@@ -1,0 +1,315 @@
+// Whisper-style log-mel front end: framed STFT -> power -> mel -> log10 -> clip-max clamp -> scale.
+//
+// Reference: transformers WhisperFeatureExtractor (reached from the reference through
+// src/rho_tts/validation/stt/stt_validator.py:78-107):
+//   transformers/models/whisper/feature_extraction_whisper.py:135-164 (_torch_extract_fbank_features),
+//   :296-303 (pad / truncate to 480 000 samples), transformers/audio_utils.py:453-544 (filterbank).
+//
+// Kernel 1 (k_logmel_frames): one CTA = 16 groups of 20 threads.  Each group runs one 400-point
+// complex FFT that carries TWO real frames (frame A in the real part, frame B in the imaginary
+// part); 400 = 20 x 20, each 20-point DFT is a twiddle-free 4x5 prime-factor transform held in
+// registers, so a frame pair makes exactly two trips through shared memory.  The power spectra
+// of the 32 frames of a batch are then projected on the (97.5 % sparse) mel filterbank, log10'd,
+// written, and the per-clip maximum is folded into an ordered-int atomicMax.
+// Kernel 2 (k_logmel_norm): max(x, clipmax-8), (x+4)/4, and the constant fill of the frames
+// that only see zero padding.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rho {
+
+constexpr int LM_GROUPS = 16;                       // FFTs per batch
+constexpr int LM_LANES = 20;                        // threads per FFT
+constexpr int LM_THREADS = LM_GROUPS * LM_LANES;    // 320
+constexpr int LM_BF = 2 * LM_GROUPS;                // frames per batch (32)
+constexpr int LM_BATCHES = 4;                       // batches per CTA
+constexpr int LM_TILE = LM_BF * LM_BATCHES;         // frames per CTA (128)
+constexpr int LM_SLAB = HOP16 * LM_BF + (N_FFT - HOP16);  // 5360 samples cover 32 frames
+constexpr int LM_FB = 424;                          // float2 per FFT buffer (20 rows x 21 + pad)
+constexpr int LM_PS = 201;                          // power row stride (odd: conflict-free across frames)
+constexpr int LM_MEL_GROUPS = LM_THREADS / 32;      // 10 warps share the mel rows
+
+struct LmSmem {
+  float slab[LM_SLAB];
+  float2 fb[LM_GROUPS * LM_FB];
+  float pw[LM_BF * LM_PS];
+  float hann[N_FFT];
+  float2 tw[N_FFT];
+  int mel_lo[MAX_MELS];
+  int mel_cnt[MAX_MELS];
+  int mel_wofs[MAX_MELS];
+  float mel_w[416];
+  float red[LM_THREADS / 32];
+};
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// forward 5-point DFT, in place
+__device__ __forceinline__ void dft5(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4) {
+  const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;   // cos(2pi/5), cos(4pi/5)
+  const float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;    // sin(2pi/5), sin(4pi/5)
+  const float2 t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
+  const float2 m1 = make_float2(x0.x + c1 * t1.x + c2 * t2.x, x0.y + c1 * t1.y + c2 * t2.y);
+  const float2 m2 = make_float2(x0.x + c2 * t1.x + c1 * t2.x, x0.y + c2 * t1.y + c1 * t2.y);
+  const float2 u1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+  const float2 u2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+  x0 = make_float2(x0.x + t1.x + t2.x, x0.y + t1.y + t2.y);
+  // y1 = m1 - i*u1, y4 = m1 + i*u1, y2 = m2 - i*u2, y3 = m2 + i*u2   ( -i*(a,b) = (b,-a) )
+  x1 = make_float2(m1.x + u1.y, m1.y - u1.x);
+  x4 = make_float2(m1.x - u1.y, m1.y + u1.x);
+  x2 = make_float2(m2.x + u2.y, m2.y - u2.x);
+  x3 = make_float2(m2.x - u2.y, m2.y + u2.x);
+}
+
+// forward 4-point DFT, in place
+__device__ __forceinline__ void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+  const float2 a = cadd(x0, x2), b = csub(x0, x2), c = cadd(x1, x3), d = csub(x1, x3);
+  x0 = cadd(a, c);
+  x2 = csub(a, c);
+  x1 = make_float2(b.x + d.y, b.y - d.x);   // b - i*d
+  x3 = make_float2(b.x - d.y, b.y + d.x);   // b + i*d
+}
+
+// forward 20-point DFT, in place, Good-Thomas 4x5 (no internal twiddles):
+//   input index n = (5a + 4b) mod 20, output index k = (5*k1 + 16*k2) mod 20.
+__device__ __forceinline__ void dft20(float2 (&v)[20]) {
+  float2 T[4][5];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+#pragma unroll
+    for (int b = 0; b < 5; ++b) T[a][b] = v[(5 * a + 4 * b) % 20];
+    dft5(T[a][0], T[a][1], T[a][2], T[a][3], T[a][4]);
+  }
+#pragma unroll
+  for (int k2 = 0; k2 < 5; ++k2) {
+    dft4(T[0][k2], T[1][k2], T[2][k2], T[3][k2]);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) v[(5 * k1 + 16 * k2) % 20] = T[k1][k2];
+  }
+}
+
+// sample i of the (zero-padded to N, reflect-extended) 16 kHz clip
+__device__ __forceinline__ float lm_sample(const float* __restrict__ xs, long long i, int n_valid, int N) {
+  if (i < 0) i = -i;
+  if (i >= N) i = 2LL * (N - 1) - i;
+  return (i >= 0 && i < n_valid) ? xs[i] : 0.f;
+}
+
+// number of frames of clip with n16 samples, and how many of them see any signal
+__device__ __forceinline__ void lm_frame_counts(int n16, int pad_frames, int* T, int* T_real, int* N, int* n_valid) {
+  if (pad_frames > 0) {
+    *N = pad_frames * HOP16;
+    *n_valid = n16 < *N ? (n16 > 0 ? n16 : 0) : *N;
+    *T = pad_frames;
+    int tz = (*n_valid + (N_FFT / 2) + HOP16 - 1) / HOP16;   // first frame whose window starts past the signal
+    if (tz < 2) tz = 2;
+    *T_real = tz < *T ? tz : *T;
+  } else {
+    *N = n16; *n_valid = n16;
+    *T = (n16 > N_FFT / 2) ? n16 / HOP16 : 0;               // reflect padding needs > n_fft/2 samples
+    *T_real = *T;
+  }
+}
+
+__global__ void k_logmel_init(int* __restrict__ clip_max, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) clip_max[i] = INT_MIN;
+}
+
+__global__ void __launch_bounds__(LM_THREADS, 2)
+k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, const int32_t* __restrict__ len16,
+                const float* __restrict__ g_hann, const float2* __restrict__ g_tw,
+                const int* __restrict__ g_lo, const int* __restrict__ g_cnt, const int* __restrict__ g_wofs,
+                const float* __restrict__ g_w, int nnz, int n_mels, int pad_frames,
+                float* __restrict__ mel, long long mel_stride, int* __restrict__ clip_max,
+                int32_t* __restrict__ n_frames_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LmSmem& S = *reinterpret_cast<LmSmem*>(smem_raw);
+  const int c = blockIdx.x;
+  int T, T_real, N, n_valid;
+  lm_frame_counts(len16[c], pad_frames, &T, &T_real, &N, &n_valid);
+  if (blockIdx.y == 0 && threadIdx.x == 0 && n_frames_out) n_frames_out[c] = T;
+  const int tile_t0 = blockIdx.y * LM_TILE;
+  if (tile_t0 >= T_real) return;
+
+  const int tid = threadIdx.x;
+  for (int i = tid; i < N_FFT; i += LM_THREADS) { S.hann[i] = g_hann[i]; S.tw[i] = g_tw[i]; }
+  for (int i = tid; i < n_mels; i += LM_THREADS) { S.mel_lo[i] = g_lo[i]; S.mel_cnt[i] = g_cnt[i]; S.mel_wofs[i] = g_wofs[i]; }
+  for (int i = tid; i < nnz; i += LM_THREADS) S.mel_w[i] = g_w[i];
+
+  const float* __restrict__ xs = x16 + off[c];
+  float* __restrict__ out = mel + (long long)c * n_mels * mel_stride;
+  const int g = tid / LM_LANES, lane = tid - g * LM_LANES;
+  float2* fb = S.fb + g * LM_FB;
+  float lmax = -INFINITY;
+
+  for (int b = 0; b < LM_BATCHES; ++b) {
+    const int t0 = tile_t0 + b * LM_BF;
+    if (t0 >= T_real) break;
+    // ---- stage the samples of frames [t0, t0+32): clip indices [160*t0-200, 160*t0-200+5360)
+    const long long i0 = (long long)HOP16 * t0 - N_FFT / 2;
+    if (i0 >= 0 && i0 + LM_SLAB <= n_valid) {
+      for (int q = tid; q < LM_SLAB / 4; q += LM_THREADS)
+        *reinterpret_cast<float4*>(S.slab + 4 * q) = *reinterpret_cast<const float4*>(xs + i0 + 4 * q);
+    } else {
+      for (int r = tid; r < LM_SLAB; r += LM_THREADS) S.slab[r] = lm_sample(xs, i0 + r, n_valid, N);
+    }
+    __syncthreads();
+    // ---- FFT stage 1: lane = n2, 20-point DFT over n1 of z[20*n1 + n2], then twiddle W400^(n2*k1)
+    float2 v[20];
+    {
+      const float* fa = S.slab + 2 * g * HOP16 + lane;
+      const float* fbm = fa + HOP16;
+#pragma unroll
+      for (int n1 = 0; n1 < 20; ++n1) {
+        const float h = S.hann[20 * n1 + lane];
+        v[n1] = make_float2(fa[20 * n1] * h, fbm[20 * n1] * h);
+      }
+    }
+    dft20(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 20; ++k1) fb[k1 * 21 + lane] = (k1 == 0) ? v[0] : cmul(v[k1], S.tw[lane * k1]);
+    __syncthreads();
+    // ---- FFT stage 2: lane = k1, 20-point DFT over n2 -> Z[k1 + 20*k2]
+#pragma unroll
+    for (int n2 = 0; n2 < 20; ++n2) v[n2] = fb[lane * 21 + n2];
+    dft20(v);
+    __syncthreads();
+#pragma unroll
+    for (int k2 = 0; k2 < 20; ++k2) fb[lane + 20 * k2] = v[k2];
+    __syncthreads();
+    // ---- split the two real spectra and take |.|^2:  A = (Z[k]+conj Z[400-k])/2, B = (Z[k]-conj Z[400-k])/(2i)
+    {
+      float* pa = S.pw + (2 * g) * LM_PS;
+      float* pb = pa + LM_PS;
+#pragma unroll
+      for (int j = 0; j < 11; ++j) {
+        const int k = lane + 20 * j;
+        if (k <= N_FFT / 2) {
+          const float2 z = fb[k];
+          const float2 w = fb[k == 0 ? 0 : N_FFT - k];
+          const float ar = z.x + w.x, ai = z.y - w.y, br = z.x - w.x, bi = z.y + w.y;
+          pa[k] = 0.25f * (ar * ar + ai * ai);
+          pb[k] = 0.25f * (br * br + bi * bi);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- mel projection + log10: lane-of-warp = frame, warp = mel row group
+    {
+      const int f = tid & 31, wg = tid >> 5;
+      const int t = t0 + f;
+      const float* p = S.pw + f * LM_PS;
+      for (int m = wg; m < n_mels; m += LM_MEL_GROUPS) {
+        const int lo = S.mel_lo[m], cnt = S.mel_cnt[m];
+        const float* w = S.mel_w + S.mel_wofs[m];
+        float acc = 0.f;
+        for (int q = 0; q < cnt; ++q) acc = fmaf(w[q], p[lo + q], acc);
+        const float ls = log10f(fmaxf(acc, 1e-10f));
+        if (t < T_real) {
+          out[(long long)m * mel_stride + t] = ls;
+          lmax = fmaxf(lmax, ls);
+        }
+      }
+    }
+    // the next batch's first barrier orders these reads before pw/slab are overwritten
+  }
+  lmax = warp_max(lmax);
+  if ((tid & 31) == 0) S.red[tid >> 5] = lmax;
+  __syncthreads();
+  if (tid < 32) {
+    float m = tid < LM_THREADS / 32 ? S.red[tid] : -INFINITY;
+    m = warp_max(m);
+    if (tid == 0 && m > -INFINITY) atomicMax(&clip_max[c], float_to_ordered(m));
+  }
+}
+
+// grid (n clips, row groups); normalises real frames and fills the zero-padding frames.
+__global__ void __launch_bounds__(256)
+k_logmel_norm(const int32_t* __restrict__ len16, int n_mels, int pad_frames, float* __restrict__ mel,
+              long long mel_stride, const int* __restrict__ clip_max, int rows_per_cta) {
+  const int c = blockIdx.x;
+  int T, T_real, N, n_valid;
+  lm_frame_counts(len16[c], pad_frames, &T, &T_real, &N, &n_valid);
+  if (T <= 0) return;
+  const float mx = ordered_to_float(clip_max[c]);
+  const float floor_v = __fsub_rn(mx, 8.0f);
+  const float fill = __fdiv_rn(__fadd_rn(fmaxf(-10.0f, floor_v), 4.0f), 4.0f);
+  float* __restrict__ base = mel + (long long)c * n_mels * mel_stride;
+  const int m0 = blockIdx.y * rows_per_cta;
+  const int m1 = min(n_mels, m0 + rows_per_cta);
+  const bool vec = (mel_stride % 4 == 0) && ((((uintptr_t)base) & 15u) == 0);
+  for (int m = m0; m < m1; ++m) {
+    float* __restrict__ row = base + (long long)m * mel_stride;
+    if (vec) {
+      const int T4 = T & ~3;
+      for (int t = 4 * threadIdx.x; t < T4; t += 4 * 256) {
+        float4 v;
+        if (t + 3 < T_real) {
+          v = *reinterpret_cast<const float4*>(row + t);
+          v.x = __fdiv_rn(__fadd_rn(fmaxf(v.x, floor_v), 4.0f), 4.0f);
+          v.y = __fdiv_rn(__fadd_rn(fmaxf(v.y, floor_v), 4.0f), 4.0f);
+          v.z = __fdiv_rn(__fadd_rn(fmaxf(v.z, floor_v), 4.0f), 4.0f);
+          v.w = __fdiv_rn(__fadd_rn(fmaxf(v.w, floor_v), 4.0f), 4.0f);
+        } else if (t >= T_real) {
+          v = make_float4(fill, fill, fill, fill);
+        } else {
+          float e[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            e[k] = (t + k < T_real) ? __fdiv_rn(__fadd_rn(fmaxf(row[t + k], floor_v), 4.0f), 4.0f) : fill;
+          v = make_float4(e[0], e[1], e[2], e[3]);
+        }
+        stg_stream4(row + t, v);
+      }
+      for (int t = T4 + threadIdx.x; t < T; t += 256)
+        row[t] = (t < T_real) ? __fdiv_rn(__fadd_rn(fmaxf(row[t], floor_v), 4.0f), 4.0f) : fill;
+    } else {
+      for (int t = threadIdx.x; t < T; t += 256)
+        row[t] = (t < T_real) ? __fdiv_rn(__fadd_rn(fmaxf(row[t], floor_v), 4.0f), 4.0f) : fill;
+    }
+  }
+}
+
+cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off, const int32_t* len16,
+                          int n, int64_t max_len16, int n_mels, int pad_frames, float* mel,
+                          int64_t mel_stride_frames, int32_t* n_frames, int* clip_max,
+                          cudaStream_t st, LaunchCtx* lc) {
+  if (n <= 0) return cudaSuccess;
+  const int which = (n_mels == 80) ? 0 : 1;
+  lc->begin(KID_LOGMEL_INIT, st);
+  k_logmel_init<<<(n + 255) / 256, 256, 0, st>>>(clip_max, n); lc->end(st);
+  int64_t max_real;
+  if (pad_frames > 0) {
+    int64_t nv = max_len16 < (int64_t)pad_frames * HOP16 ? max_len16 : (int64_t)pad_frames * HOP16;
+    max_real = (nv + N_FFT / 2 + HOP16 - 1) / HOP16;
+    if (max_real < 2) max_real = 2;
+    if (max_real > pad_frames) max_real = pad_frames;
+  } else {
+    max_real = max_len16 / HOP16;
+  }
+  unsigned tiles = (unsigned)((max_real + LM_TILE - 1) / LM_TILE);
+  if (tiles == 0) tiles = 1;
+  const size_t smem = sizeof(LmSmem);
+  cudaError_t e = cudaFuncSetAttribute(k_logmel_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((unsigned)n, tiles);
+  lc->begin(KID_LOGMEL_FRAMES, st);
+  k_logmel_frames<<<grid, LM_THREADS, smem, st>>>(x16, off, len16, tb.hann, tb.twiddle, tb.mel_lo[which],
+                                                  tb.mel_cnt[which], tb.mel_wofs[which], tb.mel_w[which],
+                                                  tb.mel_nnz[which], n_mels, pad_frames, mel, mel_stride_frames,
+                                                  clip_max, n_frames);
+  lc->end(st);
+  const int rows_per_cta = 8;
+  dim3 g2((unsigned)n, (unsigned)((n_mels + rows_per_cta - 1) / rows_per_cta));
+  lc->begin(KID_LOGMEL_NORM, st);
+  k_logmel_norm<<<g2, 256, 0, st>>>(len16, n_mels, pad_frames, mel, mel_stride_frames, clip_max, rows_per_cta);
+  lc->end(st);
+  return cudaGetLastError();
+}
+
+}  // namespace rho

@@ -1,0 +1,82 @@
+// Host-side constant tables (no CUDA): resample taps, Hann window, slaney mel filterbank,
+// FFT twiddles.  Built once per handle and uploaded; also exported through
+// rho_b200_host_table so the CPU test-suite can compare them with torchaudio/transformers.
+#include <cmath>
+#include <vector>
+#include <algorithm>
+#include "kernels.h"
+
+namespace rho {
+
+// torchaudio/functional/functional.py:1305-1405 for orig=3, new=2 (24 kHz -> 16 kHz), built in
+// fp32 like torchaudio does for an fp32 waveform (dtype=waveform.dtype, :1487).
+void host_resample_taps(float* out) {
+  const int orig = 3, nw = 2, lpw = 6;
+  const double base = std::min(orig, nw) * 0.99;           // python double
+  const int width = (int)std::ceil(lpw * orig / base);    // 10
+  const float basef = (float)base;
+  const float scale = (float)(base / orig);
+  const float pif = (float)M_PI;
+  for (int p = 0; p < nw; ++p) {
+    const float ph = (float)(-p) / (float)nw;
+    for (int i = 0; i < 2 * width + orig; ++i) {
+      const float idx = (float)(i - width) / (float)orig;
+      float t = ph + idx;
+      t = t * basef;
+      t = std::min(std::max(t, (float)-lpw), (float)lpw);
+      const float wa = ((t * pif) / (float)lpw) / 2.0f;
+      const float c = cosf(wa);
+      const float window = c * c;
+      t = t * pif;
+      const float sinc = (t == 0.0f) ? 1.0f : sinf(t) / t;
+      out[p * RS_TAPS + i] = sinc * (window * scale);
+    }
+  }
+}
+
+// torch.hann_window(400) (periodic)
+void host_hann(float* out) {
+  for (int n = 0; n < N_FFT; ++n) out[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * n / N_FFT));
+}
+
+void host_twiddles(float* out) {
+  for (int k = 0; k < N_FFT; ++k) {
+    out[2 * k] = (float)std::cos(2.0 * M_PI * k / N_FFT);
+    out[2 * k + 1] = (float)(-std::sin(2.0 * M_PI * k / N_FFT));
+  }
+}
+
+static double hz_to_mel(double f) {
+  if (f >= 1000.0) return 15.0 + std::log(f / 1000.0) * (27.0 / std::log(6.4));
+  return 3.0 * f / 200.0;
+}
+static double mel_to_hz(double m) {
+  if (m >= 15.0) return 1000.0 * std::exp((std::log(6.4) / 27.0) * (m - 15.0));
+  return 200.0 * m / 3.0;
+}
+
+// transformers/audio_utils.py:453-544 with mel_scale="slaney", norm="slaney", 0..8000 Hz, 201 bins
+// of a 16 kHz / 400-point FFT; float64 then cast to fp32 (feature_extraction_whisper.py:152).
+void host_mel_filterbank(int n_mels, float* out) {
+  const double m_lo = hz_to_mel(0.0), m_hi = hz_to_mel(8000.0);
+  std::vector<double> centres(n_mels + 2);
+  for (int i = 0; i < n_mels + 2; ++i) {
+    // numpy.linspace: start + i*step with step = (stop-start)/div; last point pinned to stop
+    const double step = (m_hi - m_lo) / (n_mels + 1);
+    const double m = (i == n_mels + 1) ? m_hi : m_lo + i * step;
+    centres[i] = mel_to_hz(m);
+  }
+  for (int k = 0; k < N_BINS; ++k) {
+    const double step = 8000.0 / (N_BINS - 1);
+    const double f = (k == N_BINS - 1) ? 8000.0 : 0.0 + k * step;
+    for (int m = 0; m < n_mels; ++m) {
+      const double down = -(centres[m] - f) / (centres[m + 1] - centres[m]);
+      const double up = (centres[m + 2] - f) / (centres[m + 2] - centres[m + 1]);
+      double v = std::max(0.0, std::min(down, up));
+      v *= 2.0 / (centres[m + 2] - centres[m]);
+      out[m * N_BINS + k] = (float)v;
+    }
+  }
+}
+
+}  // namespace rho

@@ -1,0 +1,293 @@
+"""GPU parity: librho_b200 (through the C ABI / ctypes shim) against the CPU oracle.
+
+Bar (BASELINE.json north_star): trim bounds, join lengths / segment boundaries and accept/reject
+decisions exact; waveforms, RMS, ratio, cosine and log-mel within 1e-4 (abs-or-rel, tests/util.TOL).
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import dsp as odsp
+from tests.util import TOL, assert_close, tone_clip
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def R():
+    import rho_tts_b200 as r
+    return r
+
+
+def _rb(R, clips, dev):
+    return R.RaggedBatch.from_list([torch.from_numpy(np.ascontiguousarray(c)) for c in clips], dev)
+
+
+# ----------------------------------------------------------------------------- trim
+@pytest.mark.parametrize("sr", [24000, 16000, 22050, 44100])
+def test_trim_scan_exact(R, cuda_device, sr):
+    rng = np.random.default_rng(7 + sr)
+    c = oracle.derive_constants(sr=sr)
+    lens = [1, 5, c.hop - 1, c.hop, c.hop + 1, c.window - 1, c.window, c.window + 1, 1000, 4097, sr, sr + 1,
+            3 * sr + 77, 10 * sr]
+    clips, flags = [], []
+    for i, L in enumerate(lens):
+        for tf in (3, 1, 2, 0):
+            kind = (i + tf) % 5
+            if kind == 0:
+                x = rng.normal(0, 1e-4, L).astype(np.float32)                 # all silent
+            elif kind == 1:
+                x = rng.normal(0, 0.2, L).astype(np.float32)                  # loud everywhere
+            else:
+                x = tone_clip(rng, L, lead=min(L // 4, int(rng.integers(0, sr // 2))),
+                              trail=min(L // 5, int(rng.integers(0, sr // 2))), sr=sr)
+            clips.append(x); flags.append(tf)
+    rb = _rb(R, clips, cuda_device)
+    p = R.make_params(sr=sr)
+    info = R.trim_scan_batch(rb, p, torch.tensor(flags, dtype=torch.uint8, device=cuda_device))
+    info = info.cpu().numpy().view(R.SEG_DTYPE).reshape(-1)
+    for i, (x, tf) in enumerate(zip(clips, flags)):
+        tr = odsp.trim_bounds(x, c, bool(tf & 1), bool(tf & 2))
+        assert (int(info["start"][i]), int(info["end"][i])) == (tr.start, tr.end), (i, len(x), tf, info[i], tr)
+        assert bool(info["flags"][i] & 1) == tr.all_silent, (i, len(x), tf)
+        seg = x[tr.start:tr.end]
+        if seg.size:
+            assert abs(float(info["dc"][i]) - float(seg.mean(dtype=np.float64))) <= 1e-6
+
+
+def test_trim_disabled_and_empty(R, cuda_device):
+    rng = np.random.default_rng(3)
+    clips = [tone_clip(rng, 5000, 1000, 1000), np.zeros(0, np.float32), tone_clip(rng, 300)]
+    rb = _rb(R, clips, cuda_device)
+    p = R.make_params(trim_silence=False)
+    info = R.trim_scan_batch(rb, p).cpu().numpy().view(R.SEG_DTYPE).reshape(-1)
+    assert [(int(a), int(b)) for a, b in zip(info["start"], info["end"])] == [(0, 5000), (0, 0), (0, 300)]
+    assert all(info["flags"] & 8)
+
+
+# ----------------------------------------------------------------------------- post-process
+def test_post_process_batch_vs_oracle(R, cuda_device):
+    from rho_tts_b200 import synth
+    x = synth.make_clip_block(48, 240000, 1234 + 2)                # CPU generator: bit-identical inputs
+    rb = R.RaggedBatch.from_dense(x.to(cuda_device))
+    p = R.make_params()
+    out = R.post_process_batch(rb, p, want_seg_info=True)
+    rec = out.records_host()
+    c = oracle.derive_constants()
+    n_reject = 0
+    for i in range(x.shape[0]):
+        o = oracle.post_process_clip(x[i].numpy(), c)
+        assert (rec["start"][i], rec["end"][i], rec["out_len"][i]) == (o["start"], o["end"], o["out_len"]), i
+        y = out.audio.clip(i, o["out_len"]).cpu().numpy()
+        assert_close(y, o["audio"], what=f"clip {i} audio")
+        assert_close(rec["first_rms"][i], o["first_rms"], what="first_rms")
+        assert_close(rec["last_rms"][i], o["last_rms"], what="last_rms")
+        assert abs(rec["decay_ratio"][i] - o["decay_ratio"]) <= TOL * max(1.0, abs(o["decay_ratio"]))
+        assert bool(rec["ok"][i]) == o["ok"], (i, rec["decay_ratio"][i], o["decay_ratio"])
+        n_reject += not o["ok"]
+    assert 0 < n_reject < x.shape[0]        # the workload exercises both decisions
+
+
+def test_post_process_edge_lengths(R, cuda_device):
+    rng = np.random.default_rng(11)
+    lens = [0, 1, 2, 3, 7, 119, 240, 241, 959, 960, 961, 2000, 24000, 24001, 100003]
+    clips = [tone_clip(rng, L, lead=min(L // 4, 700), trail=min(L // 5, 900)) for L in lens]
+    clips += [rng.normal(0, 1e-4, L).astype(np.float32) for L in (1, 100, 240, 5000)]      # all-silent
+    clips += [np.full(5000, 0.25, np.float32), np.zeros(4000, np.float32)]
+    rb = _rb(R, clips, cuda_device)
+    out = R.post_process_batch(rb, R.make_params())
+    rec = out.records_host()
+    c = oracle.derive_constants()
+    for i, x in enumerate(clips):
+        o = oracle.post_process_clip(x, c)
+        assert (rec["start"][i], rec["end"][i], rec["out_len"][i]) == (o["start"], o["end"], o["out_len"]), (i, len(x))
+        assert bool(rec["flags"][i] & 4) == o["all_silent"]
+        assert_close(out.audio.clip(i, o["out_len"]).cpu().numpy(), o["audio"], what=f"edge clip {i}")
+        if o["first_rms"] > 1e-6:       # away from the 1e-8 early-out, decisions must agree
+            assert bool(rec["ok"][i]) == o["ok"]
+            assert abs(rec["decay_ratio"][i] - o["decay_ratio"]) <= TOL * max(1.0, abs(o["decay_ratio"]))
+
+
+# ----------------------------------------------------------------------------- join
+def _join_case(rng, sr=24000):
+    n = int(rng.integers(1, 7))
+    segs = []
+    for _ in range(n):
+        L = int(rng.choice([0, 5, 200, 600, 1199, 1200, 1201, 1500, 2411, 5000, 30000, 48017]))
+        kind = int(rng.integers(0, 5))
+        if kind == 0:
+            segs.append(rng.normal(0, 1e-4, L).astype(np.float32))
+        else:
+            segs.append(tone_clip(rng, L, lead=min(L // 4, int(rng.integers(0, 3000))),
+                                  trail=min(L // 5, int(rng.integers(0, 3000)))))
+    return segs
+
+
+@pytest.mark.parametrize("pause_sec", [0.1, 0.0])
+def test_join_batch_vs_oracle(R, cuda_device, pause_sec):
+    rng = np.random.default_rng(2024)
+    items = [_join_case(rng) for _ in range(160)]
+    segs = [s for it in items for s in it]
+    first = np.concatenate([[0], np.cumsum([len(it) for it in items])]).astype(np.int32)
+    rb = _rb(R, segs, cuda_device)
+    p = R.make_params(inter_sentence_pause_sec=pause_sec)
+    out = R.join_batch(rb, first, p)
+    rec, seg = out.records_host(), out.seg_info_host()
+    c = oracle.derive_constants(pause_sec=pause_sec)
+    n_fb = 0
+    for i, it in enumerate(items):
+        o = oracle.smooth_segment_join(it, c)
+        assert int(rec["out_len"][i]) == o.audio.size, (i, [len(s) for s in it], rec[i], o.fallback)
+        assert bool(rec["flags"][i] & 2) == o.fallback, i
+        assert bool(rec["flags"][i] & 4) == o.two_d, i
+        for k, tr in enumerate(o.plan.trims):
+            s = first[i] + k
+            assert (int(seg["start"][s]), int(seg["end"][s])) == (tr.start, tr.end), (i, k)
+        assert_close(out.audio.clip(i, o.audio.size).cpu().numpy(), o.audio, what=f"item {i}")
+        ratio, ok, fr, lr = oracle.sound_decay(o.audio, 0.3)
+        if fr > 1e-6:
+            assert bool(rec["ok"][i]) == ok and abs(rec["decay_ratio"][i] - ratio) <= TOL * max(1, abs(ratio))
+        n_fb += o.fallback
+    assert n_fb > 10
+
+
+# ----------------------------------------------------------------------------- resample
+def test_resample_vs_oracle(R, cuda_device):
+    rng = np.random.default_rng(5)
+    lens = [0, 1, 2, 3, 4, 5, 7, 22, 23, 24, 1000, 1535, 1536, 1537, 6143, 6144, 6145, 24001, 240000, 719999]
+    clips = [rng.normal(0, 0.3, L).astype(np.float32) for L in lens]
+    rb = _rb(R, clips, cuda_device)
+    out = R.resample_batch(rb)
+    got_len = out.lengths.cpu().numpy()
+    for i, x in enumerate(clips):
+        ref = oracle.resample(x) if x.size else np.zeros(0, np.float32)
+        assert int(got_len[i]) == ref.size == -(-2 * x.size // 3), (i, x.size)
+        assert_close(out.clip(i, ref.size).cpu().numpy(), ref, what=f"resample L={x.size}")
+
+
+def test_resample_linearity_full_size(R, cuda_device):
+    from rho_tts_b200 import synth
+    x = synth.make_clip_block(64, 240000, 99, device=cuda_device)
+    a = R.resample_batch(R.RaggedBatch.from_dense(x)).data
+    b = R.resample_batch(R.RaggedBatch.from_dense((2.0 * x).contiguous())).data
+    assert torch.equal(2.0 * a, b)          # scaling by a power of two commutes exactly with an fp32 FIR
+
+
+# ----------------------------------------------------------------------------- log-mel
+@pytest.mark.parametrize("n_mels", [80, 128])
+@pytest.mark.parametrize("pad", [True, False])
+def test_logmel_vs_oracle(R, cuda_device, n_mels, pad):
+    from rho_tts_b200 import synth
+    lens = [160000, 159999, 16000, 4000, 480000 if pad else 200000, 201 if not pad else 50, 100001]
+    if pad:
+        lens += [500000, 479999, 479800]     # truncation and the right-edge reflection
+    clips = [oracle.resample(synth.make_clip_block(1, (3 * L + 1) // 2, 40 + i)[0].numpy())[:L] for i, L in enumerate(lens)]
+    rb = _rb(R, clips, cuda_device)
+    mel, n_frames = R.logmel_batch(rb, n_mels=n_mels, pad_to_30s=pad)
+    mel = mel.cpu().numpy(); n_frames = n_frames.cpu().numpy()
+    worst = 0.0
+    for i, w in enumerate(clips):
+        ref = oracle.log_mel(w, n_mels, pad)
+        assert int(n_frames[i]) == ref.shape[1], (i, len(w))
+        worst = max(worst, assert_close(mel[i][:, :ref.shape[1]], ref, what=f"logmel L16={len(w)}"))
+    print(f"log-mel {n_mels} pad={pad}: worst abs-or-rel error vs oracle {worst:.2e}")
+
+
+def test_logmel_silence_and_constant(R, cuda_device):
+    clips = [np.zeros(16000, np.float32), np.full(32000, 0.5, np.float32), np.zeros(300, np.float32)]
+    rb = _rb(R, clips, cuda_device)
+    mel, _ = R.logmel_batch(rb, 80, True)
+    mel = mel.cpu().numpy()
+    for i, w in enumerate(clips):
+        assert_close(mel[i], oracle.log_mel(w, 80, True), what=f"degenerate {i}")
+
+
+# ----------------------------------------------------------------------------- cosine
+def test_cosine_vs_oracle(R, cuda_device):
+    from rho_tts_b200 import synth
+    emb, ref = synth.make_embeddings(300, 256, 4321)
+    got = R.cosine_batch(emb.to(cuda_device), ref.to(cuda_device)).cpu().numpy()
+    want = np.array([oracle.cosine_similarity(ref.numpy(), e) for e in emb.numpy()], dtype=np.float32)
+    assert_close(got, want, what="cosine")
+    g = torch.Generator().manual_seed(1)
+    emb2 = torch.randn(17, 100, generator=g); ref2 = torch.randn(100, generator=g)     # odd dim, signed
+    got = R.cosine_batch(emb2.to(cuda_device), ref2.to(cuda_device)).cpu().numpy()
+    want = np.array([oracle.cosine_similarity(ref2.numpy(), e) for e in emb2.numpy()], dtype=np.float32)
+    assert_close(got, want, what="cosine odd dim")
+
+
+# ----------------------------------------------------------------------------- whole front end
+def _oracle_pipeline(x, c, n_mels, emb, ref):
+    o = oracle.post_process_clip(x, c)
+    w16 = oracle.resample(o["audio"])
+    return o, oracle.log_mel(w16, n_mels, True), oracle.cosine_similarity(ref, emb)
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_validate_pipeline_vs_oracle(R, cuda_device, n_mels):
+    from rho_tts_b200 import synth
+    x = synth.make_clip_block(12, 240000, 1234 + 1)
+    emb, ref = synth.make_embeddings(12)
+    rb = R.RaggedBatch.from_dense(x.to(cuda_device))
+    out = R.validate_batch(rb, R.make_params(), emb.to(cuda_device), ref.to(cuda_device), n_mels=n_mels)
+    rec = out.records_host(); mel = out.mel.cpu().numpy()
+    c = oracle.derive_constants()
+    for i in range(x.shape[0]):
+        o, m, cs = _oracle_pipeline(x[i].numpy(), c, n_mels, emb[i].numpy(), ref.numpy())
+        assert (rec["start"][i], rec["end"][i], rec["out_len"][i], bool(rec["ok"][i])) == \
+            (o["start"], o["end"], o["out_len"], o["ok"])
+        assert_close(out.audio.clip(i, o["out_len"]).cpu().numpy(), o["audio"], what="audio")
+        assert_close(mel[i], m, what=f"mel clip {i}")
+        assert_close(rec["cosine"][i], cs, what="cosine")
+
+
+def test_validate_host_matches_device_path(R, cuda_device):
+    from rho_tts_b200 import synth
+    n = 150                                   # > 2 chunks of 64, last one ragged
+    x = synth.make_clip_block(n, 48000, 77).pin_memory()
+    emb, ref = synth.make_embeddings(n)
+    p = R.make_params()
+    mel_h = torch.empty((n, 80, 3000), dtype=torch.float32).pin_memory()
+    y, mel_h, rec_h = R.validate_host(x, p, emb.pin_memory(), ref.pin_memory(), 80, mel=mel_h)
+    out = R.validate_batch(R.RaggedBatch.from_dense(x.to(cuda_device)), p, emb.to(cuda_device), ref.to(cuda_device))
+    rec_d = out.records_host(); rec_h = rec_h.numpy().view(R.REC_DTYPE).reshape(-1)
+    assert np.array_equal(rec_d["out_len"], rec_h["out_len"]) and np.array_equal(rec_d["ok"], rec_h["ok"])
+    assert np.array_equal(rec_d["cosine"], rec_h["cosine"])
+    assert torch.equal(out.mel.cpu(), mel_h)
+    for i in range(0, n, 7):
+        L = int(rec_d["out_len"][i])
+        assert torch.equal(out.audio.clip(i, L).cpu(), y[i, :L])
+
+
+# ----------------------------------------------------------------------------- size-independent properties
+def test_full_size_properties(R, cuda_device):
+    """BASELINE config C2 size: 1000 x 10 s.  Checks that do not need the oracle at full size."""
+    from rho_tts_b200 import synth
+    x = synth.make_clip_block(1000, 240000, 0xB200, device=cuda_device)
+    emb, ref = synth.make_embeddings(1000, device=cuda_device)
+    rb = R.RaggedBatch.from_dense(x)
+    p = R.make_params()
+    out = R.validate_batch(rb, p, emb, ref)
+    rec = out.records_host()
+    assert np.all(rec["out_len"] == rec["end"] - rec["start"]) and np.all(rec["start"] % 120 == 0)
+    assert np.all((rec["end"] % 120 == 0) | (rec["end"] == 240000))
+    assert 0.05 < 1.0 - rec["ok"].mean() < 0.5
+    assert np.all(np.abs(rec["cosine"]) <= 1.0 + 1e-6)
+    mel = out.mel
+    assert torch.isfinite(mel).all()
+    # frames that only see zero padding are one constant per clip: (max(-10, m-8)+4)/4
+    tail = mel[:, :, 1010:]
+    assert torch.equal(tail.amax(dim=(1, 2)), tail.amin(dim=(1, 2)))
+    # the Whisper clamp: per clip, max - min <= 8/4
+    assert float((mel.amax(dim=(1, 2)) - mel.amin(dim=(1, 2))).max()) <= 2.0 + 1e-6
+    # idempotence of the trim: the processed clip starts and ends loud, so a second scan trims at most
+    # the faded edges; DC of the output is ~0
+    means = torch.stack([out.audio.clip(i, int(rec["out_len"][i])).double().mean() for i in range(0, 1000, 50)])
+    assert float(means.abs().max()) < 1e-4
+    # spot-check 4 clips of the big batch against the oracle
+    c = oracle.derive_constants()
+    for i in (0, 333, 999):
+        o, m, cs = _oracle_pipeline(x[i].cpu().numpy(), c, 80, emb[i].cpu().numpy(), ref.cpu().numpy())
+        assert (rec["start"][i], rec["end"][i], bool(rec["ok"][i])) == (o["start"], o["end"], o["ok"])
+        assert_close(mel[i].cpu().numpy(), m, what=f"mel clip {i}")
