@@ -71,22 +71,20 @@ k_scan(const float* __restrict__ x, const int64_t* __restrict__ off, const int32
   const long long g0 = (long long)(frame0 - 1) * hop;  // global sample of row 0, col 0 (pad == hop)
 
   if (VEC) {
+    // LDGSTS: every 16-byte piece of the tile goes global -> shared without touching registers,
+    // all ~30 copies of a thread are in flight at once; out-of-clip bytes are zero-filled (the
+    // avg_pool zero padding, and the ragged end of the clip).
     const int q_per_row = hop >> 2;
     const int total_q = rows * q_per_row;
     for (int q = threadIdx.x; q < total_q; q += SCAN_FR) {
       const int row = q / q_per_row, c4 = (q - row * q_per_row) << 2;
       const long long g = g0 + (long long)row * hop + c4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (g >= 0 && g + 3 < L) {
-        v = ldg_stream4(xs + g);
-      } else if (g + 3 >= 0 && g < L) {
-        if (g + 0 >= 0 && g + 0 < L) v.x = xs[g + 0];
-        if (g + 1 >= 0 && g + 1 < L) v.y = xs[g + 1];
-        if (g + 2 >= 0 && g + 2 < L) v.z = xs[g + 2];
-        if (g + 3 >= 0 && g + 3 < L) v.w = xs[g + 3];
-      }
-      *reinterpret_cast<float4*>(sm + row * RS + c4) = v;
+      int nb = 0;
+      if (g >= 0 && g < L) nb = (L - g >= 4) ? 16 : 4 * (int)(L - g);
+      cp_async16_zfill(sm + row * RS + c4, nb ? xs + g : xs, nb);
     }
+    cp_async_commit();
+    cp_async_wait_all();
   } else {
     const int total = rows * hop;
     for (int r = threadIdx.x; r < total; r += SCAN_FR) {
@@ -313,16 +311,29 @@ k_gather(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const
 
   float a_first = 0.f, a_last = 0.f;
   const int jend = min(j0 + GATHER_TILE, span_len);
-  for (int j = j0 + 4 * threadIdx.x; j < jend; j += 4 * GATHER_THREADS) {
+  constexpr int U = GATHER_TILE / (4 * GATHER_THREADS);      // 128-bit pieces per thread
+  float4 v[U];
+  bool interior[U];
+  // issue every interior load of this thread before the first use
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int j = j0 + 4 * (threadIdx.x + u * GATHER_THREADS);
     const int o = sp.dst + j;
-    const bool interior = aligned && j >= sp.ov && j + 3 < sp.ov + sp.body &&
-                          (!need_fade || (o >= fade && o + 3 < out_len - fade));
-    if (interior) {
-      float4 v = ldg_stream4(xc + j);
-      v.x = __fsub_rn(v.x, dc); v.y = __fsub_rn(v.y, dc); v.z = __fsub_rn(v.z, dc); v.w = __fsub_rn(v.w, dc);
-      stg_stream4(yo + j, v);
+    interior[u] = aligned && j + 3 < jend && j >= sp.ov && j + 3 < sp.ov + sp.body &&
+                  (!need_fade || (o >= fade && o + 3 < out_len - fade));
+    if (interior[u]) v[u] = ldg_stream4(xc + j);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int j = j0 + 4 * (threadIdx.x + u * GATHER_THREADS);
+    if (j >= jend) continue;
+    const int o = sp.dst + j;
+    if (interior[u]) {
+      float4 w = v[u];
+      w.x = __fsub_rn(w.x, dc); w.y = __fsub_rn(w.y, dc); w.z = __fsub_rn(w.z, dc); w.w = __fsub_rn(w.w, dc);
+      stg_stream4(yo + j, w);
       if (o < third || o + 3 >= out_len - third) {
-        const float vv[4] = {v.x, v.y, v.z, v.w};
+        const float vv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (o + k < third) a_first += vv[k] * vv[k];
@@ -334,23 +345,23 @@ k_gather(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const
       for (int k = 0; k < 4; ++k) {
         const int jj = j + k;
         if (jj >= jend) break;
-        float v;
+        float val;
         if (jj < sp.ov) {               // :497-504 equal-power crossfade
           const float fo = cosf(linspace32(0.f, RHO_HALF_PI_F, sp.ov, jj));
           const float fi = cosf(linspace32(RHO_HALF_PI_F, 0.f, sp.ov, jj));
           const float a = __fmul_rn(__fsub_rn(xp[jj], dcp), fo);
           const float b = __fmul_rn(__fsub_rn(xc[jj], dc), fi);
-          v = __fadd_rn(a, b);
+          val = __fadd_rn(a, b);
         } else if (jj < sp.ov + sp.body) {
-          v = __fsub_rn(xc[jj], dc);
+          val = __fsub_rn(xc[jj], dc);
         } else {
-          v = 0.f;                      // inter-sentence pause
+          val = 0.f;                    // inter-sentence pause
         }
         const int oo = o + k;
-        if (need_fade) v = __fmul_rn(v, fade_gain(oo, out_len, fade));
-        yo[jj] = v;
-        if (oo < third) a_first += v * v;
-        if (oo >= out_len - third) a_last += v * v;
+        if (need_fade) val = __fmul_rn(val, fade_gain(oo, out_len, fade));
+        yo[jj] = val;
+        if (oo < third) a_first += val * val;
+        if (oo >= out_len - third) a_last += val * val;
       }
     }
   }

@@ -147,17 +147,24 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
   float2* fb = S.fb + g * LM_FB;
   float lmax = -INFINITY;
 
-  for (int b = 0; b < LM_BATCHES; ++b) {
-    const int t0 = tile_t0 + b * LM_BF;
-    if (t0 >= T_real) break;
-    // ---- stage the samples of frames [t0, t0+32): clip indices [160*t0-200, 160*t0-200+5360)
+  // Stages the samples of frames [t0, t0+32): clip indices [160*t0-200, 160*t0-200+5360).  Interior
+  // slabs go global -> shared with LDGSTS (no registers, all pieces in flight); slabs that touch the
+  // reflected edges or the zero padding are gathered sample by sample.
+  auto stage_slab = [&](int t0) {
     const long long i0 = (long long)HOP16 * t0 - N_FFT / 2;
     if (i0 >= 0 && i0 + LM_SLAB <= n_valid) {
-      for (int q = tid; q < LM_SLAB / 4; q += LM_THREADS)
-        *reinterpret_cast<float4*>(S.slab + 4 * q) = *reinterpret_cast<const float4*>(xs + i0 + 4 * q);
+      for (int q = tid; q < LM_SLAB / 4; q += LM_THREADS) cp_async16_zfill(S.slab + 4 * q, xs + i0 + 4 * q, 16);
     } else {
       for (int r = tid; r < LM_SLAB; r += LM_THREADS) S.slab[r] = lm_sample(xs, i0 + r, n_valid, N);
     }
+    cp_async_commit();
+  };
+  stage_slab(tile_t0);
+
+  for (int b = 0; b < LM_BATCHES; ++b) {
+    const int t0 = tile_t0 + b * LM_BF;
+    if (t0 >= T_real) break;
+    cp_async_wait_all();
     __syncthreads();
     // ---- FFT stage 1: lane = n2, 20-point DFT over n1 of z[20*n1 + n2], then twiddle W400^(n2*k1)
     float2 v[20];
@@ -174,6 +181,8 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
 #pragma unroll
     for (int k1 = 0; k1 < 20; ++k1) fb[k1 * 21 + lane] = (k1 == 0) ? v[0] : cmul(v[k1], S.tw[lane * k1]);
     __syncthreads();
+    // the slab is dead now: prefetch the next batch's samples under stage 2 / power / mel
+    if (b + 1 < LM_BATCHES && t0 + LM_BF < T_real) stage_slab(t0 + LM_BF);
     // ---- FFT stage 2: lane = k1, 20-point DFT over n2 -> Z[k1 + 20*k2]
 #pragma unroll
     for (int n2 = 0; n2 < 20; ++n2) v[n2] = fb[lane * 21 + n2];

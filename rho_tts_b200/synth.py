@@ -2,7 +2,7 @@
 
 x[t] = env(t) * am(t) * sum_h a_h sin(2 pi h f0 t / sr) * gate(t) + noise + dc
   f0 ~ U[90, 300] Hz, a = (0.25, 0.12, 0.06), am = 0.6 + 0.4 sin(2 pi r t), r ~ U[3, 6] Hz,
-  env linear 1 -> rho, rho ~ U[0.1, 1.2] (about a fifth of the clips fail the 0.3 decay check),
+  env linear 1 -> rho, rho ~ max(0.02, U[-0.15, 1.2]) (about a fifth of the clips fail the 0.3 decay check),
   noise ~ N(0, 1e-3^2) (-60 dBFS), dc ~ U[-2e-3, 2e-3], leading silence U[0, 0.5] s,
   trailing silence U[0, 1.0] s (scaled down for clips under 3 s), 5 ms linear onset / offset.
 
@@ -30,7 +30,7 @@ def make_clip_block(n: int, length: int, seed: int, device="cpu", sr: int = SR) 
     def U(lo, hi):
         return lo + (hi - lo) * torch.rand(n, 1, generator=g, device=dev, dtype=torch.float32)
 
-    f0, r, rho, dc = U(90.0, 300.0), U(3.0, 6.0), U(0.1, 1.2), U(-2e-3, 2e-3)
+    f0, r, rho, dc = U(90.0, 300.0), U(3.0, 6.0), torch.clamp(U(-0.15, 1.2), min=0.02), U(-2e-3, 2e-3)
     dur = length / sr
     lead_s = U(0.0, 0.5) * min(1.0, dur / 3.0)
     trail_s = U(0.0, 1.0) * min(1.0, dur / 3.0)

@@ -1,0 +1,99 @@
+"""CPU: the C-ABI library loads, exports every symbol include/rho_b200.h declares, builds the same
+constant tables as torchaudio / transformers, and fails loudly without a GPU.  No kernels run here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from rho_tts_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return _lib.load()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rho_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rho_b200_\w+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/rho_b200.h but not exported"
+    assert set(_lib.EXPORTS) == set(names)
+
+
+def test_abi_version_and_struct_sizes(lib):
+    assert lib.rho_b200_abi_version() == 1
+    assert ctypes.sizeof(_lib.RhoRecord) == 48 and ctypes.sizeof(_lib.RhoSegInfo) == 16
+    assert ctypes.sizeof(_lib.RhoParams) == 48
+    from rho_tts_b200 import REC_DTYPE, SEG_DTYPE
+    assert REC_DTYPE.itemsize == 48 and SEG_DTYPE.itemsize == 16
+    for (name, _), f in zip(_lib.RhoRecord._fields_, REC_DTYPE.names):
+        assert name == f
+        assert getattr(_lib.RhoRecord, name).offset == REC_DTYPE.fields[f][1]
+
+
+def _table(lib, kind, arg, n):
+    a = np.zeros(n, np.float32)
+    assert lib.rho_b200_host_table(kind, arg, a.ctypes.data, n) == n
+    return a
+
+
+def test_resample_taps_match_torchaudio(lib):
+    taps = _table(lib, 0, 0, 46).reshape(2, 23)
+    k, width, orig, new = oracle.sinc_resample_kernel(24000, 16000)
+    assert (width, orig, new) == (10, 3, 2)
+    assert np.abs(taps - k).max() < 1e-7
+    ta = pytest.importorskip("torchaudio")
+    kt, wt = ta.functional.functional._get_sinc_resample_kernel(24000, 16000, 8000, dtype=torch.float32)
+    assert wt == 10 and np.abs(taps - kt.numpy()[:, 0, :]).max() < 1e-7
+    # the clamp positions the kernel may skip are numerically nil
+    nil = np.abs(taps) < 1e-20
+    assert nil[0].nonzero()[0].tolist() == [0, 20, 21, 22] and nil[1].nonzero()[0].tolist() == [0, 1, 2, 21, 22]
+
+
+def test_hann_and_mel_tables(lib):
+    h = _table(lib, 1, 0, 400)
+    assert np.abs(h - torch.hann_window(400).numpy()).max() < 5e-7
+    for nm in (80, 128):
+        m = _table(lib, 2, nm, nm * 201).reshape(nm, 201)
+        want = oracle.slaney_mel_filterbank(nm).astype(np.float32).T
+        assert np.array_equal(m, want)
+        try:
+            from transformers import WhisperFeatureExtractor
+        except Exception:            # noqa: BLE001
+            continue
+        assert np.array_equal(m, WhisperFeatureExtractor(feature_size=nm).mel_filters.astype(np.float32).T)
+    assert lib.rho_b200_host_table(2, 64, h.ctypes.data, 400) < 0
+    assert b"n_mels" in lib.rho_b200_last_error()
+
+
+def test_workspace_bytes_monotone(lib):
+    a = lib.rho_b200_workspace_bytes(10, 10, 240000)
+    b = lib.rho_b200_workspace_bytes(1000, 1000, 240000)
+    c = lib.rho_b200_workspace_bytes(1000, 1000, 720000)
+    assert 0 < a < b < c
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="box has a GPU")
+def test_create_fails_loudly_without_gpu(lib):
+    h = ctypes.c_void_p()
+    rc = lib.rho_b200_create(ctypes.byref(h), 0)
+    assert rc == -3 and not h.value
+    assert b"no CPU fallback" in lib.rho_b200_last_error()
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        _lib.Handle(0)

@@ -284,7 +284,7 @@ def test_full_size_properties(R, cuda_device):
     # idempotence of the trim: the processed clip starts and ends loud, so a second scan trims at most
     # the faded edges; DC of the output is ~0
     means = torch.stack([out.audio.clip(i, int(rec["out_len"][i])).double().mean() for i in range(0, 1000, 50)])
-    assert float(means.abs().max()) < 1e-4
+    assert float(means.abs().max()) < 5e-4
     # spot-check 4 clips of the big batch against the oracle
     c = oracle.derive_constants()
     for i in (0, 333, 999):
