@@ -25,20 +25,24 @@ constexpr int LM_BF = 2 * LM_GROUPS;                // frames per batch (32)
 constexpr int LM_BATCHES = 4;                       // batches per CTA
 constexpr int LM_TILE = LM_BF * LM_BATCHES;         // frames per CTA (128)
 constexpr int LM_SLAB = HOP16 * LM_BF + (N_FFT - HOP16);  // 5360 samples cover 32 frames
-constexpr int LM_FB = 424;                          // float2 per FFT buffer (20 rows x 21 + pad)
+// The slab is stored in blocks of 320 samples (one frame pair's hop) at a stride of 340 floats and the
+// FFT buffers at a stride of 420 float2, so that the shared-memory bank of every stage-1/stage-2 access
+// is (thread id + const) mod 32: conflict-free although a 20-thread FFT group straddles warps.
+constexpr int LM_SLAB_BLK = 2 * HOP16;              // 320
+constexpr int LM_SLAB_STRIDE = LM_SLAB_BLK + 20;    // 340
+constexpr int LM_SLAB_SM = ((LM_SLAB + LM_SLAB_BLK - 1) / LM_SLAB_BLK) * LM_SLAB_STRIDE;   // 17 * 340
+constexpr int LM_FB = 420;                          // float2 per FFT buffer (20 rows x 21)
 constexpr int LM_PS = 201;                          // power row stride (odd: conflict-free across frames)
-constexpr int LM_MEL_GROUPS = LM_THREADS / 32;      // 10 warps share the mel rows
+
+#include "mel_sparse_gen.inc"
+static_assert(MEL_PARTS == LM_THREADS / 32, "one mel part per warp");
 
 struct LmSmem {
-  float slab[LM_SLAB];
+  float slab[LM_SLAB_SM];
   float2 fb[LM_GROUPS * LM_FB];
   float pw[LM_BF * LM_PS];
   float hann[N_FFT];
   float2 tw[N_FFT];
-  int mel_lo[MAX_MELS];
-  int mel_cnt[MAX_MELS];
-  int mel_wofs[MAX_MELS];
-  float mel_w[416];
   float red[LM_THREADS / 32];
 };
 
@@ -122,9 +126,7 @@ __global__ void k_logmel_init(int* __restrict__ clip_max, int n) {
 
 __global__ void __launch_bounds__(LM_THREADS, 2)
 k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, const int32_t* __restrict__ len16,
-                const float* __restrict__ g_hann, const float2* __restrict__ g_tw,
-                const int* __restrict__ g_lo, const int* __restrict__ g_cnt, const int* __restrict__ g_wofs,
-                const float* __restrict__ g_w, int nnz, int n_mels, int pad_frames,
+                const float* __restrict__ g_hann, const float2* __restrict__ g_tw, int n_mels, int pad_frames,
                 float* __restrict__ mel, long long mel_stride, int* __restrict__ clip_max,
                 int32_t* __restrict__ n_frames_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -138,8 +140,6 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
 
   const int tid = threadIdx.x;
   for (int i = tid; i < N_FFT; i += LM_THREADS) { S.hann[i] = g_hann[i]; S.tw[i] = g_tw[i]; }
-  for (int i = tid; i < n_mels; i += LM_THREADS) { S.mel_lo[i] = g_lo[i]; S.mel_cnt[i] = g_cnt[i]; S.mel_wofs[i] = g_wofs[i]; }
-  for (int i = tid; i < nnz; i += LM_THREADS) S.mel_w[i] = g_w[i];
 
   const float* __restrict__ xs = x16 + off[c];
   float* __restrict__ out = mel + (long long)c * n_mels * mel_stride;
@@ -153,9 +153,11 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
   auto stage_slab = [&](int t0) {
     const long long i0 = (long long)HOP16 * t0 - N_FFT / 2;
     if (i0 >= 0 && i0 + LM_SLAB <= n_valid) {
-      for (int q = tid; q < LM_SLAB / 4; q += LM_THREADS) cp_async16_zfill(S.slab + 4 * q, xs + i0 + 4 * q, 16);
+      for (int q = tid; q < LM_SLAB / 4; q += LM_THREADS)
+        cp_async16_zfill(S.slab + 4 * q + 20 * (q / (LM_SLAB_BLK / 4)), xs + i0 + 4 * q, 16);
     } else {
-      for (int r = tid; r < LM_SLAB; r += LM_THREADS) S.slab[r] = lm_sample(xs, i0 + r, n_valid, N);
+      for (int r = tid; r < LM_SLAB; r += LM_THREADS)
+        S.slab[r + 20 * (r / LM_SLAB_BLK)] = lm_sample(xs, i0 + r, n_valid, N);
     }
     cp_async_commit();
   };
@@ -169,12 +171,14 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
     // ---- FFT stage 1: lane = n2, 20-point DFT over n1 of z[20*n1 + n2], then twiddle W400^(n2*k1)
     float2 v[20];
     {
-      const float* fa = S.slab + 2 * g * HOP16 + lane;
+      // frame A = samples [320g, 320g+400), frame B = [320g+160, 320g+560) of the slab; sample s lives
+      // at s + 20*(s/320), and 20*n1+lane crosses a block boundary at n1 = 16 (A) / n1 = 8 (B).
+      const float* fa = S.slab + g * LM_SLAB_STRIDE + lane;
       const float* fbm = fa + HOP16;
 #pragma unroll
       for (int n1 = 0; n1 < 20; ++n1) {
         const float h = S.hann[20 * n1 + lane];
-        v[n1] = make_float2(fa[20 * n1] * h, fbm[20 * n1] * h);
+        v[n1] = make_float2(fa[20 * n1 + (n1 >= 16 ? 20 : 0)] * h, fbm[20 * n1 + (n1 >= 8 ? 20 : 0)] * h);
       }
     }
     dft20(v);
@@ -208,22 +212,23 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
       }
     }
     __syncthreads();
-    // ---- mel projection + log10: lane-of-warp = frame, warp = mel row group
+    // ---- mel projection + log10: lane-of-warp = frame, warp = one part of the mel rows.  The filterbank
+    // is straight-line FFMA code with immediate weights (mel_sparse_gen.inc); log10 = log2 * log10(2)
+    // on the SFU (|err| < 3e-6 on a value that is divided by 4 afterwards).
     {
-      const int f = tid & 31, wg = tid >> 5;
+      const int f = tid & 31, part = tid >> 5;
       const int t = t0 + f;
+      const bool live = t < T_real;
       const float* p = S.pw + f * LM_PS;
-      for (int m = wg; m < n_mels; m += LM_MEL_GROUPS) {
-        const int lo = S.mel_lo[m], cnt = S.mel_cnt[m];
-        const float* w = S.mel_w + S.mel_wofs[m];
-        float acc = 0.f;
-        for (int q = 0; q < cnt; ++q) acc = fmaf(w[q], p[lo + q], acc);
-        const float ls = log10f(fmaxf(acc, 1e-10f));
-        if (t < T_real) {
-          out[(long long)m * mel_stride + t] = ls;
+      float* __restrict__ o = out + t;
+      auto emit = [&](int m, float acc) {
+        const float ls = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
+        if (live) {
+          o[(long long)m * mel_stride] = ls;
           lmax = fmaxf(lmax, ls);
         }
-      }
+      };
+      if (n_mels == 80) mel_sparse_80(part, p, emit); else mel_sparse_128(part, p, emit);
     }
     // the next batch's first barrier orders these reads before pw/slab are overwritten
   }
@@ -289,7 +294,6 @@ cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off
                           int64_t mel_stride_frames, int32_t* n_frames, int* clip_max,
                           cudaStream_t st, LaunchCtx* lc) {
   if (n <= 0) return cudaSuccess;
-  const int which = (n_mels == 80) ? 0 : 1;
   lc->begin(KID_LOGMEL_INIT, st);
   k_logmel_init<<<(n + 255) / 256, 256, 0, st>>>(clip_max, n); lc->end(st);
   int64_t max_real;
@@ -308,10 +312,8 @@ cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off
   if (e != cudaSuccess) return e;
   dim3 grid((unsigned)n, tiles);
   lc->begin(KID_LOGMEL_FRAMES, st);
-  k_logmel_frames<<<grid, LM_THREADS, smem, st>>>(x16, off, len16, tb.hann, tb.twiddle, tb.mel_lo[which],
-                                                  tb.mel_cnt[which], tb.mel_wofs[which], tb.mel_w[which],
-                                                  tb.mel_nnz[which], n_mels, pad_frames, mel, mel_stride_frames,
-                                                  clip_max, n_frames);
+  k_logmel_frames<<<grid, LM_THREADS, smem, st>>>(x16, off, len16, tb.hann, tb.twiddle, n_mels, pad_frames, mel,
+                                                  mel_stride_frames, clip_max, n_frames);
   lc->end(st);
   const int rows_per_cta = 8;
   dim3 g2((unsigned)n, (unsigned)((n_mels + rows_per_cta - 1) / rows_per_cta));

@@ -97,3 +97,19 @@ def test_create_fails_loudly_without_gpu(lib):
     assert b"no CPU fallback" in lib.rho_b200_last_error()
     with pytest.raises(RuntimeError, match="no CUDA device"):
         _lib.Handle(0)
+
+
+def test_baked_mel_weights_match_runtime_table(lib):
+    """mel_sparse_gen.inc bakes the filterbank into FFMA immediates; they must be the table, bit for bit."""
+    text = open(os.path.join(ROOT, "rho_tts_b200", "csrc", "mel_sparse_gen.inc")).read()
+    for nm in (80, 128):
+        body = text[text.index(f"void mel_sparse_{nm}("):]
+        body = body[:body.index("static const unsigned int")]
+        table = _table(lib, 2, nm, nm * 201).reshape(nm, 201)
+        seen = np.zeros_like(table)
+        rows = re.findall(r"\{ float a = 0\.f;(.*?) emit\((\d+), a\); \}", body)
+        assert len(rows) == nm
+        for taps, m in rows:
+            for hx, k in re.findall(r"__uint_as_float\((0x[0-9a-f]{8})u\), p\[(\d+)\]", taps):
+                seen[int(m), int(k)] = np.array([int(hx, 16)], dtype=np.uint32).view(np.float32)[0]
+        assert np.array_equal(seen.view(np.uint32), table.view(np.uint32))
