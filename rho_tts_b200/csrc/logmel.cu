@@ -46,8 +46,12 @@ struct LmSmem {
   float red[LM_THREADS / 32];
 };
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex arithmetic on the sm_100 packed-fp32 pipe: one FADD2 / FMUL2 / FFMA2 handles the real and the
+// imaginary part together (halves the issue slots of the butterflies; same IEEE roundings as scalar code).
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+__device__ __forceinline__ float2 cscale(float s, float2 a) { return __fmul2_rn(make_float2(s, s), a); }
+__device__ __forceinline__ float2 cfma(float s, float2 a, float2 c) { return __ffma2_rn(make_float2(s, s), a, c); }  // s*a + c
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -57,11 +61,11 @@ __device__ __forceinline__ void dft5(float2& x0, float2& x1, float2& x2, float2&
   const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;   // cos(2pi/5), cos(4pi/5)
   const float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;    // sin(2pi/5), sin(4pi/5)
   const float2 t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
-  const float2 m1 = make_float2(x0.x + c1 * t1.x + c2 * t2.x, x0.y + c1 * t1.y + c2 * t2.y);
-  const float2 m2 = make_float2(x0.x + c2 * t1.x + c1 * t2.x, x0.y + c2 * t1.y + c1 * t2.y);
-  const float2 u1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-  const float2 u2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
-  x0 = make_float2(x0.x + t1.x + t2.x, x0.y + t1.y + t2.y);
+  const float2 m1 = cfma(c2, t2, cfma(c1, t1, x0));
+  const float2 m2 = cfma(c1, t2, cfma(c2, t1, x0));
+  const float2 u1 = cfma(s2, t4, cscale(s1, t3));
+  const float2 u2 = cfma(-s1, t4, cscale(s2, t3));
+  x0 = cadd(x0, cadd(t1, t2));
   // y1 = m1 - i*u1, y4 = m1 + i*u1, y2 = m2 - i*u2, y3 = m2 + i*u2   ( -i*(a,b) = (b,-a) )
   x1 = make_float2(m1.x + u1.y, m1.y - u1.x);
   x4 = make_float2(m1.x - u1.y, m1.y + u1.x);
@@ -124,6 +128,7 @@ __global__ void k_logmel_init(int* __restrict__ clip_max, int n) {
   if (i < n) clip_max[i] = INT_MIN;
 }
 
+template <int NM>
 __global__ void __launch_bounds__(LM_THREADS, 2)
 k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, const int32_t* __restrict__ len16,
                 const float* __restrict__ g_hann, const float2* __restrict__ g_tw, int n_mels, int pad_frames,
@@ -152,12 +157,15 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
   // reflected edges or the zero padding are gathered sample by sample.
   auto stage_slab = [&](int t0) {
     const long long i0 = (long long)HOP16 * t0 - N_FFT / 2;
-    if (i0 >= 0 && i0 + LM_SLAB <= n_valid) {
-      for (int q = tid; q < LM_SLAB / 4; q += LM_THREADS)
-        cp_async16_zfill(S.slab + 4 * q + 20 * (q / (LM_SLAB_BLK / 4)), xs + i0 + 4 * q, 16);
-    } else {
-      for (int r = tid; r < LM_SLAB; r += LM_THREADS)
-        S.slab[r + 20 * (r / LM_SLAB_BLK)] = lm_sample(xs, i0 + r, n_valid, N);
+    for (int q = tid; q < LM_SLAB / 4; q += LM_THREADS) {
+      float* dst = S.slab + 4 * q + 20 * (q / (LM_SLAB_BLK / 4));
+      const long long i = i0 + 4 * q;
+      if (i >= 0 && i + 3 < n_valid) {
+        cp_async16_zfill(dst, xs + i, 16);
+      } else {                                    // reflected edge / zero padding: a few pieces per clip
+        dst[0] = lm_sample(xs, i + 0, n_valid, N); dst[1] = lm_sample(xs, i + 1, n_valid, N);
+        dst[2] = lm_sample(xs, i + 2, n_valid, N); dst[3] = lm_sample(xs, i + 3, n_valid, N);
+      }
     }
     cp_async_commit();
   };
@@ -183,7 +191,7 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
     }
     dft20(v);
 #pragma unroll
-    for (int k1 = 0; k1 < 20; ++k1) fb[k1 * 21 + lane] = (k1 == 0) ? v[0] : cmul(v[k1], S.tw[lane * k1]);
+    for (int k1 = 0; k1 < 20; ++k1) fb[k1 * 21 + lane] = (k1 == 0) ? v[0] : cmul(v[k1], S.tw[k1 * 20 + lane]);
     __syncthreads();
     // the slab is dead now: prefetch the next batch's samples under stage 2 / power / mel
     if (b + 1 < LM_BATCHES && t0 + LM_BF < T_real) stage_slab(t0 + LM_BF);
@@ -228,7 +236,7 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
           lmax = fmaxf(lmax, ls);
         }
       };
-      if (n_mels == 80) mel_sparse_80(part, p, emit); else mel_sparse_128(part, p, emit);
+      if (NM == 80) mel_sparse_80(part, p, emit); else mel_sparse_128(part, p, emit);
     }
     // the next batch's first barrier orders these reads before pw/slab are overwritten
   }
@@ -308,12 +316,13 @@ cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off
   unsigned tiles = (unsigned)((max_real + LM_TILE - 1) / LM_TILE);
   if (tiles == 0) tiles = 1;
   const size_t smem = sizeof(LmSmem);
-  cudaError_t e = cudaFuncSetAttribute(k_logmel_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = (n_mels == 80) ? k_logmel_frames<80> : k_logmel_frames<128>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   dim3 grid((unsigned)n, tiles);
   lc->begin(KID_LOGMEL_FRAMES, st);
-  k_logmel_frames<<<grid, LM_THREADS, smem, st>>>(x16, off, len16, tb.hann, tb.twiddle, n_mels, pad_frames, mel,
-                                                  mel_stride_frames, clip_max, n_frames);
+  kern<<<grid, LM_THREADS, smem, st>>>(x16, off, len16, tb.hann, tb.twiddle, n_mels, pad_frames, mel,
+                                       mel_stride_frames, clip_max, n_frames);
   lc->end(st);
   const int rows_per_cta = 8;
   dim3 g2((unsigned)n, (unsigned)((n_mels + rows_per_cta - 1) / rows_per_cta));

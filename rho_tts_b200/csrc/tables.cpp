@@ -39,11 +39,15 @@ void host_hann(float* out) {
   for (int n = 0; n < N_FFT; ++n) out[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * n / N_FFT));
 }
 
+// Stage-1 twiddles of the 20 x 20 FFT, laid out [k1][n2] = exp(-2*pi*i*n2*k1/400) so that the 20 threads
+// of an FFT group read consecutive entries (conflict-free, and the same address in every group).
 void host_twiddles(float* out) {
-  for (int k = 0; k < N_FFT; ++k) {
-    out[2 * k] = (float)std::cos(2.0 * M_PI * k / N_FFT);
-    out[2 * k + 1] = (float)(-std::sin(2.0 * M_PI * k / N_FFT));
-  }
+  for (int k1 = 0; k1 < 20; ++k1)
+    for (int n2 = 0; n2 < 20; ++n2) {
+      const int k = k1 * n2;
+      out[2 * (k1 * 20 + n2)] = (float)std::cos(2.0 * M_PI * k / N_FFT);
+      out[2 * (k1 * 20 + n2) + 1] = (float)(-std::sin(2.0 * M_PI * k / N_FFT));
+    }
 }
 
 static double hz_to_mel(double f) {
