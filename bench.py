@@ -307,6 +307,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
         "k_resample3to2": 4 * sum_out + 4 * sum16,
         "k_logmel_frames": 4 * sum16 + 4 * sum_mel_real,
         "k_logmel_norm": 4 * sum_mel_real + 4.0 * N_MELS * PAD_FRAMES * n,
+        # fused apply + resample + log-mel: x[start:end] in, y out, raw log-mel frames out
+        "k_fused_features": 8 * sum_out + 4 * sum_mel_real,
     }
     peak, peak_src = load_peaks()
     kernels = {}

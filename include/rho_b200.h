@@ -175,14 +175,20 @@ int rho_b200_cosine(rho_handle* h, const float* emb, const float* ref, int n, in
 
 /* ------------------------------------------------ whole validation front end */
 /* join/post-process -> resample 24k->16k -> log-mel -> cosine, device resident.
- * scratch16 holds the 16 kHz intermediate (same offsets as y, 2/3 the length). */
+ * scratch16 holds the 16 kHz intermediate (same offsets as y, 2/3 the length).
+ * flags: RHO_V_ONE_SEGMENT_ITEMS -- the caller asserts every item is exactly one segment
+ *        (item_first_seg = 0,1,2,...): enables the fused kernel that applies DC/fades, resamples and
+ *        computes the log-mel frames in one pass over each clip (scratch16 is then unused, may be NULL).
+ *        RHO_V_NO_FUSION -- force the kernel-per-stage path (for A/B measurements). */
+#define RHO_V_ONE_SEGMENT_ITEMS 1u
+#define RHO_V_NO_FUSION 2u
 int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, const int32_t* seg_len,
                       int n_segments, int64_t max_seg_len,
                       const int32_t* item_first_seg, int n_items, int64_t max_item_len,
                       const rho_params* p, float* y, const int64_t* y_off,
                       int n_mels, int pad_frames, float* mel, int64_t mel_stride_frames,
                       const float* emb, const float* ref_emb, int emb_dim,
-                      rho_record* rec, float* scratch16,
+                      rho_record* rec, float* scratch16, uint32_t flags,
                       void* workspace, size_t ws_bytes, void* stream);
 
 /* HOST entry point: the call a non-torch embedder makes.  All pointers are HOST

@@ -22,6 +22,8 @@ F_ALL_SILENT = 1
 F_FALLBACK = 2
 F_TWO_D = 4
 F_UNTOUCHED = 8
+V_ONE_SEGMENT_ITEMS = 1
+V_NO_FUSION = 2
 
 EXPORTS = (
     "rho_b200_abi_version", "rho_b200_create", "rho_b200_destroy", "rho_b200_last_error",
@@ -87,7 +89,7 @@ def load():
             "rho_b200_logmel": (c_int, [vp, vp, vp, vp, i32, i64, c_int, c_int, vp, i64, vp, vp, c_size_t, vp]),
             "rho_b200_cosine": (c_int, [vp, vp, vp, i32, c_int, vp, c_int, vp]),
             "rho_b200_validate": (c_int, [vp, vp, vp, vp, i32, i64, vp, i32, i64, P, vp, vp, c_int, c_int, vp, i64,
-                                          vp, vp, c_int, vp, vp, vp, c_size_t, vp]),
+                                          vp, vp, c_int, vp, vp, c_uint32, vp, c_size_t, vp]),
             "rho_b200_validate_host": (c_int, [vp, vp, c_int, c_int32, P, vp, c_int, c_int, vp, vp, vp, c_int, vp]),
             "rho_b200_launch_count": (c_int64, [vp]),
             "rho_b200_profile_begin": (c_int, [vp]),

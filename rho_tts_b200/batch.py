@@ -179,7 +179,7 @@ class ValidatePlan:
     (the benchmark's steady state: allocation is not part of the hot path)."""
 
     def __init__(self, rb: RaggedBatch, item_first_seg: Sequence[int], p: RhoParams, n_mels: int = 80,
-                 pad_to_30s: bool = True):
+                 pad_to_30s: bool = True, fuse: bool = True):
         self.dev = _dev_index(rb.data)
         self.h = Handle.get(self.dev)
         self.p = p
@@ -189,6 +189,8 @@ class ValidatePlan:
         self.n_items = len(first) - 1
         self.n_seg = rb.n
         self.max_seg_len = rb.max_len
+        one_seg = self.n_items == self.n_seg and bool(np.all(np.diff(first) == 1))
+        self.flags = (_lib.V_ONE_SEGMENT_ITEMS if one_seg else 0) | (0 if fuse else _lib.V_NO_FUSION)
         pause = int(p.sr * p.pause_sec) if p.pause_sec > 0 else 0
         seg_tot = np.concatenate([[0], np.cumsum(rb.h_lengths.astype(np.int64))])
         cap = (seg_tot[first[1:]] - seg_tot[first[:-1]]) + np.maximum(0, np.diff(first) - 2) * pause
@@ -208,16 +210,16 @@ class ValidatePlan:
             _ptr(self.d_first), self.n_items, self.max_item_len, ctypes.byref(self.p),
             _ptr(self.out.data), _ptr(self.out.offsets), self.n_mels, self.pad_frames, _ptr(self.mel), self.T,
             _ptr(emb), _ptr(ref), int(emb.shape[1]) if emb is not None else 0, _ptr(self.rec),
-            _ptr(self.scratch16), _ptr(self.ws), self.ws.numel(), _stream(self.dev)), "validate")
+            _ptr(self.scratch16), self.flags, _ptr(self.ws), self.ws.numel(), _stream(self.dev)), "validate")
         return ValidateOutput(self.out, self.mel, self.rec)
 
 
 def validate_batch(rb: RaggedBatch, p: RhoParams, emb: Optional[torch.Tensor] = None,
                    ref: Optional[torch.Tensor] = None, n_mels: int = 80, pad_to_30s: bool = True,
-                   item_first_seg: Optional[Sequence[int]] = None) -> ValidateOutput:
+                   item_first_seg: Optional[Sequence[int]] = None, fuse: bool = True) -> ValidateOutput:
     """post-process/join -> resample 24k->16k -> log-mel -> cosine, all on the device."""
     first = np.arange(rb.n + 1, dtype=np.int32) if item_first_seg is None else item_first_seg
-    return ValidatePlan(rb, first, p, n_mels, pad_to_30s).run(rb, emb, ref)
+    return ValidatePlan(rb, first, p, n_mels, pad_to_30s, fuse).run(rb, emb, ref)
 
 
 def validate_host(x: torch.Tensor, p: RhoParams, emb: Optional[torch.Tensor], ref: Optional[torch.Tensor],

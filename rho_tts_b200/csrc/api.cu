@@ -46,7 +46,8 @@ using namespace rho;
 namespace rho {
 const char* const kKernelNames[KID_COUNT] = {
   "k_init", "k_scan", "k_finalize_segs", "k_plan_items", "k_gather", "k_finalize_items",
-  "k_resample3to2", "k_logmel_init", "k_logmel_frames", "k_logmel_norm", "k_cosine", "k_single_clip_helpers"};
+  "k_resample3to2", "k_logmel_init", "k_logmel_frames", "k_logmel_norm", "k_cosine", "k_single_clip_helpers",
+  "k_fused_features"};
 }
 
 struct rho_handle {
@@ -177,6 +178,7 @@ int rho_b200_create(rho_handle** out, int device) {
   std::vector<float> taps(2 * RS_TAPS), hann(N_FFT), tw(2 * N_FFT);
   host_resample_taps(taps.data()); host_hann(hann.data()); host_twiddles(tw.data());
   if ((e = upload_resample_taps(taps.data())) != cudaSuccess) { rho_b200_destroy(h); return cuda_fail(e, "taps"); }
+  if ((e = upload_fused_taps(taps.data())) != cudaSuccess) { rho_b200_destroy(h); return cuda_fail(e, "fused taps"); }
   if ((e = dev_upload(h, &h->tb.hann, hann.data(), N_FFT)) != cudaSuccess) { rho_b200_destroy(h); return cuda_fail(e, "hann"); }
   if ((e = dev_upload(h, (float**)&h->tb.twiddle, tw.data(), 2 * N_FFT)) != cudaSuccess) { rho_b200_destroy(h); return cuda_fail(e, "twiddle"); }
   for (int which = 0; which < 2; ++which) {
@@ -362,31 +364,52 @@ int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, con
                       int64_t max_item_len, const rho_params* p, float* y, const int64_t* y_off,
                       int n_mels, int pad_frames, float* mel, int64_t mel_stride_frames,
                       const float* emb, const float* ref_emb, int emb_dim, rho_record* rec, float* scratch16,
-                      void* workspace, size_t ws_bytes, void* stream) {
+                      uint32_t flags, void* workspace, size_t ws_bytes, void* stream) {
   if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
   int rc = check_params(p); if (rc) return rc;
   if (p->sr != 24000) return fail(RHO_ERR_INVALID, "validate needs 24 kHz input (3:2 resampler), got %d", p->sr);
   if (n_mels != 80 && n_mels != 128) return fail(RHO_ERR_INVALID, "n_mels must be 80 or 128, got %d", n_mels);
   if (pad_frames != 0 && pad_frames != MEL_PAD_FRAMES) return fail(RHO_ERR_INVALID, "pad_frames must be 0 or 3000");
   if (n_items <= 0) return n_items == 0 ? RHO_OK : fail(RHO_ERR_INVALID, "negative size");
-  if (!scratch16 || !mel || !rec) return fail(RHO_ERR_INVALID, "NULL device pointer");
-  rc = rho_b200_join(h, x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, p,
-                     y, y_off, rec, nullptr, workspace, ws_bytes, stream);
-  if (rc) return rc;
+  if (n_segments < 0 || max_seg_len < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (!mel || !rec || !item_first_seg || !y_off || (n_segments > 0 && (!x || !seg_off || !seg_len || !y)))
+    return fail(RHO_ERR_INVALID, "NULL device pointer");
+  const int64_t max16 = (2 * max_item_len + 2) / 3;
+  if (pad_frames == 0 && mel_stride_frames < max16 / HOP16) return fail(RHO_ERR_INVALID, "mel_stride_frames too small");
+  if (pad_frames > 0 && mel_stride_frames < pad_frames) return fail(RHO_ERR_INVALID, "mel_stride_frames too small");
   const Derived d = derive(*p);
   Workspace ws;
   rc = carve(workspace, ws_bytes, n_segments, n_items, max_seg_len, d, &ws, nullptr); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  // 16 kHz intermediate lives at the same offsets as y (it is 2/3 as long)
-  cudaError_t e = launch_resample3to2(y, y_off, &rec[0].out_len, (int)sizeof(rho_record), n_items, max_item_len,
-                                      scratch16, y_off, ws.len16, st, &h->lc);
-  if (e != cudaSuccess) return cuda_fail(e, "resample3to2");
-  const int64_t max16 = (2 * max_item_len + 2) / 3;
-  if (pad_frames == 0 && mel_stride_frames < max16 / HOP16) return fail(RHO_ERR_INVALID, "mel_stride_frames too small");
-  if (pad_frames > 0 && mel_stride_frames < pad_frames) return fail(RHO_ERR_INVALID, "mel_stride_frames too small");
-  e = launch_logmel(h->tb, scratch16, y_off, ws.len16, n_items, max16, n_mels, pad_frames, mel, mel_stride_frames,
-                    nullptr, ws.clip_max, st, &h->lc);
-  if (e != cudaSuccess) return cuda_fail(e, "logmel");
+  cudaError_t e;
+  const bool fused = (flags & RHO_V_ONE_SEGMENT_ITEMS) && !(flags & RHO_V_NO_FUSION) && n_segments == n_items;
+  if (fused) {
+    // scan -> bounds/DC -> ONE kernel for apply + resample + log-mel -> decay decision -> normalise
+    e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,
+                    rec, nullptr, ws, st, &h->lc, JOIN_PREPARE);
+    if (e != cudaSuccess) return cuda_fail(e, "join prepare");
+    if ((e = launch_logmel_init(ws.clip_max, n_items, st, &h->lc)) != cudaSuccess) return cuda_fail(e, "logmel init");
+    e = launch_fused_features(h->tb, x, seg_off, ws, item_first_seg, n_items, max_item_len, d, y, y_off, n_mels,
+                              pad_frames, mel, mel_stride_frames, st, &h->lc);
+    if (e != cudaSuccess) return cuda_fail(e, "fused features");
+    e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,
+                    rec, nullptr, ws, st, &h->lc, JOIN_FINISH);
+    if (e != cudaSuccess) return cuda_fail(e, "join finish");
+    e = launch_logmel_norm(ws.len16, n_items, n_mels, pad_frames, mel, mel_stride_frames, ws.clip_max, st, &h->lc);
+    if (e != cudaSuccess) return cuda_fail(e, "logmel norm");
+  } else {
+    if (!scratch16) return fail(RHO_ERR_INVALID, "scratch16 is NULL (needed by the unfused path)");
+    e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,
+                    rec, nullptr, ws, st, &h->lc, JOIN_ALL);
+    if (e != cudaSuccess) return cuda_fail(e, "join");
+    // 16 kHz intermediate lives at the same offsets as y (it is 2/3 as long)
+    e = launch_resample3to2(y, y_off, &rec[0].out_len, (int)sizeof(rho_record), n_items, max_item_len,
+                            scratch16, y_off, ws.len16, st, &h->lc);
+    if (e != cudaSuccess) return cuda_fail(e, "resample3to2");
+    e = launch_logmel(h->tb, scratch16, y_off, ws.len16, n_items, max16, n_mels, pad_frames, mel, mel_stride_frames,
+                      nullptr, ws.clip_max, st, &h->lc);
+    if (e != cudaSuccess) return cuda_fail(e, "logmel");
+  }
   if (emb && ref_emb) {
     e = launch_cosine(emb, ref_emb, n_items, emb_dim, &rec[0].cosine, (int)sizeof(rho_record), st, &h->lc);
     if (e != cudaSuccess) return cuda_fail(e, "cosine");
@@ -486,7 +509,7 @@ int rho_b200_validate_host(rho_handle* h, const float* x, int n, int32_t clip_le
     cudaStreamWaitEvent(sc, ev_in[s], 0);
     status = rho_b200_validate(h, d_x, d_off, d_len, cn, clip_len, d_first, cn, clip_len, p, d_y, d_off,
                                n_mels, pad_frames, d_mel, pad_frames, have_emb ? d_emb : nullptr,
-                               have_emb ? d_ref : nullptr, emb_dim, d_rec, d_16, d_ws, b_ws, sc);
+                               have_emb ? d_ref : nullptr, emb_dim, d_rec, d_16, RHO_V_ONE_SEGMENT_ITEMS, d_ws, b_ws, sc);
     if (status != RHO_OK) break;
     cudaEventRecord(ev_done[s], sc);
     cudaStreamWaitEvent(h->s_copy_out, ev_done[s], 0);

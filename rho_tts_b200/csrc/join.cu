@@ -503,25 +503,27 @@ cudaError_t launch_trim_scan(const float* x, const int64_t* off, const int32_t* 
 cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* seg_len, int n_seg, int64_t max_seg_len,
                         const int32_t* item_first_seg, int n_items, int64_t max_item_len,
                         const Derived& d, float* y, const int64_t* y_off, rho_record* rec, rho_seg_info* seg_info,
-                        const Workspace& ws, cudaStream_t st, LaunchCtx* lc) {
+                        const Workspace& ws, cudaStream_t st, LaunchCtx* lc, int stages) {
   if (n_items <= 0) return cudaSuccess;
-  lc->begin(KID_INIT, st);
-  k_init_items<<<(n_items + 255) / 256, 256, 0, st>>>(ws.seg, ws.item, item_first_seg, n_items); lc->end(st);
   cudaError_t e = cudaSuccess;
-  if (n_seg > 0) {
-    e = launch_scan(x, seg_off, seg_len, n_seg, max_seg_len, d, ws, st, lc);
-    if (e != cudaSuccess) return e;
-    lc->begin(KID_FINALIZE_SEGS, st);
-    k_finalize_segs<<<(n_seg * 32 + 255) / 256, 256, 0, st>>>(x, seg_off, seg_len, ws.seg, ws.block_sum,
-                                                            ws.blocks_per_seg, n_seg, d.window, d.hop,
-                                                            d.trim_enabled, seg_info);
+  if (stages & JOIN_PREPARE) {
+    lc->begin(KID_INIT, st);
+    k_init_items<<<(n_items + 255) / 256, 256, 0, st>>>(ws.seg, ws.item, item_first_seg, n_items); lc->end(st);
+    if (n_seg > 0) {
+      e = launch_scan(x, seg_off, seg_len, n_seg, max_seg_len, d, ws, st, lc);
+      if (e != cudaSuccess) return e;
+      lc->begin(KID_FINALIZE_SEGS, st);
+      k_finalize_segs<<<(n_seg * 32 + 255) / 256, 256, 0, st>>>(x, seg_off, seg_len, ws.seg, ws.block_sum,
+                                                              ws.blocks_per_seg, n_seg, d.window, d.hop,
+                                                              d.trim_enabled, seg_info);
+      lc->end(st);
+    }
+    lc->begin(KID_PLAN, st);
+    k_plan_items<<<(n_items + 127) / 128, 128, 0, st>>>(ws.seg, seg_len, ws.span, ws.item, item_first_seg, n_items,
+                                                       d.cf, d.pause, d.pause_on);
     lc->end(st);
   }
-  lc->begin(KID_PLAN, st);
-  k_plan_items<<<(n_items + 127) / 128, 128, 0, st>>>(ws.seg, seg_len, ws.span, ws.item, item_first_seg, n_items,
-                                                     d.cf, d.pause, d.pause_on);
-  lc->end(st);
-  if (n_seg > 0) {
+  if ((stages & JOIN_GATHER) && n_seg > 0) {
     // a segment's span is at most its own length plus one pause
     const int64_t max_span = max_seg_len + d.pause;
     const unsigned tiles = (unsigned)((max_span + GATHER_TILE - 1) / GATHER_TILE);
@@ -531,9 +533,11 @@ cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* s
     lc->end(st);
   }
   (void)max_item_len;
-  lc->begin(KID_FINALIZE_ITEMS, st);
-  k_finalize_items<<<(n_items + 255) / 256, 256, 0, st>>>(ws.seg, ws.item, item_first_seg, n_items, d.decay_thr, rec);
-  lc->end(st);
+  if (stages & JOIN_FINISH) {
+    lc->begin(KID_FINALIZE_ITEMS, st);
+    k_finalize_items<<<(n_items + 255) / 256, 256, 0, st>>>(ws.seg, ws.item, item_first_seg, n_items, d.decay_thr, rec);
+    lc->end(st);
+  }
   return cudaGetLastError();
 }
 

@@ -35,7 +35,7 @@ struct Tables {
 // (rho_b200_profile_*; bench.py uses it for the roofline line).
 enum KernelId {
   KID_INIT = 0, KID_SCAN, KID_FINALIZE_SEGS, KID_PLAN, KID_GATHER, KID_FINALIZE_ITEMS,
-  KID_RESAMPLE, KID_LOGMEL_INIT, KID_LOGMEL_FRAMES, KID_LOGMEL_NORM, KID_COSINE, KID_SINGLE, KID_COUNT
+  KID_RESAMPLE, KID_LOGMEL_INIT, KID_LOGMEL_FRAMES, KID_LOGMEL_NORM, KID_COSINE, KID_SINGLE, KID_FUSED, KID_COUNT
 };
 extern const char* const kKernelNames[KID_COUNT];
 
@@ -58,13 +58,14 @@ struct LaunchCtx {
 };
 
 // join.cu
+enum { JOIN_PREPARE = 1, JOIN_GATHER = 2, JOIN_FINISH = 4, JOIN_ALL = 7 };   // stages of launch_join
 cudaError_t launch_trim_scan(const float* x, const int64_t* off, const int32_t* len, const uint8_t* trim_flags,
                              int n_seg, int64_t max_len, const Derived& d, const Workspace& ws,
                              rho_seg_info* info, cudaStream_t st, LaunchCtx* lc);
 cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* seg_len, int n_seg, int64_t max_seg_len,
                         const int32_t* item_first_seg, int n_items, int64_t max_item_len,
                         const Derived& d, float* y, const int64_t* y_off, rho_record* rec, rho_seg_info* seg_info,
-                        const Workspace& ws, cudaStream_t st, LaunchCtx* lc);
+                        const Workspace& ws, cudaStream_t st, LaunchCtx* lc, int stages = JOIN_ALL);
 cudaError_t launch_remove_dc(float* x, int64_t n, float* dc_out, double* scratch, cudaStream_t st, LaunchCtx* lc);
 cudaError_t launch_apply_fades(float* x, int64_t n, int fade, int fade_in, int fade_out, cudaStream_t st, LaunchCtx* lc);
 cudaError_t launch_sound_decay(const float* x, int64_t n, double thr, rho_record* rec, double* scratch,
@@ -81,6 +82,17 @@ cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off
                           int n, int64_t max_len16, int n_mels, int pad_frames, float* mel,
                           int64_t mel_stride_frames, int32_t* n_frames, int* clip_max,
                           cudaStream_t st, LaunchCtx* lc);
+
+cudaError_t launch_logmel_init(int* clip_max, int n, cudaStream_t st, LaunchCtx* lc);
+cudaError_t launch_logmel_norm(const int32_t* len16, int n, int n_mels, int pad_frames, float* mel,
+                               int64_t mel_stride_frames, const int* clip_max, cudaStream_t st, LaunchCtx* lc);
+
+// fused.cu
+cudaError_t upload_fused_taps(const float* taps /* [2][23] */);
+cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_t* seg_off, const Workspace& ws,
+                                  const int32_t* item_first_seg, int n_items, int64_t max_len,
+                                  const Derived& d, float* y, const int64_t* y_off, int n_mels, int pad_frames,
+                                  float* mel, int64_t mel_stride_frames, cudaStream_t st, LaunchCtx* lc);
 
 // cosine.cu
 cudaError_t launch_cosine(const float* emb, const float* ref, int n, int dim, float* out, int out_stride_bytes,

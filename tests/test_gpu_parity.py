@@ -224,13 +224,14 @@ def _oracle_pipeline(x, c, n_mels, emb, ref):
     return o, oracle.log_mel(w16, n_mels, True), oracle.cosine_similarity(ref, emb)
 
 
+@pytest.mark.parametrize("fuse", [True, False])
 @pytest.mark.parametrize("n_mels", [80, 128])
-def test_validate_pipeline_vs_oracle(R, cuda_device, n_mels):
+def test_validate_pipeline_vs_oracle(R, cuda_device, n_mels, fuse):
     from rho_tts_b200 import synth
     x = synth.make_clip_block(12, 240000, 1234 + 1)
     emb, ref = synth.make_embeddings(12)
     rb = R.RaggedBatch.from_dense(x.to(cuda_device))
-    out = R.validate_batch(rb, R.make_params(), emb.to(cuda_device), ref.to(cuda_device), n_mels=n_mels)
+    out = R.validate_batch(rb, R.make_params(), emb.to(cuda_device), ref.to(cuda_device), n_mels=n_mels, fuse=fuse)
     rec = out.records_host(); mel = out.mel.cpu().numpy()
     c = oracle.derive_constants()
     for i in range(x.shape[0]):
@@ -240,6 +241,53 @@ def test_validate_pipeline_vs_oracle(R, cuda_device, n_mels):
         assert_close(out.audio.clip(i, o["out_len"]).cpu().numpy(), o["audio"], what="audio")
         assert_close(mel[i], m, what=f"mel clip {i}")
         assert_close(rec["cosine"][i], cs, what="cosine")
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("pad", [True, False])
+def test_validate_ragged_lengths_vs_oracle(R, cuda_device, pad, fuse):
+    """Ragged one-clip items from 4 ms to beyond Whisper's 30 s window (truncated features, full audio)."""
+    from rho_tts_b200 import synth
+    rng = np.random.default_rng(77)
+    lens = [100, 959, 5000, 7680, 24000, 100001, 184320, 480000]
+    lens += [730000] if pad else [300]
+    clips = [synth.make_clip_block(1, L, 500 + i)[0].numpy() for i, L in enumerate(lens)]
+    clips.append(rng.normal(0, 1e-4, 30000).astype(np.float32))                    # all silent -> 240 samples
+    rb = _rb(R, clips, cuda_device)
+    out = R.validate_batch(rb, R.make_params(), None, None, n_mels=80, pad_to_30s=pad, fuse=fuse)
+    rec = out.records_host(); mel = out.mel.cpu().numpy()
+    c = oracle.derive_constants()
+    for i, x in enumerate(clips):
+        o = oracle.post_process_clip(x, c)
+        assert (rec["start"][i], rec["end"][i], rec["out_len"][i]) == (o["start"], o["end"], o["out_len"]), (i, len(x))
+        assert_close(out.audio.clip(i, o["out_len"]).cpu().numpy(), o["audio"], what=f"audio {i}")
+        if o["first_rms"] > 1e-6:
+            assert bool(rec["ok"][i]) == o["ok"]
+            assert abs(rec["decay_ratio"][i] - o["decay_ratio"]) <= TOL * max(1.0, abs(o["decay_ratio"]))
+        w16 = oracle.resample(o["audio"])
+        if not pad and w16.size <= 200:
+            continue                                  # torch.stft cannot reflect-pad such a clip: no features
+        m = oracle.log_mel(w16, 80, pad)
+        assert_close(mel[i][:, :m.shape[1]], m, what=f"mel {i} (len {len(x)})")
+
+
+def test_fused_and_unfused_paths_agree(R, cuda_device):
+    from rho_tts_b200 import synth
+    x = synth.make_clip_block(40, 120000, 31, device=cuda_device)
+    emb, ref = synth.make_embeddings(40, device=cuda_device)
+    rb = R.RaggedBatch.from_dense(x)
+    a = R.validate_batch(rb, R.make_params(), emb, ref, fuse=True)
+    ra, ma, ya = a.records_host(), a.mel.clone(), a.audio.data.clone()
+    b = R.validate_batch(rb, R.make_params(), emb, ref, fuse=False)
+    rb_ = b.records_host()
+    for f in ("start", "end", "out_len", "ok", "flags", "cosine"):
+        assert np.array_equal(ra[f], rb_[f]), f
+    assert np.allclose(ra["decay_ratio"], rb_["decay_ratio"], rtol=1e-6)
+    for i in range(40):
+        L = int(ra["out_len"][i])
+        assert torch.equal(a.audio.clip(i, L), b.audio.clip(i, L)) or \
+            torch.equal(ya[a.audio.h_offsets[i]:a.audio.h_offsets[i] + L], b.audio.clip(i, L))
+    assert float((ma - b.mel).abs().max()) < 2e-5
 
 
 def test_validate_host_matches_device_path(R, cuda_device):
