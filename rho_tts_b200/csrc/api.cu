@@ -74,7 +74,7 @@ cudaError_t dev_upload(rho_handle* h, T** dst, const T* src, size_t n) {
 }
 
 struct WsPlan {
-  size_t seg, span, item, block_sum, clip_max, len16, scratch, total;
+  size_t seg, span, item, block_sum, clip_max, len16, tiles_done, scratch, total;
   int blocks_per_seg;
 };
 
@@ -89,6 +89,7 @@ WsPlan plan_ws(int n_seg, int n_items, int64_t max_seg_len) {
   w.item = o; o += align_up(sizeof(ItemState) * (size_t)(n_items > 0 ? n_items : 1), 256);
   w.clip_max = o; o += align_up(sizeof(int) * (size_t)(n_items > 0 ? n_items : 1), 256);
   w.len16 = o; o += align_up(sizeof(int32_t) * (size_t)(n_items > 0 ? n_items : 1), 256);
+  w.tiles_done = o; o += align_up(sizeof(int) * (size_t)(n_items > 0 ? n_items : 1), 256);
   w.scratch = o; o += 256;
   w.block_sum = o; o += align_up(sizeof(float) * (size_t)(n_seg > 0 ? n_seg : 1) * (size_t)w.blocks_per_seg, 256);
   w.total = o;
@@ -114,6 +115,7 @@ int carve(void* ws, size_t ws_bytes, int n_seg, int n_items, int64_t max_seg_len
   out->item = (ItemState*)(b + w.item);
   out->clip_max = (int*)(b + w.clip_max);
   out->len16 = (int32_t*)(b + w.len16);
+  out->tiles_done = (int*)(b + w.tiles_done);
   out->block_sum = (float*)(b + w.block_sum);
   out->blocks_per_seg = blocks_for(d, max_seg_len);
   if (out->blocks_per_seg > w.blocks_per_seg) return fail(RHO_ERR_WORKSPACE, "internal: block_sum sizing");
@@ -388,7 +390,7 @@ int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, con
     e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,
                     rec, nullptr, ws, st, &h->lc, JOIN_PREPARE);
     if (e != cudaSuccess) return cuda_fail(e, "join prepare");
-    if ((e = launch_logmel_init(ws.clip_max, n_items, st, &h->lc)) != cudaSuccess) return cuda_fail(e, "logmel init");
+    if ((e = launch_logmel_init(ws.clip_max, n_items, st, &h->lc, ws.tiles_done)) != cudaSuccess) return cuda_fail(e, "logmel init");
     e = launch_fused_features(h->tb, x, seg_off, ws, item_first_seg, n_items, max_item_len, d, y, y_off, n_mels,
                               pad_frames, mel, mel_stride_frames, st, &h->lc);
     if (e != cudaSuccess) return cuda_fail(e, "fused features");

@@ -26,6 +26,9 @@ cudaError_t upload_fused_taps(const float* taps) {
   return cudaMemcpyToSymbol(c_ftaps, taps, sizeof(float) * 2 * RS_TAPS);
 }
 
+#ifndef FZ_CLIP_MAJOR
+#define FZ_CLIP_MAJOR 0
+#endif
 constexpr int FZ_HALVES = 2;
 constexpr int FZ_THREADS = LM_THREADS * FZ_HALVES;          // 640
 constexpr int FZ_LEAD = 312;                                // span starts 312 samples before the batch's own range
@@ -59,6 +62,27 @@ __device__ __forceinline__ float fz_fade_gain(int o, int n, int fade) {
   return 1.f;
 }
 
+// Slow path of the apply step for the (few) 128-bit pieces that touch a fade, a clip edge or a third
+// boundary.  Kept out of line: cosf's argument-reduction code would otherwise be inlined eight times
+// into the hot loop and push it out of the instruction cache.
+__device__ __noinline__ void fz_apply_edge(float* e, int o, int n, int fade, bool need_fade, float dc, int third,
+                                           bool owned, float* __restrict__ ys, float* a_first, float* a_last) {
+  for (int k = 0; k < 4; ++k) {
+    const int oo = o + k;
+    float val = 0.f;
+    if (oo >= 0 && oo < n) {
+      val = __fsub_rn(e[k], dc);
+      if (need_fade) val = __fmul_rn(val, fz_fade_gain(oo, n, fade));
+      if (owned) {
+        ys[oo] = val;
+        if (oo < third) *a_first += val * val;
+        if (oo >= n - third) *a_last += val * val;
+      }
+    }
+    e[k] = val;
+  }
+}
+
 template <int NM>
 __global__ void __launch_bounds__(FZ_THREADS, 1)
 k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const SegState* __restrict__ seg,
@@ -66,13 +90,20 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
                  float* __restrict__ y, const int64_t* __restrict__ y_off, int fade,
                  const float* __restrict__ g_hann, const float2* __restrict__ g_tw, int pad_frames,
                  float* __restrict__ mel, long long mel_stride, int* __restrict__ clip_max,
-                 int32_t* __restrict__ len16_out) {
+                 int32_t* __restrict__ len16_out, int tile_pairs, int n_items) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FzSmem& S = *reinterpret_cast<FzSmem*>(smem_raw);
   for (int i = threadIdx.x; i < N_FFT; i += FZ_THREADS) { S.hann[i] = g_hann[i]; S.tw[i] = g_tw[i]; }
   __syncthreads();                                   // the only CTA-wide barrier: the halves run independently from here
 
-  const int c = blockIdx.x;
+  // clip-major 1-D grid: the CTAs of one clip are scheduled back to back (L2 locality of its samples)
+#if FZ_CLIP_MAJOR
+  const int c = blockIdx.x / tile_pairs;
+  const int pair = blockIdx.x - c * tile_pairs;
+#else
+  const int c = blockIdx.x % n_items;
+  const int pair = blockIdx.x / n_items;
+#endif
   const int half = threadIdx.x / LM_THREADS;
   const int tid = threadIdx.x - half * LM_THREADS;
   FzHalf& H = S.h[half];
@@ -84,9 +115,9 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   const int n16 = n > 0 ? (int)((2LL * n + 2) / 3) : 0;
   int T, T_real, N, n_valid;
   lm_frame_counts(n16, pad_frames, &T, &T_real, &N, &n_valid);
-  if (blockIdx.y == 0 && threadIdx.x == 0) len16_out[c] = n16;
+  if (pair == 0 && threadIdx.x == 0) len16_out[c] = n16;
   const int t_cover = max(T_real, (n + 239) / 240);  // batches needed for the features AND to write all of y
-  const int tile_t0 = (blockIdx.y * FZ_HALVES + half) * LM_TILE;
+  const int tile_t0 = (pair * FZ_HALVES + half) * LM_TILE;
   if (tile_t0 >= t_cover) return;
 
   const float* __restrict__ xs = x + seg_off[s] + st.start;
@@ -121,48 +152,29 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     {
       const int j0 = 240 * t0 - FZ_LEAD;
       const int own_lo = 240 * t0, own_hi = own_lo + FZ_OWN;
+      // thirds as 128-bit-piece ranges: pieces entirely inside the first / last third take the fast path
       for (int q = tid; q < FZ_SPAN / 4; q += LM_THREADS) {
         const int o = j0 + 4 * q;
         if (o + 3 < 0 || o >= n) continue;                    // zero-filled: stays zero
         float4 v = *reinterpret_cast<float4*>(H.span + 4 * q);
-        const bool interior = o >= 0 && o + 3 < n && (!need_fade || (o >= fade && o + 3 < n - fade));
-        float e[4] = {v.x, v.y, v.z, v.w};
-        if (interior) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) e[k] = __fsub_rn(e[k], dc);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int oo = o + k;
-            if (oo >= 0 && oo < n) {
-              float val = __fsub_rn(e[k], dc);
-              if (need_fade) val = __fmul_rn(val, fz_fade_gain(oo, n, fade));
-              e[k] = val;
-            } else {
-              e[k] = 0.f;
-            }
-          }
-        }
-        v = make_float4(e[0], e[1], e[2], e[3]);
-        *reinterpret_cast<float4*>(H.span + 4 * q) = v;
-        if (o + 3 >= own_lo && o < own_hi) {                  // own_lo, own_hi and o are multiples of 4
-          if (o >= 0 && o + 3 < n) {
+        const bool owned = o >= own_lo && o < own_hi;         // own_lo, own_hi and o are multiples of 4
+        const bool in_first = o + 3 < third, in_last = o >= n - third;
+        const bool clean = o >= 0 && o + 3 < n && (!need_fade || (o >= fade && o + 3 < n - fade)) &&
+                           (in_first || o >= third) && (in_last || o + 3 < n - third);
+        if (clean) {
+          v.x = __fsub_rn(v.x, dc); v.y = __fsub_rn(v.y, dc); v.z = __fsub_rn(v.z, dc); v.w = __fsub_rn(v.w, dc);
+          if (owned) {
             stg_stream4(ys + o, v);
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (o + k >= 0 && o + k < n) ys[o + k] = e[k];
+            const float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            if (in_first) a_first += ss;
+            if (in_last) a_last += ss;
           }
-          if (o < third || o + 3 >= n - third) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int oo = o + k;
-              if (oo >= 0 && oo < n) {
-                if (oo < third) a_first += e[k] * e[k];
-                if (oo >= n - third) a_last += e[k] * e[k];
-              }
-            }
-          }
+        } else {
+          float e[4] = {v.x, v.y, v.z, v.w};
+          fz_apply_edge(e, o, n, fade, need_fade, dc, third, owned, ys, &a_first, &a_last);
+          v = make_float4(e[0], e[1], e[2], e[3]);
         }
+        *reinterpret_cast<float4*>(H.span + 4 * q) = v;
       }
     }
     half_sync(half);
@@ -317,10 +329,12 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
   auto kern = (n_mels == 80) ? k_fused_features<80> : k_fused_features<128>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  dim3 grid((unsigned)n_items, gy);
+  if ((uint64_t)n_items * gy > 0x7fffffffull) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)n_items * gy);
   lc->begin(KID_FUSED, st);
   kern<<<grid, FZ_THREADS, smem, st>>>(x, seg_off, ws.seg, ws.item, item_first_seg, y, y_off, d.fade, tb.hann,
-                                       tb.twiddle, pad_frames, mel, mel_stride_frames, ws.clip_max, ws.len16);
+                                       tb.twiddle, pad_frames, mel, mel_stride_frames, ws.clip_max, ws.len16,
+                                       (int)gy, n_items);
   lc->end(st);
   return cudaGetLastError();
 }

@@ -71,20 +71,40 @@ k_scan(const float* __restrict__ x, const int64_t* __restrict__ off, const int32
   const long long g0 = (long long)(frame0 - 1) * hop;  // global sample of row 0, col 0 (pad == hop)
 
   if (VEC) {
-    // LDGSTS: every 16-byte piece of the tile goes global -> shared without touching registers,
-    // all ~30 copies of a thread are in flight at once; out-of-clip bytes are zero-filled (the
-    // avg_pool zero padding, and the ragged end of the clip).
+    // TMA bulk copies: every hop row that lies fully inside the clip is ONE cp.async.bulk (480 B at
+    // 24 kHz) issued by lane 0 of a warp and completing on an mbarrier; no registers, no per-element
+    // instructions.  The few rows that stick out of the clip (avg_pool's zero padding, the ragged
+    // end) are staged with zero-filling LDGSTS.
+    __shared__ __align__(8) uint64_t bar;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned row_bytes = (unsigned)hop * 4u;
+    // rows [r_lo, r_hi) are interior: g0 + r*hop >= 0 and g0 + (r+1)*hop <= L
+    int r_lo = 0;
+    if (g0 < 0) r_lo = (int)((-g0 + hop - 1) / hop);
+    long long r_hi_ll = (L - g0) / hop;
+    int r_hi = r_hi_ll < 0 ? 0 : (r_hi_ll > rows ? rows : (int)r_hi_ll);
+    if (r_lo > r_hi) r_lo = r_hi;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(&bar, (unsigned)(r_hi - r_lo) * row_bytes);
+    if (lane == 0) {
+      for (int row = r_lo + warp; row < r_hi; row += SCAN_FR / 32)
+        bulk_g2s(sm + row * RS, xs + (g0 + (long long)row * hop), row_bytes, &bar);
+    }
     const int q_per_row = hop >> 2;
-    const int total_q = rows * q_per_row;
-    for (int q = threadIdx.x; q < total_q; q += SCAN_FR) {
-      const int row = q / q_per_row, c4 = (q - row * q_per_row) << 2;
-      const long long g = g0 + (long long)row * hop + c4;
-      int nb = 0;
-      if (g >= 0 && g < L) nb = (L - g >= 4) ? 16 : 4 * (int)(L - g);
-      cp_async16_zfill(sm + row * RS + c4, nb ? xs + g : xs, nb);
+    for (int row = warp; row < rows; row += SCAN_FR / 32) {
+      if (row >= r_lo && row < r_hi) continue;
+      const long long grow = g0 + (long long)row * hop;
+      for (int c = lane; c < q_per_row; c += 32) {
+        const long long g = grow + 4 * c;
+        int nb = 0;
+        if (g >= 0 && g < L) nb = (L - g >= 4) ? 16 : 4 * (int)(L - g);
+        cp_async16_zfill(sm + row * RS + 4 * c, nb ? xs + g : xs, nb);
+      }
     }
     cp_async_commit();
     cp_async_wait_all();
+    mbar_wait(&bar, 0);
   } else {
     const int total = rows * hop;
     for (int r = threadIdx.x; r < total; r += SCAN_FR) {
@@ -101,26 +121,31 @@ k_scan(const float* __restrict__ x, const int64_t* __restrict__ off, const int32
   if (f < n_frames) {
     float acc = 0.f, bs = 0.f;
     if (VEC) {
+      // x*x on the packed fp32x2 pipe (same IEEE rounding per component as __fmul_rn), the 240-term
+      // sum as the strictly sequential scalar chain torch's avg_pool1d runs; DC block sum packed too.
       const float4* p0 = reinterpret_cast<const float4*>(sm + t * RS);
       const float4* p1 = reinterpret_cast<const float4*>(sm + (t + 1) * RS);
       const int nq = hop >> 2;
 #pragma unroll 6
       for (int j = 0; j < nq; ++j) {
         const float4 v = p0[j];
-        acc = __fadd_rn(acc, __fmul_rn(v.x, v.x));
-        acc = __fadd_rn(acc, __fmul_rn(v.y, v.y));
-        acc = __fadd_rn(acc, __fmul_rn(v.z, v.z));
-        acc = __fadd_rn(acc, __fmul_rn(v.w, v.w));
+        const float2 a = __fmul2_rn(make_float2(v.x, v.y), make_float2(v.x, v.y));
+        const float2 b = __fmul2_rn(make_float2(v.z, v.w), make_float2(v.z, v.w));
+        acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y);
+        acc = __fadd_rn(acc, b.x); acc = __fadd_rn(acc, b.y);
       }
+      float2 bs2 = make_float2(0.f, 0.f);
 #pragma unroll 6
       for (int j = 0; j < nq; ++j) {
         const float4 v = p1[j];
-        acc = __fadd_rn(acc, __fmul_rn(v.x, v.x));
-        acc = __fadd_rn(acc, __fmul_rn(v.y, v.y));
-        acc = __fadd_rn(acc, __fmul_rn(v.z, v.z));
-        acc = __fadd_rn(acc, __fmul_rn(v.w, v.w));
-        bs += (v.x + v.y) + (v.z + v.w);
+        const float2 a = __fmul2_rn(make_float2(v.x, v.y), make_float2(v.x, v.y));
+        const float2 b = __fmul2_rn(make_float2(v.z, v.w), make_float2(v.z, v.w));
+        acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y);
+        acc = __fadd_rn(acc, b.x); acc = __fadd_rn(acc, b.y);
+        bs2 = __fadd2_rn(bs2, make_float2(v.x, v.y));
+        bs2 = __fadd2_rn(bs2, make_float2(v.z, v.w));
       }
+      bs = bs2.x + bs2.y;
     } else {
       int left = window;
       for (int b = 0; left > 0; ++b) {

@@ -83,7 +83,7 @@ cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off
                           int64_t mel_stride_frames, int32_t* n_frames, int* clip_max,
                           cudaStream_t st, LaunchCtx* lc);
 
-cudaError_t launch_logmel_init(int* clip_max, int n, cudaStream_t st, LaunchCtx* lc);
+cudaError_t launch_logmel_init(int* clip_max, int n, cudaStream_t st, LaunchCtx* lc, int* tiles_done = nullptr);
 cudaError_t launch_logmel_norm(const int32_t* len16, int n, int n_mels, int pad_frames, float* mel,
                                int64_t mel_stride_frames, const int* clip_max, cudaStream_t st, LaunchCtx* lc);
 

@@ -26,9 +26,9 @@ struct LmSmem {
   float red[LM_THREADS / 32];
 };
 
-__global__ void k_logmel_init(int* __restrict__ clip_max, int n) {
+__global__ void k_logmel_init(int* __restrict__ clip_max, int* __restrict__ tiles_done, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) clip_max[i] = INT_MIN;
+  if (i < n) { clip_max[i] = INT_MIN; if (tiles_done) tiles_done[i] = 0; }
 }
 
 template <int NM>
@@ -230,10 +230,10 @@ cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off
   return launch_logmel_norm(len16, n, n_mels, pad_frames, mel, mel_stride_frames, clip_max, st, lc);
 }
 
-cudaError_t launch_logmel_init(int* clip_max, int n, cudaStream_t st, LaunchCtx* lc) {
+cudaError_t launch_logmel_init(int* clip_max, int n, cudaStream_t st, LaunchCtx* lc, int* tiles_done) {
   if (n <= 0) return cudaSuccess;
   lc->begin(KID_LOGMEL_INIT, st);
-  k_logmel_init<<<(n + 255) / 256, 256, 0, st>>>(clip_max, n);
+  k_logmel_init<<<(n + 255) / 256, 256, 0, st>>>(clip_max, tiles_done, n);
   lc->end(st);
   return cudaGetLastError();
 }
