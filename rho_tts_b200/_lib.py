@@ -13,7 +13,8 @@ import threading
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint8, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librho_b200.so")
+# RHO_B200_LIB: developer override used by tools/ab_fused.sh to A/B kernel variants
+LIB_PATH = os.environ.get("RHO_B200_LIB") or os.path.join(_HERE, "librho_b200.so")
 
 ABI_VERSION = 1
 

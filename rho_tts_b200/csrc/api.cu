@@ -386,7 +386,7 @@ int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, con
   cudaError_t e;
   const bool fused = (flags & RHO_V_ONE_SEGMENT_ITEMS) && !(flags & RHO_V_NO_FUSION) && n_segments == n_items;
   if (fused) {
-    // scan -> bounds/DC -> ONE kernel for apply + resample + log-mel -> decay decision -> normalise
+    // scan -> bounds/DC -> ONE kernel for apply + resample + log-mel + normalise -> decay decision
     e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,
                     rec, nullptr, ws, st, &h->lc, JOIN_PREPARE);
     if (e != cudaSuccess) return cuda_fail(e, "join prepare");
@@ -397,8 +397,12 @@ int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, con
     e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,
                     rec, nullptr, ws, st, &h->lc, JOIN_FINISH);
     if (e != cudaSuccess) return cuda_fail(e, "join finish");
-    e = launch_logmel_norm(ws.len16, n_items, n_mels, pad_frames, mel, mel_stride_frames, ws.clip_max, st, &h->lc);
-    if (e != cudaSuccess) return cuda_fail(e, "logmel norm");
+    // the clip-max clamp, the scale and the fill of the zero-padding frames happen inside the fused kernel
+    // (the half that finishes a clip last normalises it)
+    if (!fused_inline_norm()) {
+      e = launch_logmel_norm(ws.len16, n_items, n_mels, pad_frames, mel, mel_stride_frames, ws.clip_max, st, &h->lc);
+      if (e != cudaSuccess) return cuda_fail(e, "logmel norm");
+    }
   } else {
     if (!scratch16) return fail(RHO_ERR_INVALID, "scratch16 is NULL (needed by the unfused path)");
     e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,

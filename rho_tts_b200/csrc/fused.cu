@@ -10,9 +10,13 @@
 //
 // One CTA per SM, two independent 320-thread halves (named barriers), each half owns a stream of
 // 32-frame batches of one clip.  Per batch and half:
-//   span  : x[start + 240*t0 - 312 .. +8068) staged with LDGSTS (prefetched under the previous batch's FFT)
-//   apply : in place (x-dc)*fade -> y; the batch's own 7680 samples go to HBM (128-bit stores), decay sums
-//   FIR   : 2 phases x 23 taps from the span -> 5360 samples of the 16 kHz slab (reflection fixed up in smem)
+//   span  : x[start + 240*t0 - 312 .. +8068) staged by ONE TMA bulk copy (32 KB, mbarrier completion) when the
+//           span lies inside the clip, else zero-filling LDGSTS; prefetched under the previous batch's FFT
+//   apply : interior batches (no fade, no clip edge, one decay zone): y = x - dc straight from registers to
+//           HBM, the span keeps the raw x and the FIR folds dc in (FIR(x - dc) = FIR(x) - dc * sum(taps));
+//           edge batches: in place (x-dc)*fade -> y
+//   FIR   : 2 phases x 23 taps as packed fp32x2 dot products (FFMA2, taps in uniform registers) from the
+//           span -> 5360 samples of the 16 kHz slab (reflection fixed up in smem)
 //   FFT   : as k_logmel_frames (two real frames per 400-point complex FFT, 20 x 20, packed fp32x2 butterflies)
 //   mel   : immediate-weight FFMAs, SFU log2, ordered-int atomicMax of the clip maximum
 #include <algorithm>
@@ -20,15 +24,60 @@
 
 namespace rho {
 
+// Taps as float2 pairs for the packed dot products.  With V[k] = (v[2k], v[2k+1]) the four outputs are
+//   o00 = sum_k V[k] . A0[k]  (k = 0..9)    A0[k] = (k0[2k],   k0[2k+1])       k0[0] := 0
+//   o10 = sum_k V[k] . B0[k]  (k = 2..11)   B0[k] = (k0[2k-3], k0[2k-2])       k0[20] := 0
+//   o01 = sum_k V[k] . A1[k]  (k = 1..10)   A1[k] = (k1[2k],   k1[2k+1])       k1[2], k1[21] := 0
+//   o11 = sum_k V[k] . B1[k]  (k = 3..11)   B1[k] = (k1[2k-3], k1[2k-2])
+// (taps 0, 20..22 of phase 0 and 0..2, 21..22 of phase 1 sit on the window clamp, |k| ~ 3e-24: dropped).
+// c_fsum[p] = sum of the taps of phase p that are used, for folding the DC offset into the FIR.
+__constant__ float2 c_fA0[12], c_fB0[12], c_fA1[12], c_fB1[12];
+__constant__ float c_fsum[2];
 __constant__ float c_ftaps[2][RS_TAPS];
 
 cudaError_t upload_fused_taps(const float* taps) {
-  return cudaMemcpyToSymbol(c_ftaps, taps, sizeof(float) * 2 * RS_TAPS);
+  const float* k0 = taps;
+  const float* k1 = taps + RS_TAPS;
+  auto t0 = [&](int i) { return (i >= 1 && i <= 19) ? k0[i] : 0.f; };
+  auto t1 = [&](int i) { return (i >= 3 && i <= 20) ? k1[i] : 0.f; };
+  float2 A0[12], B0[12], A1[12], B1[12];
+  for (int k = 0; k < 12; ++k) {
+    A0[k] = make_float2(t0(2 * k), t0(2 * k + 1));
+    B0[k] = make_float2(t0(2 * k - 3), t0(2 * k - 2));
+    A1[k] = make_float2(t1(2 * k), t1(2 * k + 1));
+    B1[k] = make_float2(t1(2 * k - 3), t1(2 * k - 2));
+  }
+  float sum[2] = {0.f, 0.f};
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = 1; i <= 19; ++i) s0 += (double)k0[i];
+  for (int i = 3; i <= 20; ++i) s1 += (double)k1[i];
+  sum[0] = (float)s0; sum[1] = (float)s1;
+  cudaError_t e;
+  if ((e = cudaMemcpyToSymbol(c_ftaps, taps, sizeof(float) * 2 * RS_TAPS)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(c_fA0, A0, sizeof(A0))) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(c_fB0, B0, sizeof(B0))) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(c_fA1, A1, sizeof(A1))) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(c_fB1, B1, sizeof(B1))) != cudaSuccess) return e;
+  return cudaMemcpyToSymbol(c_fsum, sum, sizeof(sum));
 }
 
 #ifndef FZ_CLIP_MAJOR
 #define FZ_CLIP_MAJOR 0
 #endif
+// A/B switches (tools/ab_fused.sh builds the variants; the defaults are the product configuration)
+#ifndef FZ_BULK
+#define FZ_BULK 1          // span staged by one TMA bulk copy when it lies inside the clip
+#endif
+#ifndef FZ_FAST_APPLY
+#define FZ_FAST_APPLY 1    // interior batches: y from registers, dc folded into the FIR
+#endif
+#ifndef FZ_FFMA2_FIR
+#define FZ_FFMA2_FIR 1     // FIR as packed fp32x2 dot products
+#endif
+#ifndef FZ_INLINE_NORM
+#define FZ_INLINE_NORM 0   // 1: the half that finishes a clip last normalises its features (measured: no gain, see profiles/README.md)
+#endif
+bool fused_inline_norm() { return FZ_INLINE_NORM != 0; }
 constexpr int FZ_HALVES = 2;
 constexpr int FZ_THREADS = LM_THREADS * FZ_HALVES;          // 640
 constexpr int FZ_LEAD = 312;                                // span starts 312 samples before the batch's own range
@@ -36,19 +85,25 @@ constexpr int FZ_SPAN = 8068;                               // 24 kHz samples st
 constexpr int FZ_OWN = 240 * LM_BF;                         // 7680 output samples owned by a batch
 constexpr int FZ_DPAIRS = LM_SLAB / 4;                      // 1340 groups of 4 consecutive 16 kHz samples
 
+constexpr int FZ_TWS = 22;                                  // float2 per twiddle row (conflict-free 128-bit reads)
+
 struct alignas(16) FzHalf {
   float span[FZ_SPAN];
   float2 fb[LM_GROUPS * LM_FB];
   float pw[LM_BF * LM_PS];          // 16 kHz slab between FIR and FFT stage 1, power spectra afterwards
   double redd[2][LM_THREADS / 32];
   float redf[LM_THREADS / 32];
+  uint64_t bar;                     // mbarrier the TMA copy of the span completes on
+  int last;                         // "this half finished its clip last" broadcast
+  int pad;
 };
 static_assert(LM_SLAB_SM <= LM_BF * LM_PS, "the slab must fit in the power buffer");
+static_assert((FZ_SPAN * 4) % 16 == 0, "bulk copy size");
 
 struct FzSmem {
   FzHalf h[FZ_HALVES];
-  float hann[N_FFT];
-  float2 tw[N_FFT];
+  float hannT[N_FFT];               // [n2][n1] = hann[20*n1 + n2]: a thread's 20 window values are contiguous
+  float2 twT[20 * FZ_TWS];          // [n2][k1] = W400^(n2*k1), row stride 22
 };
 static_assert(sizeof(FzSmem) <= 232448, "shared memory budget (227 KB)");
 
@@ -90,13 +145,17 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
                  float* __restrict__ y, const int64_t* __restrict__ y_off, int fade,
                  const float* __restrict__ g_hann, const float2* __restrict__ g_tw, int pad_frames,
                  float* __restrict__ mel, long long mel_stride, int* __restrict__ clip_max,
-                 int32_t* __restrict__ len16_out, int tile_pairs, int n_items) {
+                 int32_t* __restrict__ len16_out, int* __restrict__ tiles_done, int tile_pairs, int n_items) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FzSmem& S = *reinterpret_cast<FzSmem*>(smem_raw);
-  for (int i = threadIdx.x; i < N_FFT; i += FZ_THREADS) { S.hann[i] = g_hann[i]; S.tw[i] = g_tw[i]; }
+  for (int i = threadIdx.x; i < N_FFT; i += FZ_THREADS) {
+    const int r = i / 20, c20 = i - 20 * r;
+    S.hannT[c20 * 20 + r] = g_hann[i];               // transpose: [n2][n1]
+    S.twT[r * FZ_TWS + c20] = g_tw[i];               // the table is symmetric in (k1, n2): re-stride only
+  }
+  if (threadIdx.x < FZ_HALVES) { mbar_init(&S.h[threadIdx.x].bar, 1); mbar_fence_init(); }
   __syncthreads();                                   // the only CTA-wide barrier: the halves run independently from here
 
-  // clip-major 1-D grid: the CTAs of one clip are scheduled back to back (L2 locality of its samples)
 #if FZ_CLIP_MAJOR
   const int c = blockIdx.x / tile_pairs;
   const int pair = blockIdx.x - c * tile_pairs;
@@ -125,20 +184,37 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   float* __restrict__ out = mel + (long long)c * NM * mel_stride;
   const int third = n / 3;
   const bool need_fade = fade > 0 && n >= 2 * fade;
+  const int edge_lo = need_fade ? fade : 0, edge_hi = need_fade ? n - fade : n;   // [edge_lo, edge_hi): y = x - dc
+  const bool xs_al16 = ((reinterpret_cast<uintptr_t>(xs) & 15u) == 0);
   const int g = tid / LM_LANES, lane = tid - g * LM_LANES;
   float2* fb = H.fb + g * LM_FB;
   float lmax = -INFINITY;
   float a_first = 0.f, a_last = 0.f;
+  unsigned parity = 0;
 
+  // A span that lies inside the clip is ONE bulk copy issued by one thread; spans that stick out
+  // (clip edges: zero fill) are staged in 16-byte zero-filling LDGSTS pieces by everybody.
+  auto span_is_bulk = [&](int t0) {
+    const long long j0 = 240LL * t0 - FZ_LEAD;
+    return FZ_BULK && xs_al16 && j0 >= 0 && j0 + FZ_SPAN <= n;
+  };
   auto stage_span = [&](int t0) {
     const long long j0 = 240LL * t0 - FZ_LEAD;
-    for (int q = tid; q < FZ_SPAN / 4; q += LM_THREADS) {
-      const long long j = j0 + 4 * q;
-      int nb = 0;
-      if (j >= 0 && j < n) nb = (n - j >= 4) ? 16 : 4 * (int)(n - j);
-      cp_async16_zfill(H.span + 4 * q, nb ? xs + j : xs, nb);
+    if (span_is_bulk(t0)) {
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses to the span
+        mbar_arrive_expect_tx(&H.bar, FZ_SPAN * 4);
+        bulk_g2s(H.span, xs + j0, FZ_SPAN * 4, &H.bar);
+      }
+    } else {
+      for (int q = tid; q < FZ_SPAN / 4; q += LM_THREADS) {
+        const long long j = j0 + 4 * q;
+        int nb = 0;
+        if (j >= 0 && j < n) nb = (n - j >= 4) ? 16 : 4 * (int)(n - j);
+        cp_async16_zfill(H.span + 4 * q, nb ? xs + j : xs, nb);
+      }
+      cp_async_commit();
     }
-    cp_async_commit();
   };
   stage_span(tile_t0);
 
@@ -146,28 +222,44 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     const int t0 = tile_t0 + b * LM_BF;
     if (t0 >= t_cover) break;
     const bool next = (b + 1 < LM_BATCHES) && (t0 + LM_BF < t_cover);
-    cp_async_wait_all();
-    half_sync(half);
-    // ---- apply: span <- (x - dc) * fade; the batch's own samples go to HBM; decay sums
-    {
-      const int j0 = 240 * t0 - FZ_LEAD;
-      const int own_lo = 240 * t0, own_hi = own_lo + FZ_OWN;
-      // thirds as 128-bit-piece ranges: pieces entirely inside the first / last third take the fast path
+    if (span_is_bulk(t0)) { mbar_wait(&H.bar, parity); parity ^= 1u; } else { cp_async_wait_all(); }
+    half_sync(half);                                           // also: last batch's mel reads of pw are done
+    const int j0 = 240 * t0 - FZ_LEAD;
+    const int own_lo = 240 * t0, own_hi = own_lo + FZ_OWN;
+    // interior batch: every sample of the span is plain x - dc, and the owned range lies in ONE decay zone
+    const bool in_first = own_hi <= third, in_last = own_lo >= n - third;
+    const bool fast = FZ_FAST_APPLY && j0 >= edge_lo && j0 + FZ_SPAN <= edge_hi &&
+                      (in_first || own_lo >= third) && (in_last || own_hi <= n - third);
+    if (fast) {
+      // ---- apply, interior: 6 pieces per thread, registers -> HBM; the span keeps the raw x
+      float ss = 0.f;
+      const float2 ndc = make_float2(-dc, -dc);
+#pragma unroll
+      for (int k = 0; k < FZ_OWN / 4 / LM_THREADS; ++k) {
+        const int q = FZ_LEAD / 4 + tid + k * LM_THREADS;
+        const float4 v = *reinterpret_cast<const float4*>(H.span + 4 * q);
+        const float2 lo = __fadd2_rn(make_float2(v.x, v.y), ndc), hi = __fadd2_rn(make_float2(v.z, v.w), ndc);
+        stg_stream4(ys + own_lo + 4 * (tid + k * LM_THREADS), make_float4(lo.x, lo.y, hi.x, hi.y));
+        ss = fmaf(lo.x, lo.x, ss); ss = fmaf(lo.y, lo.y, ss); ss = fmaf(hi.x, hi.x, ss); ss = fmaf(hi.y, hi.y, ss);
+      }
+      if (in_first) a_first += ss;
+      if (in_last) a_last += ss;
+    } else {
+      // ---- apply, edge batch: span <- (x - dc) * fade; the batch's own samples go to HBM; decay sums
       for (int q = tid; q < FZ_SPAN / 4; q += LM_THREADS) {
         const int o = j0 + 4 * q;
         if (o + 3 < 0 || o >= n) continue;                    // zero-filled: stays zero
         float4 v = *reinterpret_cast<float4*>(H.span + 4 * q);
         const bool owned = o >= own_lo && o < own_hi;         // own_lo, own_hi and o are multiples of 4
-        const bool in_first = o + 3 < third, in_last = o >= n - third;
-        const bool clean = o >= 0 && o + 3 < n && (!need_fade || (o >= fade && o + 3 < n - fade)) &&
-                           (in_first || o >= third) && (in_last || o + 3 < n - third);
+        const bool p_first = o + 3 < third, p_last = o >= n - third;
+        const bool clean = o >= edge_lo && o + 3 < edge_hi && (p_first || o >= third) && (p_last || o + 3 < n - third);
         if (clean) {
           v.x = __fsub_rn(v.x, dc); v.y = __fsub_rn(v.y, dc); v.z = __fsub_rn(v.z, dc); v.w = __fsub_rn(v.w, dc);
           if (owned) {
             stg_stream4(ys + o, v);
             const float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-            if (in_first) a_first += ss;
-            if (in_last) a_last += ss;
+            if (p_first) a_first += ss;
+            if (p_last) a_last += ss;
           }
         } else {
           float e[4] = {v.x, v.y, v.z, v.w};
@@ -176,34 +268,62 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
         }
         *reinterpret_cast<float4*>(H.span + 4 * q) = v;
       }
+      half_sync(half);
     }
-    half_sync(half);
     if (t0 >= T_real) {                                      // a batch that only had output samples left to write
-      if (next) stage_span(t0 + LM_BF);
+      if (next) { half_sync(half); stage_span(t0 + LM_BF); }
       continue;
     }
     // ---- FIR 24k -> 16k: slab position i holds w16[w0 + i], w0 = 160*t0 - 200;
     //      w16[2m+p] = sum_t y[3m - 10 + t] * k[p][t]  ->  span offset 2 + 3*(i/2) + t
     const int w0 = HOP16 * t0 - N_FFT / 2;
     float* slab = H.pw;
-    for (int d = tid; d < FZ_DPAIRS; d += LM_THREADS) {
-      const float2* sp = reinterpret_cast<const float2*>(H.span + 2 + 6 * d);
-      float v[26];
+    {
+      // interior batches read the raw x: start the accumulators at -dc * sum(taps)
+      const float i0 = fast ? -dc * c_fsum[0] : 0.f, i1 = fast ? -dc * c_fsum[1] : 0.f;
+#if FZ_FFMA2_FIR
+      for (int d = tid; d < FZ_DPAIRS; d += LM_THREADS) {
+        const float2* sp = reinterpret_cast<const float2*>(H.span + 2 + 6 * d);
+        float2 V[13];
 #pragma unroll
-      for (int k = 0; k < 13; ++k) { const float2 t2 = sp[k]; v[2 * k] = t2.x; v[2 * k + 1] = t2.y; }
-      float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;
-      // taps 0, 20..22 of phase 0 and 0..2, 21..22 of phase 1 sit on the window clamp (|k| ~ 3e-24): skipped
+        for (int k = 0; k < 13; ++k) V[k] = sp[k];
+        float2 o00 = make_float2(i0, 0.f), o10 = o00, o01 = make_float2(i1, 0.f), o11 = o01;
 #pragma unroll
-      for (int i = 1; i < 20; ++i) { o00 = fmaf(v[i], c_ftaps[0][i], o00); o10 = fmaf(v[i + 3], c_ftaps[0][i], o10); }
+        for (int k = 0; k < 10; ++k) o00 = __ffma2_rn(V[k], c_fA0[k], o00);
 #pragma unroll
-      for (int i = 3; i < 21; ++i) { o01 = fmaf(v[i], c_ftaps[1][i], o01); o11 = fmaf(v[i + 3], c_ftaps[1][i], o11); }
-      const int wi = w0 + 4 * d;
-      float4 r;
-      r.x = (wi + 0 < n_valid) ? o00 : 0.f;
-      r.y = (wi + 1 < n_valid) ? o01 : 0.f;
-      r.z = (wi + 2 < n_valid) ? o10 : 0.f;
-      r.w = (wi + 3 < n_valid) ? o11 : 0.f;
-      *reinterpret_cast<float4*>(slab + 4 * d + 20 * (d / (LM_SLAB_BLK / 4))) = r;
+        for (int k = 2; k < 12; ++k) o10 = __ffma2_rn(V[k], c_fB0[k], o10);
+#pragma unroll
+        for (int k = 1; k < 11; ++k) o01 = __ffma2_rn(V[k], c_fA1[k], o01);
+#pragma unroll
+        for (int k = 3; k < 12; ++k) o11 = __ffma2_rn(V[k], c_fB1[k], o11);
+        const int wi = w0 + 4 * d;
+        float4 r;
+        r.x = (wi + 0 < n_valid) ? o00.x + o00.y : 0.f;
+        r.y = (wi + 1 < n_valid) ? o01.x + o01.y : 0.f;
+        r.z = (wi + 2 < n_valid) ? o10.x + o10.y : 0.f;
+        r.w = (wi + 3 < n_valid) ? o11.x + o11.y : 0.f;
+        *reinterpret_cast<float4*>(slab + 4 * d + 20 * (d / (LM_SLAB_BLK / 4))) = r;
+      }
+#else
+      for (int d = tid; d < FZ_DPAIRS; d += LM_THREADS) {
+        const float2* sp = reinterpret_cast<const float2*>(H.span + 2 + 6 * d);
+        float v[26];
+#pragma unroll
+        for (int k = 0; k < 13; ++k) { const float2 t2 = sp[k]; v[2 * k] = t2.x; v[2 * k + 1] = t2.y; }
+        float o00 = i0, o01 = i1, o10 = i0, o11 = i1;
+#pragma unroll
+        for (int i = 1; i < 20; ++i) { o00 = fmaf(v[i], c_ftaps[0][i], o00); o10 = fmaf(v[i + 3], c_ftaps[0][i], o10); }
+#pragma unroll
+        for (int i = 3; i < 21; ++i) { o01 = fmaf(v[i], c_ftaps[1][i], o01); o11 = fmaf(v[i + 3], c_ftaps[1][i], o11); }
+        const int wi = w0 + 4 * d;
+        float4 r;
+        r.x = (wi + 0 < n_valid) ? o00 : 0.f;
+        r.y = (wi + 1 < n_valid) ? o01 : 0.f;
+        r.z = (wi + 2 < n_valid) ? o10 : 0.f;
+        r.w = (wi + 3 < n_valid) ? o11 : 0.f;
+        *reinterpret_cast<float4*>(slab + 4 * d + 20 * (d / (LM_SLAB_BLK / 4))) = r;
+      }
+#endif
     }
     half_sync(half);
     // ---- reflect padding of torch.stft(center=True): indices < 0 and >= N mirror the computed ones
@@ -232,39 +352,60 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     {
       const float* fa = slab + g * LM_SLAB_STRIDE + lane;
       const float* fbm = fa + HOP16;
+      const float4* hq = reinterpret_cast<const float4*>(S.hannT + 20 * lane);
 #pragma unroll
-      for (int n1 = 0; n1 < 20; ++n1) {
-        const float h = S.hann[20 * n1 + lane];
-        v[n1] = make_float2(fa[20 * n1 + (n1 >= 16 ? 20 : 0)] * h, fbm[20 * n1 + (n1 >= 8 ? 20 : 0)] * h);
+      for (int q = 0; q < 5; ++q) {
+        const float4 h4 = hq[q];
+        const float hh[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int n1 = 4 * q + e;
+          v[n1] = __fmul2_rn(make_float2(fa[20 * n1 + (n1 >= 16 ? 20 : 0)], fbm[20 * n1 + (n1 >= 8 ? 20 : 0)]),
+                             make_float2(hh[e], hh[e]));
+        }
       }
     }
     dft20(v);
+    {
+      const float4* tq = reinterpret_cast<const float4*>(S.twT + FZ_TWS * lane);
+      fb[lane] = v[0];
 #pragma unroll
-    for (int k1 = 0; k1 < 20; ++k1) fb[k1 * 21 + lane] = (k1 == 0) ? v[0] : cmul(v[k1], S.tw[k1 * 20 + lane]);
+      for (int q = 0; q < 10; ++q) {
+        const float4 t4 = tq[q];                              // twiddles of k1 = 2q, 2q+1
+        if (q > 0) fb[(2 * q) * 21 + lane] = cmul(v[2 * q], make_float2(t4.x, t4.y));
+        fb[(2 * q + 1) * 21 + lane] = cmul(v[2 * q + 1], make_float2(t4.z, t4.w));
+      }
+    }
     half_sync(half);
     if (next) stage_span(t0 + LM_BF);                        // span and slab are dead: prefetch under stage 2 / mel
-    // ---- FFT stage 2: lane = k1, 20-point DFT over n2 -> Z[k1 + 20*k2]
+    // ---- FFT stage 2: lane = k1, 20-point DFT over n2 -> Z[k1 + 20*k2] in v[k2]
 #pragma unroll
     for (int n2 = 0; n2 < 20; ++n2) v[n2] = fb[lane * 21 + n2];
     dft20(v);
     half_sync(half);
+    // ---- split the two real spectra and take |.|^2:  A = (Z[k]+conj Z[400-k])/2, B = (Z[k]-conj Z[400-k])/(2i).
+    // Bin k = k1 + 20*k2 <= 200 needs Z[400-k] = Z[(20-k1) + 20*(19-k2)]: the upper half (k2 >= 10) of lane
+    // 20-k1.  Every lane publishes its upper half, then reads its partner's; lane 0 is its own partner.
 #pragma unroll
-    for (int k2 = 0; k2 < 20; ++k2) fb[lane + 20 * k2] = v[k2];
+    for (int k2 = 10; k2 < 20; ++k2) fb[lane + 20 * k2] = v[k2];
     half_sync(half);
-    // ---- split the two real spectra and take |.|^2
     {
-      float* pa = H.pw + (2 * g) * LM_PS;
+      float* pa = H.pw + (2 * g) * LM_PS + lane;
       float* pb = pa + LM_PS;
+      const float2* part = fb + (20 - lane);                 // lane 0: index 20 + 20*(19-k2) stays inside fb (unused)
 #pragma unroll
-      for (int j = 0; j < 11; ++j) {
-        const int k = lane + 20 * j;
-        if (k <= N_FFT / 2) {
-          const float2 z = fb[k];
-          const float2 w = fb[k == 0 ? 0 : N_FFT - k];
-          const float ar = z.x + w.x, ai = z.y - w.y, br = z.x - w.x, bi = z.y + w.y;
-          pa[k] = 0.25f * (ar * ar + ai * ai);
-          pb[k] = 0.25f * (br * br + bi * bi);
-        }
+      for (int k2 = 0; k2 < 10; ++k2) {
+        float2 w = part[20 * (19 - k2)];
+        if (lane == 0) w = (k2 == 0) ? v[0] : v[20 - k2];
+        const float2 z = v[k2];
+        const float ar = z.x + w.x, ai = z.y - w.y, br = z.x - w.x, bi = z.y + w.y;
+        pa[20 * k2] = 0.25f * (ar * ar + ai * ai);
+        pb[20 * k2] = 0.25f * (br * br + bi * bi);
+      }
+      if (lane == 0) {                                       // k = 200: Z[200] pairs with itself
+        const float2 z = v[10];
+        pa[200] = z.x * z.x;
+        pb[200] = z.y * z.y;
       }
     }
     half_sync(half);
@@ -301,6 +442,67 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       if (m > -INFINITY) atomicMax(&clip_max[c], float_to_ordered(m));
       if (a != 0.0) atomicAdd(&item[c].s_first, a);
       if (bq != 0.0) atomicAdd(&item[c].s_last, bq);
+      // the half that finishes its clip last normalises the clip's features (no second kernel, the raw
+      // frames are still in L2)
+      int last = 0;
+      if (FZ_INLINE_NORM && tiles_done) {
+        // barrier (CTA scope) -> fence (GPU scope) -> atomic: the grid-sync idiom; makes every thread's
+        // log-mel frames of this half visible before the count is
+        __threadfence();
+        const int n_tiles = (t_cover + LM_TILE - 1) / LM_TILE;
+        last = (atomicAdd(&tiles_done[c], 1) == n_tiles - 1);
+        if (last) __threadfence();                   // acquire side: the other halves' frames and the clip maximum
+      }
+      H.last = last;
+    }
+  }
+  half_sync(half);
+  if (!H.last || T <= 0) return;
+  {
+    const float mx = ordered_to_float(__ldcg(&clip_max[c]));
+    const float floor_v = __fsub_rn(mx, 8.0f);
+    const float fill = __fdiv_rn(__fadd_rn(fmaxf(-10.0f, floor_v), 4.0f), 4.0f);
+    auto nrm = [&](float vv) { return __fdiv_rn(__fadd_rn(fmaxf(vv, floor_v), 4.0f), 4.0f); };
+    const bool vec = (mel_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+    if (vec) {
+      // one column piece (4 frames) per thread, all rows: the real / fill decision is per column
+      const int T4 = T >> 2;
+      for (int cp = tid; cp < T4; cp += LM_THREADS) {
+        const int t = 4 * cp;
+        float* col = out + t;
+        if (t >= T_real) {
+          const float4 f4 = make_float4(fill, fill, fill, fill);
+#pragma unroll 8
+          for (int m = 0; m < NM; ++m) stg_stream4(col + (long long)m * mel_stride, f4);
+        } else {
+          // 8 rows in flight per thread: the raw frames come back from L2.  The piece that straddles T_real
+          // takes the same path (its tail elements are inside the row, just not computed: replaced by the fill).
+          constexpr int NB = 8;
+          static_assert(NM % NB == 0, "row batches");
+          const bool k1 = t + 1 < T_real, k2 = t + 2 < T_real, k3 = t + 3 < T_real;
+          for (int m0 = 0; m0 < NM; m0 += NB) {
+            float4 r4[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) r4[j] = __ldcg(reinterpret_cast<const float4*>(col + (long long)(m0 + j) * mel_stride));
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+              stg_stream4(col + (long long)(m0 + j) * mel_stride,
+                          make_float4(nrm(r4[j].x), k1 ? nrm(r4[j].y) : fill, k2 ? nrm(r4[j].z) : fill,
+                                      k3 ? nrm(r4[j].w) : fill));
+          }
+        }
+      }
+      const int rem = T - 4 * T4;
+      for (int i = tid; i < NM * rem; i += LM_THREADS) {
+        const int m = i / rem, t = 4 * T4 + (i - m * rem);
+        float* row = out + (long long)m * mel_stride;
+        row[t] = (t < T_real) ? nrm(__ldcg(row + t)) : fill;
+      }
+    } else {
+      for (int m = 0; m < NM; ++m) {
+        float* row = out + (long long)m * mel_stride;
+        for (int t = tid; t < T; t += LM_THREADS) row[t] = (t < T_real) ? nrm(__ldcg(row + t)) : fill;
+      }
     }
   }
 }
@@ -334,7 +536,7 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
   lc->begin(KID_FUSED, st);
   kern<<<grid, FZ_THREADS, smem, st>>>(x, seg_off, ws.seg, ws.item, item_first_seg, y, y_off, d.fade, tb.hann,
                                        tb.twiddle, pad_frames, mel, mel_stride_frames, ws.clip_max, ws.len16,
-                                       (int)gy, n_items);
+                                       ws.tiles_done, (int)gy, n_items);
   lc->end(st);
   return cudaGetLastError();
 }

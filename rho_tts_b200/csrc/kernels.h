@@ -88,6 +88,7 @@ cudaError_t launch_logmel_norm(const int32_t* len16, int n, int n_mels, int pad_
                                int64_t mel_stride_frames, const int* clip_max, cudaStream_t st, LaunchCtx* lc);
 
 // fused.cu
+bool fused_inline_norm();   // the fused kernel finishes the features itself (no k_logmel_norm launch after it)
 cudaError_t upload_fused_taps(const float* taps /* [2][23] */);
 cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_t* seg_off, const Workspace& ws,
                                   const int32_t* item_first_seg, int n_items, int64_t max_len,

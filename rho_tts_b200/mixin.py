@@ -57,9 +57,9 @@ class B200AudioMixin:
         rb = RaggedBatch.from_list([flat], dev)
         flags = torch.tensor([(1 if from_start else 0) | (2 if from_end else 0)], dtype=torch.uint8, device=dev)
         info = trim_scan_batch(rb, params_from_tts(self), flags).cpu().numpy().view(SEG_DTYPE)[0]
-        start, end = int(info["start"]), int(info["end"])
+        start, end = int(info["start"].item()), int(info["end"].item())
         a2 = audio.unsqueeze(0) if audio.dim() == 1 else audio
-        if info["flags"] & _lib.F_ALL_SILENT:
+        if int(info["flags"].item()) & _lib.F_ALL_SILENT:
             return a2[:, start:end]                      # reference returns the 2-D view here (:380)
         return a2[:, start:end].squeeze(0)               # a view of the caller's tensor (:392)
 
