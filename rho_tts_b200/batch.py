@@ -152,6 +152,22 @@ def logmel_batch(rb16: RaggedBatch, n_mels: int = 80, pad_to_30s: bool = True,
     return mel, n_frames
 
 
+def mel_project(power: torch.Tensor, n_mels: int = 80) -> torch.Tensor:
+    """`mel_filters.T @ magnitudes` (feature_extraction_whisper.py:159) as a tensor-core GEMM (tcgen05, 3xTF32).
+    power: [n_frames, ld >= 201] fp32 on the device, ld % 4 == 0 (columns >= 201 are ignored).
+    Returns mel energies [n_mels, n_frames]."""
+    dev = _dev_index(power)
+    h = Handle.get(dev)
+    if power.dim() != 2 or power.dtype != torch.float32 or not power.is_contiguous():
+        raise RuntimeError("mel_project: power must be a contiguous fp32 [n_frames, ld] tensor")
+    n_frames, ld = power.shape
+    ld_out = (n_frames + 3) // 4 * 4
+    mel = torch.empty((n_mels, ld_out), dtype=torch.float32, device=power.device)
+    _lib.check(h.lib.rho_b200_mel_project(h.ptr, _ptr(power), n_frames, ld, int(n_mels), _ptr(mel), ld_out,
+                                          _stream(dev)), "mel_project")
+    return mel[:, :n_frames]
+
+
 def cosine_batch(emb: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
     """dot(ref, e) / (|ref| |e|) per row of emb (base_tts.py:341-344)."""
     dev = _dev_index(emb)

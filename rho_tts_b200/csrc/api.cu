@@ -47,7 +47,7 @@ namespace rho {
 const char* const kKernelNames[KID_COUNT] = {
   "k_init", "k_scan", "k_finalize_segs", "k_plan_items", "k_gather", "k_finalize_items",
   "k_resample3to2", "k_logmel_init", "k_logmel_frames", "k_logmel_norm", "k_cosine", "k_single_clip_helpers",
-  "k_fused_features"};
+  "k_fused_features", "k_mel_gemm"};
 }
 
 struct rho_handle {
@@ -349,6 +349,23 @@ int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const i
   cudaError_t e = launch_logmel(h->tb, x16, off, len16, n, max_len16, n_mels, pad_frames, mel, mel_stride_frames,
                                 n_frames, (int*)workspace, (cudaStream_t)stream, &h->lc);
   return e == cudaSuccess ? RHO_OK : cuda_fail(e, "logmel");
+}
+
+int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,
+                         float* mel, int64_t ld_mel, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  if (n_mels != 80 && n_mels != 128) return fail(RHO_ERR_INVALID, "n_mels must be 80 or 128, got %d", n_mels);
+  if (n_frames < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (n_frames == 0) return RHO_OK;
+  if (!power || !mel) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  if (ld_power < N_BINS || ld_power % 4 != 0 || (((uintptr_t)power) & 15u))
+    return fail(RHO_ERR_INVALID, "power rows must be 16-byte aligned: ld_power %% 4 == 0, ld_power >= 201 (TMA)");
+  if (ld_mel < n_frames) return fail(RHO_ERR_INVALID, "ld_mel too small");
+  int sms = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  if (e != cudaSuccess) return cuda_fail(e, "device attribute");
+  e = launch_mel_gemm(h->tb, power, n_frames, ld_power, n_mels, mel, ld_mel, sms, (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "mel_gemm");
 }
 
 int rho_b200_cosine(rho_handle* h, const float* emb, const float* ref, int n, int dim, float* out,

@@ -35,7 +35,7 @@ struct Tables {
 // (rho_b200_profile_*; bench.py uses it for the roofline line).
 enum KernelId {
   KID_INIT = 0, KID_SCAN, KID_FINALIZE_SEGS, KID_PLAN, KID_GATHER, KID_FINALIZE_ITEMS,
-  KID_RESAMPLE, KID_LOGMEL_INIT, KID_LOGMEL_FRAMES, KID_LOGMEL_NORM, KID_COSINE, KID_SINGLE, KID_FUSED, KID_COUNT
+  KID_RESAMPLE, KID_LOGMEL_INIT, KID_LOGMEL_FRAMES, KID_LOGMEL_NORM, KID_COSINE, KID_SINGLE, KID_FUSED, KID_MEL_GEMM, KID_COUNT
 };
 extern const char* const kKernelNames[KID_COUNT];
 
@@ -94,6 +94,10 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
                                   const int32_t* item_first_seg, int n_items, int64_t max_len,
                                   const Derived& d, float* y, const int64_t* y_off, int n_mels, int pad_frames,
                                   float* mel, int64_t mel_stride_frames, cudaStream_t st, LaunchCtx* lc);
+
+// mel_gemm.cu: the mel projection as a tcgen05 / TMEM / TMA GEMM (3xTF32), in isolation
+cudaError_t launch_mel_gemm(const Tables& tb, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,
+                            float* mel, int64_t ld_mel, int sm_count, cudaStream_t st, LaunchCtx* lc);
 
 // cosine.cu
 cudaError_t launch_cosine(const float* emb, const float* ref, int n, int dim, float* out, int out_stride_bytes,

@@ -343,3 +343,38 @@ def test_full_size_properties(R, cuda_device):
         o, m, cs = _oracle_pipeline(x[i].cpu().numpy(), c, 80, emb[i].cpu().numpy(), ref.cpu().numpy())
         assert (rec["start"][i], rec["end"][i], bool(rec["ok"][i])) == (o["start"], o["end"], o["ok"])
         assert_close(mel[i].cpu().numpy(), m, what=f"mel clip {i}")
+
+
+# ----------------------------------------------------------------------------- mel projection on the tensor cores
+@pytest.mark.parametrize("n_mels", [80, 128])
+@pytest.mark.parametrize("n_frames", [1, 47, 48, 49, 1000, 148 * 48 * 2 + 5])
+def test_mel_project_tensor_core_vs_fp64(R, cuda_device, n_mels, n_frames):
+    """rho_b200_mel_project (tcgen05, 3xTF32) against the float64 product with the oracle's filterbank
+    (transformers audio_utils.py:453-544): fp32-class accuracy over a power range of 100 dB per frame."""
+    g = torch.Generator().manual_seed(77 + n_frames)
+    # power spectra with a wide dynamic range, like |STFT|^2 of speech; the 7 pad columns hold garbage
+    p = torch.rand(n_frames, 208, generator=g) * torch.pow(10.0, torch.rand(n_frames, 208, generator=g) * 10.0 - 6.0)
+    p[:, 201:] = float("nan")
+    got = R.mel_project(p.to(cuda_device), n_mels).cpu().numpy().astype(np.float64)
+    bank = oracle.slaney_mel_filterbank(n_mels).astype(np.float32).astype(np.float64)       # (201, n_mels)
+    want = bank.T @ p[:, :201].numpy().astype(np.float64).T
+    assert got.shape == want.shape == (n_mels, n_frames)
+    err = np.abs(got - want) / np.maximum(np.abs(want), 1e-30)
+    assert float(err.max()) < 2e-6, float(err.max())
+
+
+def test_mel_project_matches_product_filterbank_path(R, cuda_device):
+    """The tensor-core projection of the power spectrum of real frames equals what the product log-mel
+    kernel (sparse FFMA form) writes, through the same log/clamp/scale."""
+    from rho_tts_b200 import synth
+    x = synth.make_clip_block(2, 48000, 5)
+    w16 = [oracle.resample(x[i].numpy()) for i in range(2)]
+    for w in w16:
+        power = oracle.stft_power(w).T.copy()                                                # (T, 201) fp32
+        T = power.shape[0]
+        pw = np.zeros((T, 204), np.float32); pw[:, :201] = power
+        mel = R.mel_project(torch.from_numpy(pw).to(cuda_device), 80).cpu().numpy()
+        ls = np.log10(np.maximum(mel, 1e-10)); ls = np.maximum(ls, ls.max() - 8.0)
+        got = (ls + 4.0) / 4.0
+        want = oracle.log_mel(w, 80, pad_to_30s=False)
+        assert_close(got, want, what="log-mel through the tensor-core projection")
