@@ -168,14 +168,15 @@ int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const i
                     void* workspace, size_t ws_bytes, void* stream);
 
 /* --------------------------------------------------------------- mel projection as a GEMM (a8) */
-/* mel[m*ld_mel + t] = sum_k filterbank[m][k] * power[t*ld_power + k],  m < n_mels (80|128), k < 201, t < n_frames:
+/* mel[i*item_stride + m*ld_mel + t] = sum_k filterbank[m][k] * power[(i*frames_per_item + t)*ld_power + k],
+ * m < n_mels (80|128), k < 201, i*frames_per_item + t < n_frames  (frames_per_item <= 0: one item, all frames):
  * `mel_filters.T @ magnitudes` of transformers feature_extraction_whisper.py:159, reached by the reference
  * through stt_validator.py:78-107.  Runs on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split for fp32-class
  * accuracy, filterbank resident in TMEM, power tiles streamed by TMA).  This is the contraction measured on its
  * own for the tensor-pipe number; rho_b200_logmel / rho_b200_validate keep the sparse (97.5 % zeros) FFMA form.
  * power: device, fp32, 16-byte aligned, ld_power % 4 == 0 and >= 201.  Enqueues on `stream`, never syncs. */
 int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,
-                         float* mel, int64_t ld_mel, void* stream);
+                         float* mel, int64_t ld_mel, int64_t frames_per_item, int64_t item_stride, void* stream);
 
 /* --------------------------------------------------------------- cosine (a6) */
 /* dot(ref, e) / (|ref| * |e|) for n embeddings of dimension dim (base_tts.py:341-344).

@@ -88,7 +88,7 @@ def load():
             "rho_b200_sound_decay": (c_int, [vp, vp, i64, P, vp, vp, c_size_t, vp]),
             "rho_b200_resample3to2": (c_int, [vp, vp, vp, vp, c_int, i32, i64, vp, vp, vp, vp]),
             "rho_b200_logmel": (c_int, [vp, vp, vp, vp, i32, i64, c_int, c_int, vp, i64, vp, vp, c_size_t, vp]),
-            "rho_b200_mel_project": (c_int, [vp, vp, i64, i64, c_int, vp, i64, vp]),
+            "rho_b200_mel_project": (c_int, [vp, vp, i64, i64, c_int, vp, i64, i64, i64, vp]),
             "rho_b200_cosine": (c_int, [vp, vp, vp, i32, c_int, vp, c_int, vp]),
             "rho_b200_validate": (c_int, [vp, vp, vp, vp, i32, i64, vp, i32, i64, P, vp, vp, c_int, c_int, vp, i64,
                                           vp, vp, c_int, vp, vp, c_uint32, vp, c_size_t, vp]),

@@ -152,20 +152,32 @@ def logmel_batch(rb16: RaggedBatch, n_mels: int = 80, pad_to_30s: bool = True,
     return mel, n_frames
 
 
-def mel_project(power: torch.Tensor, n_mels: int = 80) -> torch.Tensor:
+def mel_project(power: torch.Tensor, n_mels: int = 80, frames_per_item: int = 0,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """`mel_filters.T @ magnitudes` (feature_extraction_whisper.py:159) as a tensor-core GEMM (tcgen05, 3xTF32).
     power: [n_frames, ld >= 201] fp32 on the device, ld % 4 == 0 (columns >= 201 are ignored).
-    Returns mel energies [n_mels, n_frames]."""
+    frames_per_item = 0: returns mel energies [n_mels, n_frames].
+    frames_per_item = T: the frames are n_frames / T consecutive clips; returns [n_items, n_mels, T]
+    (or fills `out` [n_items, n_mels, T_out >= T], e.g. the 3000-frame Whisper layout)."""
     dev = _dev_index(power)
     h = Handle.get(dev)
     if power.dim() != 2 or power.dtype != torch.float32 or not power.is_contiguous():
         raise RuntimeError("mel_project: power must be a contiguous fp32 [n_frames, ld] tensor")
     n_frames, ld = power.shape
-    ld_out = (n_frames + 3) // 4 * 4
-    mel = torch.empty((n_mels, ld_out), dtype=torch.float32, device=power.device)
-    _lib.check(h.lib.rho_b200_mel_project(h.ptr, _ptr(power), n_frames, ld, int(n_mels), _ptr(mel), ld_out,
-                                          _stream(dev)), "mel_project")
-    return mel[:, :n_frames]
+    if frames_per_item <= 0:
+        ld_out = (n_frames + 3) // 4 * 4
+        mel = torch.empty((n_mels, ld_out), dtype=torch.float32, device=power.device)
+        _lib.check(h.lib.rho_b200_mel_project(h.ptr, _ptr(power), n_frames, ld, int(n_mels), _ptr(mel), ld_out, 0, 0,
+                                              _stream(dev)), "mel_project")
+        return mel[:, :n_frames]
+    n_items = (n_frames + frames_per_item - 1) // frames_per_item
+    if out is None:
+        out = torch.empty((n_items, n_mels, frames_per_item), dtype=torch.float32, device=power.device)
+    if out.dim() != 3 or out.shape[0] < n_items or out.shape[1] != n_mels or not out.is_contiguous():
+        raise RuntimeError("mel_project: out must be a contiguous [n_items, n_mels, T_out] tensor")
+    _lib.check(h.lib.rho_b200_mel_project(h.ptr, _ptr(power), n_frames, ld, int(n_mels), _ptr(out), out.shape[2],
+                                          frames_per_item, out.shape[1] * out.shape[2], _stream(dev)), "mel_project")
+    return out
 
 
 def cosine_batch(emb: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:

@@ -352,7 +352,7 @@ int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const i
 }
 
 int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,
-                         float* mel, int64_t ld_mel, void* stream) {
+                         float* mel, int64_t ld_mel, int64_t frames_per_item, int64_t item_stride, void* stream) {
   if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
   if (n_mels != 80 && n_mels != 128) return fail(RHO_ERR_INVALID, "n_mels must be 80 or 128, got %d", n_mels);
   if (n_frames < 0) return fail(RHO_ERR_INVALID, "negative size");
@@ -360,11 +360,14 @@ int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, in
   if (!power || !mel) return fail(RHO_ERR_INVALID, "NULL device pointer");
   if (ld_power < N_BINS || ld_power % 4 != 0 || (((uintptr_t)power) & 15u))
     return fail(RHO_ERR_INVALID, "power rows must be 16-byte aligned: ld_power %% 4 == 0, ld_power >= 201 (TMA)");
-  if (ld_mel < n_frames) return fail(RHO_ERR_INVALID, "ld_mel too small");
+  if (frames_per_item <= 0) { frames_per_item = n_frames; item_stride = 0; }
+  if (ld_mel < frames_per_item) return fail(RHO_ERR_INVALID, "ld_mel too small");
+  if (frames_per_item < n_frames && item_stride < (int64_t)n_mels * ld_mel) return fail(RHO_ERR_INVALID, "item_stride too small");
   int sms = 0;
   cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   if (e != cudaSuccess) return cuda_fail(e, "device attribute");
-  e = launch_mel_gemm(h->tb, power, n_frames, ld_power, n_mels, mel, ld_mel, sms, (cudaStream_t)stream, &h->lc);
+  e = launch_mel_gemm(h->tb, power, n_frames, ld_power, n_mels, mel, ld_mel, frames_per_item, item_stride, sms,
+                      (cudaStream_t)stream, &h->lc);
   return e == cudaSuccess ? RHO_OK : cuda_fail(e, "mel_gemm");
 }
 

@@ -97,7 +97,8 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
 
 // mel_gemm.cu: the mel projection as a tcgen05 / TMEM / TMA GEMM (3xTF32), in isolation
 cudaError_t launch_mel_gemm(const Tables& tb, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,
-                            float* mel, int64_t ld_mel, int sm_count, cudaStream_t st, LaunchCtx* lc);
+                            float* mel, int64_t ld_mel, int64_t frames_per_item, int64_t item_stride, int sm_count,
+                            cudaStream_t st, LaunchCtx* lc);
 
 // cosine.cu
 cudaError_t launch_cosine(const float* emb, const float* ref, int n, int dim, float* out, int out_stride_bytes,

@@ -11,15 +11,15 @@
 // Mapping (one persistent CTA per SM, 192 threads):
 //   A = the filterbank, padded to 128 x 208, RESIDENT IN TMEM for the whole kernel (hi: columns 0..207,
 //       lo: 208..415), written once with tcgen05.st;  M = 128 TMEM lanes = mel rows
-//   B = a tile of 48 frames x 208 bins of P, K-major in shared memory exactly as it lies in HBM: seven TMA
-//       boxes (32 bins x 48 frames, 128-byte swizzle) per tile, two stages; bins >= 201 and frames >= n_frames
-//       are zero-filled by the TMA unit
-//   D = 128 x 48 fp32 accumulator in TMEM, two buffers (columns 416..511) so the epilogue of tile i overlaps
+//   B = a tile of 32 frames x 208 bins of P, K-major in shared memory exactly as it lies in HBM: seven TMA
+//       boxes (32 bins x 32 frames, 128-byte swizzle) per tile, four stages (the loads of three tiles are in
+//       flight while one is multiplied); bins >= 201 and frames >= n_frames are zero-filled by the TMA unit
+//   D = 128 x 32 fp32 accumulator in TMEM, two buffers (columns 416..479) so the epilogue of tile i overlaps
 //       the MMAs of tile i+1
 //   warp 0   : TMA producer (one lane)
 //   warps 1-4: split the landed tile into hi / lo in place (layout-agnostic, the swizzle does not matter),
-//              then drain the previous tile's accumulator: tcgen05.ld -> 128-bit stores of mel[m][t0..t0+47]
-//   warp 5   : MMA issuer (one lane): 26 K-steps x 3 tcgen05.mma.kind::tf32 (M128 N48 K8), tcgen05.commit
+//              then drain the previous tile's accumulator: tcgen05.ld -> 128-bit stores of mel[m][t0..t0+31]
+//   warp 5   : MMA issuer (one lane): 26 K-steps x 3 tcgen05.mma.kind::tf32 (M128 N32 K8), tcgen05.commit
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include "common.cuh"
@@ -27,12 +27,12 @@
 
 namespace rho {
 
-constexpr int MG_NT = 48;                               // frames per tile (UMMA N)
+constexpr int MG_NT = 32;                               // frames per tile (UMMA N)
 constexpr int MG_NKB = 7;                               // TMA boxes per tile (7 x 32 bins >= 201)
 constexpr int MG_KSTEPS = 26;                           // UMMA K = 8 tf32 values; 26 x 8 = 208 >= 201
-constexpr int MG_BOX_BYTES = MG_NT * 128;               // 6144: 48 rows of 128 bytes
-constexpr int MG_TILE_BYTES = MG_NKB * MG_BOX_BYTES;    // 43008
-constexpr int MG_STAGES = 2;
+constexpr int MG_BOX_BYTES = MG_NT * 128;               // 4096: 32 rows of 128 bytes
+constexpr int MG_TILE_BYTES = MG_NKB * MG_BOX_BYTES;    // 28672
+constexpr int MG_STAGES = 4;                            // 4 x (hi + lo) = 224 KB: three tiles of loads in flight per SM
 constexpr int MG_THREADS = 192;
 constexpr int MG_WORKERS = 128;                         // warps 1-4
 constexpr uint32_t MG_COL_WHI = 0, MG_COL_WLO = 208, MG_COL_D = 416;
@@ -42,7 +42,7 @@ constexpr uint32_t MG_TMEM_COLS = 512;
 constexpr uint32_t MG_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MG_NT >> 3) << 17) | ((128u >> 4) << 24);
 
 struct MgSmem {
-  unsigned char hi[MG_STAGES][MG_TILE_BYTES];           // 1024-byte aligned (43008 = 42 * 1024)
+  unsigned char hi[MG_STAGES][MG_TILE_BYTES];           // 1024-byte aligned (28672 = 28 * 1024)
   unsigned char lo[MG_STAGES][MG_TILE_BYTES];
   uint64_t full[MG_STAGES];                             // TMA bytes landed
   uint64_t ready[MG_STAGES];                            // hi / lo written (128 arrivals)
@@ -66,10 +66,18 @@ __device__ __forceinline__ uint64_t mg_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ void mg_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-               :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(MG_IDESC), "r"(accumulate) : "memory");
+// The descriptor is passed as two 32-bit halves: only the 14-bit start-address field of the low word changes
+// between K-steps, so a fully unrolled issue loop costs one uniform add per tcgen05.mma.
+__device__ __forceinline__ void mg_mma(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi,
+                                       uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}"
+               :: "r"(d_tmem), "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(MG_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
 }
 __device__ __forceinline__ void mg_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -78,7 +86,7 @@ __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__flo
 
 __global__ void __launch_bounds__(MG_THREADS, 1)
 k_mel_gemm(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ F, int n_mels, long long n_frames,
-           float* __restrict__ mel, long long ld_mel, int n_tiles) {
+           float* __restrict__ mel, long long ld_mel, long long frames_per_item, long long item_stride, int n_tiles) {
   extern __shared__ unsigned char mg_raw[];
   MgSmem& S = *reinterpret_cast<MgSmem*>(mg_raw + ((1024u - (smem_u32(mg_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,35 +145,37 @@ k_mel_gemm(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ F
       }
     }
   } else if (warp == 5) {
-    // ================================ MMA issuer
-    if (lane == 0) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = it % MG_STAGES, buf = it & 1;
-        const unsigned ph = (unsigned)(it / MG_STAGES) & 1u, dph = (unsigned)(it >> 1) & 1u;
-        mbar_wait(&S.ready[s], ph);
-        mbar_wait(&S.d_empty[buf], dph ^ 1u);
-        tc_fence_after();
-        const uint32_t d = tmem + MG_COL_D + (uint32_t)(MG_NT * buf);
-        const uint32_t bh = smem_u32(S.hi[s]), bl = smem_u32(S.lo[s]);
-#pragma unroll 2
+    // ================================ MMA issuer (the warp stays converged; one elected lane issues)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int s = it % MG_STAGES, buf = it & 1;
+      const unsigned ph = (unsigned)(it / MG_STAGES) & 1u, dph = (unsigned)(it >> 1) & 1u;
+      mbar_wait(&S.ready[s], ph);
+      mbar_wait(&S.d_empty[buf], dph ^ 1u);
+      tc_fence_after();
+      const uint32_t d = tmem + MG_COL_D + (uint32_t)(MG_NT * buf);
+      const uint64_t d0 = mg_desc(smem_u32(S.hi[s])), d1 = mg_desc(smem_u32(S.lo[s]));
+      const uint32_t hi_lo = (uint32_t)d0, lo_lo = (uint32_t)d1, dhi = (uint32_t)(d0 >> 32);
+      if (elect_one()) {
+#pragma unroll
         for (int ks = 0; ks < MG_KSTEPS; ++ks) {
-          const uint32_t off = (uint32_t)((ks >> 2) * MG_BOX_BYTES + (ks & 3) * 32);
-          const uint64_t dh = mg_desc(bh + off), dl = mg_desc(bl + off);
-          mg_mma(d, tmem + MG_COL_WHI + 8 * ks, dh, ks > 0);
-          mg_mma(d, tmem + MG_COL_WLO + 8 * ks, dh, 1);
-          mg_mma(d, tmem + MG_COL_WHI + 8 * ks, dl, 1);
+          const uint32_t off = (uint32_t)(((ks >> 2) * MG_BOX_BYTES + (ks & 3) * 32) >> 4);   // start-address field units
+          mg_mma(d, tmem + MG_COL_WHI + 8 * ks, hi_lo + off, dhi, ks > 0);
+          mg_mma(d, tmem + MG_COL_WLO + 8 * ks, hi_lo + off, dhi, 1);
+          mg_mma(d, tmem + MG_COL_WHI + 8 * ks, lo_lo + off, dhi, 1);
         }
         mg_commit(&S.empty[s]);                           // shared memory of the stage may be refilled
         mg_commit(&S.d_full[buf]);                        // accumulator may be drained
       }
+      __syncwarp();
     }
   } else {
     // ================================ split + epilogue (warps 1-4)
     const int t = threadIdx.x - 32;
     const int q = warp & 3;
     const int m = 32 * q + lane;
-    const bool vec = (ld_mel % 4 == 0) && ((reinterpret_cast<uintptr_t>(mel) & 15u) == 0);
+    const bool vec = (ld_mel % 4 == 0) && (frames_per_item % 4 == 0) && (item_stride % 4 == 0) && frames_per_item >= MG_NT &&
+                     ((reinterpret_cast<uintptr_t>(mel) & 15u) == 0);
     auto epilogue = [&](int e) {
       const int buf = e & 1;
       const unsigned dph = (unsigned)(e >> 1) & 1u;
@@ -186,15 +196,30 @@ k_mel_gemm(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ F
       tc_fence_before();
       mbar_arrive(&S.d_empty[buf]);                       // the accumulator is in registers: MMAs may reuse it
       if (m < n_mels) {
-        float* row = mel + (long long)m * ld_mel + f0;
+        // frame f belongs to item f / frames_per_item (one clip's [n_mels][ld_mel] block), column f % frames_per_item
+        // (one 64-bit division per tile; a tile of 32 frames crosses at most one item boundary when
+        //  frames_per_item >= 32, which the launcher guarantees for the vector path)
+        const long long item0 = f0 / frames_per_item, t0 = f0 - item0 * frames_per_item;
+        float* rowm = mel + (long long)m * ld_mel + item0 * item_stride;
+        const long long wrap = item_stride - frames_per_item;   // added to the column once the tile crosses into the next item
         if (vec && f0 + MG_NT <= n_frames) {
 #pragma unroll
-          for (int j = 0; j < MG_NT / 4; ++j)
-            stg_stream4(row + 4 * j, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+          for (int j = 0; j < MG_NT / 4; ++j) {
+            long long t = t0 + 4 * j;
+            if (t >= frames_per_item) t += wrap;
+            stg_stream4(rowm + t, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                              __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+          }
         } else {
 #pragma unroll
-          for (int j = 0; j < MG_NT; ++j) if (f0 + j < n_frames) row[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < MG_NT; ++j) {
+            if (f0 + j < n_frames) {
+              long long t = t0 + j;                       // general case: any number of item boundaries
+              long long o = 0;
+              while (t >= frames_per_item) { t -= frames_per_item; o += item_stride; }
+              rowm[o + t] = __uint_as_float(r[j]);
+            }
+          }
         }
       }
     };
@@ -241,7 +266,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 mg_encode_fn() {
 }
 
 cudaError_t launch_mel_gemm(const Tables& tb, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,
-                            float* mel, int64_t ld_mel, int sm_count, cudaStream_t st, LaunchCtx* lc) {
+                            float* mel, int64_t ld_mel, int64_t frames_per_item, int64_t item_stride, int sm_count,
+                            cudaStream_t st, LaunchCtx* lc) {
   if (n_frames <= 0) return cudaSuccess;
   auto encode = mg_encode_fn();
   if (!encode) return cudaErrorNotSupported;
@@ -262,7 +288,8 @@ cudaError_t launch_mel_gemm(const Tables& tb, const float* power, int64_t n_fram
   const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
   const float* F = tb.mel_dense[n_mels == 80 ? 0 : 1];
   lc->begin(KID_MEL_GEMM, st);
-  k_mel_gemm<<<grid, MG_THREADS, smem, st>>>(tmap, F, n_mels, (long long)n_frames, mel, (long long)ld_mel, (int)n_tiles);
+  k_mel_gemm<<<grid, MG_THREADS, smem, st>>>(tmap, F, n_mels, (long long)n_frames, mel, (long long)ld_mel,
+                                             (long long)frames_per_item, (long long)item_stride, (int)n_tiles);
   lc->end(st);
   return cudaGetLastError();
 }

@@ -347,7 +347,7 @@ def test_full_size_properties(R, cuda_device):
 
 # ----------------------------------------------------------------------------- mel projection on the tensor cores
 @pytest.mark.parametrize("n_mels", [80, 128])
-@pytest.mark.parametrize("n_frames", [1, 47, 48, 49, 1000, 148 * 48 * 2 + 5])
+@pytest.mark.parametrize("n_frames", [1, 47, 48, 49, 1000, 148 * 32 * 5 + 5])
 def test_mel_project_tensor_core_vs_fp64(R, cuda_device, n_mels, n_frames):
     """rho_b200_mel_project (tcgen05, 3xTF32) against the float64 product with the oracle's filterbank
     (transformers audio_utils.py:453-544): fp32-class accuracy over a power range of 100 dB per frame."""
@@ -378,3 +378,19 @@ def test_mel_project_matches_product_filterbank_path(R, cuda_device):
         got = (ls + 4.0) / 4.0
         want = oracle.log_mel(w, 80, pad_to_30s=False)
         assert_close(got, want, what="log-mel through the tensor-core projection")
+
+
+def test_mel_project_batched_layout(R, cuda_device):
+    """frames of consecutive clips -> [clip][n_mels][T_out] (the Whisper feature layout), ragged last clip."""
+    g = torch.Generator().manual_seed(5)
+    n_frames, T = 5 * 100 - 37, 100
+    p = torch.rand(n_frames, 204, generator=g)
+    out = torch.full((5, 80, 128), -1.0, device=cuda_device)
+    R.mel_project(p.to(cuda_device), 80, T, out)
+    bank = oracle.slaney_mel_filterbank(80).astype(np.float32).astype(np.float64)
+    want = bank.T @ p[:, :201].numpy().astype(np.float64).T                                   # (80, n_frames)
+    got = out.cpu().numpy()
+    for i in range(5):
+        nt = min(T, n_frames - i * T)
+        np.testing.assert_allclose(got[i, :, :nt], want[:, i * T:i * T + nt], rtol=2e-6)
+        assert np.all(got[i, :, nt:] == -1.0)                                                 # nothing else is touched
