@@ -243,6 +243,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL's version / debug banner goes to stderr: stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.clips

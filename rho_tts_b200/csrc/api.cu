@@ -417,12 +417,11 @@ int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, con
     e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,
                     rec, nullptr, ws, st, &h->lc, JOIN_FINISH);
     if (e != cudaSuccess) return cuda_fail(e, "join finish");
-    // the clip-max clamp, the scale and the fill of the zero-padding frames happen inside the fused kernel
-    // (the half that finishes a clip last normalises it)
-    if (!fused_inline_norm()) {
-      e = launch_logmel_norm(ws.len16, n_items, n_mels, pad_frames, mel, mel_stride_frames, ws.clip_max, st, &h->lc);
-      if (e != cudaSuccess) return cuda_fail(e, "logmel norm");
-    }
+    // clamp / scale of the frames with signal; the constant fill of the zero-padding frames was written by the
+    // fused kernel (the half that finished each clip last)
+    e = launch_logmel_norm(ws.len16, n_items, n_mels, pad_frames, mel, mel_stride_frames, ws.clip_max, st, &h->lc,
+                           fused_inline_norm());
+    if (e != cudaSuccess) return cuda_fail(e, "logmel norm");
   } else {
     if (!scratch16) return fail(RHO_ERR_INVALID, "scratch16 is NULL (needed by the unfused path)");
     e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,

@@ -75,7 +75,7 @@ cudaError_t upload_fused_taps(const float* taps) {
 #define FZ_FFMA2_FIR 1     // FIR as packed fp32x2 dot products
 #endif
 #ifndef FZ_INLINE_NORM
-#define FZ_INLINE_NORM 0   // 1: the half that finishes a clip last normalises its features (measured: no gain, see profiles/README.md)
+#define FZ_INLINE_NORM 0   // 1: the half that finishes a clip last writes the constant fill of its zero-padding frames (measured: k_logmel_norm 0.25 -> 0.13 ms but the fused kernel +0.11 ms, one SM writes ~35 GB/s: no net gain)
 #endif
 bool fused_inline_norm() { return FZ_INLINE_NORM != 0; }
 constexpr int FZ_HALVES = 2;
@@ -442,67 +442,44 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       if (m > -INFINITY) atomicMax(&clip_max[c], float_to_ordered(m));
       if (a != 0.0) atomicAdd(&item[c].s_first, a);
       if (bq != 0.0) atomicAdd(&item[c].s_last, bq);
-      // the half that finishes its clip last normalises the clip's features (no second kernel, the raw
-      // frames are still in L2)
+      // The half that finishes its clip last knows the clip maximum: it writes the constant that fills the
+      // frames which only see zero padding (2/3 of a 10 s clip's features).  Pure stores, nothing to wait
+      // for; the frames with signal are clamped / scaled by k_logmel_norm, which then moves 1/3 of the bytes.
+      // (Normalising them here too was measured and is NOT a gain: the loads expose L2 latency on a half that
+      //  has nothing else to do, profiles/README.md.)
       int last = 0;
       if (FZ_INLINE_NORM && tiles_done) {
-        // barrier (CTA scope) -> fence (GPU scope) -> atomic: the grid-sync idiom; makes every thread's
-        // log-mel frames of this half visible before the count is
+        // barrier (CTA scope) -> fence (GPU scope) -> atomic: the grid-sync idiom
         __threadfence();
         const int n_tiles = (t_cover + LM_TILE - 1) / LM_TILE;
         last = (atomicAdd(&tiles_done[c], 1) == n_tiles - 1);
-        if (last) __threadfence();                   // acquire side: the other halves' frames and the clip maximum
+        if (last) __threadfence();                   // acquire side: the other halves' maxima
       }
       H.last = last;
     }
   }
   half_sync(half);
-  if (!H.last || T <= 0) return;
+  if (!H.last || T <= T_real) return;
   {
     const float mx = ordered_to_float(__ldcg(&clip_max[c]));
-    const float floor_v = __fsub_rn(mx, 8.0f);
-    const float fill = __fdiv_rn(__fadd_rn(fmaxf(-10.0f, floor_v), 4.0f), 4.0f);
-    auto nrm = [&](float vv) { return __fdiv_rn(__fadd_rn(fmaxf(vv, floor_v), 4.0f), 4.0f); };
+    const float fill = __fmul_rn(__fadd_rn(fmaxf(-10.0f, __fsub_rn(mx, 8.0f)), 4.0f), 0.25f);
+    const int t_lo = (T_real + 3) & ~3;              // whole 128-bit pieces from here; [T_real, t_lo) is k_logmel_norm's
     const bool vec = (mel_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
     if (vec) {
-      // one column piece (4 frames) per thread, all rows: the real / fill decision is per column
-      const int T4 = T >> 2;
+      const int T4 = (T - t_lo) >> 2;
+      const float4 f4 = make_float4(fill, fill, fill, fill);
       for (int cp = tid; cp < T4; cp += LM_THREADS) {
-        const int t = 4 * cp;
-        float* col = out + t;
-        if (t >= T_real) {
-          const float4 f4 = make_float4(fill, fill, fill, fill);
+        float* col = out + t_lo + 4 * cp;
 #pragma unroll 8
-          for (int m = 0; m < NM; ++m) stg_stream4(col + (long long)m * mel_stride, f4);
-        } else {
-          // 8 rows in flight per thread: the raw frames come back from L2.  The piece that straddles T_real
-          // takes the same path (its tail elements are inside the row, just not computed: replaced by the fill).
-          constexpr int NB = 8;
-          static_assert(NM % NB == 0, "row batches");
-          const bool k1 = t + 1 < T_real, k2 = t + 2 < T_real, k3 = t + 3 < T_real;
-          for (int m0 = 0; m0 < NM; m0 += NB) {
-            float4 r4[NB];
-#pragma unroll
-            for (int j = 0; j < NB; ++j) r4[j] = __ldcg(reinterpret_cast<const float4*>(col + (long long)(m0 + j) * mel_stride));
-#pragma unroll
-            for (int j = 0; j < NB; ++j)
-              stg_stream4(col + (long long)(m0 + j) * mel_stride,
-                          make_float4(nrm(r4[j].x), k1 ? nrm(r4[j].y) : fill, k2 ? nrm(r4[j].z) : fill,
-                                      k3 ? nrm(r4[j].w) : fill));
-          }
-        }
+        for (int m = 0; m < NM; ++m) stg_stream4(col + (long long)m * mel_stride, f4);
       }
-      const int rem = T - 4 * T4;
-      for (int i = tid; i < NM * rem; i += LM_THREADS) {
-        const int m = i / rem, t = 4 * T4 + (i - m * rem);
-        float* row = out + (long long)m * mel_stride;
-        row[t] = (t < T_real) ? nrm(__ldcg(row + t)) : fill;
+      for (int i = tid; i < NM * ((T - t_lo) & 3); i += LM_THREADS) {
+        const int rem = (T - t_lo) & 3, m = i / rem;
+        out[(long long)m * mel_stride + t_lo + 4 * T4 + (i - m * rem)] = fill;
       }
     } else {
-      for (int m = 0; m < NM; ++m) {
-        float* row = out + (long long)m * mel_stride;
-        for (int t = tid; t < T; t += LM_THREADS) row[t] = (t < T_real) ? nrm(__ldcg(row + t)) : fill;
-      }
+      for (int m = 0; m < NM; ++m)
+        for (int t = t_lo + tid; t < T; t += LM_THREADS) out[(long long)m * mel_stride + t] = fill;
     }
   }
 }

@@ -313,8 +313,8 @@ k_gather(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const
   const int s = blockIdx.x;
   const SegSpan sp = span[s];
   const int span_len = sp.ov + sp.body + sp.pause;
-  const int j0 = blockIdx.y * GATHER_TILE;
-  if (j0 >= span_len) return;
+  const int jt0 = blockIdx.y * GATHER_TILE;
+  if (jt0 >= span_len) return;
   const SegState st = seg[s];
   const ItemState is = item[st.item];
   const bool fb = (is.flags & RHO_F_FALLBACK) != 0;
@@ -335,8 +335,9 @@ k_gather(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const
   const bool aligned = (((uintptr_t)xc | (uintptr_t)yo) & 15u) == 0;
 
   float a_first = 0.f, a_last = 0.f;
-  const int jend = min(j0 + GATHER_TILE, span_len);
-  constexpr int U = GATHER_TILE / (4 * GATHER_THREADS);      // 128-bit pieces per thread
+  constexpr int U = GATHER_CHUNK / (4 * GATHER_THREADS);     // 128-bit pieces per thread and pass
+  for (int j0 = jt0; j0 < jt0 + GATHER_TILE && j0 < span_len; j0 += GATHER_CHUNK) {
+  const int jend = min(j0 + GATHER_CHUNK, span_len);
   float4 v[U];
   bool interior[U];
   // issue every interior load of this thread before the first use
@@ -389,6 +390,7 @@ k_gather(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const
         if (oo >= out_len - third) a_last += val * val;
       }
     }
+  }
   }
   // block reduction of the two decay sums, one double atomic each per CTA
   __shared__ double red[2][GATHER_THREADS / 32];

@@ -5,9 +5,16 @@
 
 namespace rho {
 
-constexpr int SCAN_FR = 128;          // energy frames (= threads) per scan CTA
+#ifndef RHO_SCAN_FR
+#define RHO_SCAN_FR 64               // measured on B200: 64 -> 0.207 ms, 128 -> 0.210 ms, 256 -> 0.304 ms (C2 scan)
+#endif
+#ifndef RHO_GATHER_CHUNKS
+#define RHO_GATHER_CHUNKS 2          // measured on C3: 1 -> 2.76 ms, 2 -> 2.62 ms, 4 -> 3.26 ms
+#endif
+constexpr int SCAN_FR = RHO_SCAN_FR;  // energy frames (= threads) per scan CTA
 constexpr int GATHER_THREADS = 256;
-constexpr int GATHER_TILE = 4096;     // output samples per gather CTA
+constexpr int GATHER_CHUNK = 4096;    // output samples per pass of a gather CTA (4 x 128-bit pieces per thread in flight)
+constexpr int GATHER_TILE = GATHER_CHUNK * RHO_GATHER_CHUNKS;   // output samples per gather CTA
 
 constexpr int RS_TAPS = 23;           // 24k->16k polyphase kernel length (width 10, orig 3)
 constexpr int N_FFT = 400;
@@ -85,10 +92,11 @@ cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off
 
 cudaError_t launch_logmel_init(int* clip_max, int n, cudaStream_t st, LaunchCtx* lc, int* tiles_done = nullptr);
 cudaError_t launch_logmel_norm(const int32_t* len16, int n, int n_mels, int pad_frames, float* mel,
-                               int64_t mel_stride_frames, const int* clip_max, cudaStream_t st, LaunchCtx* lc);
+                               int64_t mel_stride_frames, const int* clip_max, cudaStream_t st, LaunchCtx* lc,
+                               bool fill_done = false);
 
 // fused.cu
-bool fused_inline_norm();   // the fused kernel finishes the features itself (no k_logmel_norm launch after it)
+bool fused_inline_norm();   // the fused kernel writes the constant fill of the zero-padding frames itself
 cudaError_t upload_fused_taps(const float* taps /* [2][23] */);
 cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_t* seg_off, const Workspace& ws,
                                   const int32_t* item_first_seg, int n_items, int64_t max_len,

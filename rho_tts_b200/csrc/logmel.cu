@@ -156,14 +156,16 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
 // grid (n clips, row groups); normalises real frames and fills the zero-padding frames.
 __global__ void __launch_bounds__(256)
 k_logmel_norm(const int32_t* __restrict__ len16, int n_mels, int pad_frames, float* __restrict__ mel,
-              long long mel_stride, const int* __restrict__ clip_max, int rows_per_cta) {
+              long long mel_stride, const int* __restrict__ clip_max, int rows_per_cta, int fill_done) {
   const int c = blockIdx.x;
   int T, T_real, N, n_valid;
   lm_frame_counts(len16[c], pad_frames, &T, &T_real, &N, &n_valid);
   if (T <= 0) return;
+  // fill_done: the fused kernel has already written the constant for the columns >= round_up(T_real, 4)
+  if (fill_done && T > T_real) T = min(T, (T_real + 3) & ~3);
   const float mx = ordered_to_float(clip_max[c]);
   const float floor_v = __fsub_rn(mx, 8.0f);
-  const float fill = __fdiv_rn(__fadd_rn(fmaxf(-10.0f, floor_v), 4.0f), 4.0f);
+  const float fill = __fmul_rn(__fadd_rn(fmaxf(-10.0f, floor_v), 4.0f), 0.25f);
   float* __restrict__ base = mel + (long long)c * n_mels * mel_stride;
   const int m0 = blockIdx.y * rows_per_cta;
   const int m1 = min(n_mels, m0 + rows_per_cta);
@@ -176,26 +178,26 @@ k_logmel_norm(const int32_t* __restrict__ len16, int n_mels, int pad_frames, flo
         float4 v;
         if (t + 3 < T_real) {
           v = *reinterpret_cast<const float4*>(row + t);
-          v.x = __fdiv_rn(__fadd_rn(fmaxf(v.x, floor_v), 4.0f), 4.0f);
-          v.y = __fdiv_rn(__fadd_rn(fmaxf(v.y, floor_v), 4.0f), 4.0f);
-          v.z = __fdiv_rn(__fadd_rn(fmaxf(v.z, floor_v), 4.0f), 4.0f);
-          v.w = __fdiv_rn(__fadd_rn(fmaxf(v.w, floor_v), 4.0f), 4.0f);
+          v.x = __fmul_rn(__fadd_rn(fmaxf(v.x, floor_v), 4.0f), 0.25f);
+          v.y = __fmul_rn(__fadd_rn(fmaxf(v.y, floor_v), 4.0f), 0.25f);
+          v.z = __fmul_rn(__fadd_rn(fmaxf(v.z, floor_v), 4.0f), 0.25f);
+          v.w = __fmul_rn(__fadd_rn(fmaxf(v.w, floor_v), 4.0f), 0.25f);
         } else if (t >= T_real) {
           v = make_float4(fill, fill, fill, fill);
         } else {
           float e[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            e[k] = (t + k < T_real) ? __fdiv_rn(__fadd_rn(fmaxf(row[t + k], floor_v), 4.0f), 4.0f) : fill;
+            e[k] = (t + k < T_real) ? __fmul_rn(__fadd_rn(fmaxf(row[t + k], floor_v), 4.0f), 0.25f) : fill;
           v = make_float4(e[0], e[1], e[2], e[3]);
         }
         stg_stream4(row + t, v);
       }
       for (int t = T4 + threadIdx.x; t < T; t += 256)
-        row[t] = (t < T_real) ? __fdiv_rn(__fadd_rn(fmaxf(row[t], floor_v), 4.0f), 4.0f) : fill;
+        row[t] = (t < T_real) ? __fmul_rn(__fadd_rn(fmaxf(row[t], floor_v), 4.0f), 0.25f) : fill;
     } else {
       for (int t = threadIdx.x; t < T; t += 256)
-        row[t] = (t < T_real) ? __fdiv_rn(__fadd_rn(fmaxf(row[t], floor_v), 4.0f), 4.0f) : fill;
+        row[t] = (t < T_real) ? __fmul_rn(__fadd_rn(fmaxf(row[t], floor_v), 4.0f), 0.25f) : fill;
     }
   }
 }
@@ -239,12 +241,14 @@ cudaError_t launch_logmel_init(int* clip_max, int n, cudaStream_t st, LaunchCtx*
 }
 
 cudaError_t launch_logmel_norm(const int32_t* len16, int n, int n_mels, int pad_frames, float* mel,
-                               int64_t mel_stride_frames, const int* clip_max, cudaStream_t st, LaunchCtx* lc) {
+                               int64_t mel_stride_frames, const int* clip_max, cudaStream_t st, LaunchCtx* lc,
+                               bool fill_done) {
   if (n <= 0) return cudaSuccess;
   const int rows_per_cta = 8;
   dim3 g2((unsigned)n, (unsigned)((n_mels + rows_per_cta - 1) / rows_per_cta));
   lc->begin(KID_LOGMEL_NORM, st);
-  k_logmel_norm<<<g2, 256, 0, st>>>(len16, n_mels, pad_frames, mel, mel_stride_frames, clip_max, rows_per_cta);
+  k_logmel_norm<<<g2, 256, 0, st>>>(len16, n_mels, pad_frames, mel, mel_stride_frames, clip_max, rows_per_cta,
+                                    fill_done ? 1 : 0);
   lc->end(st);
   return cudaGetLastError();
 }

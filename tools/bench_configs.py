@@ -1,0 +1,124 @@
+"""The BASELINE.json configurations that are not the default bench line, at full size on one GPU:
+
+  c2u : C2 with unpadded features (T = len16 // 160)
+  c3  : 4000 ragged clips (1..30 s) grouped into items of 2..6 segments -> trim + crossfade joins (join_batch)
+  c3v : the same items through the whole front end (join -> resample -> log-mel 80 -> cosine), unfused path
+  c4  : one GPU's shard of C4: 8000 x 10 s clips, 128-bin log-mel (30 s pad), records
+
+One JSON line per configuration: device-timed step (CUDA events, inputs resident, larger than L2), audio-s/s and
+the per-kernel times with algorithmic bytes.  Results are copied to profiles/.
+    python tools/bench_configs.py [c2u c3 c3v c4] [--steps K]
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import rho_tts_b200 as R
+from rho_tts_b200 import synth
+
+SR = 24000
+dev = torch.device("cuda", 0)
+args = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c2u", "c3", "c3v", "c4"]
+steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 10
+peak = 6543.1
+try:
+    peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:   # noqa: BLE001
+    pass
+
+
+def ragged_c3(n=4000, seed=1234 + 3):
+    """C3: lengths U[1, 30] s; every clip is the same generator as C2 (blocks of equal length share a launch)."""
+    lens = synth.make_ragged_lengths(n, seed)
+    rb = R.RaggedBatch.empty_like_lengths(lens, dev)
+    order = np.argsort(lens)
+    # generate in groups of similar length (one generator call per group, cut to each clip's length)
+    for g0 in range(0, n, 50):
+        idx = order[g0:g0 + 50]
+        L = int(lens[idx].max())
+        blk = synth.make_clip_block(len(idx), L, seed * 7919 + g0, device=dev)
+        for j, i in enumerate(idx):
+            rb.clip(int(i)).copy_(blk[j, :int(lens[i])])
+    return rb, synth.make_item_partition(n, seed)
+
+
+def timed(fn, steps):
+    for _ in range(3):
+        out = fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    h = R._lib.Handle.get(0)
+    h.profile_begin()
+    for _ in range(min(steps, 5)):
+        fn()
+    prof = {k: v[0] / v[1] for k, v in h.profile_end().items()}
+    return out, ms, prof
+
+
+def line(name, workload, audio_s, ms, prof, alg):
+    ks = {}
+    for k, t in prof.items():
+        ks[k] = {"ms": round(t, 4)}
+        if k in alg:
+            ks[k]["alg_GB"] = round(alg[k] / 1e9, 3)
+            ks[k]["GBps"] = round(alg[k] / t / 1e6, 1)
+            ks[k]["frac_hbm"] = round(alg[k] / t / 1e6 / peak, 3)
+    print(json.dumps({"config": name, "workload": workload, "audio_s_per_step": audio_s, "ms_per_step": round(ms, 4),
+                      "audio_s_per_s": round(audio_s / ms * 1e3, 1), "hbm_peak_gbs": peak, "kernels": ks}), flush=True)
+
+
+p = R.make_params()
+for cfg in args:
+    torch.cuda.empty_cache()
+    if cfg in ("c2u", "c4"):
+        n, nm, pad = (1000, 80, False) if cfg == "c2u" else (8000, 128, True)
+        x = synth.make_clip_block(n, 240000, 0xB200, device=dev) if n <= 1000 else \
+            torch.cat([synth.make_clip_block(1000, 240000, 0xB200 + i, device=dev) for i in range(n // 1000)])
+        emb, ref = synth.make_embeddings(n, device=dev)
+        rb = R.RaggedBatch.from_dense(x)
+        plan = R.ValidatePlan(rb, np.arange(n + 1, dtype=np.int32), p, nm, pad)
+        out, ms, prof = timed(lambda: plan.run(rb, emb, ref), steps)
+        rec = out.records_host()
+        s_in, s_out = 4.0 * n * 240000, 4.0 * float(rec["out_len"].astype(np.int64).sum())
+        len16 = (2 * rec["out_len"].astype(np.int64) + 2) // 3
+        t_real = np.minimum(3000, np.maximum(2, (len16 + 359) // 160)) if pad else len16 // 160
+        mel_real = 4.0 * nm * float(t_real.sum())
+        mel_full = 4.0 * nm * (3000.0 * n if pad else float(t_real.sum()))
+        alg = {"k_scan": s_in, "k_fused_features": 2 * s_out + mel_real, "k_logmel_norm": mel_real + mel_full}
+        line(cfg, f"{n} x 10 s clips, post-process + log-mel {nm} ({'30 s pad' if pad else 'unpadded'}) + cosine",
+             n * 10.0, ms, prof, alg)
+        del x, rb, plan, out
+    elif cfg in ("c3", "c3v"):
+        rb, first = ragged_c3()
+        audio_s = rb.total_samples / SR
+        if cfg == "c3":
+            out, ms, prof = timed(lambda: R.join_batch(rb, first, p, want_seg_info=False), steps)
+            rec = out.records_host()
+            s_in, s_out = 4.0 * rb.total_samples, 4.0 * float(rec["out_len"].astype(np.int64).sum())
+            alg = {"k_scan": s_in, "k_gather": s_in + s_out}
+            line(cfg, f"{rb.n} ragged clips 1..30 s in {len(first) - 1} items of 2..6 segments: trim + crossfade joins "
+                 f"({rb.total_samples * 4 / 1e9:.2f} GB in)", audio_s, ms, prof, alg)
+        else:
+            emb, ref = synth.make_embeddings(len(first) - 1, device=dev)
+            plan = R.ValidatePlan(rb, first, p, 80, False)
+            out, ms, prof = timed(lambda: plan.run(rb, emb, ref), steps)
+            rec = out.records_host()
+            s_in, s_out = 4.0 * rb.total_samples, 4.0 * float(rec["out_len"].astype(np.int64).sum())
+            len16 = (2 * rec["out_len"].astype(np.int64) + 2) // 3
+            mel_b = 4.0 * 80 * float((len16 // 160).sum())
+            alg = {"k_scan": s_in, "k_gather": s_in + s_out, "k_resample3to2": s_out + s_out * 2 / 3,
+                   "k_logmel_frames": s_out * 2 / 3 + mel_b, "k_logmel_norm": 2 * mel_b}
+            line(cfg, f"{rb.n} ragged clips in {len(first) - 1} joined items -> resample -> log-mel 80 (unpadded) -> cosine",
+                 audio_s, ms, prof, alg)
+            del plan
+        del rb, out
