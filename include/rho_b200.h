@@ -178,6 +178,18 @@ int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const i
 int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,
                          float* mel, int64_t ld_mel, int64_t frames_per_item, int64_t item_stride, void* stream);
 
+/* --------------------------------------------------------------- Qwen loudness post-process (a9 / NEXT-1) */
+/* QwenTTS._post_process_audio (providers/qwen.py:268-378) for n clips: overall-RMS gate (1e-8, clip copied unchanged),
+ * windowed decay correction (2 s windows, gain to the first window's RMS capped at +18 dB, applied only when
+ * n > 2 windows and the gain range is >= 0.05; two 3-tap smoothing passes; np.interp between window centres),
+ * global gain to -23 dBFS, tanh(x / 0.95) * 0.95.  `sr` is the provider's qwen3_sr (24000 by default, :294).
+ * Clip s is read at x + off[s] (length *(int32*)((char*)len + s*len_stride_bytes), len_stride_bytes 0 = 4) and
+ * written at y + y_off[s]; y may alias x.  One read pass + one read/write pass.  Never syncs. */
+size_t rho_b200_qwen_workspace_bytes(int n, int64_t max_len, int sr);
+int rho_b200_qwen_postprocess(rho_handle* h, const float* x, const int64_t* off, const int32_t* len,
+                              int len_stride_bytes, int n, int64_t max_len, int sr, float* y, const int64_t* y_off,
+                              void* workspace, size_t ws_bytes, void* stream);
+
 /* --------------------------------------------------------------- cosine (a6) */
 /* dot(ref, e) / (|ref| * |e|) for n embeddings of dimension dim (base_tts.py:341-344).
  * out_stride_bytes lets the result land in rho_record.cosine. */

@@ -180,6 +180,23 @@ def mel_project(power: torch.Tensor, n_mels: int = 80, frames_per_item: int = 0,
     return out
 
 
+def qwen_post_process_batch(rb: RaggedBatch, sr: int = 24000, lengths: Optional[torch.Tensor] = None,
+                            len_stride: int = 4, in_place: bool = False) -> RaggedBatch:
+    """QwenTTS._post_process_audio (providers/qwen.py:268-378) for every clip of the batch: windowed decay
+    correction, -23 dBFS, tanh soft clip.  `lengths` (device int32, strided by len_stride bytes) overrides
+    rb.lengths, e.g. the out_len column of the records of a join.  Returns a batch with the same layout."""
+    dev = _dev_index(rb.data)
+    h = Handle.get(dev)
+    out = rb if in_place else RaggedBatch(torch.empty_like(rb.data), rb.offsets, rb.lengths, rb.h_offsets, rb.h_lengths)
+    nbytes = int(h.lib.rho_b200_qwen_workspace_bytes(rb.n, rb.max_len, int(sr)))
+    ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=rb.device)
+    lens = rb.lengths if lengths is None else lengths
+    _lib.check(h.lib.rho_b200_qwen_postprocess(h.ptr, _ptr(rb.data), _ptr(rb.offsets), _ptr(lens), int(len_stride),
+                                               rb.n, rb.max_len, int(sr), _ptr(out.data), _ptr(out.offsets),
+                                               _ptr(ws), ws.numel(), _stream(dev)), "qwen_postprocess")
+    return out
+
+
 def cosine_batch(emb: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
     """dot(ref, e) / (|ref| |e|) per row of emb (base_tts.py:341-344)."""
     dev = _dev_index(emb)

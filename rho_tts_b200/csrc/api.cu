@@ -47,7 +47,7 @@ namespace rho {
 const char* const kKernelNames[KID_COUNT] = {
   "k_init", "k_scan", "k_finalize_segs", "k_plan_items", "k_gather", "k_finalize_items",
   "k_resample3to2", "k_logmel_init", "k_logmel_frames", "k_logmel_norm", "k_cosine", "k_single_clip_helpers",
-  "k_fused_features", "k_mel_gemm"};
+  "k_fused_features", "k_mel_gemm", "k_qwen_moments", "k_qwen_plan", "k_qwen_apply"};
 }
 
 struct rho_handle {
@@ -369,6 +369,24 @@ int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, in
   e = launch_mel_gemm(h->tb, power, n_frames, ld_power, n_mels, mel, ld_mel, frames_per_item, item_stride, sms,
                       (cudaStream_t)stream, &h->lc);
   return e == cudaSuccess ? RHO_OK : cuda_fail(e, "mel_gemm");
+}
+
+size_t rho_b200_qwen_workspace_bytes(int n, int64_t max_len, int sr) { return qwen_workspace_bytes(n, max_len, sr); }
+
+int rho_b200_qwen_postprocess(rho_handle* h, const float* x, const int64_t* off, const int32_t* len,
+                              int len_stride_bytes, int n, int64_t max_len, int sr, float* y, const int64_t* y_off,
+                              void* workspace, size_t ws_bytes, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  if (n < 0 || max_len < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (sr <= 0) return fail(RHO_ERR_INVALID, "sample rate must be positive, got %d", sr);
+  if (n == 0 || max_len == 0) return RHO_OK;
+  if (!x || !off || !len || !y || !y_off) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  if (max_len / (2LL * sr) > 64) return fail(RHO_ERR_INVALID, "clips longer than 64 windows (128 s) are not supported");
+  const size_t need = qwen_workspace_bytes(n, max_len, sr);
+  if (!workspace || ws_bytes < need) return fail(RHO_ERR_WORKSPACE, "workspace too small: have %zu, need %zu", ws_bytes, need);
+  cudaError_t e = launch_qwen_postprocess(x, off, len, len_stride_bytes, n, max_len, sr, y, y_off, workspace,
+                                          (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "qwen_postprocess");
 }
 
 int rho_b200_cosine(rho_handle* h, const float* emb, const float* ref, int n, int dim, float* out,

@@ -42,7 +42,7 @@ struct Tables {
 // (rho_b200_profile_*; bench.py uses it for the roofline line).
 enum KernelId {
   KID_INIT = 0, KID_SCAN, KID_FINALIZE_SEGS, KID_PLAN, KID_GATHER, KID_FINALIZE_ITEMS,
-  KID_RESAMPLE, KID_LOGMEL_INIT, KID_LOGMEL_FRAMES, KID_LOGMEL_NORM, KID_COSINE, KID_SINGLE, KID_FUSED, KID_MEL_GEMM, KID_COUNT
+  KID_RESAMPLE, KID_LOGMEL_INIT, KID_LOGMEL_FRAMES, KID_LOGMEL_NORM, KID_COSINE, KID_SINGLE, KID_FUSED, KID_MEL_GEMM, KID_QWEN_MOMENTS, KID_QWEN_PLAN, KID_QWEN_APPLY, KID_COUNT
 };
 extern const char* const kKernelNames[KID_COUNT];
 
@@ -107,6 +107,12 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
 cudaError_t launch_mel_gemm(const Tables& tb, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,
                             float* mel, int64_t ld_mel, int64_t frames_per_item, int64_t item_stride, int sm_count,
                             cudaStream_t st, LaunchCtx* lc);
+
+// qwen.cu: QwenTTS._post_process_audio (windowed decay correction, -23 dBFS, tanh soft clip)
+size_t qwen_workspace_bytes(int n, int64_t max_len, int sr);
+cudaError_t launch_qwen_postprocess(const float* x, const int64_t* off, const int32_t* len, int len_stride_bytes,
+                                    int n, int64_t max_len, int sr, float* y, const int64_t* y_off,
+                                    void* workspace, cudaStream_t st, LaunchCtx* lc);
 
 // cosine.cu
 cudaError_t launch_cosine(const float* emb, const float* ref, int n, int dim, float* out, int out_stride_bytes,

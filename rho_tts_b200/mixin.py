@@ -164,9 +164,31 @@ class B200AudioMixin:
         return np.float32(cosine_batch(gen, ref).item())
 
 
+class B200QwenAudioMixin(B200AudioMixin):
+    """B200AudioMixin plus the Qwen provider's loudness hook.  BaseTTS._post_process_audio is the identity
+    (base_tts.py:601-614), so only providers that override it -- QwenTTS (providers/qwen.py:268-378) -- get
+    this one:  class QwenB200(B200QwenAudioMixin, QwenTTS)."""
+
+    def _post_process_audio(self, audio: torch.Tensor) -> torch.Tensor:
+        from .batch import qwen_post_process_batch
+        original_shape = audio.shape
+        flat = audio.squeeze() if audio.dim() > 1 else audio            # qwen.py:284-286
+        if flat.dim() != 1:
+            raise RuntimeError(f"rho_tts_b200._post_process_audio: expected one non-trivial axis, got {tuple(original_shape)}")
+        if flat.numel() == 0:
+            return audio
+        dev = self._b200_dev()
+        sr = int(getattr(self, "qwen3_sr", None) or 24000)              # :294, read at call time
+        rb = RaggedBatch.from_list([flat], dev)
+        out = qwen_post_process_batch(rb, sr, in_place=True)
+        return out.clip(0).to(device=audio.device, dtype=audio.dtype).reshape(original_shape)
+
+
 def make_b200_provider(provider_class, name: Optional[str] = None):
-    """class <Provider>B200(B200AudioMixin, <Provider>) -- the template of examples/custom_provider.py:22-51."""
-    return type(name or f"{provider_class.__name__}B200", (B200AudioMixin, provider_class), {})
+    """class <Provider>B200(B200AudioMixin, <Provider>) -- the template of examples/custom_provider.py:22-51.
+    Providers that define their own _post_process_audio named QwenTTS get the loudness hook as well."""
+    base = B200QwenAudioMixin if provider_class.__name__ == "QwenTTS" else B200AudioMixin
+    return type(name or f"{provider_class.__name__}B200", (base, provider_class), {})
 
 
 def register_b200_providers(factory=None) -> list:

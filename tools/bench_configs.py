@@ -4,6 +4,7 @@
   c3  : 4000 ragged clips (1..30 s) grouped into items of 2..6 segments -> trim + crossfade joins (join_batch)
   c3v : the same items through the whole front end (join -> resample -> log-mel 80 -> cosine), unfused path
   c4  : one GPU's shard of C4: 8000 x 10 s clips, 128-bin log-mel (30 s pad), records
+  qwen: the Qwen loudness hook (providers/qwen.py:268-378) on 1000 x 10 s post-processed clips
 
 One JSON line per configuration: device-timed step (CUDA events, inputs resident, larger than L2), audio-s/s and
 the per-kernel times with algorithmic bytes.  Results are copied to profiles/.
@@ -22,7 +23,7 @@ from rho_tts_b200 import synth
 
 SR = 24000
 dev = torch.device("cuda", 0)
-args = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c2u", "c3", "c3v", "c4"]
+args = [a for a in sys.argv[1:] if not a.startswith("--") and not a.isdigit()] or ["c2u", "c3", "c3v", "c4", "qwen"]
 steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 10
 peak = 6543.1
 try:
@@ -98,6 +99,16 @@ for cfg in args:
         line(cfg, f"{n} x 10 s clips, post-process + log-mel {nm} ({'30 s pad' if pad else 'unpadded'}) + cosine",
              n * 10.0, ms, prof, alg)
         del x, rb, plan, out
+    elif cfg == "qwen":
+        n = 1000
+        x = synth.make_clip_block(n, 240000, 0xB200, device=dev)
+        rb = R.RaggedBatch.from_dense(x)
+        out, ms, prof = timed(lambda: R.qwen_post_process_batch(rb, 24000), steps)
+        s_in = 4.0 * n * 240000
+        alg = {"k_qwen_moments": s_in, "k_qwen_apply": 2 * s_in}
+        line(cfg, f"{n} x 10 s clips, QwenTTS._post_process_audio (windowed decay correction, -23 dBFS, tanh)",
+             n * 10.0, ms, prof, alg)
+        del x, rb, out
     elif cfg in ("c3", "c3v"):
         rb, first = ragged_c3()
         audio_s = rb.total_samples / SR
