@@ -37,14 +37,23 @@ struct SegState {
   int pos;         // position inside the item
 };
 
-// Per-segment output span inside its item, produced by plan_items (32 B).
+// Per-segment output span inside its item, produced by plan_items, plus everything k_gather needs to start
+// loading samples after ONE dependent fetch (it used to chase seg -> item -> offsets: three round trips per CTA).
 struct SegSpan {
   int dst;         // first output sample of this segment's span (relative to the item)
   int ov;          // crossfade length with the previous segment (0: none)
   int body;        // samples copied after the crossfade (from processed offset `ov`)
   int pause;       // zeros appended after the body
   int prev_tail;   // processed-index in the previous segment where the crossfade tail starts
-  int pad0, pad1, pad2;
+  int item;        // owning item
+  int out_len;     // length of the whole item
+  uint32_t item_flags;
+  float dc;        // DC of this segment (0 in the fallback)
+  float dcp;       // DC of the previous segment (crossfade tail)
+  int pad0, pad1;
+  long long x_base;   // offset in x of processed sample 0 of this segment (seg_off + trim start; fallback: seg_off)
+  long long prev_x;   // offset in x of the first crossfade-tail sample of the previous segment
+  long long y_base;   // offset in y of this segment's span (y_off[item] + dst)
 };
 
 // Per-item state (32 B).

@@ -59,7 +59,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(SCAN_FR)
 k_scan(const float* __restrict__ x, const int64_t* __restrict__ off, const int32_t* __restrict__ len,
        SegState* __restrict__ seg, float* __restrict__ block_sum, int blocks_per_seg,
-       int window, int hop, int RS, float thr) {
+       int window, int hop, int RS, int skew, float thr) {
   extern __shared__ __align__(16) float sm[];
   const int s = blockIdx.x;
   const int L = len[s];
@@ -87,7 +87,12 @@ k_scan(const float* __restrict__ x, const int64_t* __restrict__ off, const int32
     if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     __syncthreads();
     if (threadIdx.x == 0) mbar_arrive_expect_tx(&bar, (unsigned)(r_hi - r_lo) * row_bytes);
-    if (lane == 0) {
+    if (RS == hop) {
+      // dense rows: the whole interior of the tile is ONE bulk copy (the TMA unit retires ~1 op per 46 cycles,
+      // so a copy per 480-byte row is what bounds the padded layout)
+      if (threadIdx.x == 0 && r_hi > r_lo)
+        bulk_g2s(sm + r_lo * RS, xs + (g0 + (long long)r_lo * hop), (unsigned)(r_hi - r_lo) * row_bytes, &bar);
+    } else if (lane == 0) {
       for (int row = r_lo + warp; row < r_hi; row += SCAN_FR / 32)
         bulk_g2s(sm + row * RS, xs + (g0 + (long long)row * hop), row_bytes, &bar);
     }
@@ -126,24 +131,36 @@ k_scan(const float* __restrict__ x, const int64_t* __restrict__ off, const int32
       const float4* p0 = reinterpret_cast<const float4*>(sm + t * RS);
       const float4* p1 = reinterpret_cast<const float4*>(sm + (t + 1) * RS);
       const int nq = hop >> 2;
+      // Dense rows (RS == hop, hop/4 = 2 mod 4) put rows r and r+4 on the same banks.  `skew`: the threads
+      // whose row has bit 2 set run ONE 128-bit step behind the others, which moves them to the odd bank
+      // groups -- every quarter-warp then covers all 32 banks.  Each thread still adds its own 240 terms
+      // strictly left to right, so the fp32 chain (and the trim decision) is unchanged.
+      const int d0 = skew ? ((t >> 2) & 1) : 0, d1 = skew ? (((t + 1) >> 2) & 1) : 0;
+      const int steps = nq + (skew ? 1 : 0);
 #pragma unroll 6
-      for (int j = 0; j < nq; ++j) {
-        const float4 v = p0[j];
-        const float2 a = __fmul2_rn(make_float2(v.x, v.y), make_float2(v.x, v.y));
-        const float2 b = __fmul2_rn(make_float2(v.z, v.w), make_float2(v.z, v.w));
-        acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y);
-        acc = __fadd_rn(acc, b.x); acc = __fadd_rn(acc, b.y);
+      for (int i = 0; i < steps; ++i) {
+        const int j = i - d0;
+        if (j >= 0 && j < nq) {
+          const float4 v = p0[j];
+          const float2 a = __fmul2_rn(make_float2(v.x, v.y), make_float2(v.x, v.y));
+          const float2 b = __fmul2_rn(make_float2(v.z, v.w), make_float2(v.z, v.w));
+          acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y);
+          acc = __fadd_rn(acc, b.x); acc = __fadd_rn(acc, b.y);
+        }
       }
       float2 bs2 = make_float2(0.f, 0.f);
 #pragma unroll 6
-      for (int j = 0; j < nq; ++j) {
-        const float4 v = p1[j];
-        const float2 a = __fmul2_rn(make_float2(v.x, v.y), make_float2(v.x, v.y));
-        const float2 b = __fmul2_rn(make_float2(v.z, v.w), make_float2(v.z, v.w));
-        acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y);
-        acc = __fadd_rn(acc, b.x); acc = __fadd_rn(acc, b.y);
-        bs2 = __fadd2_rn(bs2, make_float2(v.x, v.y));
-        bs2 = __fadd2_rn(bs2, make_float2(v.z, v.w));
+      for (int i = 0; i < steps; ++i) {
+        const int j = i - d1;
+        if (j >= 0 && j < nq) {
+          const float4 v = p1[j];
+          const float2 a = __fmul2_rn(make_float2(v.x, v.y), make_float2(v.x, v.y));
+          const float2 b = __fmul2_rn(make_float2(v.z, v.w), make_float2(v.z, v.w));
+          acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y);
+          acc = __fadd_rn(acc, b.x); acc = __fadd_rn(acc, b.y);
+          bs2 = __fadd2_rn(bs2, make_float2(v.x, v.y));
+          bs2 = __fadd2_rn(bs2, make_float2(v.z, v.w));
+        }
       }
       bs = bs2.x + bs2.y;
     } else {
@@ -233,19 +250,42 @@ __global__ void k_finalize_segs(const float* __restrict__ x, const int64_t* __re
 __global__ void k_plan_items(const SegState* __restrict__ seg, const int32_t* __restrict__ seg_len,
                              SegSpan* __restrict__ span, ItemState* __restrict__ item,
                              const int32_t* __restrict__ item_first_seg, int n_items,
-                             int cf, int pause, int pause_on) {
+                             int cf, int pause, int pause_on,
+                             const int64_t* __restrict__ seg_off, const int64_t* __restrict__ y_off) {
   const int it = blockIdx.x * blockDim.x + threadIdx.x;
   if (it >= n_items) return;
   const int s0 = item_first_seg[it], s1 = item_first_seg[it + 1];
   const int n = s1 - s0;
   if (n <= 0) { item[it].out_len = 0; item[it].flags = 0; return; }
-  SegSpan z; z.dst = 0; z.ov = 0; z.body = 0; z.pause = 0; z.prev_tail = 0; z.pad0 = z.pad1 = z.pad2 = 0;
+  SegSpan z; z.dst = 0; z.ov = 0; z.body = 0; z.pause = 0; z.prev_tail = 0; z.item = it; z.out_len = 0;
+  z.item_flags = 0; z.dc = 0.f; z.dcp = 0.f; z.pad0 = z.pad1 = 0; z.x_base = 0; z.prev_x = 0; z.y_base = 0;
+  // the part of the span record that k_gather reads instead of chasing seg -> item -> offsets
+  auto describe = [&](int out_len, uint32_t flags) {
+    if (!seg_off || !y_off) return;
+    const bool fb = (flags & RHO_F_FALLBACK) != 0;
+    const long long yb = y_off[it];
+    for (int i = 0; i < n; ++i) {
+      SegSpan sp = span[s0 + i];
+      const SegState st = seg[s0 + i];
+      sp.item = it; sp.out_len = out_len; sp.item_flags = flags;
+      sp.dc = fb ? 0.f : st.dc;
+      sp.x_base = seg_off[s0 + i] + (fb ? 0 : st.start);
+      sp.y_base = yb + sp.dst;
+      if (sp.ov > 0 && i > 0) {
+        const SegState pst = seg[s0 + i - 1];
+        sp.dcp = pst.dc;
+        sp.prev_x = seg_off[s0 + i - 1] + pst.start + sp.prev_tail;
+      }
+      span[s0 + i] = sp;
+    }
+  };
   if (n == 1) {                                        // :447-452
     const SegState st = seg[s0];
     SegSpan sp = z; sp.body = st.end - st.start;
     span[s0] = sp;
     item[it].out_len = sp.body;
     item[it].flags = (st.flags & RHO_F_ALL_SILENT) ? (RHO_F_ALL_SILENT | RHO_F_TWO_D) : (st.flags & RHO_F_UNTOUCHED);
+    describe(sp.body, item[it].flags);
     return;
   }
   bool has1 = false, has2 = false;
@@ -289,8 +329,10 @@ __global__ void k_plan_items(const SegState* __restrict__ seg, const int32_t* __
       span[s0 + i] = sp; p += sp.body;
     }
     item[it].out_len = p; item[it].flags = RHO_F_FALLBACK;
+    describe(p, RHO_F_FALLBACK);
   } else {
     item[it].out_len = pos; item[it].flags = has2 ? RHO_F_TWO_D : 0u;
+    describe(pos, has2 ? RHO_F_TWO_D : 0u);
   }
 }
 
@@ -315,22 +357,14 @@ k_gather(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const
   const int span_len = sp.ov + sp.body + sp.pause;
   const int jt0 = blockIdx.y * GATHER_TILE;
   if (jt0 >= span_len) return;
-  const SegState st = seg[s];
-  const ItemState is = item[st.item];
-  const bool fb = (is.flags & RHO_F_FALLBACK) != 0;
-  const int out_len = is.out_len;
+  const int out_len = sp.out_len;
   const int third = out_len / 3;
-  const int src0 = fb ? 0 : st.start;
-  const float dc = fb ? 0.f : st.dc;
-  const float* __restrict__ xc = x + seg_off[s] + src0;
-  float* __restrict__ yo = y + y_off[st.item] + sp.dst;
+  const float dc = sp.dc;
+  const float* __restrict__ xc = x + sp.x_base;
+  float* __restrict__ yo = y + sp.y_base;
   // previous segment (crossfade tail)
-  const float* __restrict__ xp = nullptr; float dcp = 0.f;
-  if (sp.ov > 0) {
-    const SegState pst = seg[s - 1];
-    xp = x + seg_off[s - 1] + pst.start + sp.prev_tail;
-    dcp = pst.dc;
-  }
+  const float* __restrict__ xp = x + sp.prev_x;
+  const float dcp = sp.dcp;
   const bool need_fade = fade > 0 && out_len >= 2 * fade;
   const bool aligned = (((uintptr_t)xc | (uintptr_t)yo) & 15u) == 0;
 
@@ -403,8 +437,8 @@ k_gather(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const
     dl = lane < GATHER_THREADS / 32 ? red[1][lane] : 0.0;
     df = warp_sum(df); dl = warp_sum(dl);
     if (lane == 0) {
-      if (df != 0.0) atomicAdd(&item[st.item].s_first, df);
-      if (dl != 0.0) atomicAdd(&item[st.item].s_last, dl);
+      if (df != 0.0) atomicAdd(&item[sp.item].s_first, df);
+      if (dl != 0.0) atomicAdd(&item[sp.item].s_last, dl);
     }
   }
 }
@@ -480,8 +514,20 @@ __global__ void k_decay_final_single(const double* __restrict__ sums, long long 
 }
 
 // ------------------------------------------------------------------ host launchers
-static inline int scan_row_stride(int hop, bool vec) {
-  if (vec) { int r4 = hop >> 2; if ((r4 & 1) == 0) r4 += 1; return r4 << 2; }
+#ifndef RHO_SCAN_DENSE
+#define RHO_SCAN_DENSE 1
+#endif
+// VEC: rows are read with 128-bit LDS, conflict-free when the row stride is 4 * odd.  A dense stride (== hop)
+// lets the whole tile arrive in one bulk copy; it is usable when hop/4 is odd (already conflict-free) or
+// hop/4 = 2 mod 4 (conflict-free with the one-step skew of k_scan) -- 24 kHz: hop 120, 120/4 = 30.
+static inline int scan_row_stride(int hop, bool vec, int* skew) {
+  *skew = 0;
+  if (vec) {
+    int r4 = hop >> 2;
+    if (r4 & 1) return hop;
+    if (RHO_SCAN_DENSE && (r4 & 3) == 2) { *skew = 1; return hop; }
+    return (r4 + 1) << 2;
+  }
   return hop | 1;
 }
 
@@ -489,7 +535,8 @@ cudaError_t launch_scan(const float* x, const int64_t* off, const int32_t* len, 
                         const Derived& d, const Workspace& ws, cudaStream_t st, LaunchCtx* lc) {
   if (n_seg <= 0) return cudaSuccess;
   const bool vec = (d.hop % 4 == 0) && (d.window == 2 * d.hop);
-  const int RS = scan_row_stride(d.hop, vec);
+  int skew = 0;
+  const int RS = scan_row_stride(d.hop, vec, &skew);
   const size_t smem = (size_t)(SCAN_FR + 2) * RS * sizeof(float);
   const int64_t max_frames = max_len <= 0 ? 1 : (max_len + 2 * d.hop - d.window) / d.hop + 1;
   const unsigned tiles = (unsigned)((max_frames + SCAN_FR - 1) / SCAN_FR);
@@ -500,13 +547,13 @@ cudaError_t launch_scan(const float* x, const int64_t* off, const int32_t* len, 
     if (e != cudaSuccess) return e;
     lc->begin(KID_SCAN, st);
     k_scan<true><<<grid, SCAN_FR, smem, st>>>(x, off, len, ws.seg, ws.block_sum, ws.blocks_per_seg,
-                                             d.window, d.hop, RS, d.thr);
+                                             d.window, d.hop, RS, skew, d.thr);
   } else {
     e = cudaFuncSetAttribute(k_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     lc->begin(KID_SCAN, st);
     k_scan<false><<<grid, SCAN_FR, smem, st>>>(x, off, len, ws.seg, ws.block_sum, ws.blocks_per_seg,
-                                              d.window, d.hop, RS, d.thr);
+                                              d.window, d.hop, RS, skew, d.thr);
   }
   lc->end(st);
   return cudaGetLastError();
@@ -547,7 +594,7 @@ cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* s
     }
     lc->begin(KID_PLAN, st);
     k_plan_items<<<(n_items + 127) / 128, 128, 0, st>>>(ws.seg, seg_len, ws.span, ws.item, item_first_seg, n_items,
-                                                       d.cf, d.pause, d.pause_on);
+                                                       d.cf, d.pause, d.pause_on, seg_off, y_off);
     lc->end(st);
   }
   if ((stages & JOIN_GATHER) && n_seg > 0) {
