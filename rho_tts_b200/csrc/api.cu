@@ -424,19 +424,19 @@ int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, con
   cudaError_t e;
   const bool fused = (flags & RHO_V_ONE_SEGMENT_ITEMS) && !(flags & RHO_V_NO_FUSION) && n_segments == n_items;
   if (fused) {
-    // scan -> bounds/DC -> ONE kernel for apply + resample + log-mel + normalise -> decay decision
+    // init -> scan -> bounds/DC -> plan -> ONE kernel for apply + resample + log-mel -> records (decay decision +
+    // cosine) -> clamp / scale: seven launches per batch
     e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,
-                    rec, nullptr, ws, st, &h->lc, JOIN_PREPARE);
+                    rec, nullptr, ws, st, &h->lc, JOIN_PREPARE | JOIN_INIT_FEATURES);
     if (e != cudaSuccess) return cuda_fail(e, "join prepare");
-    if ((e = launch_logmel_init(ws.clip_max, n_items, st, &h->lc, ws.tiles_done)) != cudaSuccess) return cuda_fail(e, "logmel init");
     e = launch_fused_features(h->tb, x, seg_off, ws, item_first_seg, n_items, max_item_len, d, y, y_off, n_mels,
                               pad_frames, mel, mel_stride_frames, st, &h->lc);
     if (e != cudaSuccess) return cuda_fail(e, "fused features");
     e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,
-                    rec, nullptr, ws, st, &h->lc, JOIN_FINISH);
+                    rec, nullptr, ws, st, &h->lc, JOIN_FINISH, emb, ref_emb, emb_dim);
     if (e != cudaSuccess) return cuda_fail(e, "join finish");
-    // clamp / scale of the frames with signal; the constant fill of the zero-padding frames was written by the
-    // fused kernel (the half that finished each clip last)
+    // clamp / scale of the frames with signal and the constant fill of the zero-padding frames (fill_done: the
+    // fused kernel wrote the fill itself, an option that is off by default)
     e = launch_logmel_norm(ws.len16, n_items, n_mels, pad_frames, mel, mel_stride_frames, ws.clip_max, st, &h->lc,
                            fused_inline_norm());
     if (e != cudaSuccess) return cuda_fail(e, "logmel norm");
@@ -453,7 +453,7 @@ int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, con
                       nullptr, ws.clip_max, st, &h->lc);
     if (e != cudaSuccess) return cuda_fail(e, "logmel");
   }
-  if (emb && ref_emb) {
+  if (emb && ref_emb && !fused) {
     e = launch_cosine(emb, ref_emb, n_items, emb_dim, &rec[0].cosine, (int)sizeof(rho_record), st, &h->lc);
     if (e != cudaSuccess) return cuda_fail(e, "cosine");
   }

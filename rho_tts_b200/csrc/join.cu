@@ -15,9 +15,12 @@ namespace rho {
 
 // ------------------------------------------------------------------ init
 __global__ void k_init_items(SegState* __restrict__ seg, ItemState* __restrict__ item,
-                             const int32_t* __restrict__ item_first_seg, int n_items) {
+                             const int32_t* __restrict__ item_first_seg, int n_items,
+                             int* __restrict__ clip_max, int* __restrict__ tiles_done) {
   const int it = blockIdx.x * blockDim.x + threadIdx.x;
   if (it >= n_items) return;
+  if (clip_max) clip_max[it] = INT_MIN;                // log-mel running maximum (what k_logmel_init does)
+  if (tiles_done) tiles_done[it] = 0;
   ItemState z;
   z.s_first = 0.0; z.s_last = 0.0; z.out_len = 0; z.flags = 0; z.pad0 = 0; z.pad1 = 0;
   item[it] = z;
@@ -458,17 +461,43 @@ __device__ __forceinline__ void decay_decide(double s_first, double s_last, int 
   *ratio = r; *ok = (r >= thr) ? 1 : 0;
 }
 
-__global__ void k_finalize_items(const SegState* __restrict__ seg, const ItemState* __restrict__ item,
-                                 const int32_t* __restrict__ item_first_seg, int n_items, double decay_thr,
-                                 rho_record* __restrict__ rec) {
-  const int it = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per item: lane 0 assembles the record; when embeddings are given the warp also computes the speaker
+// cosine (base_tts.py:341-344) so the validate path needs no separate k_cosine launch.
+__global__ void __launch_bounds__(256)
+k_finalize_items(const SegState* __restrict__ seg, const ItemState* __restrict__ item,
+                 const int32_t* __restrict__ item_first_seg, int n_items, double decay_thr,
+                 rho_record* __restrict__ rec, const float* __restrict__ emb, const float* __restrict__ ref, int dim) {
+  const int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (it >= n_items) return;
+  float cosv = 0.f;
+  if (emb && ref) {
+    const float* __restrict__ e = emb + (size_t)it * dim;
+    float dot = 0.f, ne = 0.f, nr = 0.f;
+    if ((dim & 3) == 0 && ((((uintptr_t)e) | ((uintptr_t)ref)) & 15u) == 0) {
+      for (int i = 4 * lane; i < dim; i += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(e + i);
+        const float4 r = __ldg(reinterpret_cast<const float4*>(ref + i));
+        dot += a.x * r.x + a.y * r.y + a.z * r.z + a.w * r.w;
+        ne += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+        nr += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
+      }
+    } else {
+      for (int i = lane; i < dim; i += 32) {
+        const float a = e[i], r = __ldg(ref + i);
+        dot += a * r; ne += a * a; nr += r * r;
+      }
+    }
+    dot = warp_sum(dot); ne = warp_sum(ne); nr = warp_sum(nr);
+    cosv = __fdiv_rn(dot, __fmul_rn(__fsqrt_rn(nr), __fsqrt_rn(ne)));
+  }
+  if (lane != 0) return;
   const ItemState is = item[it];
   const int s0 = item_first_seg[it], n = item_first_seg[it + 1] - s0;
   rho_record r;
   r.start = 0; r.end = 0; r.dc = 0.f;
   if (n > 0) { const SegState st = seg[s0]; r.start = st.start; r.end = st.end; r.dc = st.dc; }
-  r.out_len = is.out_len; r.flags = is.flags; r.cosine = 0.f; r.n_segments = n;
+  r.out_len = is.out_len; r.flags = is.flags; r.cosine = cosv; r.n_segments = n;
   decay_decide(is.s_first, is.s_last, is.out_len, decay_thr, &r.first_rms, &r.last_rms, &r.decay_ratio, &r.ok);
   rec[it] = r;
 }
@@ -577,12 +606,16 @@ cudaError_t launch_trim_scan(const float* x, const int64_t* off, const int32_t* 
 cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* seg_len, int n_seg, int64_t max_seg_len,
                         const int32_t* item_first_seg, int n_items, int64_t max_item_len,
                         const Derived& d, float* y, const int64_t* y_off, rho_record* rec, rho_seg_info* seg_info,
-                        const Workspace& ws, cudaStream_t st, LaunchCtx* lc, int stages) {
+                        const Workspace& ws, cudaStream_t st, LaunchCtx* lc, int stages,
+                        const float* emb, const float* ref_emb, int emb_dim) {
   if (n_items <= 0) return cudaSuccess;
   cudaError_t e = cudaSuccess;
   if (stages & JOIN_PREPARE) {
     lc->begin(KID_INIT, st);
-    k_init_items<<<(n_items + 255) / 256, 256, 0, st>>>(ws.seg, ws.item, item_first_seg, n_items); lc->end(st);
+    k_init_items<<<(n_items + 255) / 256, 256, 0, st>>>(ws.seg, ws.item, item_first_seg, n_items,
+                                                        (stages & JOIN_INIT_FEATURES) ? ws.clip_max : nullptr,
+                                                        (stages & JOIN_INIT_FEATURES) ? ws.tiles_done : nullptr);
+    lc->end(st);
     if (n_seg > 0) {
       e = launch_scan(x, seg_off, seg_len, n_seg, max_seg_len, d, ws, st, lc);
       if (e != cudaSuccess) return e;
@@ -609,7 +642,8 @@ cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* s
   (void)max_item_len;
   if (stages & JOIN_FINISH) {
     lc->begin(KID_FINALIZE_ITEMS, st);
-    k_finalize_items<<<(n_items + 255) / 256, 256, 0, st>>>(ws.seg, ws.item, item_first_seg, n_items, d.decay_thr, rec);
+    k_finalize_items<<<(n_items * 32 + 255) / 256, 256, 0, st>>>(ws.seg, ws.item, item_first_seg, n_items, d.decay_thr,
+                                                            rec, emb, ref_emb, emb_dim);
     lc->end(st);
   }
   return cudaGetLastError();

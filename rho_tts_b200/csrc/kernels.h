@@ -65,14 +65,16 @@ struct LaunchCtx {
 };
 
 // join.cu
-enum { JOIN_PREPARE = 1, JOIN_GATHER = 2, JOIN_FINISH = 4, JOIN_ALL = 7 };   // stages of launch_join
+enum { JOIN_PREPARE = 1, JOIN_GATHER = 2, JOIN_FINISH = 4, JOIN_ALL = 7,     // stages of launch_join
+       JOIN_INIT_FEATURES = 8 };   // with JOIN_PREPARE: also reset the log-mel clip maxima / tile counters
 cudaError_t launch_trim_scan(const float* x, const int64_t* off, const int32_t* len, const uint8_t* trim_flags,
                              int n_seg, int64_t max_len, const Derived& d, const Workspace& ws,
                              rho_seg_info* info, cudaStream_t st, LaunchCtx* lc);
 cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* seg_len, int n_seg, int64_t max_seg_len,
                         const int32_t* item_first_seg, int n_items, int64_t max_item_len,
                         const Derived& d, float* y, const int64_t* y_off, rho_record* rec, rho_seg_info* seg_info,
-                        const Workspace& ws, cudaStream_t st, LaunchCtx* lc, int stages = JOIN_ALL);
+                        const Workspace& ws, cudaStream_t st, LaunchCtx* lc, int stages = JOIN_ALL,
+                        const float* emb = nullptr, const float* ref_emb = nullptr, int emb_dim = 0);
 cudaError_t launch_remove_dc(float* x, int64_t n, float* dc_out, double* scratch, cudaStream_t st, LaunchCtx* lc);
 cudaError_t launch_apply_fades(float* x, int64_t n, int fade, int fade_in, int fade_out, cudaStream_t st, LaunchCtx* lc);
 cudaError_t launch_sound_decay(const float* x, int64_t n, double thr, rho_record* rec, double* scratch,

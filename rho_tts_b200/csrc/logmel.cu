@@ -153,10 +153,13 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
   }
 }
 
-// grid (n clips, row groups); normalises real frames and fills the zero-padding frames.
+// grid (n clips, groups of 8 rows); normalises the frames with signal and fills the zero-padding frames.
+// One 128-bit column piece per thread and pass, all 8 rows of the group: the 8 loads of a piece with signal
+// are issued before the first store (the kernel used to wait for every load: long-scoreboard bound).
+constexpr int NORM_ROWS = 8;
 __global__ void __launch_bounds__(256)
 k_logmel_norm(const int32_t* __restrict__ len16, int n_mels, int pad_frames, float* __restrict__ mel,
-              long long mel_stride, const int* __restrict__ clip_max, int rows_per_cta, int fill_done) {
+              long long mel_stride, const int* __restrict__ clip_max, int fill_done) {
   const int c = blockIdx.x;
   int T, T_real, N, n_valid;
   lm_frame_counts(len16[c], pad_frames, &T, &T_real, &N, &n_valid);
@@ -165,39 +168,46 @@ k_logmel_norm(const int32_t* __restrict__ len16, int n_mels, int pad_frames, flo
   if (fill_done && T > T_real) T = min(T, (T_real + 3) & ~3);
   const float mx = ordered_to_float(clip_max[c]);
   const float floor_v = __fsub_rn(mx, 8.0f);
-  const float fill = __fmul_rn(__fadd_rn(fmaxf(-10.0f, floor_v), 4.0f), 0.25f);
-  float* __restrict__ base = mel + (long long)c * n_mels * mel_stride;
-  const int m0 = blockIdx.y * rows_per_cta;
-  const int m1 = min(n_mels, m0 + rows_per_cta);
+  const float fill = __fmul_rn(__fadd_rn(fmaxf(-10.0f, floor_v), 4.0f), 0.25f);   // x / 4 == x * 0.25 bit for bit
+  auto nrm = [&](float v) { return __fmul_rn(__fadd_rn(fmaxf(v, floor_v), 4.0f), 0.25f); };
+  const int m0 = blockIdx.y * NORM_ROWS;
+  const int rows = min(NORM_ROWS, n_mels - m0);
+  float* __restrict__ base = mel + ((long long)c * n_mels + m0) * mel_stride;
   const bool vec = (mel_stride % 4 == 0) && ((((uintptr_t)base) & 15u) == 0);
-  for (int m = m0; m < m1; ++m) {
-    float* __restrict__ row = base + (long long)m * mel_stride;
-    if (vec) {
-      const int T4 = T & ~3;
-      for (int t = 4 * threadIdx.x; t < T4; t += 4 * 256) {
-        float4 v;
-        if (t + 3 < T_real) {
-          v = *reinterpret_cast<const float4*>(row + t);
-          v.x = __fmul_rn(__fadd_rn(fmaxf(v.x, floor_v), 4.0f), 0.25f);
-          v.y = __fmul_rn(__fadd_rn(fmaxf(v.y, floor_v), 4.0f), 0.25f);
-          v.z = __fmul_rn(__fadd_rn(fmaxf(v.z, floor_v), 4.0f), 0.25f);
-          v.w = __fmul_rn(__fadd_rn(fmaxf(v.w, floor_v), 4.0f), 0.25f);
-        } else if (t >= T_real) {
-          v = make_float4(fill, fill, fill, fill);
-        } else {
-          float e[4];
+  if (vec) {
+    const int T4 = T >> 2;
+    for (int cp = threadIdx.x; cp < T4; cp += 256) {
+      const int t = 4 * cp;
+      float* col = base + t;
+      if (t >= T_real) {
+        const float4 f4 = make_float4(fill, fill, fill, fill);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            e[k] = (t + k < T_real) ? __fmul_rn(__fadd_rn(fmaxf(row[t + k], floor_v), 4.0f), 0.25f) : fill;
-          v = make_float4(e[0], e[1], e[2], e[3]);
-        }
-        stg_stream4(row + t, v);
+        for (int m = 0; m < NORM_ROWS; ++m) if (m < rows) stg_stream4(col + (long long)m * mel_stride, f4);
+      } else {
+        // the piece that straddles T_real takes the same path: its tail is inside the row, just not computed
+        const bool k1 = t + 1 < T_real, k2 = t + 2 < T_real, k3 = t + 3 < T_real;
+        float4 r4[NORM_ROWS];
+#pragma unroll
+        for (int m = 0; m < NORM_ROWS; ++m)
+          if (m < rows) r4[m] = *reinterpret_cast<const float4*>(col + (long long)m * mel_stride);
+#pragma unroll
+        for (int m = 0; m < NORM_ROWS; ++m)
+          if (m < rows)
+            stg_stream4(col + (long long)m * mel_stride,
+                        make_float4(nrm(r4[m].x), k1 ? nrm(r4[m].y) : fill, k2 ? nrm(r4[m].z) : fill,
+                                    k3 ? nrm(r4[m].w) : fill));
       }
-      for (int t = T4 + threadIdx.x; t < T; t += 256)
-        row[t] = (t < T_real) ? __fmul_rn(__fadd_rn(fmaxf(row[t], floor_v), 4.0f), 0.25f) : fill;
-    } else {
-      for (int t = threadIdx.x; t < T; t += 256)
-        row[t] = (t < T_real) ? __fmul_rn(__fadd_rn(fmaxf(row[t], floor_v), 4.0f), 0.25f) : fill;
+    }
+    const int rem = T - 4 * T4;
+    for (int i = threadIdx.x; i < rows * rem; i += 256) {
+      const int m = i / rem, t = 4 * T4 + (i - m * rem);
+      float* row = base + (long long)m * mel_stride;
+      row[t] = (t < T_real) ? nrm(row[t]) : fill;
+    }
+  } else {
+    for (int m = 0; m < rows; ++m) {
+      float* row = base + (long long)m * mel_stride;
+      for (int t = threadIdx.x; t < T; t += 256) row[t] = (t < T_real) ? nrm(row[t]) : fill;
     }
   }
 }
@@ -244,11 +254,9 @@ cudaError_t launch_logmel_norm(const int32_t* len16, int n, int n_mels, int pad_
                                int64_t mel_stride_frames, const int* clip_max, cudaStream_t st, LaunchCtx* lc,
                                bool fill_done) {
   if (n <= 0) return cudaSuccess;
-  const int rows_per_cta = 8;
-  dim3 g2((unsigned)n, (unsigned)((n_mels + rows_per_cta - 1) / rows_per_cta));
+  dim3 g2((unsigned)n, (unsigned)((n_mels + NORM_ROWS - 1) / NORM_ROWS));
   lc->begin(KID_LOGMEL_NORM, st);
-  k_logmel_norm<<<g2, 256, 0, st>>>(len16, n_mels, pad_frames, mel, mel_stride_frames, clip_max, rows_per_cta,
-                                    fill_done ? 1 : 0);
+  k_logmel_norm<<<g2, 256, 0, st>>>(len16, n_mels, pad_frames, mel, mel_stride_frames, clip_max, fill_done ? 1 : 0);
   lc->end(st);
   return cudaGetLastError();
 }
