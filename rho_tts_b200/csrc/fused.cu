@@ -97,7 +97,9 @@ struct alignas(16) FzHalf {
   int last;                         // "this half finished its clip last" broadcast
   int pad;
 };
-static_assert(LM_SLAB_SM <= LM_BF * LM_PS, "the slab must fit in the power buffer");
+static_assert(LM_SLAB_SM <= LM_BF * LM_PS, "the slab must fit in the pw region");
+static_assert(LM_GROUPS * 200 * 2 <= LM_BF * LM_PS, "the spectrum exchange must fit in the pw region");
+static_assert(LM_BF * LM_PS * 4 <= LM_GROUPS * LM_FB * 8, "the power spectra must fit in the fb region");
 static_assert((FZ_SPAN * 4) % 16 == 0, "bulk copy size");
 
 struct FzSmem {
@@ -222,8 +224,10 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     const int t0 = tile_t0 + b * LM_BF;
     if (t0 >= t_cover) break;
     const bool next = (b + 1 < LM_BATCHES) && (t0 + LM_BF < t_cover);
-    if (span_is_bulk(t0)) { mbar_wait(&H.bar, parity); parity ^= 1u; } else { cp_async_wait_all(); }
-    half_sync(half);                                           // also: last batch's mel reads of pw are done
+    // Bulk mode needs no barrier here: every thread waits on the mbarrier itself, and nothing this batch writes
+    // before its first barrier (the slab, in the pw region) is still read by the previous batch (its power
+    // spectra live in the fb region, its partner exchange finished before its last barrier).
+    if (span_is_bulk(t0)) { mbar_wait(&H.bar, parity); parity ^= 1u; } else { cp_async_wait_all(); half_sync(half); }
     const int j0 = 240 * t0 - FZ_LEAD;
     const int own_lo = 240 * t0, own_hi = own_lo + FZ_OWN;
     // interior batch: every sample of the span is plain x - dc, and the owned range lies in ONE decay zone
@@ -382,20 +386,24 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
 #pragma unroll
     for (int n2 = 0; n2 < 20; ++n2) v[n2] = fb[lane * 21 + n2];
     dft20(v);
-    half_sync(half);
     // ---- split the two real spectra and take |.|^2:  A = (Z[k]+conj Z[400-k])/2, B = (Z[k]-conj Z[400-k])/(2i).
     // Bin k = k1 + 20*k2 <= 200 needs Z[400-k] = Z[(20-k1) + 20*(19-k2)]: the upper half (k2 >= 10) of lane
     // 20-k1.  Every lane publishes its upper half, then reads its partner's; lane 0 is its own partner.
+    // The exchange goes through the pw region (the slab in it died at the stage-1 barrier) and the power
+    // spectra go to the fb region (dead once everybody is past the barrier below): no barrier is needed between
+    // stage 2 and the publication, nor between the mel projection and the next batch's FIR.
+    float2* pub = reinterpret_cast<float2*>(H.pw) + g * 200;
 #pragma unroll
-    for (int k2 = 10; k2 < 20; ++k2) fb[lane + 20 * k2] = v[k2];
+    for (int k2 = 10; k2 < 20; ++k2) pub[lane + 20 * (k2 - 10)] = v[k2];
     half_sync(half);
+    float* power = reinterpret_cast<float*>(H.fb);
     {
-      float* pa = H.pw + (2 * g) * LM_PS + lane;
+      float* pa = power + (2 * g) * LM_PS + lane;
       float* pb = pa + LM_PS;
-      const float2* part = fb + (20 - lane);                 // lane 0: index 20 + 20*(19-k2) stays inside fb (unused)
+      const float2* part = pub + (20 - lane);                // lane 0: reads stay inside the pw region (unused)
 #pragma unroll
       for (int k2 = 0; k2 < 10; ++k2) {
-        float2 w = part[20 * (19 - k2)];
+        float2 w = part[20 * (9 - k2)];                      // partner's k2' = 19 - k2, stored at 20 * (k2' - 10)
         if (lane == 0) w = (k2 == 0) ? v[0] : v[20 - k2];
         const float2 z = v[k2];
         const float ar = z.x + w.x, ai = z.y - w.y, br = z.x - w.x, bi = z.y + w.y;
@@ -414,7 +422,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       const int f = tid & 31, part = tid >> 5;
       const int t = t0 + f;
       const bool live = t < T_real;
-      const float* p = H.pw + f * LM_PS;
+      const float* p = power + f * LM_PS;
       float* __restrict__ o = out + t;
       auto emit = [&](int m, float acc) {
         const float ls = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
@@ -425,7 +433,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       };
       if (NM == 80) mel_sparse_80(part, p, emit); else mel_sparse_128(part, p, emit);
     }
-    // the next iteration's first barrier orders these reads before pw is overwritten
+    // the next batch's barrier after its FIR orders these reads before its stage 1 overwrites the fb region
   }
   // ---- per-half reductions: clip max (ordered-int atomicMax), decay sums (double atomics)
   lmax = warp_max(lmax);
