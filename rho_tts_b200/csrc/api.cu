@@ -74,7 +74,7 @@ cudaError_t dev_upload(rho_handle* h, T** dst, const T* src, size_t n) {
 }
 
 struct WsPlan {
-  size_t seg, span, item, block_sum, clip_max, len16, tiles_done, scratch, total;
+  size_t seg, span, item, block_sum, clip_max, len16, tiles_done, work_counter, scratch, total;
   int blocks_per_seg;
 };
 
@@ -90,6 +90,7 @@ WsPlan plan_ws(int n_seg, int n_items, int64_t max_seg_len) {
   w.clip_max = o; o += align_up(sizeof(int) * (size_t)(n_items > 0 ? n_items : 1), 256);
   w.len16 = o; o += align_up(sizeof(int32_t) * (size_t)(n_items > 0 ? n_items : 1), 256);
   w.tiles_done = o; o += align_up(sizeof(int) * (size_t)(n_items > 0 ? n_items : 1), 256);
+  w.work_counter = o; o += 256;
   w.scratch = o; o += 256;
   w.block_sum = o; o += align_up(sizeof(float) * (size_t)(n_seg > 0 ? n_seg : 1) * (size_t)w.blocks_per_seg, 256);
   w.total = o;
@@ -116,6 +117,7 @@ int carve(void* ws, size_t ws_bytes, int n_seg, int n_items, int64_t max_seg_len
   out->clip_max = (int*)(b + w.clip_max);
   out->len16 = (int32_t*)(b + w.len16);
   out->tiles_done = (int*)(b + w.tiles_done);
+  out->work_counter = (int*)(b + w.work_counter);
   out->block_sum = (float*)(b + w.block_sum);
   out->blocks_per_seg = blocks_for(d, max_seg_len);
   if (out->blocks_per_seg > w.blocks_per_seg) return fail(RHO_ERR_WORKSPACE, "internal: block_sum sizing");

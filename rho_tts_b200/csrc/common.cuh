@@ -74,6 +74,7 @@ struct Workspace {
   int* clip_max;        // [n_items] running max of log10(mel) as ordered int
   int32_t* len16;       // [n_items]
   int* tiles_done;      // [n_items] tiles of the fused kernel that finished (last finisher normalises)
+  int* work_counter;    // [1] next unclaimed tile of the persistent fused kernel
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

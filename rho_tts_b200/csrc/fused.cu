@@ -95,7 +95,7 @@ struct alignas(16) FzHalf {
   float redf[LM_THREADS / 32];
   uint64_t bar;                     // mbarrier the TMA copy of the span completes on
   int last;                         // "this half finished its clip last" broadcast
-  int pad;
+  int next_unit;                    // the tile this half works on next (claimed one tile ahead)
 };
 static_assert(LM_SLAB_SM <= LM_BF * LM_PS, "the slab must fit in the pw region");
 static_assert(LM_GROUPS * 200 * 2 <= LM_BF * LM_PS, "the spectrum exchange must fit in the pw region");
@@ -147,7 +147,8 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
                  float* __restrict__ y, const int64_t* __restrict__ y_off, int fade,
                  const float* __restrict__ g_hann, const float2* __restrict__ g_tw, int pad_frames,
                  float* __restrict__ mel, long long mel_stride, int* __restrict__ clip_max,
-                 int32_t* __restrict__ len16_out, int* __restrict__ tiles_done, int tile_pairs, int n_items) {
+                 int32_t* __restrict__ len16_out, int* __restrict__ tiles_done, int* __restrict__ work_counter,
+                 int tile_pairs, int n_items) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FzSmem& S = *reinterpret_cast<FzSmem*>(smem_raw);
   for (int i = threadIdx.x; i < N_FFT; i += FZ_THREADS) {
@@ -158,17 +159,25 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   if (threadIdx.x < FZ_HALVES) { mbar_init(&S.h[threadIdx.x].bar, 1); mbar_fence_init(); }
   __syncthreads();                                   // the only CTA-wide barrier: the halves run independently from here
 
-#if FZ_CLIP_MAJOR
-  const int c = blockIdx.x / tile_pairs;
-  const int pair = blockIdx.x - c * tile_pairs;
-#else
-  const int c = blockIdx.x % n_items;
-  const int pair = blockIdx.x / n_items;
-#endif
   const int half = threadIdx.x / LM_THREADS;
   const int tid = threadIdx.x - half * LM_THREADS;
   FzHalf& H = S.h[half];
+  unsigned parity = 0;                               // phase of H.bar, carried across tiles
 
+  // Persistent CTA: one per SM.  Every half claims its own 128-frame tiles from a global counter (tile-major
+  // order: the short last tiles of the clips come at the end) and runs at its own pace -- a half never waits
+  // for its partner, and no SM is left with one tile more than the others.  The next claim is issued at the
+  // start of a tile and consumed at its end, so the atomic's round trip is never exposed.
+  const int n_units = n_items * tile_pairs * FZ_HALVES;
+  if (tid == 0) H.next_unit = atomicAdd(work_counter, 1);
+  for (;;) {
+  half_sync(half);                                   // the claim written by tid 0 is visible
+  const int u = H.next_unit;
+  half_sync(half);                                   // ... and read by everybody before it is replaced
+  if (u >= n_units) break;
+  if (tid == 0) H.next_unit = atomicAdd(work_counter, 1);
+  const int c = u % n_items;
+  const int tile = u / n_items;
   const int s = item_first_seg[c];
   const SegState st = seg[s];
   const int n = st.end - st.start;                   // samples of y
@@ -176,10 +185,10 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   const int n16 = n > 0 ? (int)((2LL * n + 2) / 3) : 0;
   int T, T_real, N, n_valid;
   lm_frame_counts(n16, pad_frames, &T, &T_real, &N, &n_valid);
-  if (pair == 0 && threadIdx.x == 0) len16_out[c] = n16;
+  if (tile == 0 && tid == 0) len16_out[c] = n16;
   const int t_cover = max(T_real, (n + 239) / 240);  // batches needed for the features AND to write all of y
-  const int tile_t0 = (pair * FZ_HALVES + half) * LM_TILE;
-  if (tile_t0 >= t_cover) return;
+  const int tile_t0 = tile * LM_TILE;
+  if (tile_t0 >= t_cover) continue;
 
   const float* __restrict__ xs = x + seg_off[s] + st.start;
   float* __restrict__ ys = y + y_off[c];
@@ -192,7 +201,6 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   float2* fb = H.fb + g * LM_FB;
   float lmax = -INFINITY;
   float a_first = 0.f, a_last = 0.f;
-  unsigned parity = 0;
 
   // A span that lies inside the clip is ONE bulk copy issued by one thread; spans that stick out
   // (clip edges: zero fill) are staged in 16-byte zero-filling LDGSTS pieces by everybody.
@@ -467,8 +475,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     }
   }
   half_sync(half);
-  if (!H.last || T <= T_real) return;
-  {
+  if (H.last && T > T_real) {
     const float mx = ordered_to_float(__ldcg(&clip_max[c]));
     const float fill = __fmul_rn(__fadd_rn(fmaxf(-10.0f, __fsub_rn(mx, 8.0f)), 4.0f), 0.25f);
     const int t_lo = (T_real + 3) & ~3;              // whole 128-bit pieces from here; [T_real, t_lo) is k_logmel_norm's
@@ -490,6 +497,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
         for (int t = t_lo + tid; t < T; t += LM_THREADS) out[(long long)m * mel_stride + t] = fill;
     }
   }
+  }   // tiles of this half
 }
 
 cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_t* seg_off, const Workspace& ws,
@@ -516,12 +524,19 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
   auto kern = (n_mels == 80) ? k_fused_features<80> : k_fused_features<128>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  if ((uint64_t)n_items * gy > 0x7fffffffull) return cudaErrorInvalidValue;
-  dim3 grid((unsigned)n_items * gy);
+  if ((uint64_t)n_items * gy * FZ_HALVES > 0x7fffffffull) return cudaErrorInvalidValue;
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  }
+  const uint64_t n_work = (uint64_t)n_items * gy;
+  dim3 grid((unsigned)(n_work < (uint64_t)sm_count ? n_work : (uint64_t)sm_count));   // persistent: one CTA per SM
   lc->begin(KID_FUSED, st);
   kern<<<grid, FZ_THREADS, smem, st>>>(x, seg_off, ws.seg, ws.item, item_first_seg, y, y_off, d.fade, tb.hann,
                                        tb.twiddle, pad_frames, mel, mel_stride_frames, ws.clip_max, ws.len16,
-                                       ws.tiles_done, (int)gy, n_items);
+                                       ws.tiles_done, ws.work_counter, (int)gy, n_items);
   lc->end(st);
   return cudaGetLastError();
 }

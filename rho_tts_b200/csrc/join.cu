@@ -16,8 +16,10 @@ namespace rho {
 // ------------------------------------------------------------------ init
 __global__ void k_init_items(SegState* __restrict__ seg, ItemState* __restrict__ item,
                              const int32_t* __restrict__ item_first_seg, int n_items,
-                             int* __restrict__ clip_max, int* __restrict__ tiles_done) {
+                             int* __restrict__ clip_max, int* __restrict__ tiles_done,
+                             int* __restrict__ work_counter) {
   const int it = blockIdx.x * blockDim.x + threadIdx.x;
+  if (it == 0 && work_counter) *work_counter = 0;
   if (it >= n_items) return;
   if (clip_max) clip_max[it] = INT_MIN;                // log-mel running maximum (what k_logmel_init does)
   if (tiles_done) tiles_done[it] = 0;
@@ -614,7 +616,8 @@ cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* s
     lc->begin(KID_INIT, st);
     k_init_items<<<(n_items + 255) / 256, 256, 0, st>>>(ws.seg, ws.item, item_first_seg, n_items,
                                                         (stages & JOIN_INIT_FEATURES) ? ws.clip_max : nullptr,
-                                                        (stages & JOIN_INIT_FEATURES) ? ws.tiles_done : nullptr);
+                                                        (stages & JOIN_INIT_FEATURES) ? ws.tiles_done : nullptr,
+                                                        (stages & JOIN_INIT_FEATURES) ? ws.work_counter : nullptr);
     lc->end(st);
     if (n_seg > 0) {
       e = launch_scan(x, seg_off, seg_len, n_seg, max_seg_len, d, ws, st, lc);
