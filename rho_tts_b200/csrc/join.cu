@@ -353,14 +353,57 @@ __device__ __forceinline__ float fade_gain(int o, int out_len, int fade) {
 }
 
 // grid (n_seg, tiles); each CTA writes GATHER_TILE consecutive samples of one segment's span.
-__global__ void __launch_bounds__(GATHER_THREADS)
+// Slow path of k_gather for the (few) 128-bit pieces that touch a crossfade, a pause, a fade, a span edge or an
+// unaligned segment.  Out of line on purpose: inlined eight times with its four cosf argument reductions it made
+// the kernel 260 KB of code, and the instruction cache (not HBM) was what the interior stream waited for.
+__device__ __noinline__ void gather_edge_piece(int sp_dst, int sp_ov, int sp_body, const float* __restrict__ xc,
+                                               const float* __restrict__ xp, float* __restrict__ yo, int j, int jend,
+                                               float dc, float dcp, bool need_fade, int fade, int out_len, int third,
+                                               float* a_first, float* a_last) {
+  const int o = sp_dst + j;
+  for (int k = 0; k < 4; ++k) {
+    const int jj = j + k;
+    if (jj >= jend) break;
+    float val;
+    if (jj < sp_ov) {               // :497-504 equal-power crossfade
+      const float fo = cosf(linspace32(0.f, RHO_HALF_PI_F, sp_ov, jj));
+      const float fi = cosf(linspace32(RHO_HALF_PI_F, 0.f, sp_ov, jj));
+      const float a = __fmul_rn(__fsub_rn(xp[jj], dcp), fo);
+      const float b = __fmul_rn(__fsub_rn(xc[jj], dc), fi);
+      val = __fadd_rn(a, b);
+    } else if (jj < sp_ov + sp_body) {
+      val = __fsub_rn(xc[jj], dc);
+    } else {
+      val = 0.f;                    // inter-sentence pause
+    }
+    const int oo = o + k;
+    if (need_fade) val = __fmul_rn(val, fade_gain(oo, out_len, fade));
+    yo[jj] = val;
+    if (oo < third) *a_first += val * val;
+    if (oo >= out_len - third) *a_last += val * val;
+  }
+}
+
+#ifndef RHO_GATHER_TILE_MAJOR
+#define RHO_GATHER_TILE_MAJOR 1
+#endif
+#ifndef RHO_GATHER_MINB
+#define RHO_GATHER_MINB 5            // CTAs per SM the register budget is sized for; measured on C3: 4 -> 2.41 ms, 5 -> 2.23, 6 -> 2.22, 8 -> 2.41
+#endif
+__global__ void __launch_bounds__(GATHER_THREADS, RHO_GATHER_MINB)
 k_gather(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const SegState* __restrict__ seg,
          const SegSpan* __restrict__ span, ItemState* __restrict__ item,
-         float* __restrict__ y, const int64_t* __restrict__ y_off, int fade) {
-  const int s = blockIdx.x;
+         float* __restrict__ y, const int64_t* __restrict__ y_off, int fade, int tiles) {
+#if RHO_GATHER_TILE_MAJOR
+  const int s = (int)(blockIdx.x / (unsigned)tiles);                                              // tile index runs fastest
+  const int tile = (int)(blockIdx.x - (unsigned)s * (unsigned)tiles);
+#else
+  const int s = (int)(blockIdx.x % (unsigned)(gridDim.x / (unsigned)tiles));                       // segment runs fastest
+  const int tile = (int)(blockIdx.x / (unsigned)(gridDim.x / (unsigned)tiles));
+#endif
   const SegSpan sp = span[s];
   const int span_len = sp.ov + sp.body + sp.pause;
-  const int jt0 = blockIdx.y * GATHER_TILE;
+  const int jt0 = tile * GATHER_TILE;
   if (jt0 >= span_len) return;
   const int out_len = sp.out_len;
   const int third = out_len / 3;
@@ -377,24 +420,41 @@ k_gather(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const
   constexpr int U = GATHER_CHUNK / (4 * GATHER_THREADS);     // 128-bit pieces per thread and pass
   for (int j0 = jt0; j0 < jt0 + GATHER_TILE && j0 < span_len; j0 += GATHER_CHUNK) {
   const int jend = min(j0 + GATHER_CHUNK, span_len);
-  float4 v[U];
-  bool interior[U];
-  // issue every interior load of this thread before the first use
+  {
+    // Interior pass (the bulk of every segment): plain body samples, no fade, one decay zone, aligned.  A lean
+    // loop -- 8 independent 128-bit loads per thread in flight, no per-piece predicates -- because this stream
+    // is bound by the bytes in flight per SM, not by anything it computes.
+    const int o0 = sp.dst + j0;
+    const bool zone_first = o0 + GATHER_CHUNK <= third, zone_last = o0 >= out_len - third;
+    const bool zone_mid = o0 >= third && o0 + GATHER_CHUNK <= out_len - third;
+    if (aligned && jend - j0 == GATHER_CHUNK && j0 >= sp.ov && j0 + GATHER_CHUNK <= sp.ov + sp.body &&
+        (!need_fade || (o0 >= fade && o0 + GATHER_CHUNK <= out_len - fade)) && (zone_first || zone_last || zone_mid)) {
+      float4 w[U];
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int j = j0 + 4 * (threadIdx.x + u * GATHER_THREADS);
-    const int o = sp.dst + j;
-    interior[u] = aligned && j + 3 < jend && j >= sp.ov && j + 3 < sp.ov + sp.body &&
-                  (!need_fade || (o >= fade && o + 3 < out_len - fade));
-    if (interior[u]) v[u] = ldg_stream4(xc + j);
+      for (int u = 0; u < U; ++u) w[u] = ldg_stream4(xc + j0 + 4 * (threadIdx.x + u * GATHER_THREADS));
+      float ss = 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        w[u].x = __fsub_rn(w[u].x, dc); w[u].y = __fsub_rn(w[u].y, dc);
+        w[u].z = __fsub_rn(w[u].z, dc); w[u].w = __fsub_rn(w[u].w, dc);
+        stg_stream4(yo + j0 + 4 * (threadIdx.x + u * GATHER_THREADS), w[u]);
+        ss += w[u].x * w[u].x + w[u].y * w[u].y + w[u].z * w[u].z + w[u].w * w[u].w;
+      }
+      if (zone_first) a_first += ss;
+      if (zone_last) a_last += ss;
+      continue;
+    }
   }
-#pragma unroll
+  // Generic pass (span edges, crossfades, pauses, fades, decay-zone boundaries, unaligned segments): piece by
+  // piece, no batching -- it runs on a few passes per segment only.
   for (int u = 0; u < U; ++u) {
     const int j = j0 + 4 * (threadIdx.x + u * GATHER_THREADS);
-    if (j >= jend) continue;
+    if (j >= jend) break;
     const int o = sp.dst + j;
-    if (interior[u]) {
-      float4 w = v[u];
+    const bool interior = aligned && j + 3 < jend && j >= sp.ov && j + 3 < sp.ov + sp.body &&
+                          (!need_fade || (o >= fade && o + 3 < out_len - fade));
+    if (interior) {
+      float4 w = ldg_stream4(xc + j);
       w.x = __fsub_rn(w.x, dc); w.y = __fsub_rn(w.y, dc); w.z = __fsub_rn(w.z, dc); w.w = __fsub_rn(w.w, dc);
       stg_stream4(yo + j, w);
       if (o < third || o + 3 >= out_len - third) {
@@ -406,28 +466,8 @@ k_gather(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const
         }
       }
     } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int jj = j + k;
-        if (jj >= jend) break;
-        float val;
-        if (jj < sp.ov) {               // :497-504 equal-power crossfade
-          const float fo = cosf(linspace32(0.f, RHO_HALF_PI_F, sp.ov, jj));
-          const float fi = cosf(linspace32(RHO_HALF_PI_F, 0.f, sp.ov, jj));
-          const float a = __fmul_rn(__fsub_rn(xp[jj], dcp), fo);
-          const float b = __fmul_rn(__fsub_rn(xc[jj], dc), fi);
-          val = __fadd_rn(a, b);
-        } else if (jj < sp.ov + sp.body) {
-          val = __fsub_rn(xc[jj], dc);
-        } else {
-          val = 0.f;                    // inter-sentence pause
-        }
-        const int oo = o + k;
-        if (need_fade) val = __fmul_rn(val, fade_gain(oo, out_len, fade));
-        yo[jj] = val;
-        if (oo < third) a_first += val * val;
-        if (oo >= out_len - third) a_last += val * val;
-      }
+      gather_edge_piece(sp.dst, sp.ov, sp.body, xc, xp, yo, j, jend, dc, dcp, need_fade, fade, out_len, third,
+                        &a_first, &a_last);
     }
   }
   }
@@ -637,9 +677,11 @@ cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* s
     // a segment's span is at most its own length plus one pause
     const int64_t max_span = max_seg_len + d.pause;
     const unsigned tiles = (unsigned)((max_span + GATHER_TILE - 1) / GATHER_TILE);
-    dim3 grid((unsigned)n_seg, tiles ? tiles : 1u);
+    const unsigned tl = tiles ? tiles : 1u;
+    if ((uint64_t)n_seg * tl > 0x7fffffffull) return cudaErrorInvalidValue;
     lc->begin(KID_GATHER, st);
-    k_gather<<<grid, GATHER_THREADS, 0, st>>>(x, seg_off, ws.seg, ws.span, ws.item, y, y_off, d.fade);
+    k_gather<<<(unsigned)n_seg * tl, GATHER_THREADS, 0, st>>>(x, seg_off, ws.seg, ws.span, ws.item, y, y_off, d.fade,
+                                                              (int)tl);
     lc->end(st);
   }
   (void)max_item_len;

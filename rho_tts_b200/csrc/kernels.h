@@ -9,11 +9,14 @@ namespace rho {
 #define RHO_SCAN_FR 64               // measured on B200: 64 -> 0.207 ms, 128 -> 0.210 ms, 256 -> 0.304 ms (C2 scan)
 #endif
 #ifndef RHO_GATHER_CHUNKS
-#define RHO_GATHER_CHUNKS 2          // measured on C3: 1 -> 2.76 ms, 2 -> 2.62 ms, 4 -> 3.26 ms
+#define RHO_GATHER_CHUNKS 1          // passes per gather CTA
 #endif
 constexpr int SCAN_FR = RHO_SCAN_FR;  // energy frames (= threads) per scan CTA
 constexpr int GATHER_THREADS = 256;
-constexpr int GATHER_CHUNK = 4096;    // output samples per pass of a gather CTA (4 x 128-bit pieces per thread in flight)
+#ifndef RHO_GATHER_CHUNK
+#define RHO_GATHER_CHUNK 8192
+#endif
+constexpr int GATHER_CHUNK = RHO_GATHER_CHUNK;   // output samples per pass of a gather CTA (8 x 128-bit pieces per thread in flight)
 constexpr int GATHER_TILE = GATHER_CHUNK * RHO_GATHER_CHUNKS;   // output samples per gather CTA
 
 constexpr int RS_TAPS = 23;           // 24k->16k polyphase kernel length (width 10, orig 3)

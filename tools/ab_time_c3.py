@@ -6,7 +6,7 @@ for lib in libs:
     env = dict(os.environ)
     if lib:
         env["RHO_B200_LIB"] = lib
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_configs.py"), "c3", "c2u", "--steps", "10"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_configs.py"), "c3", "--steps", "10"],
                        env=env, capture_output=True, text=True)
     name = os.path.basename(lib) or "product"
     for ln in r.stdout.strip().splitlines():
