@@ -77,6 +77,16 @@ cudaError_t upload_fused_taps(const float* taps) {
 #ifndef FZ_INLINE_NORM
 #define FZ_INLINE_NORM 0   // 1: the half that finishes a clip last writes the constant fill of its zero-padding frames (measured: k_logmel_norm 0.25 -> 0.13 ms but the fused kernel +0.11 ms, one SM writes ~35 GB/s: no net gain)
 #endif
+#ifndef FZ_TC_MEL
+// 0: mel projection as immediate-weight FFMAs (the bank is 97.5 % zeros)             -> 0.864 ms   <- product
+// 1: on the tensor cores inside this kernel (tcgen05, 3xTF32, filterbank in TMEM)     -> 1.033 ms
+// 2: same with two products, P rounded to TF32 (accuracy 4.2e-5 -> 6.6e-5 vs float64) -> 0.981 ms
+// Both tensor-core variants pass every parity test; they lose because the power spectra have to be re-laid out
+// as hi / lo UMMA operands in shared memory (44 scattered stores per thread and batch instead of 20, plus 80 KB of
+// operand reads by the tensor core) on the resource this kernel is shortest of, and 78 M128 N32 K8 MMAs per
+// 32 frames keep the accumulator busy well into the next batch (profiles/ab_r01_tc_mel.log).
+#define FZ_TC_MEL 0
+#endif
 bool fused_inline_norm() { return FZ_INLINE_NORM != 0; }
 constexpr int FZ_HALVES = 2;
 constexpr int FZ_THREADS = LM_THREADS * FZ_HALVES;          // 640
@@ -87,13 +97,14 @@ constexpr int FZ_DPAIRS = LM_SLAB / 4;                      // 1340 groups of 4 
 
 constexpr int FZ_TWS = 22;                                  // float2 per twiddle row (conflict-free 128-bit reads)
 
-struct alignas(16) FzHalf {
+struct alignas(1024) FzHalf {
+  float2 fb[LM_GROUPS * LM_FB];     // FFT buffers; afterwards the power spectra (FZ_TC_MEL: as UMMA operands, 512-byte atoms)
   float span[FZ_SPAN];
-  float2 fb[LM_GROUPS * LM_FB];
-  float pw[LM_BF * LM_PS];          // 16 kHz slab between FIR and FFT stage 1, power spectra afterwards
+  float pw[LM_BF * LM_PS];          // 16 kHz slab between FIR and FFT stage 1, then the spectrum exchange
   double redd[2][LM_THREADS / 32];
   float redf[LM_THREADS / 32];
   uint64_t bar;                     // mbarrier the TMA copy of the span completes on
+  uint64_t mma_bar;                 // mbarrier the tensor-core mel projection of a batch commits to
   int last;                         // "this half finished its clip last" broadcast
   int next_unit;                    // the tile this half works on next (claimed one tile ahead)
 };
@@ -106,8 +117,95 @@ struct FzSmem {
   FzHalf h[FZ_HALVES];
   float hannT[N_FFT];               // [n2][n1] = hann[20*n1 + n2]: a thread's 20 window values are contiguous
   float2 twT[20 * FZ_TWS];          // [n2][k1] = W400^(n2*k1), row stride 22
+  uint32_t tmem_base;
 };
-static_assert(sizeof(FzSmem) <= 232448, "shared memory budget (227 KB)");
+static_assert(sizeof(FzSmem) + 1024 <= 232448, "shared memory budget (227 KB, incl. the slack to align to 1024)");
+
+// ---- tensor-core mel projection (FZ_TC_MEL) ---------------------------------------------------------------
+// mel[m][f] = sum_k F[m][k] * P[f][k] for the 32 frames of a batch, as tcgen05.mma.kind::tf32 M128 N32 K8:
+//   A = the filterbank (hi | lo, 2 x 208 TMEM columns, rows >= n_mels and bins >= 201 are zero), written once per
+//       CTA with tcgen05.st; the kernel is persistent, so once per SM and launch
+//   B = the batch's power spectra, K-major with the 64-byte swizzle, written by the spectrum-split step straight
+//       into the (dead) FFT buffers as hi (top 19 bits) and lo (remainder): 13 blocks of 16 bins x 32 frames x 64 B
+//   D = 128 x 32 fp32 in TMEM (columns 416 + 32 * half), read back by the first four warps of the half one batch
+//       later (after the next FIR: the MMAs have long retired) -> log10, clip maximum, 128-byte row stores
+// 3xTF32 (Fhi*Phi + Flo*Phi + Fhi*Plo): fp32-class accuracy, < 2e-6 relative (tests/test_gpu_parity.py).
+constexpr int TC_KSTEPS = 26;                                 // 26 x 8 = 208 >= 201 bins
+constexpr int TC_OPERAND_BYTES = 13 * LM_BF * 64;             // 26624 per hi / lo buffer
+constexpr uint32_t TC_COL_WHI = 0, TC_COL_WLO = 208, TC_COL_D = 416, TC_TMEM_COLS = 512;
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(LM_BF >> 3) << 17) | ((128u >> 4) << 24);
+static_assert(2 * TC_OPERAND_BYTES <= LM_GROUPS * LM_FB * 8, "hi + lo operands must fit in the fb region");
+static_assert(LM_BF == 32, "the MMA shape and the epilogue assume 32 frames per batch");
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ float tc_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+__device__ __forceinline__ uint32_t tc_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi,
+                                       uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}"
+               :: "r"(d_tmem), "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(TC_IDESC), "r"(accumulate) : "memory");
+}
+// byte offset of power[frame f][bin k] inside an operand buffer: block of 16 bins, row of 64 B, 16-byte chunks
+// XOR-swizzled with bits [7,9) of the address (= (f >> 1) & 3)
+__device__ __forceinline__ uint32_t tc_off(int f, int k) {
+  return ((uint32_t)(k >> 4) << 11) | ((uint32_t)f << 6) | ((((uint32_t)(k >> 2) ^ (uint32_t)(f >> 1)) & 3u) << 4) |
+         ((uint32_t)(k & 3) << 2);
+}
+
+// Drains the accumulator of the batch that started at frame t0p: the first four warps of the half, one mel row
+// per thread.  Waits for the commit of that batch's MMAs first (they were issued about one FIR ago).
+template <int NM>
+__device__ __noinline__ void fz_tc_epilogue(uint64_t* mma_bar, unsigned parity, uint32_t d_tmem, int tid, int t0p,
+                                            int T_real, float* __restrict__ out, long long mel_stride, float* lmax) {
+  mbar_wait(mma_bar, parity);
+  tc_fence_after();
+  const int q = (threadIdx.x >> 5) & 3;                        // the TMEM lane quarter of this warp
+  const int m = 32 * q + (tid & 31);
+  uint32_t r[32];
+  const uint32_t a = d_tmem + ((uint32_t)(32 * q) << 16);
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[16 * j + 0]), "=r"(r[16 * j + 1]), "=r"(r[16 * j + 2]), "=r"(r[16 * j + 3]),
+                   "=r"(r[16 * j + 4]), "=r"(r[16 * j + 5]), "=r"(r[16 * j + 6]), "=r"(r[16 * j + 7]),
+                   "=r"(r[16 * j + 8]), "=r"(r[16 * j + 9]), "=r"(r[16 * j + 10]), "=r"(r[16 * j + 11]),
+                   "=r"(r[16 * j + 12]), "=r"(r[16 * j + 13]), "=r"(r[16 * j + 14]), "=r"(r[16 * j + 15])
+                 : "r"(a + 16 * j) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  tc_fence_before();
+  if (m >= NM) return;
+  float* __restrict__ row = out + (long long)m * mel_stride + t0p;
+  float mx = *lmax;
+  const bool full = t0p + 32 <= T_real && (mel_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
+  if (full) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 v;
+      v.x = __log2f(fmaxf(__uint_as_float(r[4 * j + 0]), 1e-10f)) * 0.30102999566398120f;
+      v.y = __log2f(fmaxf(__uint_as_float(r[4 * j + 1]), 1e-10f)) * 0.30102999566398120f;
+      v.z = __log2f(fmaxf(__uint_as_float(r[4 * j + 2]), 1e-10f)) * 0.30102999566398120f;
+      v.w = __log2f(fmaxf(__uint_as_float(r[4 * j + 3]), 1e-10f)) * 0.30102999566398120f;
+      mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+      *reinterpret_cast<float4*>(row + 4 * j) = v;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (t0p + j < T_real) {
+        const float ls = __log2f(fmaxf(__uint_as_float(r[j]), 1e-10f)) * 0.30102999566398120f;
+        row[j] = ls;
+        mx = fmaxf(mx, ls);
+      }
+    }
+  }
+  *lmax = mx;
+}
 
 __device__ __forceinline__ void half_sync(int half) {
   asm volatile("bar.sync %0, %1;" :: "r"(half + 1), "r"(LM_THREADS) : "memory");
@@ -148,21 +246,62 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
                  const float* __restrict__ g_hann, const float2* __restrict__ g_tw, int pad_frames,
                  float* __restrict__ mel, long long mel_stride, int* __restrict__ clip_max,
                  int32_t* __restrict__ len16_out, int* __restrict__ tiles_done, int* __restrict__ work_counter,
-                 int tile_pairs, int n_items) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FzSmem& S = *reinterpret_cast<FzSmem*>(smem_raw);
+                 int tile_pairs, int n_items, const float* __restrict__ mel_dense) {
+  extern __shared__ unsigned char smem_raw[];
+  FzSmem& S = *reinterpret_cast<FzSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   for (int i = threadIdx.x; i < N_FFT; i += FZ_THREADS) {
     const int r = i / 20, c20 = i - 20 * r;
     S.hannT[c20 * 20 + r] = g_hann[i];               // transpose: [n2][n1]
     S.twT[r * FZ_TWS + c20] = g_tw[i];               // the table is symmetric in (k1, n2): re-stride only
   }
-  if (threadIdx.x < FZ_HALVES) { mbar_init(&S.h[threadIdx.x].bar, 1); mbar_fence_init(); }
-  __syncthreads();                                   // the only CTA-wide barrier: the halves run independently from here
+  if (threadIdx.x < FZ_HALVES) {
+    mbar_init(&S.h[threadIdx.x].bar, 1); mbar_init(&S.h[threadIdx.x].mma_bar, 1); mbar_fence_init();
+  }
+#if FZ_TC_MEL
+  if (threadIdx.x < 32) {                            // warp 0 allocates all 512 TMEM columns (one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&S.tmem_base)), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = S.tmem_base;
+  if (threadIdx.x < 128) {                           // filterbank -> TMEM: lane = mel row, column = bin, hi | lo
+    const int q = threadIdx.x >> 5, m = threadIdx.x;
+    const uint32_t rowa = tmem + ((uint32_t)(32 * q) << 16);
+    for (int kc = 0; kc < TC_KSTEPS; ++kc) {
+      uint32_t hh[8], ll[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = 8 * kc + j;
+        const float wv = (m < NM && k < N_BINS) ? mel_dense[m * N_BINS + k] : 0.f;
+        const float wh = tc_hi(wv);
+        hh[j] = __float_as_uint(wh);
+        ll[j] = __float_as_uint(tc_hi(wv - wh));
+      }
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                   :: "r"(rowa + TC_COL_WHI + 8 * kc), "r"(hh[0]), "r"(hh[1]), "r"(hh[2]), "r"(hh[3]), "r"(hh[4]), "r"(hh[5]), "r"(hh[6]), "r"(hh[7]) : "memory");
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                   :: "r"(rowa + TC_COL_WLO + 8 * kc), "r"(ll[0]), "r"(ll[1]), "r"(ll[2]), "r"(ll[3]), "r"(ll[4]), "r"(ll[5]), "r"(ll[6]), "r"(ll[7]) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+#endif
+  __syncthreads();                                   // the last CTA-wide barrier before the end: the halves run independently
+#if FZ_TC_MEL
+  tc_fence_after();
+#endif
 
   const int half = threadIdx.x / LM_THREADS;
   const int tid = threadIdx.x - half * LM_THREADS;
   FzHalf& H = S.h[half];
   unsigned parity = 0;                               // phase of H.bar, carried across tiles
+#if FZ_TC_MEL
+  unsigned mma_parity = 0;                           // phase of H.mma_bar the next epilogue waits for
+  const uint32_t d_tmem = tmem + TC_COL_D + (uint32_t)(LM_BF * half);
+  const bool epi_warp = tid < 128 && 32 * ((threadIdx.x >> 5) & 3) < NM;   // first four warps of the half: one TMEM lane quarter each
+#endif
 
   // Persistent CTA: one per SM.  Every half claims its own 128-frame tiles from a global counter (tile-major
   // order: the short last tiles of the clips come at the end) and runs at its own pace -- a half never waits
@@ -201,6 +340,10 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   float2* fb = H.fb + g * LM_FB;
   float lmax = -INFINITY;
   float a_first = 0.f, a_last = 0.f;
+#if FZ_TC_MEL
+  bool pending = false;                              // a batch's mel projection is in flight on the tensor cores
+  int pend_t0 = 0;
+#endif
 
   // A span that lies inside the clip is ONE bulk copy issued by one thread; spans that stick out
   // (clip edges: zero fill) are staged in 16-byte zero-filling LDGSTS pieces by everybody.
@@ -337,6 +480,15 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       }
 #endif
     }
+#if FZ_TC_MEL
+    // the previous batch's mel projection has had a whole FIR to finish: drain it.  The waiting warps also
+    // make sure the tensor core is done reading the fb region before stage 1 below overwrites it.
+    if (pending) {
+      if (epi_warp) fz_tc_epilogue<NM>(&H.mma_bar, mma_parity, d_tmem, tid, pend_t0, T_real, out, mel_stride, &lmax);
+      mma_parity ^= 1u;
+      pending = false;
+    }
+#endif
     half_sync(half);
     // ---- reflect padding of torch.stft(center=True): indices < 0 and >= N mirror the computed ones
     const bool left = w0 < 0, right = (long long)w0 + LM_SLAB > N;
@@ -404,6 +556,69 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
 #pragma unroll
     for (int k2 = 10; k2 < 20; ++k2) pub[lane + 20 * (k2 - 10)] = v[k2];
     half_sync(half);
+#if FZ_TC_MEL
+    {
+      // power spectra as tensor-core operands: hi (top 19 bits) and lo (remainder), K-major, 64-byte swizzle
+      unsigned char* opb = reinterpret_cast<unsigned char*>(H.fb);
+      const int odd = g & 1;                                 // odd groups store frame B first: the two groups a warp
+      const int f0 = 2 * g + odd, f1 = 2 * g + 1 - odd;      // straddles then hit different banks
+      const float2* part = pub + (20 - lane);                // lane 0: reads stay inside the pw region (unused)
+      auto put = [&](int f, int k, float pv) {
+        const uint32_t o = tc_off(f, k);
+#if FZ_TC_MEL == 2
+        // two products (Fhi + Flo) * P with P rounded to nearest TF32: half the operand traffic, 2^-12 per term
+        *reinterpret_cast<float*>(opb + o) = __uint_as_float((__float_as_uint(pv) + 0x1000u) & 0xffffe000u);
+#else
+        const float h = tc_hi(pv);
+        *reinterpret_cast<float*>(opb + o) = h;
+        *reinterpret_cast<float*>(opb + TC_OPERAND_BYTES + o) = pv - h;
+#endif
+      };
+#pragma unroll
+      for (int k2 = 0; k2 < 10; ++k2) {
+        float2 w = part[20 * (9 - k2)];                      // partner's k2' = 19 - k2, stored at 20 * (k2' - 10)
+        if (lane == 0) w = (k2 == 0) ? v[0] : v[20 - k2];
+        const float2 z = v[k2];
+        const float ar = z.x + w.x, ai = z.y - w.y, br = z.x - w.x, bi = z.y + w.y;
+        const float pA = 0.25f * (ar * ar + ai * ai), pB = 0.25f * (br * br + bi * bi);
+        const int k = lane + 20 * k2;
+        put(f0, k, odd ? pB : pA);
+        put(f1, k, odd ? pA : pB);
+      }
+      if (lane == 0) {                                       // k = 200: Z[200] pairs with itself
+        const float2 z = v[10];
+        put(2 * g, 200, z.x * z.x);
+        put(2 * g + 1, 200, z.y * z.y);
+      } else if (lane < 8) {                                 // bins 201..207 pad K to 208: must be finite (x 0)
+        put(2 * g, 200 + lane, 0.f);
+        put(2 * g + 1, 200 + lane, 0.f);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> the tensor core's async reads
+    }
+    half_sync(half);
+    if (tid < 32) {
+      tc_fence_after();
+      if (tc_elect_one()) {
+        const uint32_t b_hi = (smem_u32(H.fb) >> 4) & 0x3FFFu, b_lo = ((smem_u32(H.fb) + TC_OPERAND_BYTES) >> 4) & 0x3FFFu;
+        constexpr uint32_t DLO = 1u << 16;                                   // leading byte offset field (unused: 1)
+        constexpr uint32_t DHI = (512u >> 4) | (1u << 14) | (4u << 29);      // SBO 512 B, version 1, SWIZZLE_64B
+#pragma unroll
+        for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+          const uint32_t off = (uint32_t)(((ks >> 1) * 2048 + (ks & 1) * 32) >> 4);
+          tc_mma(d_tmem, tmem + TC_COL_WHI + 8 * ks, (b_hi + off) | DLO, DHI, ks > 0);
+          tc_mma(d_tmem, tmem + TC_COL_WLO + 8 * ks, (b_hi + off) | DLO, DHI, 1);
+#if FZ_TC_MEL != 2
+          tc_mma(d_tmem, tmem + TC_COL_WHI + 8 * ks, (b_lo + off) | DLO, DHI, 1);
+#endif
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&H.mma_bar)) : "memory");
+      }
+      __syncwarp();
+    }
+    pending = true;
+    pend_t0 = t0;
+    // (the accumulator is drained after the next batch's FIR, or at the end of the tile)
+#else
     float* power = reinterpret_cast<float*>(H.fb);
     {
       float* pa = power + (2 * g) * LM_PS + lane;
@@ -441,8 +656,16 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       };
       if (NM == 80) mel_sparse_80(part, p, emit); else mel_sparse_128(part, p, emit);
     }
+#endif
     // the next batch's barrier after its FIR orders these reads before its stage 1 overwrites the fb region
   }
+#if FZ_TC_MEL
+  if (pending) {                                     // the last batch of the tile
+    if (epi_warp) fz_tc_epilogue<NM>(&H.mma_bar, mma_parity, d_tmem, tid, pend_t0, T_real, out, mel_stride, &lmax);
+    mma_parity ^= 1u;
+    pending = false;
+  }
+#endif
   // ---- per-half reductions: clip max (ordered-int atomicMax), decay sums (double atomics)
   lmax = warp_max(lmax);
   const double df = warp_sum((double)a_first), dl = warp_sum((double)a_last);
@@ -498,6 +721,14 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     }
   }
   }   // tiles of this half
+#if FZ_TC_MEL
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+  }
+#endif
 }
 
 cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_t* seg_off, const Workspace& ws,
@@ -520,7 +751,7 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
   unsigned tiles = (unsigned)((cover + LM_TILE - 1) / LM_TILE);
   if (tiles == 0) tiles = 1;
   const unsigned gy = (tiles + FZ_HALVES - 1) / FZ_HALVES;
-  const size_t smem = sizeof(FzSmem);
+  const size_t smem = sizeof(FzSmem) + 1024;      // slack to align the halves to 1024 bytes (swizzle atoms)
   auto kern = (n_mels == 80) ? k_fused_features<80> : k_fused_features<128>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -536,7 +767,8 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
   lc->begin(KID_FUSED, st);
   kern<<<grid, FZ_THREADS, smem, st>>>(x, seg_off, ws.seg, ws.item, item_first_seg, y, y_off, d.fade, tb.hann,
                                        tb.twiddle, pad_frames, mel, mel_stride_frames, ws.clip_max, ws.len16,
-                                       ws.tiles_done, ws.work_counter, (int)gy, n_items);
+                                       ws.tiles_done, ws.work_counter, (int)gy, n_items,
+                                       tb.mel_dense[n_mels == 80 ? 0 : 1]);
   lc->end(st);
   return cudaGetLastError();
 }
