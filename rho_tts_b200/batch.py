@@ -142,12 +142,14 @@ def logmel_batch(rb16: RaggedBatch, n_mels: int = 80, pad_to_30s: bool = True,
     h = Handle.get(dev)
     n = rb16.n
     T = 3000 if pad_to_30s else max(rb16.max_len // 160, 1)
-    mel = torch.empty((n, n_mels, T), dtype=torch.float32, device=rb16.device)
+    T_alloc = (T + 3) // 4 * 4            # rows 16-byte aligned: the normaliser's 128-bit path
+    mel_buf = torch.empty((n, n_mels, T_alloc), dtype=torch.float32, device=rb16.device)
+    mel = mel_buf[:, :, :T]
     n_frames = torch.zeros(n, dtype=torch.int32, device=rb16.device)
     ws = torch.empty(max(256, 4 * n + 256), dtype=torch.uint8, device=rb16.device)
     lens = rb16.lengths if lengths is None else lengths
     _lib.check(h.lib.rho_b200_logmel(h.ptr, _ptr(rb16.data), _ptr(rb16.offsets), _ptr(lens), n, rb16.max_len,
-                                     int(n_mels), 3000 if pad_to_30s else 0, _ptr(mel), T, _ptr(n_frames),
+                                     int(n_mels), 3000 if pad_to_30s else 0, _ptr(mel_buf), T_alloc, _ptr(n_frames),
                                      _ptr(ws), ws.numel(), _stream(dev)), "logmel")
     return mel, n_frames
 
@@ -243,7 +245,9 @@ class ValidatePlan:
         self.out = RaggedBatch.empty_like_lengths(cap.astype(np.int32), rb.device)
         self.scratch16 = torch.empty_like(self.out.data)
         self.T = 3000 if pad_to_30s else max(((2 * self.max_item_len + 2) // 3) // 160, 1)
-        self.mel = torch.empty((self.n_items, self.n_mels, self.T), dtype=torch.float32, device=rb.device)
+        self.T_alloc = (self.T + 3) // 4 * 4      # rows 16-byte aligned: the normaliser's 128-bit path
+        self.mel_buf = torch.empty((self.n_items, self.n_mels, self.T_alloc), dtype=torch.float32, device=rb.device)
+        self.mel = self.mel_buf[:, :, :self.T]
         self.rec = torch.empty((self.n_items, 48), dtype=torch.uint8, device=rb.device)
         self.d_first = torch.from_numpy(first).to(rb.device)
         self.ws = _workspace(self.h, self.n_seg, self.n_items, self.max_seg_len, rb.device)
@@ -253,7 +257,7 @@ class ValidatePlan:
         _lib.check(h.lib.rho_b200_validate(
             h.ptr, _ptr(rb.data), _ptr(rb.offsets), _ptr(rb.lengths), self.n_seg, self.max_seg_len,
             _ptr(self.d_first), self.n_items, self.max_item_len, ctypes.byref(self.p),
-            _ptr(self.out.data), _ptr(self.out.offsets), self.n_mels, self.pad_frames, _ptr(self.mel), self.T,
+            _ptr(self.out.data), _ptr(self.out.offsets), self.n_mels, self.pad_frames, _ptr(self.mel_buf), self.T_alloc,
             _ptr(emb), _ptr(ref), int(emb.shape[1]) if emb is not None else 0, _ptr(self.rec),
             _ptr(self.scratch16), self.flags, _ptr(self.ws), self.ws.numel(), _stream(self.dev)), "validate")
         return ValidateOutput(self.out, self.mel, self.rec)

@@ -157,7 +157,8 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
 // One 128-bit column piece per thread and pass, all 8 rows of the group: the 8 loads of a piece with signal
 // are issued before the first store (the kernel used to wait for every load: long-scoreboard bound).
 constexpr int NORM_ROWS = 8;
-__global__ void __launch_bounds__(256)
+constexpr int NORM_BATCH = 4;     // rows in flight per thread: 48 registers -> 5 CTAs per SM (8 in flight needed 78 -> 3 CTAs)
+__global__ void __launch_bounds__(256, 5)
 k_logmel_norm(const int32_t* __restrict__ len16, int n_mels, int pad_frames, float* __restrict__ mel,
               long long mel_stride, const int* __restrict__ clip_max, int fill_done) {
   const int c = blockIdx.x;
@@ -186,16 +187,19 @@ k_logmel_norm(const int32_t* __restrict__ len16, int n_mels, int pad_frames, flo
       } else {
         // the piece that straddles T_real takes the same path: its tail is inside the row, just not computed
         const bool k1 = t + 1 < T_real, k2 = t + 2 < T_real, k3 = t + 3 < T_real;
-        float4 r4[NORM_ROWS];
 #pragma unroll
-        for (int m = 0; m < NORM_ROWS; ++m)
-          if (m < rows) r4[m] = *reinterpret_cast<const float4*>(col + (long long)m * mel_stride);
+        for (int mb = 0; mb < NORM_ROWS; mb += NORM_BATCH) {
+          float4 r4[NORM_BATCH];
 #pragma unroll
-        for (int m = 0; m < NORM_ROWS; ++m)
-          if (m < rows)
-            stg_stream4(col + (long long)m * mel_stride,
-                        make_float4(nrm(r4[m].x), k1 ? nrm(r4[m].y) : fill, k2 ? nrm(r4[m].z) : fill,
-                                    k3 ? nrm(r4[m].w) : fill));
+          for (int j = 0; j < NORM_BATCH; ++j)
+            if (mb + j < rows) r4[j] = *reinterpret_cast<const float4*>(col + (long long)(mb + j) * mel_stride);
+#pragma unroll
+          for (int j = 0; j < NORM_BATCH; ++j)
+            if (mb + j < rows)
+              stg_stream4(col + (long long)(mb + j) * mel_stride,
+                          make_float4(nrm(r4[j].x), k1 ? nrm(r4[j].y) : fill, k2 ? nrm(r4[j].z) : fill,
+                                      k3 ? nrm(r4[j].w) : fill));
+        }
       }
     }
     const int rem = T - 4 * T4;

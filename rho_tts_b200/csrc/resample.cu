@@ -8,83 +8,102 @@
 // Reference call sites: base_tts.py:632 and the 16 kHz loaders behind base_tts.py:338 /
 // stt_validator.py:78-107.
 //
-// HBM-bound: 4 B in + 2.67 B out per input sample.  Each CTA stages 3*M+24 input samples in
-// shared memory with 128-bit loads and every thread produces 4 consecutive outputs (2 pairs)
-// with a single 128-bit store; taps sit in __constant__ (warp-uniform operand of the FFMA).
+// HBM-bound: 4 B in + 2.67 B out per input sample.  Each CTA stages the 6144 + 24 input samples of its 4096
+// outputs in shared memory with zero-filling LDGSTS -- all 24 KB in flight at once, no registers (the stream is
+// bound by the bytes in flight per SM) -- and every thread then produces 4 x 4 consecutive outputs, each quad
+// as four packed fp32x2 dot products (39 FFMA2, taps in uniform registers) and one 128-bit store.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace rho {
 
-__constant__ float c_taps[2][RS_TAPS];
+// Taps as float2 pairs for the packed dot products.  With V[k] = (v[2k], v[2k+1]) the four outputs of a quad are
+//   o00 = sum_k V[k] . A0[k]  (k = 0..11)   A0[k] = (k0[2k],   k0[2k+1])
+//   o10 = sum_k V[k] . B0[k]  (k = 1..12)   B0[k] = (k0[2k-3], k0[2k-2])
+//   o01 = sum_k V[k] . A1[k]  (k = 0..11)   A1[k] = (k1[2k],   k1[2k+1])
+//   o11 = sum_k V[k] . B1[k]  (k = 1..12)   B1[k] = (k1[2k-3], k1[2k-2])        (k[p][i] = 0 outside 0..22)
+// All 23 taps of each phase are used, as torchaudio's conv1d does.
+__constant__ float2 c_rA0[13], c_rB0[13], c_rA1[13], c_rB1[13];
 
 cudaError_t upload_resample_taps(const float* taps) {
-  return cudaMemcpyToSymbol(c_taps, taps, sizeof(float) * 2 * RS_TAPS);
+  const float* k0 = taps;
+  const float* k1 = taps + RS_TAPS;
+  auto t0 = [&](int i) { return (i >= 0 && i < RS_TAPS) ? k0[i] : 0.f; };
+  auto t1 = [&](int i) { return (i >= 0 && i < RS_TAPS) ? k1[i] : 0.f; };
+  float2 A0[13], B0[13], A1[13], B1[13];
+  for (int k = 0; k < 13; ++k) {
+    A0[k] = make_float2(t0(2 * k), t0(2 * k + 1));
+    B0[k] = make_float2(t0(2 * k - 3), t0(2 * k - 2));
+    A1[k] = make_float2(t1(2 * k), t1(2 * k + 1));
+    B1[k] = make_float2(t1(2 * k - 3), t1(2 * k - 2));
+  }
+  cudaError_t e;
+  if ((e = cudaMemcpyToSymbol(c_rA0, A0, sizeof(A0))) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(c_rB0, B0, sizeof(B0))) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(c_rA1, A1, sizeof(A1))) != cudaSuccess) return e;
+  return cudaMemcpyToSymbol(c_rB1, B1, sizeof(B1));
 }
 
 constexpr int RSM_THREADS = 256;
-constexpr int RSM_SUB = RSM_THREADS * 2;       // output pairs per sub-tile (2 per thread)
-constexpr int RSM_ITERS = 4;                   // sub-tiles per CTA
-constexpr int RSM_PAIRS = RSM_SUB * RSM_ITERS; // 2048 pairs = 4096 outputs = 6144 inputs per CTA
-constexpr int RSM_SMEM = 3 * RSM_SUB + 32;     // floats staged per sub-tile (halo 12 left, 14+ right)
+constexpr int RSM_QUADS = 4;                                  // output quads per thread
+constexpr int RSM_PAIRS = RSM_THREADS * 2 * RSM_QUADS;        // 2048 pairs = 4096 outputs = 6144 inputs per CTA
+constexpr int RSM_SMEM = 3 * RSM_PAIRS + 32;                  // floats staged per CTA (halo 12 left, 14+ right)
 
 __global__ void __launch_bounds__(RSM_THREADS)
 k_resample3to2(const float* __restrict__ x, const int64_t* __restrict__ off, const char* __restrict__ len_base,
                int len_stride, float* __restrict__ y, const int64_t* __restrict__ y_off, int32_t* __restrict__ y_len) {
-  __shared__ __align__(16) float sm[2][RSM_SMEM];
+  __shared__ __align__(16) float sm[RSM_SMEM];
   const int c = blockIdx.x;
   const int L = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
   const int target = L <= 0 ? 0 : (int)((2LL * L + 2) / 3);     // ceil(2L/3)
   if (blockIdx.y == 0 && threadIdx.x == 0 && y_len) y_len[c] = target;
   const int n_pairs = (target + 1) >> 1;
-  const int tile_m0 = blockIdx.y * RSM_PAIRS;
-  if (tile_m0 >= n_pairs) return;
+  const int m0 = blockIdx.y * RSM_PAIRS;
+  if (m0 >= n_pairs) return;
   const float* __restrict__ xs = x + off[c];
   float* __restrict__ ys = y + y_off[c];
-
-  for (int it = 0; it < RSM_ITERS; ++it) {
-    const int m0 = tile_m0 + it * RSM_SUB;
-    if (m0 >= n_pairs) break;
-    float* s = sm[it & 1];
-    // stage x[a0 .. a0 + 3*SUB + 24), a0 = 3*m0 - 12 (multiple of 4)
-    const long long a0 = 3LL * m0 - 12;
-    for (int q = threadIdx.x; q < RSM_SMEM / 4; q += RSM_THREADS) {
-      const long long g = a0 + 4 * q;
+  // stage x[a0 .. a0 + 3*PAIRS + 32), a0 = 3*m0 - 12 (multiple of 4); bytes outside [0, L) are zero-filled
+  const long long a0 = 3LL * m0 - 12;
+  const bool al = (reinterpret_cast<uintptr_t>(xs) & 15u) == 0;
+  for (int q = threadIdx.x; q < RSM_SMEM / 4; q += RSM_THREADS) {
+    const long long g = a0 + 4 * q;
+    if (al && g >= 0 && g < L) {
+      cp_async16_zfill(sm + 4 * q, xs + g, (L - g >= 4) ? 16 : 4 * (int)(L - g));
+    } else {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (g >= 0 && g + 3 < L) v = ldg_stream4(xs + g);
-      else if (g + 3 >= 0 && g < L) {
-        if (g + 0 >= 0 && g + 0 < L) v.x = xs[g + 0];
-        if (g + 1 >= 0 && g + 1 < L) v.y = xs[g + 1];
-        if (g + 2 >= 0 && g + 2 < L) v.z = xs[g + 2];
-        if (g + 3 >= 0 && g + 3 < L) v.w = xs[g + 3];
-      }
-      *reinterpret_cast<float4*>(s + 4 * q) = v;
+      if (g + 0 >= 0 && g + 0 < L) v.x = xs[g + 0];
+      if (g + 1 >= 0 && g + 1 < L) v.y = xs[g + 1];
+      if (g + 2 >= 0 && g + 2 < L) v.z = xs[g + 2];
+      if (g + 3 >= 0 && g + 3 < L) v.w = xs[g + 3];
+      *reinterpret_cast<float4*>(sm + 4 * q) = v;
     }
-    __syncthreads();   // double-buffered: the next iteration writes the other buffer
-    // thread u -> pairs m0+2u, m0+2u+1; needs s[6u+2 .. 6u+28)
-    const int u = threadIdx.x;
-    float v[26];
-    const float2* sp = reinterpret_cast<const float2*>(s + 6 * u + 2);
+  }
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 13; ++k) { const float2 t = sp[k]; v[2 * k] = t.x; v[2 * k + 1] = t.y; }
-    float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;
-    // taps 0 and 20..22 of phase 0, and 0..2, 21..22 of phase 1, sit on the clamp of the
-    // window (|k| ~ 3e-24): they are included anyway, 46 FMAs per pair.
+  for (int it = 0; it < RSM_QUADS; ++it) {
+    // quad u -> pairs m0+2u, m0+2u+1 -> outputs 4u .. 4u+3 of the tile; needs sm[6u+2 .. 6u+28)
+    const int u = threadIdx.x + it * RSM_THREADS;
+    if (m0 + 2 * u >= n_pairs) break;
+    const float2* sp = reinterpret_cast<const float2*>(sm + 6 * u + 2);
+    float2 V[13];
 #pragma unroll
-    for (int i = 0; i < RS_TAPS; ++i) {
-      o00 = fmaf(v[i], c_taps[0][i], o00);
-      o01 = fmaf(v[i], c_taps[1][i], o01);
-      o10 = fmaf(v[i + 3], c_taps[0][i], o10);
-      o11 = fmaf(v[i + 3], c_taps[1][i], o11);
-    }
+    for (int k = 0; k < 13; ++k) V[k] = sp[k];
+    float2 o00 = make_float2(0.f, 0.f), o10 = o00, o01 = o00, o11 = o00;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { o00 = __ffma2_rn(V[k], c_rA0[k], o00); o01 = __ffma2_rn(V[k], c_rA1[k], o01); }
+#pragma unroll
+    for (int k = 1; k < 13; ++k) { o10 = __ffma2_rn(V[k], c_rB0[k], o10); o11 = __ffma2_rn(V[k], c_rB1[k], o11); }
+    const float r0 = o00.x + o00.y, r1 = o01.x + o01.y, r2 = o10.x + o10.y, r3 = o11.x + o11.y;
     const int o = 2 * (m0 + 2 * u);
     if (o + 3 < target) {
-      stg_stream4(ys + o, make_float4(o00, o01, o10, o11));
+      stg_stream4(ys + o, make_float4(r0, r1, r2, r3));
     } else {
-      if (o + 0 < target) ys[o + 0] = o00;
-      if (o + 1 < target) ys[o + 1] = o01;
-      if (o + 2 < target) ys[o + 2] = o10;
-      if (o + 3 < target) ys[o + 3] = o11;
+      if (o + 0 < target) ys[o + 0] = r0;
+      if (o + 1 < target) ys[o + 1] = r1;
+      if (o + 2 < target) ys[o + 2] = r2;
+      if (o + 3 < target) ys[o + 3] = r3;
     }
   }
 }
