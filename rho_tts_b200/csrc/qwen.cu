@@ -164,6 +164,9 @@ k_qwen_apply(const float* __restrict__ x, const int64_t* __restrict__ off, const
   const int nw = P.n_windows;
   const double window = 2.0 * (double)half;
   const double c0 = 0.5 * window, cl = ((double)nw - 0.5) * window;
+  const long long W = 2LL * half;
+  const long long kt = (t0 >= half) ? (t0 - half) / W : -1;    // segment of the tile's first sample (-1: left of the first centre)
+  const long long b1 = half + (kt + 1) * W;                    // the next window centre
   auto env = [&](long long t) -> float {                                  // float(np.interp(t, centres, knots))
     const double td = (double)t;
     if (td <= c0) return (float)P.knots[0];
@@ -172,9 +175,12 @@ k_qwen_apply(const float* __restrict__ x, const int64_t* __restrict__ off, const
     if (k > nw - 2) k = nw - 2;
     return (float)(P.slopes[k] * (td - ((double)k + 0.5) * window) + P.knots[k]);   // slope * (x - xp[j]) + fp[j]
   };
+  // tanh(z) = 1 - 2 / (exp(2z) + 1) on the SFU (ex2.approx + rcp.approx): absolute error < 3e-7 on outputs bounded
+  // by 1 (libm's tanhf costs ~30 instructions a sample and made this kernel issue-bound); saturates correctly.
   auto tail = [&](float v) -> float {
     v = __fmul_rn(v, g);
-    return __fmul_rn(tanhf(__fdiv_rn(v, 0.95f)), 0.95f);
+    const float e2 = __expf(v * (2.0f / 0.95f));            // exp(2 * (v / 0.95)); the quotient's last ulp is immaterial here
+    return __fmul_rn(1.0f - __fdividef(2.0f, e2 + 1.0f), 0.95f);
   };
   auto fin = [&](float v, long long t) -> float {
     if (mode == 0) return v;
@@ -183,26 +189,43 @@ k_qwen_apply(const float* __restrict__ x, const int64_t* __restrict__ off, const
   };
   const bool al = ((reinterpret_cast<uintptr_t>(xs) | reinterpret_cast<uintptr_t>(ys)) & 15u) == 0;
   const int n4 = al ? (cnt >> 2) : 0;
-  for (int q = threadIdx.x; q < n4; q += QW_THREADS) {
-    float4 v = ldg_stream4(xs + 4 * q);
-    const long long t = t0 + 4 * q;
-    if (mode == 2) {
-      // four consecutive samples almost always share an interpolation segment: one knot / slope fetch
-      const double td = (double)t;
-      int k = (int)((td - c0) / window);
-      if (td > c0 && td + 3.0 < cl && k <= nw - 2 && td + 3.0 < ((double)k + 1.5) * window) {
-        const double sl = P.slopes[k], fk = P.knots[k], u = td - ((double)k + 0.5) * window;
-        v.x = __fmul_rn(v.x, (float)(sl * u + fk));
-        v.y = __fmul_rn(v.y, (float)(sl * (u + 1.0) + fk));
-        v.z = __fmul_rn(v.z, (float)(sl * (u + 2.0) + fk));
-        v.w = __fmul_rn(v.w, (float)(sl * (u + 3.0) + fk));
-      } else {
-        v.x = __fmul_rn(v.x, env(t)); v.y = __fmul_rn(v.y, env(t + 1));
-        v.z = __fmul_rn(v.z, env(t + 2)); v.w = __fmul_rn(v.w, env(t + 3));
-      }
+  // four 128-bit pieces per thread in flight (the stream is bound by the bytes in flight per SM)
+  constexpr int QU = 4;
+  for (int q0 = threadIdx.x; q0 < n4; q0 += QU * QW_THREADS) {
+    float4 vv[QU];
+#pragma unroll
+    for (int u = 0; u < QU; ++u) {
+      const int q = q0 + u * QW_THREADS;
+      if (q < n4) vv[u] = ldg_stream4(xs + 4 * q);
     }
-    if (mode != 0) { v.x = tail(v.x); v.y = tail(v.y); v.z = tail(v.z); v.w = tail(v.w); }
-    stg_stream4(ys + 4 * q, v);
+#pragma unroll
+    for (int u = 0; u < QU; ++u) {
+      const int q = q0 + u * QW_THREADS;
+      if (q >= n4) break;
+      float4 v = vv[u];
+      const long long t = t0 + 4 * q;
+      if (mode == 2) {
+        // four consecutive samples almost always share an interpolation segment, and the tile spans at most two
+        // (kt, kt + 1: found once per CTA, no per-piece division); k = -1 / >= nw-1 are np.interp's clamped ends
+        long long k = -2;
+        if (t + 3 < b1) k = kt; else if (t >= b1 && t + 3 < b1 + W) k = kt + 1;
+        if (k == -1 || (k >= nw - 1 && k != -2)) {
+          const float e = (float)P.knots[k < 0 ? 0 : nw - 1];
+          v.x = __fmul_rn(v.x, e); v.y = __fmul_rn(v.y, e); v.z = __fmul_rn(v.z, e); v.w = __fmul_rn(v.w, e);
+        } else if (k >= 0) {
+          const double sl = P.slopes[k], fk = P.knots[k], u0 = (double)(t - (half + k * W));
+          v.x = __fmul_rn(v.x, (float)(sl * u0 + fk));
+          v.y = __fmul_rn(v.y, (float)(sl * (u0 + 1.0) + fk));
+          v.z = __fmul_rn(v.z, (float)(sl * (u0 + 2.0) + fk));
+          v.w = __fmul_rn(v.w, (float)(sl * (u0 + 3.0) + fk));
+        } else {
+          v.x = __fmul_rn(v.x, env(t)); v.y = __fmul_rn(v.y, env(t + 1));
+          v.z = __fmul_rn(v.z, env(t + 2)); v.w = __fmul_rn(v.w, env(t + 3));
+        }
+      }
+      if (mode != 0) { v.x = tail(v.x); v.y = tail(v.y); v.z = tail(v.z); v.w = tail(v.w); }
+      stg_stream4(ys + 4 * q, v);
+    }
   }
   for (int i = 4 * n4 + threadIdx.x; i < cnt; i += QW_THREADS) ys[i] = fin(xs[i], t0 + i);
 }
