@@ -178,6 +178,18 @@ int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const i
 int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,
                          float* mel, int64_t ld_mel, int64_t frames_per_item, int64_t item_stride, void* stream);
 
+/* --------------------------------------------------------------- any-ratio resample (NEXT-4, speed control) */
+/* torchaudio.functional.resample(x, orig_freq, new_freq) (sinc_interp_hann, width 6, rolloff 0.99; functional.py:1305-1432)
+ * for n clips: what BaseTTS._apply_speed_pitch does for speed != 1 (base_tts.py:631-637: orig = int(sr * speed), new = sr).
+ * Clip s is read at x + off[s] and written at y + y_off[s]; y_len[s] (optional) receives
+ * rho_b200_resample_out_len(len[s], ...) = ceil(new * len / orig) after reduction by the gcd.  The first call with a
+ * new reduced ratio builds its tap table on the host and uploads it (synchronously); later calls only enqueue.
+ * orig_freq == new_freq is refused (torchaudio returns its input; so does the host mirror). */
+int64_t rho_b200_resample_out_len(int64_t len, int orig_freq, int new_freq);
+int rho_b200_resample(rho_handle* h, const float* x, const int64_t* off, const int32_t* len, int len_stride_bytes,
+                      int n, int64_t max_len, int orig_freq, int new_freq, float* y, const int64_t* y_off,
+                      int32_t* y_len, void* stream);
+
 /* --------------------------------------------------------------- Qwen loudness post-process (a9 / NEXT-1) */
 /* QwenTTS._post_process_audio (providers/qwen.py:268-378) for n clips: overall-RMS gate (1e-8, clip copied unchanged),
  * windowed decay correction (2 s windows, gain to the first window's RMS capped at +18 dB, applied only when

@@ -134,6 +134,22 @@ def resample_batch(rb: RaggedBatch, lengths: Optional[torch.Tensor] = None, len_
     return out          # out.lengths (device) now holds ceil(2*len/3)
 
 
+def resample_any_batch(rb: RaggedBatch, orig_freq: int, new_freq: int) -> RaggedBatch:
+    """torchaudio.functional.resample(x, orig_freq, new_freq) per clip, any ratio -- the speed control of
+    BaseTTS._apply_speed_pitch (base_tts.py:631-637)."""
+    dev = _dev_index(rb.data)
+    h = Handle.get(dev)
+    if int(orig_freq) == int(new_freq):
+        return rb
+    cap = np.asarray([int(h.lib.rho_b200_resample_out_len(int(L), int(orig_freq), int(new_freq)))
+                      for L in rb.h_lengths], dtype=np.int32)
+    out = RaggedBatch.empty_like_lengths(cap, rb.device)
+    _lib.check(h.lib.rho_b200_resample(h.ptr, _ptr(rb.data), _ptr(rb.offsets), _ptr(rb.lengths), 4, rb.n, rb.max_len,
+                                       int(orig_freq), int(new_freq), _ptr(out.data), _ptr(out.offsets),
+                                       _ptr(out.lengths), _stream(dev)), "resample")
+    return out
+
+
 def logmel_batch(rb16: RaggedBatch, n_mels: int = 80, pad_to_30s: bool = True,
                  lengths: Optional[torch.Tensor] = None):
     """WhisperFeatureExtractor features.  Returns (mel [n, n_mels, T], n_frames int32 [n]) on the device;

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <map>
 #include <mutex>
 #include "kernels.h"
 
@@ -47,7 +48,7 @@ namespace rho {
 const char* const kKernelNames[KID_COUNT] = {
   "k_init", "k_scan", "k_finalize_segs", "k_plan_items", "k_gather", "k_finalize_items",
   "k_resample3to2", "k_logmel_init", "k_logmel_frames", "k_logmel_norm", "k_cosine", "k_single_clip_helpers",
-  "k_fused_features", "k_mel_gemm", "k_qwen_moments", "k_qwen_plan", "k_qwen_apply"};
+  "k_fused_features", "k_mel_gemm", "k_qwen_moments", "k_qwen_plan", "k_qwen_apply", "k_resample_general"};
 }
 
 struct rho_handle {
@@ -61,6 +62,8 @@ struct rho_handle {
   cudaStream_t s_copy_in, s_compute, s_copy_out;
   bool streams_ok;
   std::mutex mu;
+  // tap tables of rho_b200_resample, one per reduced ratio seen so far: key = (orig << 32) | new
+  std::map<uint64_t, float*> resample_taps;
 };
 
 namespace {
@@ -333,6 +336,50 @@ int rho_b200_resample3to2(rho_handle* h, const float* x, const int64_t* off, con
   cudaError_t e = launch_resample3to2(x, off, len, len_stride_bytes, n, max_len, y, y_off, y_len,
                                       (cudaStream_t)stream, &h->lc);
   return e == cudaSuccess ? RHO_OK : cuda_fail(e, "resample3to2");
+}
+
+static long long gcd_ll(long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; }
+
+int64_t rho_b200_resample_out_len(int64_t len, int orig_freq, int new_freq) {
+  if (len <= 0 || orig_freq <= 0 || new_freq <= 0) return 0;
+  const long long g = gcd_ll(orig_freq, new_freq);
+  const long long o = orig_freq / g, n = new_freq / g;
+  return (int64_t)((n * len + o - 1) / o);
+}
+
+int rho_b200_resample(rho_handle* h, const float* x, const int64_t* off, const int32_t* len, int len_stride_bytes,
+                      int n, int64_t max_len, int orig_freq, int new_freq, float* y, const int64_t* y_off,
+                      int32_t* y_len, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  if (n < 0 || max_len < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (orig_freq <= 0 || new_freq <= 0) return fail(RHO_ERR_INVALID, "sample rates must be positive");
+  if (orig_freq == new_freq) return fail(RHO_ERR_INVALID, "orig_freq == new_freq: torchaudio returns the input unchanged, so does the caller");
+  if (n == 0 || max_len == 0) return RHO_OK;
+  if (!x || !off || !len || !y || !y_off) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  const long long g = gcd_ll(orig_freq, new_freq);
+  const int orig = (int)(orig_freq / g), nw = (int)(new_freq / g);
+  const int width = host_resample_width(orig, nw);
+  const int K = 2 * width + orig;
+  if ((long long)K + orig > 8192) return fail(RHO_ERR_INVALID, "ratio %d:%d needs %d taps per phase: not supported", orig, nw, K);
+  float* taps = nullptr;
+  {
+    // first use of a ratio builds and uploads its tap table (the one place this call allocates)
+    std::lock_guard<std::mutex> lock(h->mu);
+    const uint64_t key = ((uint64_t)(uint32_t)orig << 32) | (uint32_t)nw;
+    auto it = h->resample_taps.find(key);
+    if (it == h->resample_taps.end()) {
+      std::vector<float> t((size_t)nw * K);
+      host_resample_taps_general(orig, nw, t.data());
+      cudaError_t e = dev_upload(h, &taps, t.data(), t.size());
+      if (e != cudaSuccess) return cuda_fail(e, "resample taps");
+      h->resample_taps[key] = taps;
+    } else {
+      taps = it->second;
+    }
+  }
+  cudaError_t e = launch_resample_general(x, off, len, len_stride_bytes, n, max_len, orig, nw, width, taps, y, y_off,
+                                          y_len, (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "resample");
 }
 
 int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const int32_t* len16, int n,

@@ -45,7 +45,7 @@ struct Tables {
 // (rho_b200_profile_*; bench.py uses it for the roofline line).
 enum KernelId {
   KID_INIT = 0, KID_SCAN, KID_FINALIZE_SEGS, KID_PLAN, KID_GATHER, KID_FINALIZE_ITEMS,
-  KID_RESAMPLE, KID_LOGMEL_INIT, KID_LOGMEL_FRAMES, KID_LOGMEL_NORM, KID_COSINE, KID_SINGLE, KID_FUSED, KID_MEL_GEMM, KID_QWEN_MOMENTS, KID_QWEN_PLAN, KID_QWEN_APPLY, KID_COUNT
+  KID_RESAMPLE, KID_LOGMEL_INIT, KID_LOGMEL_FRAMES, KID_LOGMEL_NORM, KID_COSINE, KID_SINGLE, KID_FUSED, KID_MEL_GEMM, KID_QWEN_MOMENTS, KID_QWEN_PLAN, KID_QWEN_APPLY, KID_RESAMPLE_GENERAL, KID_COUNT
 };
 extern const char* const kKernelNames[KID_COUNT];
 
@@ -89,6 +89,10 @@ cudaError_t launch_resample3to2(const float* x, const int64_t* off, const int32_
                                 int n, int64_t max_len, float* y, const int64_t* y_off, int32_t* y_len,
                                 cudaStream_t st, LaunchCtx* lc);
 
+cudaError_t launch_resample_general(const float* x, const int64_t* off, const int32_t* len, int len_stride_bytes,
+                                    int n, int64_t max_len, int orig, int nw, int width, const float* taps,
+                                    float* y, const int64_t* y_off, int32_t* y_len, cudaStream_t st, LaunchCtx* lc);
+
 // logmel.cu
 cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off, const int32_t* len16,
                           int n, int64_t max_len16, int n_mels, int pad_frames, float* mel,
@@ -125,6 +129,8 @@ cudaError_t launch_cosine(const float* emb, const float* ref, int n, int dim, fl
 
 // tables.cpp (host only, no CUDA)
 void host_resample_taps(float* out /* [2][23] */);
+int host_resample_width(int orig, int nw);
+void host_resample_taps_general(int orig, int nw, float* out /* [nw][2*width+orig] */);
 void host_hann(float* out /* [400] */);
 void host_mel_filterbank(int n_mels, float* out /* [n_mels][201] */);
 void host_twiddles(float* out /* [400][2] */);

@@ -108,6 +108,74 @@ k_resample3to2(const float* __restrict__ x, const int64_t* __restrict__ off, con
   }
 }
 
+// ---------------------------------------------------------------------------------------------- any ratio
+// torchaudio.functional.resample(x, orig_freq, new_freq) for a reduced ratio orig:new -- the speed control of
+// BaseTTS._apply_speed_pitch (base_tts.py:631-637: resample(audio, int(sr * speed), sr)).
+//   y[new*m + p] = sum_i xpad[orig*m + i] * k[p][i],  xpad[j] = x[j - width] (0 outside [0, L)),  K = 2*width + orig,
+//   truncated to ceil(new * L / orig) samples.
+// One CTA per M_tile input blocks: the orig*M_tile + K samples it needs are staged in shared memory (zero fill at the
+// clip ends), taps come from L1/L2 (the table is [new][K] fp32, 47 KB for the 103:100 of speed 1.03).
+constexpr int RSG_THREADS = 256;
+constexpr int RSG_SMEM_FLOATS = 8192;                         // staged inputs per CTA (32 KB)
+
+__global__ void __launch_bounds__(RSG_THREADS)
+k_resample_general(const float* __restrict__ x, const int64_t* __restrict__ off, const char* __restrict__ len_base,
+                   int len_stride, float* __restrict__ y, const int64_t* __restrict__ y_off,
+                   int32_t* __restrict__ y_len, int orig, int nw, int width, int K, const float* __restrict__ taps,
+                   int m_tile) {
+  __shared__ float sm[RSG_SMEM_FLOATS];
+  const int c = blockIdx.x;
+  const long long L = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
+  const long long target = L <= 0 ? 0 : ((long long)nw * L + orig - 1) / orig;     // ceil(new * L / orig)
+  if (blockIdx.y == 0 && threadIdx.x == 0 && y_len) y_len[c] = (int32_t)target;
+  const long long n_blocks = (target + nw - 1) / nw;
+  const long long m0 = (long long)blockIdx.y * m_tile;
+  if (m0 >= n_blocks) return;
+  const float* __restrict__ xs = x + off[c];
+  float* __restrict__ ys = y + y_off[c];
+  const int mt = (int)min((long long)m_tile, n_blocks - m0);
+  const int count = orig * (mt - 1) + K;
+  const long long a0 = (long long)orig * m0 - width;
+  for (int i = threadIdx.x; i < count; i += RSG_THREADS) {
+    const long long g = a0 + i;
+    sm[i] = (g >= 0 && g < L) ? xs[g] : 0.f;
+  }
+  __syncthreads();
+  const int n_out = mt * nw;
+  for (int ol = threadIdx.x; ol < n_out; ol += RSG_THREADS) {
+    const int m = ol / nw, p = ol - m * nw;
+    const long long o = (long long)nw * m0 + ol;
+    if (o >= target) continue;
+    const float* __restrict__ s = sm + orig * m;
+    const float* __restrict__ k = taps + (size_t)p * K;
+    float a0f = 0.f, a1f = 0.f;
+    int i = 0;
+    for (; i + 1 < K; i += 2) { a0f = fmaf(s[i], __ldg(k + i), a0f); a1f = fmaf(s[i + 1], __ldg(k + i + 1), a1f); }
+    if (i < K) a0f = fmaf(s[i], __ldg(k + i), a0f);
+    ys[o] = a0f + a1f;
+  }
+}
+
+cudaError_t launch_resample_general(const float* x, const int64_t* off, const int32_t* len, int len_stride_bytes,
+                                    int n, int64_t max_len, int orig, int nw, int width, const float* taps,
+                                    float* y, const int64_t* y_off, int32_t* y_len, cudaStream_t st, LaunchCtx* lc) {
+  if (n <= 0) return cudaSuccess;
+  const int K = 2 * width + orig;
+  if (K + orig > RSG_SMEM_FLOATS) return cudaErrorInvalidValue;
+  const int m_tile = (RSG_SMEM_FLOATS - K) / orig + 1;
+  const int64_t target = ((int64_t)nw * max_len + orig - 1) / orig;
+  const int64_t n_blocks = (target + nw - 1) / nw;
+  unsigned tiles = (unsigned)((n_blocks + m_tile - 1) / m_tile);
+  if (tiles == 0) tiles = 1;
+  if (tiles > 65535u) return cudaErrorInvalidValue;
+  lc->begin(KID_RESAMPLE_GENERAL, st);
+  k_resample_general<<<dim3((unsigned)n, tiles), RSG_THREADS, 0, st>>>(
+      x, off, reinterpret_cast<const char*>(len), len_stride_bytes ? len_stride_bytes : (int)sizeof(int32_t), y, y_off,
+      y_len, orig, nw, width, K, taps, m_tile);
+  lc->end(st);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_resample3to2(const float* x, const int64_t* off, const int32_t* len, int len_stride_bytes,
                                 int n, int64_t max_len, float* y, const int64_t* y_off, int32_t* y_len,
                                 cudaStream_t st, LaunchCtx* lc) {

@@ -34,6 +34,37 @@ void host_resample_taps(float* out) {
   }
 }
 
+// The same for any reduced ratio orig:new (torchaudio/functional/functional.py:1305-1405): width and the
+// [new][2*width + orig] tap table, every step in fp32 as torchaudio does for an fp32 waveform.
+int host_resample_width(int orig, int nw) {
+  const double base = std::min(orig, nw) * 0.99;
+  return (int)std::ceil(6 * orig / base);
+}
+void host_resample_taps_general(int orig, int nw, float* out) {
+  const int lpw = 6;
+  const double base = std::min(orig, nw) * 0.99;
+  const int width = (int)std::ceil(lpw * orig / base);
+  const int K = 2 * width + orig;
+  const float basef = (float)base;
+  const float scale = (float)(base / orig);
+  const float pif = (float)M_PI;
+  for (int p = 0; p < nw; ++p) {
+    const float ph = (float)(-p) / (float)nw;
+    for (int i = 0; i < K; ++i) {
+      const float idx = (float)(i - width) / (float)orig;
+      float t = ph + idx;
+      t = t * basef;
+      t = std::min(std::max(t, (float)-lpw), (float)lpw);
+      const float wa = ((t * pif) / (float)lpw) / 2.0f;
+      const float c = cosf(wa);
+      const float window = c * c;
+      t = t * pif;
+      const float sinc = (t == 0.0f) ? 1.0f : sinf(t) / t;
+      out[(size_t)p * K + i] = sinc * (window * scale);
+    }
+  }
+}
+
 // torch.hann_window(400) (periodic)
 void host_hann(float* out) {
   for (int n = 0; n < N_FFT; ++n) out[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * n / N_FFT));

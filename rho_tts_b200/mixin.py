@@ -157,6 +157,28 @@ class B200AudioMixin:
         generated = self.voice_encoder.embed_utterance(preprocess_wav(wav_np, source_sr=self.sample_rate))
         return self._b200_cosine(self.reference_embedding, generated)
 
+    # ------------------------------------------------------------------ base_tts.py:618-650
+    def _apply_speed_pitch(self, audio: torch.Tensor, speed: float, pitch_semitones: float) -> torch.Tensor:
+        """Speed = torchaudio.functional.resample(audio, int(sr * speed), sr) on the B200 (any ratio).  The pitch
+        shift (torchaudio's phase vocoder) is not part of this path: it is delegated to the class after the
+        mixin in the MRO, i.e. to the reference's own code."""
+        if speed != 1.0:
+            from .batch import resample_any_batch
+            orig = int(self.sample_rate * speed)
+            two_d = audio.dim() == 2
+            flat = self._b200_mono(audio, "_apply_speed_pitch")
+            if orig != self.sample_rate and flat.numel() > 0:
+                dev = self._b200_dev()
+                out = resample_any_batch(RaggedBatch.from_list([flat], dev), orig, self.sample_rate)
+                y = out.clip(0).clone().to(device=audio.device, dtype=audio.dtype)
+                audio = y.unsqueeze(0) if two_d and audio.shape[0] != 1 else y      # (1, L) comes back squeezed (:636-637)
+        if pitch_semitones != 0.0:
+            parent = super()
+            if not hasattr(parent, "_apply_speed_pitch"):
+                raise RuntimeError("rho_tts_b200: pitch shifting is delegated to the provider class, which has no _apply_speed_pitch")
+            audio = parent._apply_speed_pitch(audio, 1.0, pitch_semitones)
+        return audio
+
     def _b200_cosine(self, reference_embedding, generated_embedding) -> np.float32:
         dev = self._b200_dev()
         ref = torch.as_tensor(np.asarray(reference_embedding, dtype=np.float32), device=dev)
