@@ -303,14 +303,17 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
     sum16 = float(len16.sum())
     t_real = np.minimum(PAD_FRAMES, np.maximum(2, (len16 + 200 + 159) // 160))
     sum_mel_real = float(t_real.sum()) * N_MELS
+    fused_fills = bool(R._lib.load().rho_b200_build_flags() & 1)   # who writes the zero-padding frames' constant
+    t_lo = np.minimum(PAD_FRAMES, (t_real + 3) // 4 * 4)
+    fill_bytes = 4.0 * N_MELS * float((PAD_FRAMES - t_lo).sum())
     alg = {
         "k_scan": 4 * sum_in,
         "k_gather": 8 * sum_out,
         "k_resample3to2": 4 * sum_out + 4 * sum16,
         "k_logmel_frames": 4 * sum16 + 4 * sum_mel_real,
-        "k_logmel_norm": 4 * sum_mel_real + 4.0 * N_MELS * PAD_FRAMES * n,
-        # fused apply + resample + log-mel: x[start:end] in, y out, raw log-mel frames out
-        "k_fused_features": 8 * sum_out + 4 * sum_mel_real,
+        "k_logmel_norm": 8 * sum_mel_real if fused_fills else 4 * sum_mel_real + 4.0 * N_MELS * PAD_FRAMES * n,
+        # fused apply + resample + log-mel: x[start:end] in, y out, raw log-mel frames out (+ the padding constant)
+        "k_fused_features": 8 * sum_out + 4 * sum_mel_real + (fill_bytes if fused_fills else 0.0),
     }
     peak, peak_src = load_peaks()
     kernels = {}

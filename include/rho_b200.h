@@ -247,6 +247,9 @@ int64_t rho_b200_launch_count(rho_handle* h);
  * names them.  Returns the number of kernel ids, or a negative status.  Not for timed runs. */
 int rho_b200_profile_begin(rho_handle* h);
 int rho_b200_profile_end(rho_handle* h, double* ms_per_kernel, int64_t* launches_per_kernel, int capacity);
+/* How this build splits work between kernels (affects only which kernel the bench charges which bytes to). */
+#define RHO_BUILD_FUSED_WRITES_FILL 1   /* k_fused_features writes the constant of the zero-padding frames, not k_logmel_norm */
+int rho_b200_build_flags(void);
 const char* rho_b200_kernel_name(int id);
 
 #ifdef __cplusplus

@@ -32,7 +32,7 @@ EXPORTS = (
     "rho_b200_remove_dc", "rho_b200_apply_fades", "rho_b200_sound_decay", "rho_b200_resample3to2",
     "rho_b200_resample_out_len", "rho_b200_resample", "rho_b200_logmel", "rho_b200_mel_project", "rho_b200_qwen_workspace_bytes", "rho_b200_qwen_postprocess",
     "rho_b200_cosine", "rho_b200_validate", "rho_b200_validate_host",
-    "rho_b200_launch_count", "rho_b200_profile_begin", "rho_b200_profile_end", "rho_b200_kernel_name",
+    "rho_b200_build_flags", "rho_b200_launch_count", "rho_b200_profile_begin", "rho_b200_profile_end", "rho_b200_kernel_name",
 )
 
 
@@ -98,6 +98,7 @@ def load():
             "rho_b200_validate": (c_int, [vp, vp, vp, vp, i32, i64, vp, i32, i64, P, vp, vp, c_int, c_int, vp, i64,
                                           vp, vp, c_int, vp, vp, c_uint32, vp, c_size_t, vp]),
             "rho_b200_validate_host": (c_int, [vp, vp, c_int, c_int32, P, vp, c_int, c_int, vp, vp, vp, c_int, vp]),
+            "rho_b200_build_flags": (c_int, []),
             "rho_b200_launch_count": (c_int64, [vp]),
             "rho_b200_profile_begin": (c_int, [vp]),
             "rho_b200_profile_end": (c_int, [vp, POINTER(c_double), POINTER(c_int64), c_int]),

@@ -254,6 +254,8 @@ int rho_b200_profile_end(rho_handle* h, double* ms_per_kernel, int64_t* launches
   return rc == RHO_OK ? KID_COUNT : rc;
 }
 
+int rho_b200_build_flags(void) { return fused_inline_norm() ? RHO_BUILD_FUSED_WRITES_FILL : 0; }
+
 const char* rho_b200_kernel_name(int id) { return (id >= 0 && id < KID_COUNT) ? kKernelNames[id] : ""; }
 
 size_t rho_b200_workspace_bytes(int n_segments, int n_items, int64_t max_seg_len) {

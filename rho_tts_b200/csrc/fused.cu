@@ -75,7 +75,7 @@ cudaError_t upload_fused_taps(const float* taps) {
 #define FZ_FFMA2_FIR 1     // FIR as packed fp32x2 dot products
 #endif
 #ifndef FZ_INLINE_NORM
-#define FZ_INLINE_NORM 0   // 1: the half that finishes a clip last writes the constant fill of its zero-padding frames (measured: k_logmel_norm 0.25 -> 0.13 ms but the fused kernel +0.11 ms, one SM writes ~35 GB/s: no net gain)
+#define FZ_INLINE_NORM 1   // the half that finishes a clip last writes the constant fill of its zero-padding frames at once: k_logmel_norm 0.249 -> 0.113 ms, this kernel 0.866 -> 0.975 ms, step -2 % (0: k_logmel_norm writes the fill; sliced / dedicated-warp variants: profiles/ncu_r01_v7_summary.md)
 #endif
 #ifndef FZ_TC_MEL
 // 0: mel projection as immediate-weight FFMAs (the bank is 97.5 % zeros)             -> 0.864 ms   <- product

@@ -95,7 +95,10 @@ for cfg in args:
         t_real = np.minimum(3000, np.maximum(2, (len16 + 359) // 160)) if pad else len16 // 160
         mel_real = 4.0 * nm * float(t_real.sum())
         mel_full = 4.0 * nm * (3000.0 * n if pad else float(t_real.sum()))
-        alg = {"k_scan": s_in, "k_fused_features": 2 * s_out + mel_real, "k_logmel_norm": mel_real + mel_full}
+        fills = bool(R._lib.load().rho_b200_build_flags() & 1) and pad
+        fill_b = 4.0 * nm * float((3000 - np.minimum(3000, (t_real + 3) // 4 * 4)).sum()) if pad else 0.0
+        alg = {"k_scan": s_in, "k_fused_features": 2 * s_out + mel_real + (fill_b if fills else 0.0),
+               "k_logmel_norm": 2 * mel_real if fills else mel_real + mel_full}
         line(cfg, f"{n} x 10 s clips, post-process + log-mel {nm} ({'30 s pad' if pad else 'unpadded'}) + cosine",
              n * 10.0, ms, prof, alg)
         del x, rb, plan, out
