@@ -226,7 +226,7 @@ int rho_b200_destroy(rho_handle* h) {
   return RHO_OK;
 }
 
-int64_t rho_b200_launch_count(rho_handle* h) { return h ? h->lc.launches : 0; }
+int64_t rho_b200_launch_count(rho_handle* h) { return h ? h->lc.launches.load() : (int64_t)0; }
 
 int rho_b200_profile_begin(rho_handle* h) {
   if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");

@@ -756,12 +756,9 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if ((uint64_t)n_items * gy * FZ_HALVES > 0x7fffffffull) return cudaErrorInvalidValue;
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-    if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-  }
+  int dev = 0, sm_count = 0;                         // per call: a process may drive several devices
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   const uint64_t n_work = (uint64_t)n_items * gy;
   dim3 grid((unsigned)(n_work < (uint64_t)sm_count ? n_work : (uint64_t)sm_count));   // persistent: one CTA per SM
   lc->begin(KID_FUSED, st);

@@ -228,7 +228,17 @@ __global__ void k_finalize_segs(const float* __restrict__ x, const int64_t* __re
     int kb0 = (start + hop - 1) / hop, kb1 = end / hop;
     if (kb1 > blocks_per_seg) kb1 = blocks_per_seg;
     if (kb0 <= kb1) {
-      for (int k = kb0 + lane; k < kb1; k += 32) acc += (double)block_sum[(size_t)s * blocks_per_seg + k];
+      // eight independent loads per lane in flight (one at a time made this a 19 us chain of L2 round trips)
+      const float* __restrict__ bs = block_sum + (size_t)s * blocks_per_seg;
+      int k = kb0 + lane;
+      for (; k + 7 * 32 < kb1; k += 8 * 32) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(bs + k + 32 * j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += (double)v[j];
+      }
+      for (; k < kb1; k += 32) acc += (double)__ldg(bs + k);
       for (int g = start + lane; g < kb0 * hop; g += 32) acc += (double)xs[g];
       for (int g = kb1 * hop + lane; g < end; g += 32) acc += (double)xs[g];
     } else {

@@ -1,5 +1,6 @@
 // Internal launcher declarations shared by the translation units of librho_b200.
 #pragma once
+#include <atomic>
 #include <vector>
 #include "common.cuh"
 
@@ -50,7 +51,7 @@ enum KernelId {
 extern const char* const kKernelNames[KID_COUNT];
 
 struct LaunchCtx {
-  int64_t launches = 0;
+  std::atomic<int64_t> launches{0};   // a handle may be shared by concurrent sessions (ui/state.py:85-87 of the reference)
   bool profiling = false;
   struct Span { int id; cudaEvent_t a, b; };
   std::vector<Span> spans;
