@@ -17,20 +17,25 @@
 
 namespace rho {
 
-struct LmSmem {
-  float slab[LM_SLAB_SM];
-  float2 fb[LM_GROUPS * LM_FB];
-  float pw[LM_BF * LM_PS];
-  float hann[N_FFT];
-  float2 tw[N_FFT];
+constexpr int LM_TWS = 22;                        // float2 per twiddle row (conflict-free 128-bit reads)
+
+struct alignas(16) LmSmem {
+  float2 fb[LM_GROUPS * LM_FB];                   // FFT buffers; afterwards the power spectra of the batch
+  float slab[LM_SLAB_SM];                         // 16 kHz samples of the batch (prefetched under stage 2 / mel)
+  float pw[LM_BF * LM_PS];                        // spectrum exchange between partner lanes
+  float hannT[N_FFT];                             // [n2][n1] = hann[20*n1 + n2]: a thread's 20 window values are contiguous
+  float2 twT[20 * LM_TWS];                        // [n2][k1] = W400^(n2*k1)
   float red[LM_THREADS / 32];
 };
+static_assert(LM_GROUPS * 200 * 2 <= LM_BF * LM_PS, "the spectrum exchange must fit in the pw region");
+static_assert(LM_BF * LM_PS * 4 <= LM_GROUPS * LM_FB * 8, "the power spectra must fit in the fb region");
 
 __global__ void k_logmel_init(int* __restrict__ clip_max, int* __restrict__ tiles_done, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { clip_max[i] = INT_MIN; if (tiles_done) tiles_done[i] = 0; }
 }
 
+// Same FFT / split / mel structure as k_fused_features (fused.cu), fed from a 16 kHz signal in HBM.
 template <int NM>
 __global__ void __launch_bounds__(LM_THREADS, 2)
 k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, const int32_t* __restrict__ len16,
@@ -47,7 +52,11 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
   if (tile_t0 >= T_real) return;
 
   const int tid = threadIdx.x;
-  for (int i = tid; i < N_FFT; i += LM_THREADS) { S.hann[i] = g_hann[i]; S.tw[i] = g_tw[i]; }
+  for (int i = tid; i < N_FFT; i += LM_THREADS) {
+    const int r = i / 20, c20 = i - 20 * r;
+    S.hannT[c20 * 20 + r] = g_hann[i];            // transpose: [n2][n1]
+    S.twT[r * LM_TWS + c20] = g_tw[i];            // the table is symmetric in (k1, n2): re-stride only
+  }
 
   const float* __restrict__ xs = x16 + off[c];
   float* __restrict__ out = mel + (long long)c * n_mels * mel_stride;
@@ -78,7 +87,7 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
     const int t0 = tile_t0 + b * LM_BF;
     if (t0 >= T_real) break;
     cp_async_wait_all();
-    __syncthreads();
+    __syncthreads();                              // slab (and, first time, the tables) visible; last batch's mel reads done
     // ---- FFT stage 1: lane = n2, 20-point DFT over n1 of z[20*n1 + n2], then twiddle W400^(n2*k1)
     float2 v[20];
     {
@@ -86,40 +95,62 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
       // at s + 20*(s/320), and 20*n1+lane crosses a block boundary at n1 = 16 (A) / n1 = 8 (B).
       const float* fa = S.slab + g * LM_SLAB_STRIDE + lane;
       const float* fbm = fa + HOP16;
+      const float4* hq = reinterpret_cast<const float4*>(S.hannT + 20 * lane);
 #pragma unroll
-      for (int n1 = 0; n1 < 20; ++n1) {
-        const float h = S.hann[20 * n1 + lane];
-        v[n1] = make_float2(fa[20 * n1 + (n1 >= 16 ? 20 : 0)] * h, fbm[20 * n1 + (n1 >= 8 ? 20 : 0)] * h);
+      for (int q = 0; q < 5; ++q) {
+        const float4 h4 = hq[q];
+        const float hh[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int n1 = 4 * q + e;
+          v[n1] = __fmul2_rn(make_float2(fa[20 * n1 + (n1 >= 16 ? 20 : 0)], fbm[20 * n1 + (n1 >= 8 ? 20 : 0)]),
+                             make_float2(hh[e], hh[e]));
+        }
       }
     }
     dft20(v);
+    {
+      const float4* tq = reinterpret_cast<const float4*>(S.twT + LM_TWS * lane);
+      fb[lane] = v[0];
 #pragma unroll
-    for (int k1 = 0; k1 < 20; ++k1) fb[k1 * 21 + lane] = (k1 == 0) ? v[0] : cmul(v[k1], S.tw[k1 * 20 + lane]);
+      for (int q = 0; q < 10; ++q) {
+        const float4 t4 = tq[q];                  // twiddles of k1 = 2q, 2q+1
+        if (q > 0) fb[(2 * q) * 21 + lane] = cmul(v[2 * q], make_float2(t4.x, t4.y));
+        fb[(2 * q + 1) * 21 + lane] = cmul(v[2 * q + 1], make_float2(t4.z, t4.w));
+      }
+    }
     __syncthreads();
     // the slab is dead now: prefetch the next batch's samples under stage 2 / power / mel
     if (b + 1 < LM_BATCHES && t0 + LM_BF < T_real) stage_slab(t0 + LM_BF);
-    // ---- FFT stage 2: lane = k1, 20-point DFT over n2 -> Z[k1 + 20*k2]
+    // ---- FFT stage 2: lane = k1, 20-point DFT over n2 -> Z[k1 + 20*k2] in v[k2]
 #pragma unroll
     for (int n2 = 0; n2 < 20; ++n2) v[n2] = fb[lane * 21 + n2];
     dft20(v);
-    __syncthreads();
+    // ---- split the two real spectra and take |.|^2:  A = (Z[k]+conj Z[400-k])/2, B = (Z[k]-conj Z[400-k])/(2i).
+    // Bin k = k1 + 20*k2 <= 200 needs Z[400-k]: the upper half (k2 >= 10) of lane 20-k1.  Every lane publishes its
+    // upper half in the pw region and reads its partner's; the power spectra go to the fb region.
+    float2* pub = reinterpret_cast<float2*>(S.pw) + g * 200;
 #pragma unroll
-    for (int k2 = 0; k2 < 20; ++k2) fb[lane + 20 * k2] = v[k2];
+    for (int k2 = 10; k2 < 20; ++k2) pub[lane + 20 * (k2 - 10)] = v[k2];
     __syncthreads();
-    // ---- split the two real spectra and take |.|^2:  A = (Z[k]+conj Z[400-k])/2, B = (Z[k]-conj Z[400-k])/(2i)
+    float* power = reinterpret_cast<float*>(S.fb);
     {
-      float* pa = S.pw + (2 * g) * LM_PS;
+      float* pa = power + (2 * g) * LM_PS + lane;
       float* pb = pa + LM_PS;
+      const float2* part = pub + (20 - lane);     // lane 0: reads stay inside the pw region (unused)
 #pragma unroll
-      for (int j = 0; j < 11; ++j) {
-        const int k = lane + 20 * j;
-        if (k <= N_FFT / 2) {
-          const float2 z = fb[k];
-          const float2 w = fb[k == 0 ? 0 : N_FFT - k];
-          const float ar = z.x + w.x, ai = z.y - w.y, br = z.x - w.x, bi = z.y + w.y;
-          pa[k] = 0.25f * (ar * ar + ai * ai);
-          pb[k] = 0.25f * (br * br + bi * bi);
-        }
+      for (int k2 = 0; k2 < 10; ++k2) {
+        float2 w = part[20 * (9 - k2)];
+        if (lane == 0) w = (k2 == 0) ? v[0] : v[20 - k2];
+        const float2 z = v[k2];
+        const float ar = z.x + w.x, ai = z.y - w.y, br = z.x - w.x, bi = z.y + w.y;
+        pa[20 * k2] = 0.25f * (ar * ar + ai * ai);
+        pb[20 * k2] = 0.25f * (br * br + bi * bi);
+      }
+      if (lane == 0) {                            // k = 200: Z[200] pairs with itself
+        const float2 z = v[10];
+        pa[200] = z.x * z.x;
+        pb[200] = z.y * z.y;
       }
     }
     __syncthreads();
@@ -130,7 +161,7 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
       const int f = tid & 31, part = tid >> 5;
       const int t = t0 + f;
       const bool live = t < T_real;
-      const float* p = S.pw + f * LM_PS;
+      const float* p = power + f * LM_PS;
       float* __restrict__ o = out + t;
       auto emit = [&](int m, float acc) {
         const float ls = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
@@ -141,7 +172,7 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
       };
       if (NM == 80) mel_sparse_80(part, p, emit); else mel_sparse_128(part, p, emit);
     }
-    // the next batch's first barrier orders these reads before pw/slab are overwritten
+    // the next batch's first barrier orders these reads before stage 1 overwrites the fb region
   }
   lmax = warp_max(lmax);
   if ((tid & 31) == 0) S.red[tid >> 5] = lmax;
