@@ -178,6 +178,15 @@ int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const i
 int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,
                          float* mel, int64_t ld_mel, int64_t frames_per_item, int64_t item_stride, void* stream);
 
+/* --------------------------------------------------------------- batched decay check on finished audio (a5) */
+/* _validate_sound_decay (base_tts.py:297-323) for n clips that are already final, e.g. after the Qwen loudness hook,
+ * which the pipeline runs between the join and the decay check (base_tts.py:911-926).  Rewrites first_rms, last_rms,
+ * decay_ratio and ok of rec[s] (everything else is kept); clip s is y + off[s], length read with len_stride_bytes
+ * like the other entry points.  workspace: 16 bytes per clip, 8-byte aligned. */
+int rho_b200_sound_decay_batch(rho_handle* h, const float* y, const int64_t* off, const int32_t* len,
+                               int len_stride_bytes, int n, int64_t max_len, const rho_params* p, rho_record* rec,
+                               void* workspace, size_t ws_bytes, void* stream);
+
 /* --------------------------------------------------------------- any-ratio resample (NEXT-4, speed control) */
 /* torchaudio.functional.resample(x, orig_freq, new_freq) (sinc_interp_hann, width 6, rolloff 0.99; functional.py:1305-1432)
  * for n clips: what BaseTTS._apply_speed_pitch does for speed != 1 (base_tts.py:631-637: orig = int(sr * speed), new = sr).

@@ -215,6 +215,25 @@ def qwen_post_process_batch(rb: RaggedBatch, sr: int = 24000, lengths: Optional[
     return out
 
 
+def qwen_pipeline_batch(rb: RaggedBatch, item_first_seg: Sequence[int], p: RhoParams, qwen3_sr: int = 24000) -> JoinOutput:
+    """What BaseTTS._run_pipeline does to the segments of every item of a Qwen provider (base_tts.py:911-926):
+    _smooth_segment_join -> QwenTTS._post_process_audio -> _validate_sound_decay ON THE HOOKED AUDIO.
+    Returns the join's output with the audio replaced by the hook's and the decay fields of the records recomputed."""
+    out = join_batch(rb, item_first_seg, p, want_seg_info=False)
+    dev = _dev_index(rb.data)
+    h = Handle.get(dev)
+    n = out.audio.n
+    if n == 0:
+        return out
+    lens = out.records[:, 8:12].contiguous().view(torch.int32).reshape(-1)        # out_len of every item (device)
+    qwen_post_process_batch(out.audio, qwen3_sr, lengths=lens, in_place=True)
+    ws = torch.empty(max(16 * n, 256), dtype=torch.uint8, device=rb.device)
+    _lib.check(h.lib.rho_b200_sound_decay_batch(h.ptr, _ptr(out.audio.data), _ptr(out.audio.offsets), _ptr(lens), 4, n,
+                                                out.audio.max_len, ctypes.byref(p), _ptr(out.records), _ptr(ws),
+                                                ws.numel(), _stream(dev)), "sound_decay_batch")
+    return out
+
+
 def cosine_batch(emb: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
     """dot(ref, e) / (|ref| |e|) per row of emb (base_tts.py:341-344)."""
     dev = _dev_index(emb)

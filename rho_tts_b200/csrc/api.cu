@@ -422,6 +422,23 @@ int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, in
   return e == cudaSuccess ? RHO_OK : cuda_fail(e, "mel_gemm");
 }
 
+int rho_b200_sound_decay_batch(rho_handle* h, const float* y, const int64_t* off, const int32_t* len,
+                               int len_stride_bytes, int n, int64_t max_len, const rho_params* p, rho_record* rec,
+                               void* workspace, size_t ws_bytes, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  int rc = check_params(p); if (rc) return rc;
+  if (n < 0 || max_len < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (n == 0) return RHO_OK;
+  if (!y || !off || !len || !rec) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  const size_t need = 2 * sizeof(double) * (size_t)n;
+  if (!workspace || ws_bytes < need) return fail(RHO_ERR_WORKSPACE, "workspace too small: have %zu, need %zu", ws_bytes, need);
+  if (((uintptr_t)workspace) & 7u) return fail(RHO_ERR_INVALID, "workspace must be 8-byte aligned");
+  const Derived d = derive(*p);
+  cudaError_t e = launch_sound_decay_batch(y, off, len, len_stride_bytes, n, max_len, d.decay_thr, rec,
+                                           (double*)workspace, (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "sound_decay_batch");
+}
+
 size_t rho_b200_qwen_workspace_bytes(int n, int64_t max_len, int sr) { return qwen_workspace_bytes(n, max_len, sr); }
 
 int rho_b200_qwen_postprocess(rho_handle* h, const float* x, const int64_t* off, const int32_t* len,

@@ -594,6 +594,75 @@ __global__ void k_decay_final_single(const double* __restrict__ sums, long long 
   *rec = r;
 }
 
+// ------------------------------------------------------------------ batched decay check on finished audio
+// _validate_sound_decay (base_tts.py:297-323) for n clips that are already final -- e.g. after the Qwen loudness
+// hook, which runs between the join and the decay check (base_tts.py:911-926).  Pass 1: sum y^2 over the first and
+// the last third (16384 samples per CTA, double atomics per clip); pass 2: the decision, written into the records.
+__global__ void __launch_bounds__(256)
+k_decay_sums_batch(const float* __restrict__ y, const int64_t* __restrict__ off, const char* __restrict__ len_base,
+                   int len_stride, double* __restrict__ sums, int tile) {
+  const int c = blockIdx.x;
+  const int n = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
+  const int third = n / 3;
+  const long long t0 = (long long)blockIdx.y * tile;
+  if (third < 1 || t0 >= n) return;
+  // the two thirds are [0, third) and [n - third, n); a tile in the middle has nothing to do
+  const long long t1 = min((long long)n, t0 + tile);
+  if (t0 >= third && t1 <= n - third) return;
+  const float* __restrict__ p = y + off[c];
+  float a = 0.f, b = 0.f;
+  for (long long i = t0 + threadIdx.x; i < t1; i += 256) {
+    const float v = p[i], q = v * v;
+    if (i < third) a += q;
+    if (i >= n - third) b += q;
+  }
+  __shared__ double red[2][8];
+  double da = warp_sum((double)a), db = warp_sum((double)b);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][w] = da; red[1][w] = db; }
+  __syncthreads();
+  if (w == 0) {
+    da = lane < 8 ? red[0][lane] : 0.0; db = lane < 8 ? red[1][lane] : 0.0;
+    da = warp_sum(da); db = warp_sum(db);
+    if (lane == 0) {
+      if (da != 0.0) atomicAdd(&sums[2 * c], da);
+      if (db != 0.0) atomicAdd(&sums[2 * c + 1], db);
+    }
+  }
+}
+
+__global__ void k_decay_final_batch(const double* __restrict__ sums, const char* __restrict__ len_base, int len_stride,
+                                    int n_clips, double thr, rho_record* __restrict__ rec) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_clips) return;
+  const int n = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
+  rho_record r = rec[c];
+  decay_decide(sums[2 * c], sums[2 * c + 1], n, thr, &r.first_rms, &r.last_rms, &r.decay_ratio, &r.ok);
+  rec[c] = r;
+}
+
+cudaError_t launch_sound_decay_batch(const float* y, const int64_t* off, const int32_t* len, int len_stride_bytes,
+                                     int n, int64_t max_len, double thr, rho_record* rec, double* sums,
+                                     cudaStream_t st, LaunchCtx* lc) {
+  if (n <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(sums, 0, 2 * sizeof(double) * (size_t)n, st);
+  if (e != cudaSuccess) return e;
+  const char* lb = reinterpret_cast<const char*>(len);
+  const int ls = len_stride_bytes ? len_stride_bytes : (int)sizeof(int32_t);
+  const int tile = 16384;
+  const unsigned tiles = (unsigned)((max_len + tile - 1) / tile);
+  if (tiles > 0) {
+    if (tiles > 65535u) return cudaErrorInvalidValue;
+    lc->begin(KID_SINGLE, st);
+    k_decay_sums_batch<<<dim3((unsigned)n, tiles), 256, 0, st>>>(y, off, lb, ls, sums, tile);
+    lc->end(st);
+  }
+  lc->begin(KID_SINGLE, st);
+  k_decay_final_batch<<<(n + 127) / 128, 128, 0, st>>>(sums, lb, ls, n, thr, rec);
+  lc->end(st);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ host launchers
 #ifndef RHO_SCAN_DENSE
 #define RHO_SCAN_DENSE 1

@@ -83,6 +83,9 @@ cudaError_t launch_remove_dc(float* x, int64_t n, float* dc_out, double* scratch
 cudaError_t launch_apply_fades(float* x, int64_t n, int fade, int fade_in, int fade_out, cudaStream_t st, LaunchCtx* lc);
 cudaError_t launch_sound_decay(const float* x, int64_t n, double thr, rho_record* rec, double* scratch,
                                cudaStream_t st, LaunchCtx* lc);
+cudaError_t launch_sound_decay_batch(const float* y, const int64_t* off, const int32_t* len, int len_stride_bytes,
+                                     int n, int64_t max_len, double thr, rho_record* rec, double* sums,
+                                     cudaStream_t st, LaunchCtx* lc);
 
 // resample.cu
 cudaError_t upload_resample_taps(const float* taps /* [2][23] */);

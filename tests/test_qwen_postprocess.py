@@ -167,3 +167,32 @@ class TestWindowedNormalizationOnMixin:
         tts.qwen3_sr = 16000                                                             # read at call time
         y16 = tts._post_process_audio(torch.from_numpy(CLIPS[0].copy())).numpy()
         assert_close(y16[keep_index(y16.size)], G["out0_sr16k"], what="mixin sr 16000")
+
+
+@pytest.mark.gpu
+def test_gpu_qwen_pipeline_join_hook_decay(cuda_device):
+    """The Qwen provider's order of operations (base_tts.py:911-926): join -> loudness hook -> decay check on the
+    HOOKED audio, batched, against the oracle chain; the accept / reject decision must be the same."""
+    import oracle
+    import rho_tts_b200 as R
+    from rho_tts_b200 import synth
+    lens = synth.make_ragged_lengths(24, 9, 1.0, 7.0)
+    clips = [c.numpy() for c in synth.make_clips(lens, 21)]
+    first = synth.make_item_partition(24, 5, 1, 4)
+    p = R.make_params()
+    rb = R.RaggedBatch.from_list([torch.from_numpy(c) for c in clips], cuda_device)
+    out = R.qwen_pipeline_batch(rb, first, p, 24000)
+    rec = out.records_host()
+    c = oracle.derive_constants()
+    flips = 0
+    for i in range(len(first) - 1):
+        segs = clips[first[i]:first[i + 1]]
+        j = oracle.smooth_segment_join(segs, c).audio
+        hooked = oq.post_process(j)
+        ratio, ok, fr, lr = oracle.sound_decay(hooked, 0.3)
+        L = int(rec["out_len"][i])
+        assert L == hooked.size
+        assert_close(out.audio.clip(i, L).cpu().numpy(), hooked, what=f"item {i}")
+        assert bool(rec["ok"][i]) == ok and abs(rec["decay_ratio"][i] - ratio) <= 1e-4 * max(1.0, abs(ratio))
+        flips += int(abs(ratio - oracle.sound_decay(j, 0.3)[0]) > 1e-3 * max(1.0, abs(ratio)))
+    assert flips > 0            # the ratio is the hooked audio's, not the joined audio's: the order of operations matters
