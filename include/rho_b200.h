@@ -178,6 +178,21 @@ int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const i
 int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,
                          float* mel, int64_t ld_mel, int64_t frames_per_item, int64_t item_stride, void* stream);
 
+/* --------------------------------------------------------------- pitch shift (NEXT-4, the pitch half) */
+/* The pitch branch of BaseTTS._apply_speed_pitch (base_tts.py:639-648): torchaudio.functional.pitch_shift(audio,
+ * sample_rate, n_steps) = stft(512, hop 128) -> phase_vocoder(rate = 2^(-n_steps / 12)) -> istft(round(L / rate)) ->
+ * resample(int(sample_rate / rate) -> sample_rate) -> crop / zero-pad to L (functional.py:1596-1713, 723-803), for n
+ * clips; y[s] has the length of x[s].  The fp32 reference is sensitive to its own rounding (phase accumulator ~1e6
+ * rad): arange_vec is the lane count of the vectorised torch.arange kernel of the torch build being mirrored (8 for
+ * the 2.11 CPU wheels; 0 = float(rate * j)).  min_len is the caller's statement of the shortest clip: like
+ * torch.stft's reflect padding the call refuses clips of <= 256 samples.  n_steps == 0 is refused (the reference
+ * never makes that call).  Exact mirror of the time steps up to 32768 output frames per clip (~170 s at 24 kHz).
+ * workspace: rho_b200_pitch_workspace_bytes(n, max_len, n_steps), 256-byte aligned. */
+size_t rho_b200_pitch_workspace_bytes(int n, int64_t max_len, double n_steps);
+int rho_b200_pitch_shift(rho_handle* h, const float* x, const int64_t* off, const int32_t* len, int len_stride_bytes,
+                         int n, int64_t min_len, int64_t max_len, int sample_rate, double n_steps, int arange_vec,
+                         float* y, const int64_t* y_off, void* workspace, size_t ws_bytes, void* stream);
+
 /* --------------------------------------------------------------- batched decay check on finished audio (a5) */
 /* _validate_sound_decay (base_tts.py:297-323) for n clips that are already final, e.g. after the Qwen loudness hook,
  * which the pipeline runs between the join and the decay check (base_tts.py:911-926).  Rewrites first_rms, last_rms,

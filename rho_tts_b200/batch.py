@@ -150,6 +150,28 @@ def resample_any_batch(rb: RaggedBatch, orig_freq: int, new_freq: int) -> Ragged
     return out
 
 
+TORCH_ARANGE_LANES = 8      # lanes of the vectorised torch.arange CPU kernel in the torch 2.11 wheels (oracle/pitch.py)
+
+
+def pitch_shift_batch(rb: RaggedBatch, sample_rate: int, n_steps: float,
+                      arange_lanes: int = TORCH_ARANGE_LANES) -> RaggedBatch:
+    """torchaudio.functional.pitch_shift(x, sample_rate, n_steps) per clip (same lengths out) -- the pitch control of
+    BaseTTS._apply_speed_pitch (base_tts.py:639-648).  Clips of <= 256 samples are refused like torch.stft's reflect
+    padding refuses them."""
+    dev = _dev_index(rb.data)
+    h = Handle.get(dev)
+    if float(n_steps) == 0.0 or rb.n == 0:
+        return rb
+    out = RaggedBatch.empty_like_lengths(np.asarray(rb.h_lengths, dtype=np.int32), rb.device)
+    need = int(h.lib.rho_b200_pitch_workspace_bytes(rb.n, rb.max_len, float(n_steps)))
+    ws = torch.empty(max(need, 256), dtype=torch.uint8, device=rb.device)
+    _lib.check(h.lib.rho_b200_pitch_shift(h.ptr, _ptr(rb.data), _ptr(rb.offsets), _ptr(rb.lengths), 4, rb.n,
+                                          int(min(rb.h_lengths)), rb.max_len, int(sample_rate), float(n_steps),
+                                          int(arange_lanes), _ptr(out.data), _ptr(out.offsets), _ptr(ws), ws.numel(),
+                                          _stream(dev)), "pitch_shift")
+    return out
+
+
 def logmel_batch(rb16: RaggedBatch, n_mels: int = 80, pad_to_30s: bool = True,
                  lengths: Optional[torch.Tensor] = None):
     """WhisperFeatureExtractor features.  Returns (mel [n, n_mels, T], n_frames int32 [n]) on the device;

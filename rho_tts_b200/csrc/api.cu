@@ -48,7 +48,8 @@ namespace rho {
 const char* const kKernelNames[KID_COUNT] = {
   "k_init", "k_scan", "k_finalize_segs", "k_plan_items", "k_gather", "k_finalize_items",
   "k_resample3to2", "k_logmel_init", "k_logmel_frames", "k_logmel_norm", "k_cosine", "k_single_clip_helpers",
-  "k_fused_features", "k_mel_gemm", "k_qwen_moments", "k_qwen_plan", "k_qwen_apply", "k_resample_general"};
+  "k_fused_features", "k_mel_gemm", "k_qwen_moments", "k_qwen_plan", "k_qwen_apply", "k_resample_general",
+  "k_pv_stft", "k_pv_phase", "k_pv_cumsum", "k_pv_istft", "k_resample_windowed"};
 }
 
 struct rho_handle {
@@ -64,6 +65,11 @@ struct rho_handle {
   std::mutex mu;
   // tap tables of rho_b200_resample, one per reduced ratio seen so far: key = (orig << 32) | new
   std::map<uint64_t, float*> resample_taps;
+  // rho_b200_pitch_shift: FFT / window / phase-advance tables (built on first use) and windowed tap tables per ratio
+  PitchTables pitch_tb{};
+  bool pitch_tb_ok = false;
+  struct WinTaps { float* taps; int* ilo; };
+  std::map<uint64_t, WinTaps> windowed_taps;
 };
 
 namespace {
@@ -382,6 +388,70 @@ int rho_b200_resample(rho_handle* h, const float* x, const int64_t* off, const i
   cudaError_t e = launch_resample_general(x, off, len, len_stride_bytes, n, max_len, orig, nw, width, taps, y, y_off,
                                           y_len, (cudaStream_t)stream, &h->lc);
   return e == cudaSuccess ? RHO_OK : cuda_fail(e, "resample");
+}
+
+static double pitch_rate(double n_steps) { return std::pow(2.0, -n_steps / 12.0); }     // functional.py:1638
+
+size_t rho_b200_pitch_workspace_bytes(int n, int64_t max_len, double n_steps) {
+  if (n <= 0 || max_len <= 0) return 0;
+  return pitch_plan(n, max_len, pitch_rate(n_steps)).total;
+}
+
+int rho_b200_pitch_shift(rho_handle* h, const float* x, const int64_t* off, const int32_t* len, int len_stride_bytes,
+                         int n, int64_t min_len, int64_t max_len, int sample_rate, double n_steps, int arange_vec,
+                         float* y, const int64_t* y_off, void* workspace, size_t ws_bytes, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  if (n < 0 || max_len < 0 || min_len > max_len) return fail(RHO_ERR_INVALID, "bad sizes");
+  if (sample_rate <= 0) return fail(RHO_ERR_INVALID, "sample_rate must be positive");
+  if (!(std::fabs(n_steps) <= 48.0)) return fail(RHO_ERR_INVALID, "n_steps must be within +-48 semitones, got %g", n_steps);
+  if (n_steps == 0.0) return fail(RHO_ERR_INVALID, "n_steps == 0: the reference skips the call (base_tts.py:639)");
+  if (n == 0) return RHO_OK;
+  // torch.stft(center=True, pad_mode='reflect') refuses clips of <= n_fft / 2 samples
+  if (min_len <= 256) return fail(RHO_ERR_INVALID, "pitch shift needs clips longer than 256 samples (reflect padding of the 512-point STFT), shortest is %lld", (long long)min_len);
+  if (n > 65535) return fail(RHO_ERR_INVALID, "at most 65535 clips per call");
+  if (!x || !off || !len || !y || !y_off) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  const double rate = pitch_rate(n_steps);
+  const PitchPlan pl = pitch_plan(n, max_len, rate);
+  if (!workspace || ws_bytes < pl.total) return fail(RHO_ERR_WORKSPACE, "workspace too small: have %zu, need %zu", ws_bytes, pl.total);
+  if (((uintptr_t)workspace) & 255u) return fail(RHO_ERR_INVALID, "workspace must be 256-byte aligned");
+  const int orig_freq = (int)((double)sample_rate / rate);                     // functional.py:1639
+  if (orig_freq <= 0) return fail(RHO_ERR_INVALID, "int(sample_rate / rate) is not positive");
+  const long long g = gcd_ll(orig_freq, sample_rate);
+  const int orig = (int)(orig_freq / g), nw = (int)(sample_rate / g);
+  const int width = host_resample_width(orig, nw);
+  const int W = 2 * width + 2;
+  rho_handle::WinTaps wt{nullptr, nullptr};
+  {
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!h->pitch_tb_ok) {
+      std::vector<float> w256(512), w512(514), hn(512), pv(257);
+      host_pitch_tables(w256.data(), w512.data(), hn.data(), pv.data());
+      cudaError_t e;
+      if ((e = dev_upload(h, (float**)&h->pitch_tb.w256, w256.data(), w256.size())) != cudaSuccess ||
+          (e = dev_upload(h, (float**)&h->pitch_tb.w512, w512.data(), w512.size())) != cudaSuccess ||
+          (e = dev_upload(h, &h->pitch_tb.hann, hn.data(), hn.size())) != cudaSuccess ||
+          (e = dev_upload(h, &h->pitch_tb.padv, pv.data(), pv.size())) != cudaSuccess)
+        return cuda_fail(e, "pitch tables");
+      h->pitch_tb_ok = true;
+    }
+    const uint64_t key = ((uint64_t)(uint32_t)orig << 32) | (uint32_t)nw;
+    auto it = h->windowed_taps.find(key);
+    if (it == h->windowed_taps.end()) {
+      std::vector<float> t((size_t)nw * W);
+      std::vector<int> lo((size_t)nw);
+      host_resample_taps_windowed(orig, nw, width, W, t.data(), lo.data());
+      cudaError_t e;
+      if ((e = dev_upload(h, &wt.taps, t.data(), t.size())) != cudaSuccess ||
+          (e = dev_upload(h, &wt.ilo, lo.data(), lo.size())) != cudaSuccess)
+        return cuda_fail(e, "windowed resample taps");
+      h->windowed_taps[key] = wt;
+    } else {
+      wt = it->second;
+    }
+  }
+  cudaError_t e = launch_pitch_shift(h->pitch_tb, x, off, len, len_stride_bytes, n, max_len, rate, arange_vec, orig, nw,
+                                     width, W, wt.taps, wt.ilo, y, y_off, workspace, (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "pitch_shift");
 }
 
 int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const int32_t* len16, int n,

@@ -46,7 +46,8 @@ struct Tables {
 // (rho_b200_profile_*; bench.py uses it for the roofline line).
 enum KernelId {
   KID_INIT = 0, KID_SCAN, KID_FINALIZE_SEGS, KID_PLAN, KID_GATHER, KID_FINALIZE_ITEMS,
-  KID_RESAMPLE, KID_LOGMEL_INIT, KID_LOGMEL_FRAMES, KID_LOGMEL_NORM, KID_COSINE, KID_SINGLE, KID_FUSED, KID_MEL_GEMM, KID_QWEN_MOMENTS, KID_QWEN_PLAN, KID_QWEN_APPLY, KID_RESAMPLE_GENERAL, KID_COUNT
+  KID_RESAMPLE, KID_LOGMEL_INIT, KID_LOGMEL_FRAMES, KID_LOGMEL_NORM, KID_COSINE, KID_SINGLE, KID_FUSED, KID_MEL_GEMM, KID_QWEN_MOMENTS, KID_QWEN_PLAN, KID_QWEN_APPLY, KID_RESAMPLE_GENERAL,
+  KID_PV_STFT, KID_PV_PHASE, KID_PV_CUMSUM, KID_PV_ISTFT, KID_PV_RESAMPLE, KID_COUNT
 };
 extern const char* const kKernelNames[KID_COUNT];
 
@@ -127,6 +128,23 @@ cudaError_t launch_qwen_postprocess(const float* x, const int64_t* off, const in
                                     int n, int64_t max_len, int sr, float* y, const int64_t* y_off,
                                     void* workspace, cudaStream_t st, LaunchCtx* lc);
 
+// pitch.cu: torchaudio.functional.pitch_shift (stft 512/128 -> phase vocoder -> istft -> resample -> crop / pad)
+struct PitchTables {
+  float2* w256;    // [256] exp(-2 pi i k / 256)
+  float2* w512;    // [257] exp(-2 pi i k / 512)
+  float* hann;     // [512] torch.hann_window(512)
+  float* padv;     // [257] torch.linspace(0, pi * 128, 257): phase_advance
+};
+struct PitchPlan {
+  int64_t T_max, J_max, LS_max;
+  size_t spec, mag, ph, wave, total;
+};
+PitchPlan pitch_plan(int n, int64_t max_len, double rate);
+cudaError_t launch_pitch_shift(const PitchTables& tb, const float* x, const int64_t* off, const int32_t* len,
+                               int len_stride_bytes, int n, int64_t max_len, double rate, int arange_vec, int orig,
+                               int nw, int width, int W, const float* taps, const int* ilo, float* y,
+                               const int64_t* y_off, void* workspace, cudaStream_t st, LaunchCtx* lc);
+
 // cosine.cu
 cudaError_t launch_cosine(const float* emb, const float* ref, int n, int dim, float* out, int out_stride_bytes,
                           cudaStream_t st, LaunchCtx* lc);
@@ -135,6 +153,8 @@ cudaError_t launch_cosine(const float* emb, const float* ref, int n, int dim, fl
 void host_resample_taps(float* out /* [2][23] */);
 int host_resample_width(int orig, int nw);
 void host_resample_taps_general(int orig, int nw, float* out /* [nw][2*width+orig] */);
+void host_resample_taps_windowed(int orig, int nw, int width, int W, float* taps /* [nw][W] */, int* ilo /* [nw] */);
+void host_pitch_tables(float* w256 /* [256][2] */, float* w512 /* [257][2] */, float* hann512, float* padv /* [257] */);
 void host_hann(float* out /* [400] */);
 void host_mel_filterbank(int n_mels, float* out /* [n_mels][201] */);
 void host_twiddles(float* out /* [400][2] */);

@@ -1,0 +1,376 @@
+// Pitch shift of a ragged batch of clips: the pitch half of BaseTTS._apply_speed_pitch (base_tts.py:639-648), i.e.
+// torchaudio.functional.pitch_shift (functional.py:1596-1641):
+//   stft(512, hop 128, periodic hann, centre, reflect)        k_pv_stft      real FFT as a 256-point complex
+//   phase_vocoder(rate = 2^(-n_steps/12))  (:723-803)         k_pv_phase     wrapped phase increments + magnitudes
+//                                                             k_pv_cumsum    phase accumulator (double, rounded to fp32)
+//   istft(length = round(L / rate))                           k_pv_istft     polar -> inverse FFT -> window -> overlap-add
+//   resample(int(sr / rate) -> sr), crop / zero-pad to L      k_resample_windowed
+//
+// The fp32 reference is sensitive to its own rounding: the phase accumulator reaches ~1e6 rad on the top bins, where
+// one fp32 ulp is 0.06 rad (fp32 pitch_shift differs from the same algorithm in fp64 by 1e-4 .. 5e-4).  So the phase
+// path repeats torch's fp32 operations one by one, in torch's order, with explicitly rounded intrinsics (no FMA
+// contraction): the time steps as the vectorised arange kernel makes them, phase_advance as linspace makes it (table
+// from the host), the wrap as a true division + round-half-even, the accumulator in double rounded to fp32 per element
+// (torch.cumsum on CPU), and the magnitude interpolation as two products and a sum.  oracle/pitch.py documents how
+// each of these was pinned against torch.
+#include <cmath>
+#include "kernels.h"
+
+namespace rho {
+
+constexpr int PV_NFFT = 512;
+constexpr int PV_HOP = 128;
+constexpr int PV_NFREQ = 257;
+constexpr int PV_LD = 264;               // row stride of the spectrogram planes (elements)
+constexpr int PV_STFT_FR = 16;           // frames per CTA of k_pv_stft
+constexpr int PV_OUT_HOPS = 16;          // output hops (of 128 samples) per CTA of k_pv_istft
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// One radix-4 Stockham pass of a 256-point complex FFT held in shared memory; thread t of 64 owns butterfly t.
+// Four passes (Ns = 1, 4, 16, 64) leave the transform in natural order.  INV: conjugate twiddles, +i rotation.
+template <bool INV>
+__device__ __forceinline__ void fft256_pass(const float2* __restrict__ in, float2* __restrict__ out,
+                                            const float2* __restrict__ w256, int t, int Ns) {
+  const int k = t & (Ns - 1);
+  float2 v0 = in[t], v1 = in[t + 64], v2 = in[t + 128], v3 = in[t + 192];
+  if (Ns > 1) {
+    const int s = 64 / Ns;
+    float2 w1 = w256[k * s], w2 = w256[2 * k * s], w3 = w256[3 * k * s];
+    if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+    v1 = cmul(v1, w1); v2 = cmul(v2, w2); v3 = cmul(v3, w3);
+  }
+  const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
+  const float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+  const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
+  const float2 d = make_float2(v1.x - v3.x, v1.y - v3.y);
+  const float2 a3 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);      // d * (+i)  /  d * (-i)
+  const int j0 = ((t - k) << 2) + k;
+  out[j0] = make_float2(a0.x + a2.x, a0.y + a2.y);
+  out[j0 + Ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
+  out[j0 + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
+  out[j0 + 3 * Ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
+}
+
+__device__ __forceinline__ int pv_frames(long long L) { return (int)(1 + L / PV_HOP); }
+__device__ __forceinline__ int pv_out_frames(int T, double rate) { return (int)ceil((double)T / rate); }
+__device__ __forceinline__ long long pv_stretch_len(long long L, double rate) { return (long long)rint((double)L / rate); }
+
+// torch.arange(0, T, rate, dtype=float32)[j] as the CPU range kernel evaluates it (oracle/pitch.py arange_f32)
+__device__ __forceinline__ float pv_time_step(int j, int J, double rate, int vec) {
+  if (vec > 0) {
+    const int full = (J / (2 * vec)) * (2 * vec);
+    if (j < full) {
+      const int j0 = (j / vec) * vec;
+      const float base = (float)__dmul_rn((double)j0, rate);
+      return (float)__dadd_rn((double)base, __dmul_rn((double)(j - j0), rate));
+    }
+  }
+  return (float)__dmul_rn((double)j, rate);
+}
+
+// ------------------------------------------------------------------ STFT
+__global__ void __launch_bounds__(256)
+k_pv_stft(const float* __restrict__ x, const int64_t* __restrict__ off, const char* __restrict__ len_base, int len_stride,
+          const float2* __restrict__ g_w256, const float2* __restrict__ g_w512, const float* __restrict__ g_hann,
+          float2* __restrict__ spec, long long spec_stride) {
+  __shared__ float2 A[4][256], B[4][256];
+  __shared__ float2 w256[256], w512[PV_NFREQ];
+  __shared__ float hann[PV_NFFT];
+  const int c = blockIdx.y;
+  const long long L = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
+  if (L <= PV_NFFT / 2) return;                      // reflect padding needs L > 256 (the host refuses such calls)
+  const int T = pv_frames(L);
+  const int f0 = blockIdx.x * PV_STFT_FR;
+  if (f0 >= T) return;
+  for (int i = threadIdx.x; i < 256; i += 256) w256[i] = g_w256[i];
+  for (int i = threadIdx.x; i < PV_NFREQ; i += 256) w512[i] = g_w512[i];
+  for (int i = threadIdx.x; i < PV_NFFT; i += 256) hann[i] = g_hann[i];
+  __syncthreads();
+  const float* __restrict__ xs = x + off[c];
+  float2* __restrict__ sp = spec + (size_t)c * spec_stride;
+  const int g = threadIdx.x >> 6, t = threadIdx.x & 63;
+  for (int it = 0; it < PV_STFT_FR / 4; ++it) {
+    const int f = f0 + it * 4 + g;
+    const bool live = f < T;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int n = t + 64 * r;
+      float2 v = make_float2(0.f, 0.f);
+      if (live) {
+        long long i0 = (long long)f * PV_HOP + 2 * n - PV_NFFT / 2, i1 = i0 + 1;
+        i0 = i0 < 0 ? -i0 : (i0 >= L ? 2 * (L - 1) - i0 : i0);
+        i1 = i1 < 0 ? -i1 : (i1 >= L ? 2 * (L - 1) - i1 : i1);
+        v = make_float2(xs[i0] * hann[2 * n], xs[i1] * hann[2 * n + 1]);
+      }
+      A[g][n] = v;
+    }
+    __syncthreads();
+    fft256_pass<false>(A[g], B[g], w256, t, 1);  __syncthreads();
+    fft256_pass<false>(B[g], A[g], w256, t, 4);  __syncthreads();
+    fft256_pass<false>(A[g], B[g], w256, t, 16); __syncthreads();
+    fft256_pass<false>(B[g], A[g], w256, t, 64); __syncthreads();
+    if (live) {
+      // X[k] = E + W512^k * O,  E = (Z[k] + conj(Z[256-k])) / 2,  O = -i/2 * (Z[k] - conj(Z[256-k]))
+      for (int k = t; k <= 256; k += 64) {
+        const float2 zk = A[g][k & 255], zc = A[g][(256 - k) & 255];
+        const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+        const float2 dd = make_float2(zk.x - zc.x, zk.y + zc.y);
+        const float2 o = make_float2(0.5f * dd.y, -0.5f * dd.x);
+        const float2 wo = cmul(w512[k], o);
+        sp[(size_t)f * PV_LD + k] = make_float2(e.x + wo.x, e.y + wo.y);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ phase vocoder: increments and magnitudes
+__global__ void __launch_bounds__(256)
+k_pv_phase(const float2* __restrict__ spec, long long spec_stride, const char* __restrict__ len_base, int len_stride,
+           const float* __restrict__ g_padv, double rate, int vec, float* __restrict__ mag, float* __restrict__ ph,
+           long long plane_stride) {
+  const int c = blockIdx.y;
+  const long long L = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
+  if (L <= PV_NFFT / 2) return;
+  const int T = pv_frames(L);
+  const int J = pv_out_frames(T, rate);
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= J) return;
+  const int lane = threadIdx.x & 31;
+  const float ts = pv_time_step(j, J, rate, vec);
+  const float alpha = ts - truncf(ts);                           // ts % 1.0
+  const long long i0 = (long long)ts, i1 = (long long)__fadd_rn(ts, 1.0f);
+  const float2* __restrict__ sp = spec + (size_t)c * spec_stride;
+  float* __restrict__ mg = mag + (size_t)c * plane_stride + (size_t)j * PV_LD;
+  float* __restrict__ pc = ph + (size_t)c * plane_stride;
+  const float two_pi = 6.283185307179586f;
+  const float one_m = __fsub_rn(1.0f, alpha);
+  for (int k = lane; k < PV_NFREQ; k += 32) {
+    const float2 s0 = i0 < T ? sp[(size_t)i0 * PV_LD + k] : make_float2(0.f, 0.f);     // two zero frames of padding
+    const float2 s1 = i1 < T ? sp[(size_t)i1 * PV_LD + k] : make_float2(0.f, 0.f);
+    const float a0 = atan2f(s0.y, s0.x), a1 = atan2f(s1.y, s1.x);
+    const float n0 = hypotf(s0.x, s0.y), n1 = hypotf(s1.x, s1.y);
+    const float adv = g_padv[k];
+    float p = __fsub_rn(__fsub_rn(a1, a0), adv);
+    p = __fsub_rn(p, __fmul_rn(two_pi, rintf(__fdiv_rn(p, two_pi))));
+    p = __fadd_rn(p, adv);
+    mg[k] = __fadd_rn(__fmul_rn(alpha, n1), __fmul_rn(one_m, n0));
+    if (j == 0) pc[k] = a0;                                      // phase_0
+    if (j + 1 < J) pc[(size_t)(j + 1) * PV_LD + k] = p;          // cat([phase_0, phase[..., :-1]])
+  }
+}
+
+// phase_acc = cumsum(phase): double accumulator, every element rounded to fp32 (torch.cumsum on CPU)
+__global__ void __launch_bounds__(64)
+k_pv_cumsum(const char* __restrict__ len_base, int len_stride, double rate, float* __restrict__ ph,
+            long long plane_stride) {
+  const int c = blockIdx.y;
+  const int k = blockIdx.x * 64 + threadIdx.x;
+  const long long L = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
+  if (L <= PV_NFFT / 2 || k >= PV_NFREQ) return;
+  const int J = pv_out_frames(pv_frames(L), rate);
+  float* __restrict__ p = ph + (size_t)c * plane_stride + k;
+  double acc = 0.0;
+  int j = 0;
+  for (; j + 8 <= J; j += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(j + u) * PV_LD];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { acc += (double)v[u]; p[(size_t)(j + u) * PV_LD] = (float)acc; }
+  }
+  for (; j < J; ++j) { acc += (double)p[(size_t)j * PV_LD]; p[(size_t)j * PV_LD] = (float)acc; }
+}
+
+// ------------------------------------------------------------------ inverse STFT
+// One CTA makes 16 hops (2048 samples) of the stretched waveform.  Full-signal sample nf = n + 256 receives frames
+// nf/128 - 3 .. nf/128; the 19 frames a tile needs are transformed in 4 rounds of 5 frames that are 512 samples
+// apart (so the frames of a round never touch the same output sample and the sum order is fixed).
+__global__ void __launch_bounds__(320)
+k_pv_istft(const float* __restrict__ mag, const float* __restrict__ ph, long long plane_stride,
+           const char* __restrict__ len_base, int len_stride, const float2* __restrict__ g_w256,
+           const float2* __restrict__ g_w512, const float* __restrict__ g_hann, double rate,
+           float* __restrict__ wave, long long wave_stride) {
+  __shared__ float2 A[5][256], B[5][PV_LD];
+  __shared__ float2 w256[256], w512[PV_NFREQ];
+  __shared__ float hann[PV_NFFT];
+  __shared__ float acc[PV_OUT_HOPS * PV_HOP];
+  const int c = blockIdx.y;
+  const long long L = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
+  if (L <= PV_NFFT / 2) return;
+  const int J = pv_out_frames(pv_frames(L), rate);
+  const long long LS = pv_stretch_len(L, rate);
+  const int h0 = blockIdx.x * PV_OUT_HOPS;
+  if ((long long)h0 * PV_HOP >= LS) return;
+  for (int i = threadIdx.x; i < 256; i += 320) w256[i] = g_w256[i];
+  for (int i = threadIdx.x; i < PV_NFREQ; i += 320) w512[i] = g_w512[i];
+  for (int i = threadIdx.x; i < PV_NFFT; i += 320) hann[i] = g_hann[i];
+  for (int i = threadIdx.x; i < PV_OUT_HOPS * PV_HOP; i += 320) acc[i] = 0.f;
+  __syncthreads();
+  const int g = threadIdx.x >> 6, t = threadIdx.x & 63;
+  const long long F0 = (long long)(h0 + 2) * PV_HOP;            // first full-signal sample of the tile
+  const float* __restrict__ mg = mag + (size_t)c * plane_stride;
+  const float* __restrict__ pc = ph + (size_t)c * plane_stride;
+  for (int r = 0; r < 4; ++r) {
+    const int j = h0 - 1 + r + 4 * g;
+    const bool live = j >= 0 && j < J && j <= h0 + 17;
+    // torch.polar(mag, phase_acc): the fp32 phase is reduced in double (exact input, error ~1e-10 rad)
+    for (int k = t; k <= 256; k += 64) {
+      float2 X = make_float2(0.f, 0.f);
+      if (live) {
+        const float m = mg[(size_t)j * PV_LD + k];
+        const double p = (double)pc[(size_t)j * PV_LD + k];
+        const double q = rint(p * 0.15915494309189535);
+        const double red = fma(-q, 1.2246467991473532e-16 * 2.0, fma(-q, 6.283185307179586, p));
+        float sn, cs;
+        sincosf((float)red, &sn, &cs);
+        X = make_float2(m * cs, (k == 0 || k == 256) ? 0.f : m * sn);     // c2r ignores Im of DC and Nyquist
+      }
+      B[g][k] = X;
+    }
+    __syncthreads();
+    // Z[k] = (X[k] + conj(X[256-k])) + i * (X[k] - conj(X[256-k])) * conj(W512^k)
+#pragma unroll
+    for (int m4 = 0; m4 < 4; ++m4) {
+      const int k = t + 64 * m4;
+      const float2 a = B[g][k], b = B[g][256 - k];
+      const float2 e = make_float2(a.x + b.x, a.y - b.y);
+      const float2 d = make_float2(a.x - b.x, a.y + b.y);
+      const float2 w = w512[k];
+      const float2 o = cmul(d, make_float2(w.x, -w.y));
+      A[g][k] = make_float2(e.x - o.y, e.y + o.x);
+    }
+    __syncthreads();
+    fft256_pass<true>(A[g], B[g], w256, t, 1);  __syncthreads();
+    fft256_pass<true>(B[g], A[g], w256, t, 4);  __syncthreads();
+    fft256_pass<true>(A[g], B[g], w256, t, 16); __syncthreads();
+    fft256_pass<true>(B[g], A[g], w256, t, 64); __syncthreads();
+    if (live) {
+      const long long base = (long long)j * PV_HOP - F0;
+#pragma unroll
+      for (int m4 = 0; m4 < 4; ++m4) {
+        const int n = t + 64 * m4;
+        const float2 z = A[g][n];
+        const long long p0 = base + 2 * n;
+        if (p0 >= 0 && p0 < PV_OUT_HOPS * PV_HOP) {              // p0 is even, so p0 + 1 is inside as well
+          acc[p0] += (z.x * (1.0f / 512.0f)) * hann[2 * n];
+          acc[p0 + 1] += (z.y * (1.0f / 512.0f)) * hann[2 * n + 1];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const long long full = PV_NFFT + (long long)PV_HOP * (J - 1);
+  float* __restrict__ w = wave + (size_t)c * wave_stride;
+  for (int i = threadIdx.x; i < PV_OUT_HOPS * PV_HOP; i += 320) {
+    const long long nf = F0 + i, n = nf - PV_NFFT / 2;
+    if (n >= LS) break;
+    float out = 0.f;
+    if (nf < full) {
+      long long jlo = (nf - (PV_NFFT - 1) + PV_HOP - 1) / PV_HOP;
+      if (nf - (PV_NFFT - 1) < 0) jlo = 0;
+      const long long jhi = min((long long)J - 1, nf / PV_HOP);
+      float env = 0.f;
+      for (long long jj = jlo; jj <= jhi; ++jj) { const float hw = hann[nf - jj * PV_HOP]; env = __fadd_rn(env, __fmul_rn(hw, hw)); }
+      out = __fdiv_rn(acc[i], env);
+    }
+    w[n] = out;
+  }
+}
+
+// ------------------------------------------------------------------ windowed-sinc resample, any ratio, then crop / pad
+// out[o] = sum_w taps[p][w] * in[q * orig + ilo[p] + w - width],  p = o mod new, q = o / new: only the taps inside the
+// Hann window (2 * width + 2 per phase) are kept -- outside it torchaudio's fp32 taps are ~1e-23.  Output o >= the
+// resampled length is zero (functional.py:1708-1713 pads), o >= L is not produced (crop).
+__global__ void __launch_bounds__(256)
+k_resample_windowed(const float* __restrict__ wave, long long wave_stride, const char* __restrict__ len_base,
+                    int len_stride, double rate, int orig, int nw, int width, int W, const float* __restrict__ taps,
+                    const int* __restrict__ ilo, float* __restrict__ y, const int64_t* __restrict__ y_off) {
+  const int c = blockIdx.y;
+  const long long L = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
+  if (L <= PV_NFFT / 2) return;
+  const long long LS = pv_stretch_len(L, rate);
+  const long long target = ((long long)nw * LS + orig - 1) / orig;
+  const float* __restrict__ in = wave + (size_t)c * wave_stride;
+  float* __restrict__ out = y + y_off[c];
+  const long long o0 = (long long)blockIdx.x * 1024;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long long o = o0 + u * 256 + threadIdx.x;
+    if (o >= L) return;
+    float a = 0.f;
+    if (o < target) {
+      const long long q = o / nw;
+      const int p = (int)(o - q * nw);
+      const long long s0 = q * orig + ilo[p] - width;
+      const float* __restrict__ k = taps + (size_t)p * W;
+      if (s0 >= 0 && s0 + W <= LS) {
+        for (int w = 0; w < W; ++w) a = fmaf(in[s0 + w], __ldg(k + w), a);
+      } else {
+        for (int w = 0; w < W; ++w) { const long long s = s0 + w; if (s >= 0 && s < LS) a = fmaf(in[s], __ldg(k + w), a); }
+      }
+    }
+    out[o] = a;
+  }
+}
+
+// ------------------------------------------------------------------ host side
+PitchPlan pitch_plan(int n, int64_t max_len, double rate) {
+  PitchPlan p;
+  p.T_max = 1 + max_len / PV_HOP;
+  p.J_max = (int64_t)std::ceil((double)p.T_max / rate);
+  p.LS_max = ((int64_t)std::nearbyint((double)max_len / rate) + 3) / 4 * 4;
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  size_t o = 0;
+  p.spec = o; o += align_up(nn * (size_t)p.T_max * PV_LD * sizeof(float2), 256);
+  p.mag = o;  o += align_up(nn * (size_t)p.J_max * PV_LD * sizeof(float), 256);
+  p.ph = o;   o += align_up(nn * (size_t)p.J_max * PV_LD * sizeof(float), 256);
+  p.wave = o; o += align_up(nn * (size_t)p.LS_max * sizeof(float), 256);
+  p.total = o;
+  return p;
+}
+
+cudaError_t launch_pitch_shift(const PitchTables& tb, const float* x, const int64_t* off, const int32_t* len,
+                               int len_stride_bytes, int n, int64_t max_len, double rate, int arange_vec, int orig,
+                               int nw, int width, int W, const float* taps, const int* ilo, float* y,
+                               const int64_t* y_off, void* workspace, cudaStream_t st, LaunchCtx* lc) {
+  if (n <= 0 || max_len <= 0) return cudaSuccess;
+  const PitchPlan p = pitch_plan(n, max_len, rate);
+  char* ws = (char*)workspace;
+  float2* spec = (float2*)(ws + p.spec);
+  float* mag = (float*)(ws + p.mag);
+  float* ph = (float*)(ws + p.ph);
+  float* wave = (float*)(ws + p.wave);
+  const char* lb = reinterpret_cast<const char*>(len);
+  const int ls = len_stride_bytes ? len_stride_bytes : (int)sizeof(int32_t);
+  const long long spec_stride = (long long)p.T_max * PV_LD, plane_stride = (long long)p.J_max * PV_LD;
+  const unsigned gx_stft = (unsigned)((p.T_max + PV_STFT_FR - 1) / PV_STFT_FR);
+  const unsigned gx_ph = (unsigned)((p.J_max + 7) / 8);
+  const unsigned gx_is = (unsigned)((p.LS_max + PV_OUT_HOPS * PV_HOP - 1) / (PV_OUT_HOPS * PV_HOP));
+  const unsigned gx_rs = (unsigned)((max_len + 1023) / 1024);
+  if (gx_stft > 0x7fffffffu || n > 65535) return cudaErrorInvalidValue;
+  lc->begin(KID_PV_STFT, st);
+  k_pv_stft<<<dim3(gx_stft, (unsigned)n), 256, 0, st>>>(x, off, lb, ls, tb.w256, tb.w512, tb.hann, spec, spec_stride);
+  lc->end(st);
+  lc->begin(KID_PV_PHASE, st);
+  k_pv_phase<<<dim3(gx_ph, (unsigned)n), 256, 0, st>>>(spec, spec_stride, lb, ls, tb.padv, rate, arange_vec, mag, ph,
+                                                       plane_stride);
+  lc->end(st);
+  lc->begin(KID_PV_CUMSUM, st);
+  k_pv_cumsum<<<dim3((PV_NFREQ + 63) / 64, (unsigned)n), 64, 0, st>>>(lb, ls, rate, ph, plane_stride);
+  lc->end(st);
+  lc->begin(KID_PV_ISTFT, st);
+  k_pv_istft<<<dim3(gx_is > 0 ? gx_is : 1, (unsigned)n), 320, 0, st>>>(mag, ph, plane_stride, lb, ls, tb.w256, tb.w512,
+                                                                      tb.hann, rate, wave, (long long)p.LS_max);
+  lc->end(st);
+  lc->begin(KID_PV_RESAMPLE, st);
+  k_resample_windowed<<<dim3(gx_rs, (unsigned)n), 256, 0, st>>>(wave, (long long)p.LS_max, lb, ls, rate, orig, nw, width,
+                                                                W, taps, ilo, y, y_off);
+  lc->end(st);
+  return cudaGetLastError();
+}
+
+}  // namespace rho

@@ -65,6 +65,65 @@ void host_resample_taps_general(int orig, int nw, float* out) {
   }
 }
 
+// The same taps, but only those inside the Hann window of each phase: tap i of phase p sits at
+// t = (-p / nw + (i - width) / orig) * base and the window clamps |t| to 6, where the fp32 tap is ~1e-23.  The W =
+// 2 * width + 2 taps from ilo[p] = floor(p * orig / nw + width - 6 * orig / base) cover every tap with |t| < 6.
+void host_resample_taps_windowed(int orig, int nw, int width, int W, float* taps, int* ilo) {
+  const int lpw = 6;
+  const double base = std::min(orig, nw) * 0.99;
+  const int K = 2 * width + orig;
+  const float basef = (float)base;
+  const float scale = (float)(base / orig);
+  const float pif = (float)M_PI;
+  for (int p = 0; p < nw; ++p) {
+    const double centre = (double)p * orig / nw + width;
+    int lo = (int)std::floor(centre - lpw * orig / base);
+    if (lo < 0) lo = 0;
+    ilo[p] = lo;
+    const float ph = (float)(-p) / (float)nw;
+    for (int w = 0; w < W; ++w) {
+      const int i = lo + w;
+      float v = 0.f;
+      if (i < K) {
+        const float idx = (float)(i - width) / (float)orig;
+        float t = ph + idx;
+        t = t * basef;
+        t = std::min(std::max(t, (float)-lpw), (float)lpw);
+        const float wa = ((t * pif) / (float)lpw) / 2.0f;
+        const float c = cosf(wa);
+        const float window = c * c;
+        t = t * pif;
+        const float sinc = (t == 0.0f) ? 1.0f : sinf(t) / t;
+        v = sinc * (window * scale);
+      }
+      taps[(size_t)p * W + w] = v;
+    }
+  }
+}
+
+// Tables of the pitch shifter: FFT twiddles, torch.hann_window(512), and phase_advance =
+// torch.linspace(0, pi * 128, 257) as torch's fp32 CPU kernel makes it: step = float(end) / 256 in fp32, the first
+// half float(step * i), the second half end - step * (256 - i) as one fused multiply-subtract (oracle/pitch.py
+// linspace_f32 pins this element by element against torch).
+void host_pitch_tables(float* w256, float* w512, float* hann512, float* padv) {
+  for (int k = 0; k < 256; ++k) {
+    w256[2 * k] = (float)std::cos(2.0 * M_PI * k / 256);
+    w256[2 * k + 1] = (float)(-std::sin(2.0 * M_PI * k / 256));
+  }
+  for (int k = 0; k <= 256; ++k) {
+    w512[2 * k] = (float)std::cos(2.0 * M_PI * k / 512);
+    w512[2 * k + 1] = (float)(-std::sin(2.0 * M_PI * k / 512));
+  }
+  for (int n = 0; n < 512; ++n) hann512[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * n / 512));
+  const int n = 257;
+  const float end = (float)(M_PI * 128);
+  const float step = end / (float)(n - 1);
+  for (int i = 0; i < n; ++i) {
+    volatile float prod = step * (float)i;      // volatile: keep the product a separately rounded fp32 value
+    padv[i] = i < n / 2 ? (float)prod : std::fmaf(-step, (float)(n - 1 - i), end);
+  }
+}
+
 // torch.hann_window(400) (periodic)
 void host_hann(float* out) {
   for (int n = 0; n < N_FFT; ++n) out[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * n / N_FFT));

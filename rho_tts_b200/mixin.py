@@ -159,9 +159,9 @@ class B200AudioMixin:
 
     # ------------------------------------------------------------------ base_tts.py:618-650
     def _apply_speed_pitch(self, audio: torch.Tensor, speed: float, pitch_semitones: float) -> torch.Tensor:
-        """Speed = torchaudio.functional.resample(audio, int(sr * speed), sr) on the B200 (any ratio).  The pitch
-        shift (torchaudio's phase vocoder) is not part of this path: it is delegated to the class after the
-        mixin in the MRO, i.e. to the reference's own code."""
+        """Speed = torchaudio.functional.resample(audio, int(sr * speed), sr) (any ratio) and pitch =
+        torchaudio.functional.pitch_shift(audio, sr, pitch_semitones) (stft -> phase vocoder -> istft -> resample),
+        both on the B200, in the reference's order."""
         if speed != 1.0:
             from .batch import resample_any_batch
             orig = int(self.sample_rate * speed)
@@ -173,10 +173,12 @@ class B200AudioMixin:
                 y = out.clip(0).clone().to(device=audio.device, dtype=audio.dtype)
                 audio = y.unsqueeze(0) if two_d and audio.shape[0] != 1 else y      # (1, L) comes back squeezed (:636-637)
         if pitch_semitones != 0.0:
-            parent = super()
-            if not hasattr(parent, "_apply_speed_pitch"):
-                raise RuntimeError("rho_tts_b200: pitch shifting is delegated to the provider class, which has no _apply_speed_pitch")
-            audio = parent._apply_speed_pitch(audio, 1.0, pitch_semitones)
+            from .batch import pitch_shift_batch
+            shape = audio.shape                                                     # :640-648: the shape is kept
+            flat = self._b200_mono(audio, "_apply_speed_pitch")
+            dev = self._b200_dev()
+            out = pitch_shift_batch(RaggedBatch.from_list([flat], dev), int(self.sample_rate), float(pitch_semitones))
+            audio = out.clip(0).clone().to(device=audio.device, dtype=audio.dtype).reshape(shape)
         return audio
 
     def _b200_cosine(self, reference_embedding, generated_embedding) -> np.float32:

@@ -120,6 +120,3 @@ class TestSpeedOnMixin:
         y2 = tts._apply_speed_pitch(torch.from_numpy(X.copy()).unsqueeze(0), 1.1, 0.0)
         assert y2.dim() == 1                                        # (1, L) is squeezed (:636-637)
 
-    def test_pitch_is_delegated(self, cuda_device):
-        with pytest.raises(RuntimeError):
-            self._tts()._apply_speed_pitch(torch.randn(16000), 1.0, 2.0)   # no provider class behind the mixin here
