@@ -419,7 +419,7 @@ int rho_b200_pitch_shift(rho_handle* h, const float* x, const int64_t* off, cons
   const long long g = gcd_ll(orig_freq, sample_rate);
   const int orig = (int)(orig_freq / g), nw = (int)(sample_rate / g);
   const int width = host_resample_width(orig, nw);
-  const int W = 2 * width + 2;
+  const int W = (2 * width + 2 + 3) / 4 * 4;          // rows of the tap table stay 16-byte aligned
   rho_handle::WinTaps wt{nullptr, nullptr};
   {
     std::lock_guard<std::mutex> lock(h->mu);

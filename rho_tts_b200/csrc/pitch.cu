@@ -23,7 +23,7 @@ constexpr int PV_HOP = 128;
 constexpr int PV_NFREQ = 257;
 constexpr int PV_LD = 264;               // row stride of the spectrogram planes (elements)
 constexpr int PV_STFT_FR = 16;           // frames per CTA of k_pv_stft
-constexpr int PV_OUT_HOPS = 16;          // output hops (of 128 samples) per CTA of k_pv_istft
+constexpr int PV_OUT_HOPS = 32;          // output hops (of 128 samples) per CTA of k_pv_istft
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
@@ -120,7 +120,10 @@ k_pv_stft(const float* __restrict__ x, const int64_t* __restrict__ off, const ch
         const float2 dd = make_float2(zk.x - zc.x, zk.y + zc.y);
         const float2 o = make_float2(0.5f * dd.y, -0.5f * dd.x);
         const float2 wo = cmul(w512[k], o);
-        sp[(size_t)f * PV_LD + k] = make_float2(e.x + wo.x, e.y + wo.y);
+        // stored as (|X|, angle(X)): the vocoder needs exactly these two of every frame (functional.py:783-787), and
+        // each frame is used by ~2 / rate output frames
+        const float re = e.x + wo.x, im = e.y + wo.y;
+        sp[(size_t)f * PV_LD + k] = make_float2(hypotf(re, im), atan2f(im, re));
       }
     }
     __syncthreads();
@@ -149,10 +152,9 @@ k_pv_phase(const float2* __restrict__ spec, long long spec_stride, const char* _
   const float two_pi = 6.283185307179586f;
   const float one_m = __fsub_rn(1.0f, alpha);
   for (int k = lane; k < PV_NFREQ; k += 32) {
-    const float2 s0 = i0 < T ? sp[(size_t)i0 * PV_LD + k] : make_float2(0.f, 0.f);     // two zero frames of padding
-    const float2 s1 = i1 < T ? sp[(size_t)i1 * PV_LD + k] : make_float2(0.f, 0.f);
-    const float a0 = atan2f(s0.y, s0.x), a1 = atan2f(s1.y, s1.x);
-    const float n0 = hypotf(s0.x, s0.y), n1 = hypotf(s1.x, s1.y);
+    const float2 s0 = i0 < T ? sp[(size_t)i0 * PV_LD + k] : make_float2(0.f, 0.f);     // two zero frames of padding:
+    const float2 s1 = i1 < T ? sp[(size_t)i1 * PV_LD + k] : make_float2(0.f, 0.f);     // |0| = 0, angle(0) = 0
+    const float n0 = s0.x, a0 = s0.y, n1 = s1.x, a1 = s1.y;
     const float adv = g_padv[k];
     float p = __fsub_rn(__fsub_rn(a1, a0), adv);
     p = __fsub_rn(p, __fmul_rn(two_pi, rintf(__fdiv_rn(p, two_pi))));
@@ -186,9 +188,9 @@ k_pv_cumsum(const char* __restrict__ len_base, int len_stride, double rate, floa
 }
 
 // ------------------------------------------------------------------ inverse STFT
-// One CTA makes 16 hops (2048 samples) of the stretched waveform.  Full-signal sample nf = n + 256 receives frames
-// nf/128 - 3 .. nf/128; the 19 frames a tile needs are transformed in 4 rounds of 5 frames that are 512 samples
-// apart (so the frames of a round never touch the same output sample and the sum order is fixed).
+// One CTA makes 32 hops (4096 samples) of the stretched waveform.  Full-signal sample nf = n + 256 receives frames
+// nf/128 - 3 .. nf/128; the 35 frames a tile needs are transformed in 7 rounds of 5 frames that are 7 hops apart
+// (so the frames of a round never touch the same output sample and the sum order is fixed).
 __global__ void __launch_bounds__(320)
 k_pv_istft(const float* __restrict__ mag, const float* __restrict__ ph, long long plane_stride,
            const char* __restrict__ len_base, int len_stride, const float2* __restrict__ g_w256,
@@ -214,9 +216,9 @@ k_pv_istft(const float* __restrict__ mag, const float* __restrict__ ph, long lon
   const long long F0 = (long long)(h0 + 2) * PV_HOP;            // first full-signal sample of the tile
   const float* __restrict__ mg = mag + (size_t)c * plane_stride;
   const float* __restrict__ pc = ph + (size_t)c * plane_stride;
-  for (int r = 0; r < 4; ++r) {
-    const int j = h0 - 1 + r + 4 * g;
-    const bool live = j >= 0 && j < J && j <= h0 + 17;
+  for (int r = 0; r < 7; ++r) {
+    const int j = h0 - 1 + r + 7 * g;
+    const bool live = j >= 0 && j < J;
     // torch.polar(mag, phase_acc): the fp32 phase is reduced in double (exact input, error ~1e-10 rad)
     for (int k = t; k <= 256; k += 64) {
       float2 X = make_float2(0.f, 0.f);
@@ -226,7 +228,7 @@ k_pv_istft(const float* __restrict__ mag, const float* __restrict__ ph, long lon
         const double q = rint(p * 0.15915494309189535);
         const double red = fma(-q, 1.2246467991473532e-16 * 2.0, fma(-q, 6.283185307179586, p));
         float sn, cs;
-        sincosf((float)red, &sn, &cs);
+        __sincosf((float)red, &sn, &cs);                                  // |red| <= pi: abs error < 5e-7
         X = make_float2(m * cs, (k == 0 || k == 256) ? 0.f : m * sn);     // c2r ignores Im of DC and Nyquist
       }
       B[g][k] = X;
@@ -285,18 +287,40 @@ k_pv_istft(const float* __restrict__ mag, const float* __restrict__ ph, long lon
 // out[o] = sum_w taps[p][w] * in[q * orig + ilo[p] + w - width],  p = o mod new, q = o / new: only the taps inside the
 // Hann window (2 * width + 2 per phase) are kept -- outside it torchaudio's fp32 taps are ~1e-23.  Output o >= the
 // resampled length is zero (functional.py:1708-1713 pads), o >= L is not produced (crop).
+constexpr int RW_OUT = 1024;              // outputs per CTA
+constexpr int RW_SPAN = 4608;             // staged input samples per CTA (covers ratios up to 4:1 at W <= 500)
+
+// The CTA's 1024 outputs read a contiguous input span (the first tap index q * orig + ilo[p] never decreases with
+// o): it is staged in shared memory once (zero outside the clip), each thread then makes 4 outputs from it with the
+// taps of its phase read from the table with 128-bit loads (rows are W floats, W % 4 == 0 -> 16-byte aligned).
+template <int WT>
 __global__ void __launch_bounds__(256)
 k_resample_windowed(const float* __restrict__ wave, long long wave_stride, const char* __restrict__ len_base,
                     int len_stride, double rate, int orig, int nw, int width, int W, const float* __restrict__ taps,
                     const int* __restrict__ ilo, float* __restrict__ y, const int64_t* __restrict__ y_off) {
+  __shared__ __align__(16) float sm[RW_SPAN];
   const int c = blockIdx.y;
   const long long L = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
   if (L <= PV_NFFT / 2) return;
+  const long long o0 = (long long)blockIdx.x * RW_OUT;
+  if (o0 >= L) return;
   const long long LS = pv_stretch_len(L, rate);
   const long long target = ((long long)nw * LS + orig - 1) / orig;
   const float* __restrict__ in = wave + (size_t)c * wave_stride;
   float* __restrict__ out = y + y_off[c];
-  const long long o0 = (long long)blockIdx.x * 1024;
+  const long long o_last = min(min(o0 + RW_OUT, L), max(target, o0 + 1)) - 1;
+  const long long q0 = o0 / nw, q1 = o_last / nw;
+  const long long span0 = q0 * orig + ilo[(int)(o0 - q0 * nw)] - width;
+  const long long span1 = q1 * orig + ilo[(int)(o_last - q1 * nw)] - width + W;
+  const int span = (int)(span1 - span0);
+  const bool staged = span <= RW_SPAN;
+  if (staged) {
+    for (int i = threadIdx.x; i < span; i += 256) {
+      const long long g = span0 + i;
+      sm[i] = (g >= 0 && g < LS) ? in[g] : 0.f;
+    }
+  }
+  __syncthreads();
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const long long o = o0 + u * 256 + threadIdx.x;
@@ -307,10 +331,22 @@ k_resample_windowed(const float* __restrict__ wave, long long wave_stride, const
       const int p = (int)(o - q * nw);
       const long long s0 = q * orig + ilo[p] - width;
       const float* __restrict__ k = taps + (size_t)p * W;
-      if (s0 >= 0 && s0 + W <= LS) {
-        for (int w = 0; w < W; ++w) a = fmaf(in[s0 + w], __ldg(k + w), a);
+      if (staged) {
+        const float* __restrict__ v = sm + (int)(s0 - span0);
+        if (WT > 0) {
+          float a1 = 0.f;
+#pragma unroll
+          for (int w = 0; w < WT; w += 4) {
+            const float4 kk = __ldg(reinterpret_cast<const float4*>(k + w));
+            a = fmaf(v[w], kk.x, a); a1 = fmaf(v[w + 1], kk.y, a1);
+            a = fmaf(v[w + 2], kk.z, a); a1 = fmaf(v[w + 3], kk.w, a1);
+          }
+          a += a1;
+        } else {
+          for (int w = 0; w < W; ++w) a = fmaf(v[w], __ldg(k + w), a);
+        }
       } else {
-        for (int w = 0; w < W; ++w) { const long long s = s0 + w; if (s >= 0 && s < LS) a = fmaf(in[s], __ldg(k + w), a); }
+        for (int w = 0; w < W; ++w) { const long long si = s0 + w; if (si >= 0 && si < LS) a = fmaf(in[si], __ldg(k + w), a); }
       }
     }
     out[o] = a;
@@ -367,8 +403,12 @@ cudaError_t launch_pitch_shift(const PitchTables& tb, const float* x, const int6
                                                                       tb.hann, rate, wave, (long long)p.LS_max);
   lc->end(st);
   lc->begin(KID_PV_RESAMPLE, st);
-  k_resample_windowed<<<dim3(gx_rs, (unsigned)n), 256, 0, st>>>(wave, (long long)p.LS_max, lb, ls, rate, orig, nw, width,
-                                                                W, taps, ilo, y, y_off);
+  if (W == 16)
+    k_resample_windowed<16><<<dim3(gx_rs, (unsigned)n), 256, 0, st>>>(wave, (long long)p.LS_max, lb, ls, rate, orig, nw,
+                                                                      width, W, taps, ilo, y, y_off);
+  else
+    k_resample_windowed<0><<<dim3(gx_rs, (unsigned)n), 256, 0, st>>>(wave, (long long)p.LS_max, lb, ls, rate, orig, nw,
+                                                                     width, W, taps, ilo, y, y_off);
   lc->end(st);
   return cudaGetLastError();
 }

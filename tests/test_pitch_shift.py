@@ -5,9 +5,13 @@ CPU: oracle/pitch.py against golden vectors made by the reference method / torch
 (tests/golden/make_golden_pitch.py), stage by stage (time steps, phase_advance: bit-exact; stft, vocoder, istft) and
 end to end.  GPU: rho_b200_pitch_shift and the mixin's _apply_speed_pitch against the same vectors and the oracle.
 
-Tolerance: 1e-4 absolute on waveforms of peak ~0.4 (the task's float tolerance).  The fp32 reference differs from
-its own float64 evaluation by 1e-4 .. 5e-4 (phase accumulator ~1e6 rad), so this only holds because the oracle and
-the kernels repeat torch's fp32 roundings; typical errors are 1e-5 .. 3e-5."""
+Tolerance: 1e-4 absolute on waveforms of peak ~0.4 (the task's float tolerance) for clips up to 1.5 s.  The fp32
+reference differs from its own float64 evaluation by 1e-4 .. 9e-4 (phase accumulator ~1e6 rad, ulp 0.06), so this only
+holds because the oracle and the kernels repeat torch's fp32 roundings; typical errors are 1e-5 .. 4e-5.  On long
+tonal clips the accumulated phase is rounded to fp32 at magnitudes where one ulp is 0.016 rad on an audible partial:
+last-bit differences of the FFT / atan2 (MKL, Sleef) flip ~1 % of those roundings, and no independent implementation
+-- the numpy oracle included -- tracks the fp32 run to 1e-4 there (2.6e-4 on the 10 s case).  That case is bounded
+by the reference's own fp32 noise instead (LONG_CASE)."""
 import math
 import os
 import sys
@@ -20,7 +24,7 @@ from oracle import pitch as OP
 from tests.util import assert_close
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
-from pitch_inputs import COMBINED_CASES, PITCH_CASES, pitch_input  # noqa: E402
+from pitch_inputs import COMBINED_CASES, LONG_CASE, PITCH_CASES, pitch_input  # noqa: E402
 from qwen_inputs import keep_index  # noqa: E402
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_pitch_v1.npz"))
@@ -59,6 +63,26 @@ def test_oracle_vs_golden(i):
     assert_close(y[keep_index(n)], G[f"out{i}"], tol=TOL, what=f"n_steps {steps}")
     s1, s2 = G[f"out_sum{i}"]
     assert abs((y.astype(np.float64) ** 2).sum() - s2) <= 2e-3 * s2
+
+
+def _long_case_check(y, what):
+    """10 s tonal clip: the distance to the fp32 reference is bounded by the reference's own fp32 noise (its distance
+    to the float64 run of the same code), and the distance to the float64 run is no worse than the reference's."""
+    n = LONG_CASE[0]
+    k = keep_index(n)
+    noise_max, noise_rms = G["long_noise"]
+    d32 = np.abs(y[k].astype(np.float64) - G["long32"])
+    d64 = np.abs(y[k].astype(np.float64) - G["long64"])
+    ref64 = np.abs(G["long32"].astype(np.float64) - G["long64"])
+    assert noise_max > TOL                                        # the premise: the reference is noisier than 1e-4 here
+    assert d32.max() <= noise_max, f"{what}: {d32.max():.2e} from the fp32 reference, its own noise is {noise_max:.2e}"
+    assert np.sqrt((d32 ** 2).mean()) <= noise_rms
+    assert d64.max() <= 1.25 * ref64.max() and np.sqrt((d64 ** 2).mean()) <= 1.25 * np.sqrt((ref64 ** 2).mean())
+
+
+def test_oracle_long_tonal_clip_within_reference_noise():
+    n, steps = LONG_CASE
+    _long_case_check(OP.pitch_shift(pitch_input(n, 200), SR, steps), "oracle")
 
 
 def test_windowed_resample_equals_dense():
@@ -102,6 +126,14 @@ def test_gpu_pitch_ragged_batch_vs_oracle(cuda_device):
         for k, n in enumerate(lens):
             assert_close(out.clip(k, n).cpu().numpy(), OP.pitch_shift(xs[k], SR, steps), tol=TOL,
                          what=f"n_steps {steps}, n {n}")
+
+
+@pytest.mark.gpu
+def test_gpu_long_tonal_clip_within_reference_noise(cuda_device):
+    import rho_tts_b200 as R
+    n, steps = LONG_CASE
+    rb = R.RaggedBatch.from_list([torch.from_numpy(pitch_input(n, 200))], cuda_device)
+    _long_case_check(R.pitch_shift_batch(rb, SR, steps).clip(0).cpu().numpy(), "gpu")
 
 
 @pytest.mark.gpu

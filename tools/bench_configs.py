@@ -11,6 +11,7 @@ the per-kernel times with algorithmic bytes.  Results are copied to profiles/.
     python tools/bench_configs.py [c2u c3 c3v c4] [--steps K]
 """
 import json
+import math
 import os
 import sys
 
@@ -111,6 +112,23 @@ for cfg in args:
         alg = {"k_qwen_moments": s_in, "k_qwen_apply": 2 * s_in}
         line(cfg, f"{n} x 10 s clips, QwenTTS._post_process_audio (windowed decay correction, -23 dBFS, tanh)",
              n * 10.0, ms, prof, alg)
+        del x, rb, out
+    elif cfg.startswith("pitch"):
+        n = 1000
+        n_steps = float(cfg[5:]) if len(cfg) > 5 else 2.0
+        x = synth.make_clip_block(n, 240000, 0xB200, device=dev)
+        rb = R.RaggedBatch.from_dense(x)
+        out, ms, prof = timed(lambda: R.pitch_shift_batch(rb, 24000, n_steps), steps)
+        rate = 2.0 ** (-n_steps / 12.0)
+        T = 1 + 240000 // 128
+        J = math.ceil(T / rate)
+        LS = round(240000 / rate)
+        s_in = 4.0 * n * 240000
+        spec_b, plane_b = 8.0 * 257 * T * n, 4.0 * 257 * J * n
+        alg = {"k_pv_stft": s_in + spec_b, "k_pv_phase": spec_b + 2 * plane_b, "k_pv_cumsum": 2 * plane_b,
+               "k_pv_istft": 2 * plane_b + 4.0 * LS * n, "k_resample_windowed": 4.0 * LS * n + s_in}
+        line(cfg, f"{n} x 10 s clips, torchaudio.functional.pitch_shift n_steps={n_steps:+g} "
+             "(stft 512/128 -> phase vocoder -> istft -> resample -> crop)", n * 10.0, ms, prof, alg)
         del x, rb, out
     elif cfg in ("c3", "c3v"):
         rb, first = ragged_c3()
