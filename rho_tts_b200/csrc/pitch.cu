@@ -22,8 +22,7 @@ constexpr int PV_NFFT = 512;
 constexpr int PV_HOP = 128;
 constexpr int PV_NFREQ = 257;
 constexpr int PV_LD = 264;               // row stride of the spectrogram planes (elements)
-constexpr int PV_STFT_FR = 16;           // frames per CTA of k_pv_stft
-constexpr int PV_OUT_HOPS = 32;          // output hops (of 128 samples) per CTA of k_pv_istft
+constexpr int PV_OUT_HOPS = 37;          // output hops (of 128 samples) per CTA of k_pv_istft
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
@@ -72,61 +71,77 @@ __device__ __forceinline__ float pv_time_step(int j, int J, double rate, int vec
 }
 
 // ------------------------------------------------------------------ STFT
-__global__ void __launch_bounds__(256)
+// One WARP per frame (8 frames in flight per CTA, 4 frames per warp): the 512 windowed samples are packed into a
+// 256-point complex sequence in the warp's own shared-memory buffers, each lane does two radix-4 butterflies per pass
+// (only __syncwarp between passes), and the real spectrum is unpacked in (k, 256 - k) pairs:
+//   E = (Z[k] + conj(Z[256-k])) / 2,  O = -i/2 (Z[k] - conj(Z[256-k])),  X[k] = E + W512^k O,  X[256-k] = conj(E - W512^k O)
+// Stored as (|X|, angle(X)): the vocoder needs exactly these two of every frame (functional.py:783-787) and each
+// frame is used by ~2 / rate output frames.
+constexpr int PV_STFT_WARPS = 8;
+constexpr int PV_STFT_FPW = 4;           // frames per warp
+
+// |X| as sqrt(re^2 + im^2) (one fma + IEEE sqrt, <= 1 ulp like hypotf; audio spectra are far from overflow / underflow)
+__device__ __forceinline__ float2 pv_abs_angle(float re, float im) { return make_float2(__fsqrt_rn(fmaf(re, re, im * im)), atan2f(im, re)); }
+
+__global__ void __launch_bounds__(32 * PV_STFT_WARPS)
 k_pv_stft(const float* __restrict__ x, const int64_t* __restrict__ off, const char* __restrict__ len_base, int len_stride,
           const float2* __restrict__ g_w256, const float2* __restrict__ g_w512, const float* __restrict__ g_hann,
           float2* __restrict__ spec, long long spec_stride) {
-  __shared__ float2 A[4][256], B[4][256];
-  __shared__ float2 w256[256], w512[PV_NFREQ];
-  __shared__ float hann[PV_NFFT];
+  __shared__ float2 A[PV_STFT_WARPS][256], B[PV_STFT_WARPS][256];
+  __shared__ float2 w256[256];
   const int c = blockIdx.y;
   const long long L = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
   if (L <= PV_NFFT / 2) return;                      // reflect padding needs L > 256 (the host refuses such calls)
   const int T = pv_frames(L);
-  const int f0 = blockIdx.x * PV_STFT_FR;
+  const int f0 = blockIdx.x * (PV_STFT_WARPS * PV_STFT_FPW);
   if (f0 >= T) return;
-  for (int i = threadIdx.x; i < 256; i += 256) w256[i] = g_w256[i];
-  for (int i = threadIdx.x; i < PV_NFREQ; i += 256) w512[i] = g_w512[i];
-  for (int i = threadIdx.x; i < PV_NFFT; i += 256) hann[i] = g_hann[i];
+  w256[threadIdx.x] = g_w256[threadIdx.x];
   __syncthreads();
   const float* __restrict__ xs = x + off[c];
   float2* __restrict__ sp = spec + (size_t)c * spec_stride;
-  const int g = threadIdx.x >> 6, t = threadIdx.x & 63;
-  for (int it = 0; it < PV_STFT_FR / 4; ++it) {
-    const int f = f0 + it * 4 + g;
-    const bool live = f < T;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* __restrict__ a = A[w];
+  float2* __restrict__ b = B[w];
+  for (int it = 0; it < PV_STFT_FPW; ++it) {
+    const int f = f0 + it * PV_STFT_WARPS + w;
+    if (f >= T) break;                               // warp-uniform
+    const long long base = (long long)f * PV_HOP - PV_NFFT / 2;
+    const bool interior = base >= 0 && base + PV_NFFT <= L;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int n = t + 64 * r;
-      float2 v = make_float2(0.f, 0.f);
-      if (live) {
-        long long i0 = (long long)f * PV_HOP + 2 * n - PV_NFFT / 2, i1 = i0 + 1;
+    for (int r = 0; r < 8; ++r) {
+      const int n = lane + 32 * r;
+      long long i0 = base + 2 * n, i1 = i0 + 1;
+      if (!interior) {
         i0 = i0 < 0 ? -i0 : (i0 >= L ? 2 * (L - 1) - i0 : i0);
         i1 = i1 < 0 ? -i1 : (i1 >= L ? 2 * (L - 1) - i1 : i1);
-        v = make_float2(xs[i0] * hann[2 * n], xs[i1] * hann[2 * n + 1]);
       }
-      A[g][n] = v;
+      const float2 h = __ldg(reinterpret_cast<const float2*>(g_hann) + n);
+      a[n] = make_float2(xs[i0] * h.x, xs[i1] * h.y);
     }
-    __syncthreads();
-    fft256_pass<false>(A[g], B[g], w256, t, 1);  __syncthreads();
-    fft256_pass<false>(B[g], A[g], w256, t, 4);  __syncthreads();
-    fft256_pass<false>(A[g], B[g], w256, t, 16); __syncthreads();
-    fft256_pass<false>(B[g], A[g], w256, t, 64); __syncthreads();
-    if (live) {
-      // X[k] = E + W512^k * O,  E = (Z[k] + conj(Z[256-k])) / 2,  O = -i/2 * (Z[k] - conj(Z[256-k]))
-      for (int k = t; k <= 256; k += 64) {
-        const float2 zk = A[g][k & 255], zc = A[g][(256 - k) & 255];
-        const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
-        const float2 dd = make_float2(zk.x - zc.x, zk.y + zc.y);
-        const float2 o = make_float2(0.5f * dd.y, -0.5f * dd.x);
-        const float2 wo = cmul(w512[k], o);
-        // stored as (|X|, angle(X)): the vocoder needs exactly these two of every frame (functional.py:783-787), and
-        // each frame is used by ~2 / rate output frames
-        const float re = e.x + wo.x, im = e.y + wo.y;
-        sp[(size_t)f * PV_LD + k] = make_float2(hypotf(re, im), atan2f(im, re));
-      }
+    __syncwarp();
+    fft256_pass<false>(a, b, w256, lane, 1);  fft256_pass<false>(a, b, w256, lane + 32, 1);  __syncwarp();
+    fft256_pass<false>(b, a, w256, lane, 4);  fft256_pass<false>(b, a, w256, lane + 32, 4);  __syncwarp();
+    fft256_pass<false>(a, b, w256, lane, 16); fft256_pass<false>(a, b, w256, lane + 32, 16); __syncwarp();
+    fft256_pass<false>(b, a, w256, lane, 64); fft256_pass<false>(b, a, w256, lane + 32, 64); __syncwarp();
+    float2* __restrict__ row = sp + (size_t)f * PV_LD;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int k = lane + 32 * m;                   // 0..127, partner 256 - k
+      const float2 zk = a[k], zc = a[(256 - k) & 255];
+      const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+      const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+      const float2 wo = cmul(__ldg(g_w512 + k), o);
+      // DC and Nyquist of a real transform have an exactly zero (+0) imaginary part: angle is 0 or +pi
+      row[k] = pv_abs_angle(e.x + wo.x, k ? e.y + wo.y : 0.f);
+      row[256 - k] = pv_abs_angle(e.x - wo.x, k ? -(e.y - wo.y) : 0.f);
     }
-    __syncthreads();
+    if (lane == 0) {                                 // k = 128 is its own partner
+      const float2 z = a[128];
+      const float2 e = make_float2(z.x, 0.f), o = make_float2(z.y, 0.f);
+      const float2 wo = cmul(__ldg(g_w512 + 128), o);
+      row[128] = pv_abs_angle(e.x + wo.x, e.y + wo.y);
+    }
+    __syncwarp();
   }
 }
 
@@ -188,18 +203,37 @@ k_pv_cumsum(const char* __restrict__ len_base, int len_stride, double rate, floa
 }
 
 // ------------------------------------------------------------------ inverse STFT
-// One CTA makes 32 hops (4096 samples) of the stretched waveform.  Full-signal sample nf = n + 256 receives frames
-// nf/128 - 3 .. nf/128; the 35 frames a tile needs are transformed in 7 rounds of 5 frames that are 7 hops apart
-// (so the frames of a round never touch the same output sample and the sum order is fixed).
-__global__ void __launch_bounds__(320)
+// One CTA makes PV_OUT_HOPS = 37 hops (4736 samples) of the stretched waveform, one WARP per frame.  Full-signal
+// sample nf = n + 256 receives frames nf/128 - 3 .. nf/128, so the tile needs 40 frames: 5 rounds of 8 frames that
+// are 5 hops apart (the frames of a round never touch the same output sample, so the overlap-add needs no atomics and
+// its order is fixed), one CTA barrier per round.  Per frame: polar(mag, phase_acc) in (k, 256 - k) pairs ->
+//   Z[k] = e + i o,  Z[256-k] = conj(e) + i conj(o),  e = X[k] + conj(X[256-k]),  o = (X[k] - conj(X[256-k])) conj(W512^k)
+// -> inverse 256-point complex FFT (x[2n] = Re z[n] / 512, x[2n+1] = Im z[n] / 512) -> window -> add.
+constexpr int PV_IS_WARPS = 8;
+constexpr int PV_IS_ROUNDS = 5;
+constexpr int PV_IS_SMEM = (int)(sizeof(float2) * (256 + 2 * PV_IS_WARPS * 256) + sizeof(float) * PV_OUT_HOPS * PV_HOP);
+static_assert(PV_OUT_HOPS == PV_IS_WARPS * PV_IS_ROUNDS - 3, "tile = frames - 3 hops");
+
+// torch.polar(mag, phase_acc)[k]: the fp32 phase is reduced in double (exact input, error ~1e-10 rad)
+__device__ __forceinline__ float2 pv_polar(const float* __restrict__ mg, const float* __restrict__ pc, int k) {
+  const float m = mg[k];
+  const double p = (double)pc[k];
+  const double q = rint(p * 0.15915494309189535);
+  const double red = fma(-q, 2.4492935982947064e-16, fma(-q, 6.283185307179586, p));
+  float sn, cs;
+  __sincosf((float)red, &sn, &cs);                                        // |red| <= pi: abs error < 5e-7
+  return make_float2(m * cs, (k == 0 || k == 256) ? 0.f : m * sn);        // c2r ignores Im of DC and Nyquist
+}
+
+__global__ void __launch_bounds__(32 * PV_IS_WARPS)
 k_pv_istft(const float* __restrict__ mag, const float* __restrict__ ph, long long plane_stride,
            const char* __restrict__ len_base, int len_stride, const float2* __restrict__ g_w256,
            const float2* __restrict__ g_w512, const float* __restrict__ g_hann, double rate,
            float* __restrict__ wave, long long wave_stride) {
-  __shared__ float2 A[5][256], B[5][PV_LD];
-  __shared__ float2 w256[256], w512[PV_NFREQ];
-  __shared__ float hann[PV_NFFT];
-  __shared__ float acc[PV_OUT_HOPS * PV_HOP];
+  extern __shared__ __align__(16) unsigned char pv_smem[];
+  float2* w256 = reinterpret_cast<float2*>(pv_smem);
+  float2* AB = w256 + 256;
+  float* acc = reinterpret_cast<float*>(AB + 2 * PV_IS_WARPS * 256);
   const int c = blockIdx.y;
   const long long L = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
   if (L <= PV_NFFT / 2) return;
@@ -207,67 +241,64 @@ k_pv_istft(const float* __restrict__ mag, const float* __restrict__ ph, long lon
   const long long LS = pv_stretch_len(L, rate);
   const int h0 = blockIdx.x * PV_OUT_HOPS;
   if ((long long)h0 * PV_HOP >= LS) return;
-  for (int i = threadIdx.x; i < 256; i += 320) w256[i] = g_w256[i];
-  for (int i = threadIdx.x; i < PV_NFREQ; i += 320) w512[i] = g_w512[i];
-  for (int i = threadIdx.x; i < PV_NFFT; i += 320) hann[i] = g_hann[i];
-  for (int i = threadIdx.x; i < PV_OUT_HOPS * PV_HOP; i += 320) acc[i] = 0.f;
+  w256[threadIdx.x] = g_w256[threadIdx.x];
+  for (int i = threadIdx.x; i < PV_OUT_HOPS * PV_HOP; i += 32 * PV_IS_WARPS) acc[i] = 0.f;
   __syncthreads();
-  const int g = threadIdx.x >> 6, t = threadIdx.x & 63;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* __restrict__ a = AB + (size_t)w * 512;
+  float2* __restrict__ b = a + 256;
   const long long F0 = (long long)(h0 + 2) * PV_HOP;            // first full-signal sample of the tile
-  const float* __restrict__ mg = mag + (size_t)c * plane_stride;
-  const float* __restrict__ pc = ph + (size_t)c * plane_stride;
-  for (int r = 0; r < 7; ++r) {
-    const int j = h0 - 1 + r + 7 * g;
-    const bool live = j >= 0 && j < J;
-    // torch.polar(mag, phase_acc): the fp32 phase is reduced in double (exact input, error ~1e-10 rad)
-    for (int k = t; k <= 256; k += 64) {
-      float2 X = make_float2(0.f, 0.f);
-      if (live) {
-        const float m = mg[(size_t)j * PV_LD + k];
-        const double p = (double)pc[(size_t)j * PV_LD + k];
-        const double q = rint(p * 0.15915494309189535);
-        const double red = fma(-q, 1.2246467991473532e-16 * 2.0, fma(-q, 6.283185307179586, p));
-        float sn, cs;
-        __sincosf((float)red, &sn, &cs);                                  // |red| <= pi: abs error < 5e-7
-        X = make_float2(m * cs, (k == 0 || k == 256) ? 0.f : m * sn);     // c2r ignores Im of DC and Nyquist
-      }
-      B[g][k] = X;
-    }
-    __syncthreads();
-    // Z[k] = (X[k] + conj(X[256-k])) + i * (X[k] - conj(X[256-k])) * conj(W512^k)
+  const float* __restrict__ mgc = mag + (size_t)c * plane_stride;
+  const float* __restrict__ pcc = ph + (size_t)c * plane_stride;
+  for (int r = 0; r < PV_IS_ROUNDS; ++r) {
+    const int j = h0 - 1 + r + PV_IS_ROUNDS * w;
+    if (j >= 0 && j < J) {                                       // warp-uniform
+      const float* __restrict__ mg = mgc + (size_t)j * PV_LD;
+      const float* __restrict__ pc = pcc + (size_t)j * PV_LD;
 #pragma unroll
-    for (int m4 = 0; m4 < 4; ++m4) {
-      const int k = t + 64 * m4;
-      const float2 a = B[g][k], b = B[g][256 - k];
-      const float2 e = make_float2(a.x + b.x, a.y - b.y);
-      const float2 d = make_float2(a.x - b.x, a.y + b.y);
-      const float2 w = w512[k];
-      const float2 o = cmul(d, make_float2(w.x, -w.y));
-      A[g][k] = make_float2(e.x - o.y, e.y + o.x);
-    }
-    __syncthreads();
-    fft256_pass<true>(A[g], B[g], w256, t, 1);  __syncthreads();
-    fft256_pass<true>(B[g], A[g], w256, t, 4);  __syncthreads();
-    fft256_pass<true>(A[g], B[g], w256, t, 16); __syncthreads();
-    fft256_pass<true>(B[g], A[g], w256, t, 64); __syncthreads();
-    if (live) {
+      for (int m = 0; m < 4; ++m) {
+        const int k = lane + 32 * m;                             // 0..127, partner 256 - k
+        const float2 xa = pv_polar(mg, pc, k), xb = pv_polar(mg, pc, 256 - k);
+        const float2 e = make_float2(xa.x + xb.x, xa.y - xb.y);
+        const float2 d = make_float2(xa.x - xb.x, xa.y + xb.y);
+        const float2 wk = __ldg(g_w512 + k);
+        const float2 o = cmul(d, make_float2(wk.x, -wk.y));
+        a[k] = make_float2(e.x - o.y, e.y + o.x);
+        if (k) a[256 - k] = make_float2(e.x + o.y, -e.y + o.x);  // conj(e) + i conj(o)
+      }
+      if (lane == 0) {                                           // k = 128 is its own partner
+        const float2 xa = pv_polar(mg, pc, 128);
+        const float2 e = make_float2(2.f * xa.x, 0.f), d = make_float2(0.f, 2.f * xa.y);
+        const float2 wk = __ldg(g_w512 + 128);
+        const float2 o = cmul(d, make_float2(wk.x, -wk.y));
+        a[128] = make_float2(e.x - o.y, e.y + o.x);
+      }
+      __syncwarp();
+      fft256_pass<true>(a, b, w256, lane, 1);  fft256_pass<true>(a, b, w256, lane + 32, 1);  __syncwarp();
+      fft256_pass<true>(b, a, w256, lane, 4);  fft256_pass<true>(b, a, w256, lane + 32, 4);  __syncwarp();
+      fft256_pass<true>(a, b, w256, lane, 16); fft256_pass<true>(a, b, w256, lane + 32, 16); __syncwarp();
+      fft256_pass<true>(b, a, w256, lane, 64); fft256_pass<true>(b, a, w256, lane + 32, 64); __syncwarp();
       const long long base = (long long)j * PV_HOP - F0;
 #pragma unroll
-      for (int m4 = 0; m4 < 4; ++m4) {
-        const int n = t + 64 * m4;
-        const float2 z = A[g][n];
+      for (int m = 0; m < 8; ++m) {
+        const int n = lane + 32 * m;
+        const float2 z = a[n];
+        const float2 h = __ldg(reinterpret_cast<const float2*>(g_hann) + n);
         const long long p0 = base + 2 * n;
         if (p0 >= 0 && p0 < PV_OUT_HOPS * PV_HOP) {              // p0 is even, so p0 + 1 is inside as well
-          acc[p0] += (z.x * (1.0f / 512.0f)) * hann[2 * n];
-          acc[p0 + 1] += (z.y * (1.0f / 512.0f)) * hann[2 * n + 1];
+          float2* dst = reinterpret_cast<float2*>(acc + p0);
+          float2 v = *dst;
+          v.x += (z.x * (1.0f / 512.0f)) * h.x;
+          v.y += (z.y * (1.0f / 512.0f)) * h.y;
+          *dst = v;
         }
       }
     }
     __syncthreads();
   }
   const long long full = PV_NFFT + (long long)PV_HOP * (J - 1);
-  float* __restrict__ w = wave + (size_t)c * wave_stride;
-  for (int i = threadIdx.x; i < PV_OUT_HOPS * PV_HOP; i += 320) {
+  float* __restrict__ wv = wave + (size_t)c * wave_stride;
+  for (int i = threadIdx.x; i < PV_OUT_HOPS * PV_HOP; i += 32 * PV_IS_WARPS) {
     const long long nf = F0 + i, n = nf - PV_NFFT / 2;
     if (n >= LS) break;
     float out = 0.f;
@@ -276,10 +307,10 @@ k_pv_istft(const float* __restrict__ mag, const float* __restrict__ ph, long lon
       if (nf - (PV_NFFT - 1) < 0) jlo = 0;
       const long long jhi = min((long long)J - 1, nf / PV_HOP);
       float env = 0.f;
-      for (long long jj = jlo; jj <= jhi; ++jj) { const float hw = hann[nf - jj * PV_HOP]; env = __fadd_rn(env, __fmul_rn(hw, hw)); }
+      for (long long jj = jlo; jj <= jhi; ++jj) { const float hw = __ldg(g_hann + (nf - jj * PV_HOP)); env = __fadd_rn(env, __fmul_rn(hw, hw)); }
       out = __fdiv_rn(acc[i], env);
     }
-    w[n] = out;
+    wv[n] = out;
   }
 }
 
@@ -287,64 +318,58 @@ k_pv_istft(const float* __restrict__ mag, const float* __restrict__ ph, long lon
 // out[o] = sum_w taps[p][w] * in[q * orig + ilo[p] + w - width],  p = o mod new, q = o / new: only the taps inside the
 // Hann window (2 * width + 2 per phase) are kept -- outside it torchaudio's fp32 taps are ~1e-23.  Output o >= the
 // resampled length is zero (functional.py:1708-1713 pads), o >= L is not produced (crop).
-constexpr int RW_OUT = 1024;              // outputs per CTA
-constexpr int RW_SPAN = 4608;             // staged input samples per CTA (covers ratios up to 4:1 at W <= 500)
+constexpr int RW_QC = 8;                  // outputs per thread: the same phase in 8 consecutive blocks of `nw` outputs
 
-// The CTA's 1024 outputs read a contiguous input span (the first tap index q * orig + ilo[p] never decreases with
-// o): it is staged in shared memory once (zero outside the clip), each thread then makes 4 outputs from it with the
-// taps of its phase read from the table with 128-bit loads (rows are W floats, W % 4 == 0 -> 16-byte aligned).
+// Outputs o and o + nw share their phase, i.e. their taps: a thread keeps the W taps of ONE phase in registers and
+// makes that phase's output in RW_QC consecutive blocks (o = q * nw + p), so the tap table is read once per 8 outputs
+// instead of once per output (64 B per output from L2 otherwise: that was the bound).  Consecutive threads hold
+// consecutive phases: input reads (stride orig / nw samples across lanes) and output writes are coalesced.
 template <int WT>
 __global__ void __launch_bounds__(256)
 k_resample_windowed(const float* __restrict__ wave, long long wave_stride, const char* __restrict__ len_base,
                     int len_stride, double rate, int orig, int nw, int width, int W, const float* __restrict__ taps,
-                    const int* __restrict__ ilo, float* __restrict__ y, const int64_t* __restrict__ y_off) {
-  __shared__ __align__(16) float sm[RW_SPAN];
+                    const int* __restrict__ ilo, float* __restrict__ y, const int64_t* __restrict__ y_off, int qc_len) {
   const int c = blockIdx.y;
   const long long L = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
   if (L <= PV_NFFT / 2) return;
-  const long long o0 = (long long)blockIdx.x * RW_OUT;
-  if (o0 >= L) return;
+  // qc_len = RW_QC: phase-major (thread = one phase, 8 blocks); qc_len = 1: thread = one output (ratios with few
+  // phases, e.g. the octaves: the table is a few rows and stays in L1, and phase-major writes would not coalesce)
+  const long long v = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long qc = v / nw;
+  const int p = (int)(v - qc * nw);
+  const long long q_total = (L + nw - 1) / nw;
+  const long long q0 = qc * qc_len;
+  if (q0 >= q_total) return;
   const long long LS = pv_stretch_len(L, rate);
   const long long target = ((long long)nw * LS + orig - 1) / orig;
   const float* __restrict__ in = wave + (size_t)c * wave_stride;
   float* __restrict__ out = y + y_off[c];
-  const long long o_last = min(min(o0 + RW_OUT, L), max(target, o0 + 1)) - 1;
-  const long long q0 = o0 / nw, q1 = o_last / nw;
-  const long long span0 = q0 * orig + ilo[(int)(o0 - q0 * nw)] - width;
-  const long long span1 = q1 * orig + ilo[(int)(o_last - q1 * nw)] - width + W;
-  const int span = (int)(span1 - span0);
-  const bool staged = span <= RW_SPAN;
-  if (staged) {
-    for (int i = threadIdx.x; i < span; i += 256) {
-      const long long g = span0 + i;
-      sm[i] = (g >= 0 && g < LS) ? in[g] : 0.f;
+  const float* __restrict__ k = taps + (size_t)p * W;
+  const long long s_base = (long long)ilo[p] - width;
+  float kr[WT > 0 ? WT : 1];
+  if (WT > 0) {
+#pragma unroll
+    for (int w = 0; w < WT; w += 4) {
+      const float4 kk = __ldg(reinterpret_cast<const float4*>(k + w));
+      kr[w] = kk.x; kr[w + 1] = kk.y; kr[w + 2] = kk.z; kr[w + 3] = kk.w;
     }
   }
-  __syncthreads();
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const long long o = o0 + u * 256 + threadIdx.x;
-    if (o >= L) return;
+  const long long q1 = min(q0 + qc_len, q_total);
+  for (long long q = q0; q < q1; ++q) {
+    const long long o = q * nw + p;
+    if (o >= L) break;
     float a = 0.f;
     if (o < target) {
-      const long long q = o / nw;
-      const int p = (int)(o - q * nw);
-      const long long s0 = q * orig + ilo[p] - width;
-      const float* __restrict__ k = taps + (size_t)p * W;
-      if (staged) {
-        const float* __restrict__ v = sm + (int)(s0 - span0);
-        if (WT > 0) {
-          float a1 = 0.f;
+      const long long s0 = q * orig + s_base;
+      const float* __restrict__ src = in + s0;
+      if (WT > 0 && s0 >= 0 && s0 + WT <= LS) {
+        float a1 = 0.f;
 #pragma unroll
-          for (int w = 0; w < WT; w += 4) {
-            const float4 kk = __ldg(reinterpret_cast<const float4*>(k + w));
-            a = fmaf(v[w], kk.x, a); a1 = fmaf(v[w + 1], kk.y, a1);
-            a = fmaf(v[w + 2], kk.z, a); a1 = fmaf(v[w + 3], kk.w, a1);
-          }
-          a += a1;
-        } else {
-          for (int w = 0; w < W; ++w) a = fmaf(v[w], __ldg(k + w), a);
-        }
+        for (int w = 0; w < WT; w += 2) { a = fmaf(src[w], kr[w], a); a1 = fmaf(src[w + 1], kr[w + 1], a1); }
+        a += a1;
+      } else if (WT > 0) {
+#pragma unroll
+        for (int w = 0; w < WT; ++w) { const long long si = s0 + w; if (si >= 0 && si < LS) a = fmaf(in[si], kr[w], a); }
       } else {
         for (int w = 0; w < W; ++w) { const long long si = s0 + w; if (si >= 0 && si < LS) a = fmaf(in[si], __ldg(k + w), a); }
       }
@@ -383,13 +408,16 @@ cudaError_t launch_pitch_shift(const PitchTables& tb, const float* x, const int6
   const char* lb = reinterpret_cast<const char*>(len);
   const int ls = len_stride_bytes ? len_stride_bytes : (int)sizeof(int32_t);
   const long long spec_stride = (long long)p.T_max * PV_LD, plane_stride = (long long)p.J_max * PV_LD;
-  const unsigned gx_stft = (unsigned)((p.T_max + PV_STFT_FR - 1) / PV_STFT_FR);
+  const int stft_fr = PV_STFT_WARPS * PV_STFT_FPW;
+  const unsigned gx_stft = (unsigned)((p.T_max + stft_fr - 1) / stft_fr);
   const unsigned gx_ph = (unsigned)((p.J_max + 7) / 8);
   const unsigned gx_is = (unsigned)((p.LS_max + PV_OUT_HOPS * PV_HOP - 1) / (PV_OUT_HOPS * PV_HOP));
-  const unsigned gx_rs = (unsigned)((max_len + 1023) / 1024);
+  const int qc_len = nw >= 256 ? RW_QC : 1;
+  const int64_t q_chunks = ((max_len + nw - 1) / nw + qc_len - 1) / qc_len;
+  const unsigned gx_rs = (unsigned)((q_chunks * nw + 255) / 256);
   if (gx_stft > 0x7fffffffu || n > 65535) return cudaErrorInvalidValue;
   lc->begin(KID_PV_STFT, st);
-  k_pv_stft<<<dim3(gx_stft, (unsigned)n), 256, 0, st>>>(x, off, lb, ls, tb.w256, tb.w512, tb.hann, spec, spec_stride);
+  k_pv_stft<<<dim3(gx_stft, (unsigned)n), 32 * PV_STFT_WARPS, 0, st>>>(x, off, lb, ls, tb.w256, tb.w512, tb.hann, spec, spec_stride);
   lc->end(st);
   lc->begin(KID_PV_PHASE, st);
   k_pv_phase<<<dim3(gx_ph, (unsigned)n), 256, 0, st>>>(spec, spec_stride, lb, ls, tb.padv, rate, arange_vec, mag, ph,
@@ -398,17 +426,22 @@ cudaError_t launch_pitch_shift(const PitchTables& tb, const float* x, const int6
   lc->begin(KID_PV_CUMSUM, st);
   k_pv_cumsum<<<dim3((PV_NFREQ + 63) / 64, (unsigned)n), 64, 0, st>>>(lb, ls, rate, ph, plane_stride);
   lc->end(st);
+  {
+    // per device, and cheap: set on every call (a process may hold handles on several devices)
+    cudaError_t e = cudaFuncSetAttribute(k_pv_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, PV_IS_SMEM);
+    if (e != cudaSuccess) return e;
+  }
   lc->begin(KID_PV_ISTFT, st);
-  k_pv_istft<<<dim3(gx_is > 0 ? gx_is : 1, (unsigned)n), 320, 0, st>>>(mag, ph, plane_stride, lb, ls, tb.w256, tb.w512,
+  k_pv_istft<<<dim3(gx_is > 0 ? gx_is : 1, (unsigned)n), 32 * PV_IS_WARPS, PV_IS_SMEM, st>>>(mag, ph, plane_stride, lb, ls, tb.w256, tb.w512,
                                                                       tb.hann, rate, wave, (long long)p.LS_max);
   lc->end(st);
   lc->begin(KID_PV_RESAMPLE, st);
   if (W == 16)
     k_resample_windowed<16><<<dim3(gx_rs, (unsigned)n), 256, 0, st>>>(wave, (long long)p.LS_max, lb, ls, rate, orig, nw,
-                                                                      width, W, taps, ilo, y, y_off);
+                                                                      width, W, taps, ilo, y, y_off, qc_len);
   else
     k_resample_windowed<0><<<dim3(gx_rs, (unsigned)n), 256, 0, st>>>(wave, (long long)p.LS_max, lb, ls, rate, orig, nw,
-                                                                     width, W, taps, ilo, y, y_off);
+                                                                     width, W, taps, ilo, y, y_off, qc_len);
   lc->end(st);
   return cudaGetLastError();
 }
