@@ -28,29 +28,87 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
-// One radix-4 Stockham pass of a 256-point complex FFT held in shared memory; thread t of 64 owns butterfly t.
-// Four passes (Ns = 1, 4, 16, 64) leave the transform in natural order.  INV: conjugate twiddles, +i rotation.
+// 256-point complex FFT of one warp, 8 points per lane, as radix-8 x radix-8 x radix-4 with the butterflies in
+// registers: lane l starts with v[r] = x[l + 32 r].
+//   1. radix-8 over r, twiddle W256^(l k1)                      -> Y[k1][n2 = l]
+//   2. exchange through shared memory (rows of 36 float2: conflict-free both ways); lane (k1 = l >> 2, q = l & 3)
+//      takes Y[k1][q + 4 s], radix-8 over s, twiddle W32^(q a)  -> V[k1][a][q]
+//   3. radix-4 over q = the four lanes of a quad, two xor-shuffle rounds
+// and ends with v[a] = X[k1 + 8 a + 64 b], b = 2 (q & 1) + (q >> 1).  One shared-memory round trip instead of four, no
+// strided twiddle reads (the 14 twiddles a lane needs come from two small conflict-free tables, tw1[k1][lane] and
+// tw2[a][q]).  INV: conjugated constants and tables.  The caller must __syncwarp() before re-using E.
+constexpr int PV_E_LD = 36;                  // row stride of the exchange buffer (float2)
+constexpr int PV_E_SIZE = 8 * PV_E_LD;       // 288 float2 per warp; also holds a padded natural-order copy (pv_nat)
+__device__ __forceinline__ int pv_nat(int k) { return k + 8 * (k >> 6); }   // natural-order index -> padded position
+
 template <bool INV>
-__device__ __forceinline__ void fft256_pass(const float2* __restrict__ in, float2* __restrict__ out,
-                                            const float2* __restrict__ w256, int t, int Ns) {
-  const int k = t & (Ns - 1);
-  float2 v0 = in[t], v1 = in[t + 64], v2 = in[t + 128], v3 = in[t + 192];
-  if (Ns > 1) {
-    const int s = 64 / Ns;
-    float2 w1 = w256[k * s], w2 = w256[2 * k * s], w3 = w256[3 * k * s];
-    if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
-    v1 = cmul(v1, w1); v2 = cmul(v2, w2); v3 = cmul(v3, w3);
+__device__ __forceinline__ void radix4(float2 a0, float2 a1, float2 a2, float2 a3, float2& x0, float2& x1, float2& x2,
+                                       float2& x3) {
+  const float2 e0 = make_float2(a0.x + a2.x, a0.y + a2.y), e1 = make_float2(a0.x - a2.x, a0.y - a2.y);
+  const float2 o0 = make_float2(a1.x + a3.x, a1.y + a3.y), d = make_float2(a1.x - a3.x, a1.y - a3.y);
+  const float2 o1 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);       // d * (+i) / d * (-i)
+  x0 = make_float2(e0.x + o0.x, e0.y + o0.y); x1 = make_float2(e1.x + o1.x, e1.y + o1.y);
+  x2 = make_float2(e0.x - o0.x, e0.y - o0.y); x3 = make_float2(e1.x - o1.x, e1.y - o1.y);
+}
+
+template <bool INV>
+__device__ __forceinline__ void radix8(float2 (&v)[8]) {
+  const float c = 0.70710678118654752f;
+  float2 s[4], d[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s[i] = make_float2(v[i].x + v[i + 4].x, v[i].y + v[i + 4].y);
+    d[i] = make_float2(v[i].x - v[i + 4].x, v[i].y - v[i + 4].y);
   }
-  const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
-  const float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
-  const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
-  const float2 d = make_float2(v1.x - v3.x, v1.y - v3.y);
-  const float2 a3 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);      // d * (+i)  /  d * (-i)
-  const int j0 = ((t - k) << 2) + k;
-  out[j0] = make_float2(a0.x + a2.x, a0.y + a2.y);
-  out[j0 + Ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
-  out[j0 + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
-  out[j0 + 3 * Ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
+  // d[i] *= W8^i
+  d[1] = INV ? make_float2(c * (d[1].x - d[1].y), c * (d[1].x + d[1].y)) : make_float2(c * (d[1].x + d[1].y), c * (d[1].y - d[1].x));
+  d[2] = INV ? make_float2(-d[2].y, d[2].x) : make_float2(d[2].y, -d[2].x);
+  d[3] = INV ? make_float2(-c * (d[3].x + d[3].y), c * (d[3].x - d[3].y)) : make_float2(c * (d[3].y - d[3].x), -c * (d[3].x + d[3].y));
+  radix4<INV>(s[0], s[1], s[2], s[3], v[0], v[2], v[4], v[6]);
+  radix4<INV>(d[0], d[1], d[2], d[3], v[1], v[3], v[5], v[7]);
+}
+
+template <bool INV>
+__device__ __forceinline__ void warp_fft256(float2 (&v)[8], float2* __restrict__ E, const float2* __restrict__ tw1,
+                                            const float2* __restrict__ tw2, int lane) {
+  radix8<INV>(v);
+#pragma unroll
+  for (int k1 = 1; k1 < 8; ++k1) v[k1] = cmul(v[k1], tw1[k1 * 32 + lane]);
+#pragma unroll
+  for (int k1 = 0; k1 < 8; ++k1) E[k1 * PV_E_LD + lane] = v[k1];
+  __syncwarp();
+  const int q = lane & 3;
+  const float2* __restrict__ row = E + (lane >> 2) * PV_E_LD + q;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) v[t] = row[4 * t];
+  radix8<INV>(v);
+#pragma unroll
+  for (int a = 1; a < 8; ++a) v[a] = cmul(v[a], tw2[a * 4 + q]);
+  const bool hi = (q & 2) != 0, odd = (q & 1) != 0;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    float2 own = v[a];
+    float2 par = make_float2(__shfl_xor_sync(0xffffffffu, own.x, 2), __shfl_xor_sync(0xffffffffu, own.y, 2));
+    own = hi ? make_float2(par.x - own.x, par.y - own.y) : make_float2(own.x + par.x, own.y + par.y);
+    par = make_float2(__shfl_xor_sync(0xffffffffu, own.x, 1), __shfl_xor_sync(0xffffffffu, own.y, 1));
+    // quad lanes 0 / 1 hold e0 / o0 -> X0 = e0 + o0, X2 = e0 - o0; lanes 2 / 3 hold e1 / o1 -> X1 = e1 + w o1, X3 = e1 - w o1
+    const float2 t = odd ? own : par;                                           // the "o" term of this pair
+    const float2 wt = !hi ? t : (INV ? make_float2(-t.y, t.x) : make_float2(t.y, -t.x));
+    const float2 e = odd ? par : own;                                           // the "e" term
+    v[a] = odd ? make_float2(e.x - wt.x, e.y - wt.y) : make_float2(e.x + wt.x, e.y + wt.y);
+  }
+}
+
+// tw1[k1][lane] = W256^(lane k1), tw2[a][q] = W32^(q a); conjugated for the inverse.  Filled by the whole CTA.
+constexpr int PV_TW_SIZE = 8 * 32 + 8 * 4;
+template <bool INV>
+__device__ __forceinline__ void pv_fill_twiddles(const float2* __restrict__ g_w256, float2* __restrict__ tw) {
+  for (int i = threadIdx.x; i < PV_TW_SIZE; i += blockDim.x) {
+    const int e = i < 256 ? (i >> 5) * (i & 31) : 8 * ((i - 256) >> 2) * ((i - 256) & 3);
+    float2 t = __ldg(g_w256 + e);
+    if (INV) t.y = -t.y;
+    tw[i] = t;
+  }
 }
 
 __device__ __forceinline__ int pv_frames(long long L) { return (int)(1 + L / PV_HOP); }
@@ -87,47 +145,57 @@ __global__ void __launch_bounds__(32 * PV_STFT_WARPS)
 k_pv_stft(const float* __restrict__ x, const int64_t* __restrict__ off, const char* __restrict__ len_base, int len_stride,
           const float2* __restrict__ g_w256, const float2* __restrict__ g_w512, const float* __restrict__ g_hann,
           float2* __restrict__ spec, long long spec_stride) {
-  __shared__ float2 A[PV_STFT_WARPS][256], B[PV_STFT_WARPS][256];
-  __shared__ float2 w256[256];
+  __shared__ float2 Eall[PV_STFT_WARPS][PV_E_SIZE];
+  __shared__ float2 tw[PV_TW_SIZE];
   const int c = blockIdx.y;
   const long long L = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
   if (L <= PV_NFFT / 2) return;                      // reflect padding needs L > 256 (the host refuses such calls)
   const int T = pv_frames(L);
   const int f0 = blockIdx.x * (PV_STFT_WARPS * PV_STFT_FPW);
   if (f0 >= T) return;
-  w256[threadIdx.x] = g_w256[threadIdx.x];
-  __syncthreads();
   const float* __restrict__ xs = x + off[c];
   float2* __restrict__ sp = spec + (size_t)c * spec_stride;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float2* __restrict__ a = A[w];
-  float2* __restrict__ b = B[w];
+  float2* __restrict__ E = Eall[w];
+  pv_fill_twiddles<false>(g_w256, tw);
+  __syncthreads();
+  const float2* __restrict__ tw1 = tw;
+  const float2* __restrict__ tw2 = tw + 256;
+  const int k1 = lane >> 2, q = lane & 3, bq = ((q & 1) << 1) | (q >> 1);
   for (int it = 0; it < PV_STFT_FPW; ++it) {
     const int f = f0 + it * PV_STFT_WARPS + w;
     if (f >= T) break;                               // warp-uniform
     const long long base = (long long)f * PV_HOP - PV_NFFT / 2;
     const bool interior = base >= 0 && base + PV_NFFT <= L;
+    const bool vec2 = interior && ((reinterpret_cast<uintptr_t>(xs + base) & 7u) == 0);
+    float2 v[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int n = lane + 32 * r;
-      long long i0 = base + 2 * n, i1 = i0 + 1;
-      if (!interior) {
-        i0 = i0 < 0 ? -i0 : (i0 >= L ? 2 * (L - 1) - i0 : i0);
-        i1 = i1 < 0 ? -i1 : (i1 >= L ? 2 * (L - 1) - i1 : i1);
-      }
       const float2 h = __ldg(reinterpret_cast<const float2*>(g_hann) + n);
-      a[n] = make_float2(xs[i0] * h.x, xs[i1] * h.y);
+      float2 xv;
+      if (vec2) {
+        xv = *reinterpret_cast<const float2*>(xs + base + 2 * n);
+      } else {
+        long long i0 = base + 2 * n, i1 = i0 + 1;
+        if (!interior) {
+          i0 = i0 < 0 ? -i0 : (i0 >= L ? 2 * (L - 1) - i0 : i0);
+          i1 = i1 < 0 ? -i1 : (i1 >= L ? 2 * (L - 1) - i1 : i1);
+        }
+        xv = make_float2(xs[i0], xs[i1]);
+      }
+      v[r] = make_float2(xv.x * h.x, xv.y * h.y);
     }
+    warp_fft256<false>(v, E, tw1, tw2, lane);
     __syncwarp();
-    fft256_pass<false>(a, b, w256, lane, 1);  fft256_pass<false>(a, b, w256, lane + 32, 1);  __syncwarp();
-    fft256_pass<false>(b, a, w256, lane, 4);  fft256_pass<false>(b, a, w256, lane + 32, 4);  __syncwarp();
-    fft256_pass<false>(a, b, w256, lane, 16); fft256_pass<false>(a, b, w256, lane + 32, 16); __syncwarp();
-    fft256_pass<false>(b, a, w256, lane, 64); fft256_pass<false>(b, a, w256, lane + 32, 64); __syncwarp();
+#pragma unroll
+    for (int a = 0; a < 8; ++a) E[k1 + 8 * a + 72 * bq] = v[a];       // pv_nat(k1 + 8 a + 64 b)
+    __syncwarp();
     float2* __restrict__ row = sp + (size_t)f * PV_LD;
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
       const int k = lane + 32 * m;                   // 0..127, partner 256 - k
-      const float2 zk = a[k], zc = a[(256 - k) & 255];
+      const float2 zk = E[pv_nat(k)], zc = E[pv_nat((256 - k) & 255)];
       const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
       const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
       const float2 wo = cmul(__ldg(g_w512 + k), o);
@@ -136,7 +204,7 @@ k_pv_stft(const float* __restrict__ x, const int64_t* __restrict__ off, const ch
       row[256 - k] = pv_abs_angle(e.x - wo.x, k ? -(e.y - wo.y) : 0.f);
     }
     if (lane == 0) {                                 // k = 128 is its own partner
-      const float2 z = a[128];
+      const float2 z = E[pv_nat(128)];
       const float2 e = make_float2(z.x, 0.f), o = make_float2(z.y, 0.f);
       const float2 wo = cmul(__ldg(g_w512 + 128), o);
       row[128] = pv_abs_angle(e.x + wo.x, e.y + wo.y);
@@ -211,7 +279,7 @@ k_pv_cumsum(const char* __restrict__ len_base, int len_stride, double rate, floa
 // -> inverse 256-point complex FFT (x[2n] = Re z[n] / 512, x[2n+1] = Im z[n] / 512) -> window -> add.
 constexpr int PV_IS_WARPS = 8;
 constexpr int PV_IS_ROUNDS = 5;
-constexpr int PV_IS_SMEM = (int)(sizeof(float2) * (256 + 2 * PV_IS_WARPS * 256) + sizeof(float) * PV_OUT_HOPS * PV_HOP);
+constexpr int PV_ACC_F2 = PV_OUT_HOPS * 72;      // the tile as float2 pairs, 64 per hop padded to 72 (pv_nat): conflict-free adds
 static_assert(PV_OUT_HOPS == PV_IS_WARPS * PV_IS_ROUNDS - 3, "tile = frames - 3 hops");
 
 // torch.polar(mag, phase_acc)[k]: the fp32 phase is reduced in double (exact input, error ~1e-10 rad)
@@ -230,10 +298,9 @@ k_pv_istft(const float* __restrict__ mag, const float* __restrict__ ph, long lon
            const char* __restrict__ len_base, int len_stride, const float2* __restrict__ g_w256,
            const float2* __restrict__ g_w512, const float* __restrict__ g_hann, double rate,
            float* __restrict__ wave, long long wave_stride) {
-  extern __shared__ __align__(16) unsigned char pv_smem[];
-  float2* w256 = reinterpret_cast<float2*>(pv_smem);
-  float2* AB = w256 + 256;
-  float* acc = reinterpret_cast<float*>(AB + 2 * PV_IS_WARPS * 256);
+  __shared__ float2 Eall[PV_IS_WARPS][PV_E_SIZE];
+  __shared__ float2 tw[PV_TW_SIZE];
+  __shared__ float2 acc[PV_ACC_F2];
   const int c = blockIdx.y;
   const long long L = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
   if (L <= PV_NFFT / 2) return;
@@ -241,12 +308,15 @@ k_pv_istft(const float* __restrict__ mag, const float* __restrict__ ph, long lon
   const long long LS = pv_stretch_len(L, rate);
   const int h0 = blockIdx.x * PV_OUT_HOPS;
   if ((long long)h0 * PV_HOP >= LS) return;
-  w256[threadIdx.x] = g_w256[threadIdx.x];
-  for (int i = threadIdx.x; i < PV_OUT_HOPS * PV_HOP; i += 32 * PV_IS_WARPS) acc[i] = 0.f;
+  for (int i = threadIdx.x; i < PV_ACC_F2; i += 32 * PV_IS_WARPS) acc[i] = make_float2(0.f, 0.f);
+  pv_fill_twiddles<true>(g_w256, tw);
   __syncthreads();
+  const float2* __restrict__ tw1 = tw;
+  const float2* __restrict__ tw2 = tw + 256;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float2* __restrict__ a = AB + (size_t)w * 512;
-  float2* __restrict__ b = a + 256;
+  float2* __restrict__ E = Eall[w];
+  const int k1 = lane >> 2, q = lane & 3, bq = ((q & 1) << 1) | (q >> 1);
+  const int src = (32 - lane) & 31;
   const long long F0 = (long long)(h0 + 2) * PV_HOP;            // first full-signal sample of the tile
   const float* __restrict__ mgc = mag + (size_t)c * plane_stride;
   const float* __restrict__ pcc = ph + (size_t)c * plane_stride;
@@ -255,42 +325,45 @@ k_pv_istft(const float* __restrict__ mag, const float* __restrict__ ph, long lon
     if (j >= 0 && j < J) {                                       // warp-uniform
       const float* __restrict__ mg = mgc + (size_t)j * PV_LD;
       const float* __restrict__ pc = pcc + (size_t)j * PV_LD;
+      // Z[k] and Z[256 - k] of the packed transform from the pair X[k], X[256 - k] (k = lane + 32 m)
+      float2 v[8], zp[4];
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        const int k = lane + 32 * m;                             // 0..127, partner 256 - k
+        const int k = lane + 32 * m;
         const float2 xa = pv_polar(mg, pc, k), xb = pv_polar(mg, pc, 256 - k);
         const float2 e = make_float2(xa.x + xb.x, xa.y - xb.y);
         const float2 d = make_float2(xa.x - xb.x, xa.y + xb.y);
         const float2 wk = __ldg(g_w512 + k);
         const float2 o = cmul(d, make_float2(wk.x, -wk.y));
-        a[k] = make_float2(e.x - o.y, e.y + o.x);
-        if (k) a[256 - k] = make_float2(e.x + o.y, -e.y + o.x);  // conj(e) + i conj(o)
+        v[m] = make_float2(e.x - o.y, e.y + o.x);
+        zp[m] = make_float2(e.x + o.y, -e.y + o.x);              // conj(e) + i conj(o) = Z[256 - k]
       }
-      if (lane == 0) {                                           // k = 128 is its own partner
-        const float2 xa = pv_polar(mg, pc, 128);
-        const float2 e = make_float2(2.f * xa.x, 0.f), d = make_float2(0.f, 2.f * xa.y);
-        const float2 wk = __ldg(g_w512 + 128);
-        const float2 o = cmul(d, make_float2(wk.x, -wk.y));
-        a[128] = make_float2(e.x - o.y, e.y + o.x);
-      }
-      __syncwarp();
-      fft256_pass<true>(a, b, w256, lane, 1);  fft256_pass<true>(a, b, w256, lane + 32, 1);  __syncwarp();
-      fft256_pass<true>(b, a, w256, lane, 4);  fft256_pass<true>(b, a, w256, lane + 32, 4);  __syncwarp();
-      fft256_pass<true>(a, b, w256, lane, 16); fft256_pass<true>(a, b, w256, lane + 32, 16); __syncwarp();
-      fft256_pass<true>(b, a, w256, lane, 64); fft256_pass<true>(b, a, w256, lane + 32, 64); __syncwarp();
-      const long long base = (long long)j * PV_HOP - F0;
+      // lane l needs Z[l + 32 r], r = 4..7 = Z[256 - (32 - l) - 32 (7 - r)]: pair 7 - r of lane 32 - l; lane 0 holds its
+      // own (Z[32 r] = pair 8 - r) and Z[128], which is its own partner
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int n = lane + 32 * m;
-        const float2 z = a[n];
-        const float2 h = __ldg(reinterpret_cast<const float2*>(g_hann) + n);
-        const long long p0 = base + 2 * n;
-        if (p0 >= 0 && p0 < PV_OUT_HOPS * PV_HOP) {              // p0 is even, so p0 + 1 is inside as well
-          float2* dst = reinterpret_cast<float2*>(acc + p0);
-          float2 v = *dst;
-          v.x += (z.x * (1.0f / 512.0f)) * h.x;
-          v.y += (z.y * (1.0f / 512.0f)) * h.y;
-          *dst = v;
+      for (int rr = 4; rr < 8; ++rr)
+        v[rr] = make_float2(__shfl_sync(0xffffffffu, zp[7 - rr].x, src), __shfl_sync(0xffffffffu, zp[7 - rr].y, src));
+      if (lane == 0) {
+        const float2 xa = pv_polar(mg, pc, 128);
+        const float2 wk = __ldg(g_w512 + 128);
+        const float2 o = cmul(make_float2(0.f, 2.f * xa.y), make_float2(wk.x, -wk.y));
+        v[4] = make_float2(2.f * xa.x - o.y, o.x);
+        v[5] = zp[3]; v[6] = zp[2]; v[7] = zp[1];
+      }
+      warp_fft256<true>(v, E, tw1, tw2, lane);
+      __syncwarp();
+      // v[a] = z[n], n = k1 + 8 a + 64 b: samples 2n, 2n + 1 of frame j
+      const int hop = j - (h0 + 2);                              // -3 .. 36
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const int n = k1 + 8 * a + 64 * bq;
+        const int i2 = 64 * hop + n;
+        if (i2 >= 0 && i2 < PV_OUT_HOPS * 64) {
+          const float2 h = __ldg(reinterpret_cast<const float2*>(g_hann) + n);
+          float2 t = acc[pv_nat(i2)];
+          t.x += (v[a].x * (1.0f / 512.0f)) * h.x;
+          t.y += (v[a].y * (1.0f / 512.0f)) * h.y;
+          acc[pv_nat(i2)] = t;
         }
       }
     }
@@ -298,6 +371,7 @@ k_pv_istft(const float* __restrict__ mag, const float* __restrict__ ph, long lon
   }
   const long long full = PV_NFFT + (long long)PV_HOP * (J - 1);
   float* __restrict__ wv = wave + (size_t)c * wave_stride;
+  const float* __restrict__ accf = reinterpret_cast<const float*>(acc);
   for (int i = threadIdx.x; i < PV_OUT_HOPS * PV_HOP; i += 32 * PV_IS_WARPS) {
     const long long nf = F0 + i, n = nf - PV_NFFT / 2;
     if (n >= LS) break;
@@ -308,7 +382,7 @@ k_pv_istft(const float* __restrict__ mag, const float* __restrict__ ph, long lon
       const long long jhi = min((long long)J - 1, nf / PV_HOP);
       float env = 0.f;
       for (long long jj = jlo; jj <= jhi; ++jj) { const float hw = __ldg(g_hann + (nf - jj * PV_HOP)); env = __fadd_rn(env, __fmul_rn(hw, hw)); }
-      out = __fdiv_rn(acc[i], env);
+      out = __fdiv_rn(accf[2 * pv_nat(i >> 1) + (i & 1)], env);
     }
     wv[n] = out;
   }
@@ -426,13 +500,8 @@ cudaError_t launch_pitch_shift(const PitchTables& tb, const float* x, const int6
   lc->begin(KID_PV_CUMSUM, st);
   k_pv_cumsum<<<dim3((PV_NFREQ + 63) / 64, (unsigned)n), 64, 0, st>>>(lb, ls, rate, ph, plane_stride);
   lc->end(st);
-  {
-    // per device, and cheap: set on every call (a process may hold handles on several devices)
-    cudaError_t e = cudaFuncSetAttribute(k_pv_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, PV_IS_SMEM);
-    if (e != cudaSuccess) return e;
-  }
   lc->begin(KID_PV_ISTFT, st);
-  k_pv_istft<<<dim3(gx_is > 0 ? gx_is : 1, (unsigned)n), 32 * PV_IS_WARPS, PV_IS_SMEM, st>>>(mag, ph, plane_stride, lb, ls, tb.w256, tb.w512,
+  k_pv_istft<<<dim3(gx_is > 0 ? gx_is : 1, (unsigned)n), 32 * PV_IS_WARPS, 0, st>>>(mag, ph, plane_stride, lb, ls, tb.w256, tb.w512,
                                                                       tb.hann, rate, wave, (long long)p.LS_max);
   lc->end(st);
   lc->begin(KID_PV_RESAMPLE, st);
