@@ -109,7 +109,7 @@ struct alignas(1024) FzHalf {
   int next_unit;                    // the tile this half works on next (claimed one tile ahead)
 };
 static_assert(LM_SLAB_SM <= LM_BF * LM_PS, "the slab must fit in the pw region");
-static_assert(LM_GROUPS * 200 * 2 <= LM_BF * LM_PS, "the spectrum exchange must fit in the pw region");
+static_assert(LM_GROUPS * 201 * 2 <= LM_BF * LM_PS, "the spectrum exchange must fit in the pw region");
 static_assert(LM_BF * LM_PS * 4 <= LM_GROUPS * LM_FB * 8, "the power spectra must fit in the fb region");
 static_assert((FZ_SPAN * 4) % 16 == 0, "bulk copy size");
 
@@ -531,13 +531,20 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     }
     dft20(v);
     {
-      const float4* tq = reinterpret_cast<const float4*>(S.twT + FZ_TWS * lane);
-      fb[lane] = v[0];
+      const float4* __restrict__ tq = reinterpret_cast<const float4*>(S.twT + FZ_TWS * lane);
+      float2* __restrict__ fbw = fb;
+      fbw[lane] = v[0];
 #pragma unroll
-      for (int q = 0; q < 10; ++q) {
-        const float4 t4 = tq[q];                              // twiddles of k1 = 2q, 2q+1
-        if (q > 0) fb[(2 * q) * 21 + lane] = cmul(v[2 * q], make_float2(t4.x, t4.y));
-        fb[(2 * q + 1) * 21 + lane] = cmul(v[2 * q + 1], make_float2(t4.z, t4.w));
+      for (int q5 = 0; q5 < 10; q5 += 5) {
+        float4 t4[5];                                         // twiddles of k1 = 2q, 2q+1: five loads ahead of the stores
+#pragma unroll
+        for (int q = 0; q < 5; ++q) t4[q] = tq[q5 + q];
+#pragma unroll
+        for (int qq = 0; qq < 5; ++qq) {
+          const int q = q5 + qq;
+          if (q > 0) fbw[(2 * q) * 21 + lane] = cmul(v[2 * q], make_float2(t4[qq].x, t4[qq].y));
+          fbw[(2 * q + 1) * 21 + lane] = cmul(v[2 * q + 1], make_float2(t4[qq].z, t4[qq].w));
+        }
       }
     }
     half_sync(half);
@@ -552,9 +559,12 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     // The exchange goes through the pw region (the slab in it died at the stage-1 barrier) and the power
     // spectra go to the fb region (dead once everybody is past the barrier below): no barrier is needed between
     // stage 2 and the publication, nor between the mel projection and the next batch's FIR.
-    float2* pub = reinterpret_cast<float2*>(H.pw) + g * 200;
+    // Lane 0 pairs with itself, one k2 later (Z[400 - 20 k2] = Z[20 (20 - k2)]): with part = pub + 20 its reads land on
+    // its own published column, and on pub[200] = Z[400] = Z[0] for k2 = 0, which it publishes as well.
+    float2* __restrict__ pub = reinterpret_cast<float2*>(H.pw) + g * 201;
 #pragma unroll
     for (int k2 = 10; k2 < 20; ++k2) pub[lane + 20 * (k2 - 10)] = v[k2];
+    if (lane == 0) pub[200] = v[0];
     half_sync(half);
 #if FZ_TC_MEL
     {
@@ -621,13 +631,15 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
 #else
     float* power = reinterpret_cast<float*>(H.fb);
     {
-      float* pa = power + (2 * g) * LM_PS + lane;
-      float* pb = pa + LM_PS;
-      const float2* part = pub + (20 - lane);                // lane 0: reads stay inside the pw region (unused)
+      float* __restrict__ pa = power + (2 * g) * LM_PS + lane;
+      float* __restrict__ pb = pa + LM_PS;
+      const float2* __restrict__ part = pub + (20 - lane);
+      float2 wp[10];                                         // all ten partner reads in flight before the first use
+#pragma unroll
+      for (int k2 = 0; k2 < 10; ++k2) wp[k2] = part[20 * (9 - k2)];   // partner's k2' = 19 - k2, stored at 20 * (k2' - 10)
 #pragma unroll
       for (int k2 = 0; k2 < 10; ++k2) {
-        float2 w = part[20 * (9 - k2)];                      // partner's k2' = 19 - k2, stored at 20 * (k2' - 10)
-        if (lane == 0) w = (k2 == 0) ? v[0] : v[20 - k2];
+        const float2 w = wp[k2];
         const float2 z = v[k2];
         const float ar = z.x + w.x, ai = z.y - w.y, br = z.x - w.x, bi = z.y + w.y;
         pa[20 * k2] = 0.25f * (ar * ar + ai * ai);
