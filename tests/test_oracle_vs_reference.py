@@ -105,3 +105,32 @@ def test_log_mel_matches_transformers(n_mels):
     assert_close(oracle.log_mel(w, n_mels, True), want, tol=TOL, what="log-mel 30 s pad")
     want = fe(w, sampling_rate=16000, return_tensors="np", padding="longest", truncation=False)["input_features"][0]
     assert_close(oracle.log_mel(w, n_mels, False), want, tol=TOL, what="log-mel unpadded")
+
+
+def test_pitch_shift_matches_torchaudio_on_random_cases():
+    """oracle/pitch.py against the live torchaudio.functional.pitch_shift (what base_tts.py:644 calls) on random
+    lengths and fractional steps; clips <= 1.3 s, where the fp32 reference is reproducible to 1e-4 (tests/test_pitch_shift.py
+    explains the long-clip case)."""
+    ta = pytest.importorskip("torchaudio")
+    from oracle import pitch as OP
+    rng = np.random.default_rng(77)
+    for case in range(6):
+        L = int(rng.integers(257, 31000))
+        steps = float(np.round(rng.uniform(-6, 6), 2)) or 1.0
+        x = tone_clip(rng, L, amp=0.35) + rng.normal(0, 0.003, L).astype(np.float32)
+        want = ta.functional.pitch_shift(torch.from_numpy(x)[None], 24000, steps)[0].numpy()
+        got = OP.pitch_shift(x, 24000, steps)
+        assert got.shape == want.shape == x.shape
+        assert_close(got, want, tol=TOL, what=f"pitch_shift L={L} n_steps={steps}")
+
+
+def test_pitch_time_steps_match_torch_arange_for_all_semitones():
+    """The fp32 time steps of the phase vocoder, bit for bit, for every half-semitone in +-12 and 20 frame counts."""
+    from oracle import pitch as OP
+    for half in range(-24, 25):
+        if half == 0:
+            continue
+        rate = OP.pitch_rate(half / 2.0)
+        for T in range(3, 2400, 123):
+            want = torch.arange(0, T, rate, dtype=torch.float32).numpy()
+            assert np.array_equal(OP.arange_f32(want.size, rate), want), (half, T)
