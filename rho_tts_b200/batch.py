@@ -256,6 +256,27 @@ def qwen_pipeline_batch(rb: RaggedBatch, item_first_seg: Sequence[int], p: RhoPa
     return out
 
 
+def qwen_validate_batch(rb: RaggedBatch, item_first_seg: Sequence[int], p: RhoParams,
+                        emb: Optional[torch.Tensor] = None, ref: Optional[torch.Tensor] = None, n_mels: int = 80,
+                        pad_to_30s: bool = True, qwen3_sr: int = 24000) -> "ValidateOutput":
+    """validate_batch for a Qwen provider: join -> loudness hook -> decay check, then the features of the HOOKED audio
+    (resample 24k->16k -> log-mel) and the cosine, in the order _run_pipeline applies them (base_tts.py:911-926)."""
+    out = qwen_pipeline_batch(rb, item_first_seg, p, qwen3_sr)
+    dev = _dev_index(rb.data)
+    h = Handle.get(dev)
+    n = out.audio.n
+    lens = out.records[:, 8:12].contiguous().view(torch.int32).reshape(-1)        # out_len (device)
+    rb16 = resample_batch(out.audio, lengths=lens)
+    mel, _ = logmel_batch(rb16, n_mels, pad_to_30s, lengths=rb16.lengths)
+    if emb is not None and n:
+        emb = emb.contiguous().float()
+        ref = ref.contiguous().float().to(emb.device)
+        cos_ptr = ctypes.c_void_p(out.records.data_ptr() + 28)                   # the cosine column of the 48-byte records
+        _lib.check(h.lib.rho_b200_cosine(h.ptr, _ptr(emb), _ptr(ref), n, emb.shape[1], cos_ptr, 48, _stream(dev)),
+                   "cosine")
+    return ValidateOutput(out.audio, mel, out.records)
+
+
 def cosine_batch(emb: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
     """dot(ref, e) / (|ref| |e|) per row of emb (base_tts.py:341-344)."""
     dev = _dev_index(emb)

@@ -196,3 +196,37 @@ def test_gpu_qwen_pipeline_join_hook_decay(cuda_device):
         assert bool(rec["ok"][i]) == ok and abs(rec["decay_ratio"][i] - ratio) <= 1e-4 * max(1.0, abs(ratio))
         flips += int(abs(ratio - oracle.sound_decay(j, 0.3)[0]) > 1e-3 * max(1.0, abs(ratio)))
     assert flips > 0            # the ratio is the hooked audio's, not the joined audio's: the order of operations matters
+
+
+@pytest.mark.gpu
+def test_gpu_qwen_validate_features_of_hooked_audio(cuda_device):
+    """qwen_validate_batch: the log-mel features and the cosine belong to the audio AFTER the loudness hook."""
+    import oracle
+    import rho_tts_b200 as R
+    from rho_tts_b200 import synth
+    lens = synth.make_ragged_lengths(10, 31, 1.5, 6.0)
+    clips = [c.numpy() for c in synth.make_clips(lens, 33)]
+    first = synth.make_item_partition(10, 7, 1, 3)
+    n_items = len(first) - 1
+    emb, ref = synth.make_embeddings(n_items, device=cuda_device)
+    p = R.make_params()
+    rb = R.RaggedBatch.from_list([torch.from_numpy(c) for c in clips], cuda_device)
+    v = R.qwen_validate_batch(rb, first, p, emb, ref, n_mels=80, pad_to_30s=False)
+    rec = v.records_host()
+    c = oracle.derive_constants()
+    for i in range(n_items):
+        j = oracle.smooth_segment_join(clips[first[i]:first[i + 1]], c).audio
+        hooked = oq.post_process(j)
+        L = int(rec["out_len"][i])
+        got_audio = v.audio.clip(i, L).cpu().numpy()
+        assert_close(got_audio, hooked, what=f"hooked item {i}")
+        # stage parity on identical inputs: the oracle's features of the GPU's hooked audio.  End to end the bound is
+        # looser: a 1e-7 relative difference of the waveform is a noise floor at -140 dB, i.e. 1e-3 relative on bins just
+        # above the normaliser's -80 dB clamp, 4e-4 in log10 units.
+        want = oracle.log_mel(oracle.resample(got_audio), 80, False)
+        T = want.shape[1]
+        assert_close(v.mel[i, :, :T].cpu().numpy(), want, what=f"log-mel of the hooked item {i}")
+        assert_close(v.mel[i, :, :T].cpu().numpy(), oracle.log_mel(oracle.resample(hooked), 80, False), tol=4e-4,
+                     what=f"log-mel end to end, item {i}")
+        assert abs(rec["cosine"][i] - oracle.cosine_similarity(ref.cpu().numpy(), emb[i].cpu().numpy())) <= 1e-5
+        assert bool(rec["ok"][i]) == oracle.sound_decay(hooked, 0.3)[1]
