@@ -11,7 +11,8 @@
 // One CTA per SM, two independent 320-thread halves (named barriers), each half owns a stream of
 // 32-frame batches of one clip.  Per batch and half:
 //   span  : x[start + 240*t0 - 312 .. +8068) staged by ONE TMA bulk copy (32 KB, mbarrier completion) when the
-//           span lies inside the clip, else zero-filling LDGSTS; prefetched under the previous batch's FFT
+//           span lies inside the clip, else zero-filling LDGSTS; prefetched under the previous batch's FFT -- across
+//           tiles too: thread 0 resolves the half's next unit one tile ahead (FzNext)
 //   apply : interior batches (no fade, no clip edge, one decay zone): y = x - dc straight from registers to
 //           HBM, the span keeps the raw x and the FIR folds dc in (FIR(x - dc) = FIR(x) - dc * sum(taps));
 //           edge batches: in place (x-dc)*fade -> y
@@ -97,6 +98,16 @@ constexpr int FZ_DPAIRS = LM_SLAB / 4;                      // 1340 groups of 4 
 
 constexpr int FZ_TWS = 22;                                  // float2 per twiddle row (conflict-free 128-bit reads)
 
+// The unit (clip c, 128-frame tile) a half works on next, resolved by its thread 0 one tile ahead so that a tile
+// starts from shared memory instead of a chain of dependent global loads, with its first span already in flight.
+struct FzNext {
+  long long x_off;                  // seg_off[s] + start: first sample of y in x
+  long long y_off;
+  int u, c, start, end;
+  float dc;
+  int prefetched;                   // the unit's first span is a bulk copy already issued on FzHalf::bar
+};
+
 struct alignas(1024) FzHalf {
   float2 fb[LM_GROUPS * LM_FB];     // FFT buffers; afterwards the power spectra (FZ_TC_MEL: as UMMA operands, 512-byte atoms)
   float span[FZ_SPAN];
@@ -107,6 +118,7 @@ struct alignas(1024) FzHalf {
   uint64_t mma_bar;                 // mbarrier the tensor-core mel projection of a batch commits to
   int last;                         // "this half finished its clip last" broadcast
   int next_unit;                    // the tile this half works on next (claimed one tile ahead)
+  FzNext nd;
 };
 static_assert(LM_SLAB_SM <= LM_BF * LM_PS, "the slab must fit in the pw region");
 static_assert(LM_GROUPS * 201 * 2 <= LM_BF * LM_PS, "the spectrum exchange must fit in the pw region");
@@ -308,17 +320,50 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   // for its partner, and no SM is left with one tile more than the others.  The next claim is issued at the
   // start of a tile and consumed at its end, so the atomic's round trip is never exposed.
   const int n_units = n_items * tile_pairs * FZ_HALVES;
-  if (tid == 0) H.next_unit = atomicAdd(work_counter, 1);
+  // thread 0 of the half only: resolve unit `un` into H.nd
+  auto fill_desc = [&](int un) {
+    FzNext d;
+    d.u = un; d.c = 0; d.start = 0; d.end = 0; d.dc = 0.f; d.prefetched = 0; d.x_off = 0; d.y_off = 0;
+    if (un < n_units) {
+      d.c = un % n_items;
+      const int sn = item_first_seg[d.c];
+      const SegState sn_st = seg[sn];
+      d.start = sn_st.start; d.end = sn_st.end; d.dc = sn_st.dc;
+      d.x_off = seg_off[sn] + sn_st.start;
+      d.y_off = y_off[d.c];
+    }
+    H.nd = d;
+  };
+  // thread 0 only, once the span buffer is dead: issue the bulk copy of the next unit's first span
+  auto prefetch_next_tile = [&]() {
+    const FzNext d = H.nd;
+    if (!FZ_BULK || d.u >= n_units) return;
+    const int nn = d.end - d.start;
+    const int nn16 = nn > 0 ? (int)((2LL * nn + 2) / 3) : 0;
+    int Tn, Tn_real, Nn, nvn;
+    lm_frame_counts(nn16, pad_frames, &Tn, &Tn_real, &Nn, &nvn);
+    const int tt0 = (d.u / n_items) * LM_TILE;
+    if (tt0 >= max(Tn_real, (nn + 239) / 240)) return;
+    const float* xsn = x + d.x_off;
+    const long long j0 = 240LL * tt0 - FZ_LEAD;
+    if ((reinterpret_cast<uintptr_t>(xsn) & 15u) != 0 || j0 < 0 || j0 + FZ_SPAN > nn) return;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive_expect_tx(&H.bar, FZ_SPAN * 4);
+    bulk_g2s(H.span, xsn + j0, FZ_SPAN * 4, &H.bar);
+    H.nd.prefetched = 1;
+  };
+  if (tid == 0) fill_desc(atomicAdd(work_counter, 1));
   for (;;) {
-  half_sync(half);                                   // the claim written by tid 0 is visible
-  const int u = H.next_unit;
+  half_sync(half);                                   // the descriptor written by tid 0 is visible
+  const FzNext nd = H.nd;
   half_sync(half);                                   // ... and read by everybody before it is replaced
+  const int u = nd.u;
   if (u >= n_units) break;
   if (tid == 0) H.next_unit = atomicAdd(work_counter, 1);
-  const int c = u % n_items;
+  const int c = nd.c;
   const int tile = u / n_items;
-  const int s = item_first_seg[c];
-  const SegState st = seg[s];
+  SegState st;
+  st.start = nd.start; st.end = nd.end; st.dc = nd.dc;
   const int n = st.end - st.start;                   // samples of y
   const float dc = st.dc;
   const int n16 = n > 0 ? (int)((2LL * n + 2) / 3) : 0;
@@ -327,10 +372,10 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   if (tile == 0 && tid == 0) len16_out[c] = n16;
   const int t_cover = max(T_real, (n + 239) / 240);  // batches needed for the features AND to write all of y
   const int tile_t0 = tile * LM_TILE;
-  if (tile_t0 >= t_cover) continue;
+  if (tile_t0 >= t_cover) { if (tid == 0) fill_desc(H.next_unit); continue; }
 
-  const float* __restrict__ xs = x + seg_off[s] + st.start;
-  float* __restrict__ ys = y + y_off[c];
+  const float* __restrict__ xs = x + nd.x_off;
+  float* __restrict__ ys = y + nd.y_off;
   float* __restrict__ out = mel + (long long)c * NM * mel_stride;
   const int third = n / 3;
   const bool need_fade = fade > 0 && n >= 2 * fade;
@@ -369,12 +414,15 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       cp_async_commit();
     }
   };
-  stage_span(tile_t0);
+  if (!nd.prefetched) stage_span(tile_t0);
 
   for (int b = 0; b < LM_BATCHES; ++b) {
     const int t0 = tile_t0 + b * LM_BF;
     if (t0 >= t_cover) break;
     const bool next = (b + 1 < LM_BATCHES) && (t0 + LM_BF < t_cover);
+    // the claim issued at the start of the tile has long returned: resolve it during the second batch, or at the
+    // last batch's prefetch point if the tile has only one
+    if (b == 1 && tid == 0) fill_desc(H.next_unit);
     // Bulk mode needs no barrier here: every thread waits on the mbarrier itself, and nothing this batch writes
     // before its first barrier (the slab, in the pw region) is still read by the previous batch (its power
     // spectra live in the fb region, its partner exchange finished before its last barrier).
@@ -427,6 +475,10 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     }
     if (t0 >= T_real) {                                      // a batch that only had output samples left to write
       if (next) { half_sync(half); stage_span(t0 + LM_BF); }
+      else {
+        half_sync(half);
+        if (tid == 0) { if (b == 0) fill_desc(H.next_unit); prefetch_next_tile(); }
+      }
       continue;
     }
     // ---- FIR 24k -> 16k: slab position i holds w16[w0 + i], w0 = 160*t0 - 200;
@@ -549,6 +601,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     }
     half_sync(half);
     if (next) stage_span(t0 + LM_BF);                        // span and slab are dead: prefetch under stage 2 / mel
+    else if (tid == 0) { if (b == 0) fill_desc(H.next_unit); prefetch_next_tile(); }
     // ---- FFT stage 2: lane = k1, 20-point DFT over n2 -> Z[k1 + 20*k2] in v[k2]
 #pragma unroll
     for (int n2 = 0; n2 < 20; ++n2) v[n2] = fb[lane * 21 + n2];
