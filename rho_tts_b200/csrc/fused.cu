@@ -21,6 +21,8 @@
 //   FFT   : as k_logmel_frames (two real frames per 400-point complex FFT, 20 x 20, packed fp32x2 butterflies)
 //   mel   : immediate-weight FFMAs, SFU log2, ordered-int atomicMax of the clip maximum
 #include <algorithm>
+#include <vector>
+#include <cstdlib>
 #include "logmel_dev.cuh"
 
 namespace rho {
@@ -98,7 +100,16 @@ constexpr int FZ_DPAIRS = LM_SLAB / 4;                      // 1340 groups of 4 
 
 constexpr int FZ_TWS = 22;                                  // float2 per twiddle row (conflict-free 128-bit reads)
 
-// The unit (clip c, 128-frame tile) a half works on next, resolved by its thread 0 one tile ahead so that a tile
+// How the frames of a clip are cut into tiles: tile k covers the 32-frame batches [start[k], start[k+1])
+// (launch_fused_features picks the sizes per call).  Units are handed out tile-major: the last tiles of the clips,
+// which are the short ones, come at the end and level the halves.
+constexpr int FZ_MAX_TILES = 24;
+struct FzSched {
+  int n_tiles;
+  int start[FZ_MAX_TILES + 1];
+};
+
+// The unit (clip c, tile) a half works on next, resolved by its thread 0 one tile ahead so that a tile
 // starts from shared memory instead of a chain of dependent global loads, with its first span already in flight.
 struct FzNext {
   long long x_off;                  // seg_off[s] + start: first sample of y in x
@@ -258,7 +269,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
                  const float* __restrict__ g_hann, const float2* __restrict__ g_tw, int pad_frames,
                  float* __restrict__ mel, long long mel_stride, int* __restrict__ clip_max,
                  int32_t* __restrict__ len16_out, int* __restrict__ tiles_done, int* __restrict__ work_counter,
-                 int tile_pairs, int n_items, const float* __restrict__ mel_dense) {
+                 const __grid_constant__ FzSched sched, int n_items, const float* __restrict__ mel_dense) {
   extern __shared__ unsigned char smem_raw[];
   FzSmem& S = *reinterpret_cast<FzSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   for (int i = threadIdx.x; i < N_FFT; i += FZ_THREADS) {
@@ -319,7 +330,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   // order: the short last tiles of the clips come at the end) and runs at its own pace -- a half never waits
   // for its partner, and no SM is left with one tile more than the others.  The next claim is issued at the
   // start of a tile and consumed at its end, so the atomic's round trip is never exposed.
-  const int n_units = n_items * tile_pairs * FZ_HALVES;
+  const int n_units = n_items * sched.n_tiles;       // unit u = (clip u % n_items, tile u / n_items): big tiles first
   // thread 0 of the half only: resolve unit `un` into H.nd
   auto fill_desc = [&](int un) {
     FzNext d;
@@ -342,7 +353,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     const int nn16 = nn > 0 ? (int)((2LL * nn + 2) / 3) : 0;
     int Tn, Tn_real, Nn, nvn;
     lm_frame_counts(nn16, pad_frames, &Tn, &Tn_real, &Nn, &nvn);
-    const int tt0 = (d.u / n_items) * LM_TILE;
+    const int tt0 = sched.start[d.u / n_items] * LM_BF;
     if (tt0 >= max(Tn_real, (nn + 239) / 240)) return;
     const float* xsn = x + d.x_off;
     const long long j0 = 240LL * tt0 - FZ_LEAD;
@@ -371,7 +382,8 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   lm_frame_counts(n16, pad_frames, &T, &T_real, &N, &n_valid);
   if (tile == 0 && tid == 0) len16_out[c] = n16;
   const int t_cover = max(T_real, (n + 239) / 240);  // batches needed for the features AND to write all of y
-  const int tile_t0 = tile * LM_TILE;
+  const int tile_t0 = sched.start[tile] * LM_BF;
+  const int tile_batches = sched.start[tile + 1] - sched.start[tile];
   if (tile_t0 >= t_cover) { if (tid == 0) fill_desc(H.next_unit); continue; }
 
   const float* __restrict__ xs = x + nd.x_off;
@@ -416,10 +428,10 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   };
   if (!nd.prefetched) stage_span(tile_t0);
 
-  for (int b = 0; b < LM_BATCHES; ++b) {
+  for (int b = 0; b < tile_batches; ++b) {
     const int t0 = tile_t0 + b * LM_BF;
     if (t0 >= t_cover) break;
-    const bool next = (b + 1 < LM_BATCHES) && (t0 + LM_BF < t_cover);
+    const bool next = (b + 1 < tile_batches) && (t0 + LM_BF < t_cover);
     // the claim issued at the start of the tile has long returned: resolve it during the second batch, or at the
     // last batch's prefetch point if the tile has only one
     if (b == 1 && tid == 0) fill_desc(H.next_unit);
@@ -755,8 +767,9 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       if (FZ_INLINE_NORM && tiles_done) {
         // barrier (CTA scope) -> fence (GPU scope) -> atomic: the grid-sync idiom
         __threadfence();
-        const int n_tiles = (t_cover + LM_TILE - 1) / LM_TILE;
-        last = (atomicAdd(&tiles_done[c], 1) == n_tiles - 1);
+        int clip_tiles = 0;                          // tiles of the schedule that start inside this clip
+        while (clip_tiles < sched.n_tiles && sched.start[clip_tiles] * LM_BF < t_cover) ++clip_tiles;
+        last = (atomicAdd(&tiles_done[c], 1) == clip_tiles - 1);
         if (last) __threadfence();                   // acquire side: the other halves' maxima
       }
       H.last = last;
@@ -813,23 +826,52 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
     max_real = max16 / HOP16;
   }
   const int64_t cover = std::max<int64_t>(max_real, (max_len + 239) / 240);
-  unsigned tiles = (unsigned)((cover + LM_TILE - 1) / LM_TILE);
-  if (tiles == 0) tiles = 1;
-  const unsigned gy = (tiles + FZ_HALVES - 1) / FZ_HALVES;
-  const size_t smem = sizeof(FzSmem) + 1024;      // slack to align the halves to 1024 bytes (swizzle atoms)
-  auto kern = (n_mels == 80) ? k_fused_features<80> : k_fused_features<128>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  if ((uint64_t)n_items * gy * FZ_HALVES > 0x7fffffffull) return cudaErrorInvalidValue;
   int dev = 0, sm_count = 0;                         // per call: a process may drive several devices
+  cudaError_t e;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-  const uint64_t n_work = (uint64_t)n_items * gy;
+  // Unit = (clip, tile).  Every tile ends with a reduction, three atomics and a fence and starts with an empty
+  // pipeline (~3 us together), so tiles should be long -- but the halves draw units from one counter, and whoever draws
+  // a long tile last finishes last.  Measured on 1000 x 10 s (32 batches per clip), k_fused_features in ms:
+  //   uniform tiles of 2 / 4 / 8 / 11 / 13 / 16 batches   1.019 / 0.961 / 0.933 / 0.934 / 0.918 / 0.936
+  //   13,13,6  14,14,4  16,13,3  15,15,2  22,8,2  30,2     0.919   0.925   0.928   0.944   0.928  1.027
+  //   guided (each tile 40 % of the rest: 13,8,5,3,2,1)    0.952   (twice the tiles: the per-tile cost wins)
+  // Policy: tiles of 40 % of the longest clip (two long tiles and a half-size one to level the end), capped with few
+  // clips so that there are a few units per half.  RHO_FUSED_SCHED / RHO_FUSED_TILE_BATCHES override it for A/B runs.
+  const int64_t n_b = std::max<int64_t>(1, (cover + LM_BF - 1) / LM_BF);
+  static const int forced_bpt = [] { const char* v = getenv("RHO_FUSED_TILE_BATCHES"); return v ? atoi(v) : 0; }();   // A/B tool: uniform tiles
+  const int64_t halves = (int64_t)FZ_HALVES * sm_count;
+  int64_t cap = std::max<int64_t>(1, (n_b * n_items) / (4 * halves));      // >= ~4 units per half before the tail
+  FzSched sched;
+  sched.n_tiles = 0;
+  sched.start[0] = 0;
+  static const std::vector<int> forced_sched = [] {                        // A/B tool: explicit sizes, last one repeats
+    std::vector<int> v;
+    if (const char* e = getenv("RHO_FUSED_SCHED")) for (const char* q = e; *q;) { v.push_back(atoi(q)); while (*q && *q != ',') ++q; if (*q) ++q; }
+    return v;
+  }();
+  for (int64_t pos = 0; pos < n_b;) {
+    int64_t left = n_b - pos, sz;
+    if (!forced_sched.empty()) sz = std::max(1, forced_sched[std::min<size_t>(sched.n_tiles, forced_sched.size() - 1)]);
+    else if (forced_bpt > 0) sz = forced_bpt;
+    else sz = std::min<int64_t>(std::max<int64_t>((n_b * 2 + 4) / 5, 1), cap);
+    if (sched.n_tiles == FZ_MAX_TILES - 1) sz = left;                      // table full: the rest in one tile
+    sz = std::min(sz, left);
+    pos += sz;
+    sched.start[++sched.n_tiles] = (int)pos;
+  }
+  const int64_t tiles = sched.n_tiles;
+  const size_t smem = sizeof(FzSmem) + 1024;      // slack to align the halves to 1024 bytes (swizzle atoms)
+  auto kern = (n_mels == 80) ? k_fused_features<80> : k_fused_features<128>;
+  if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+  const uint64_t n_units = (uint64_t)n_items * (uint64_t)tiles;
+  if (n_units > 0x7fffffffull) return cudaErrorInvalidValue;
+  const uint64_t n_work = (n_units + FZ_HALVES - 1) / FZ_HALVES;
   dim3 grid((unsigned)(n_work < (uint64_t)sm_count ? n_work : (uint64_t)sm_count));   // persistent: one CTA per SM
   lc->begin(KID_FUSED, st);
   kern<<<grid, FZ_THREADS, smem, st>>>(x, seg_off, ws.seg, ws.item, item_first_seg, y, y_off, d.fade, tb.hann,
                                        tb.twiddle, pad_frames, mel, mel_stride_frames, ws.clip_max, ws.len16,
-                                       ws.tiles_done, ws.work_counter, (int)gy, n_items,
+                                       ws.tiles_done, ws.work_counter, sched, n_items,
                                        tb.mel_dense[n_mels == 80 ? 0 : 1]);
   lc->end(st);
   return cudaGetLastError();

@@ -5,4 +5,4 @@ import sys
 for line in sys.stdin:
     if line.startswith("{"):
         d = json.loads(line)
-        print(d["config"], d["ms_per_step"], {k: (v["ms"], v["frac_hbm"]) for k, v in d["kernels"].items()})
+        print(d["config"], d["ms_per_step"], {k: (v["ms"], v.get("frac_hbm")) for k, v in d["kernels"].items()})
