@@ -193,6 +193,18 @@ int rho_b200_pitch_shift(rho_handle* h, const float* x, const int64_t* off, cons
                          int n, int64_t min_len, int64_t max_len, int sample_rate, double n_steps, int arange_vec,
                          float* y, const int64_t* y_off, void* workspace, size_t ws_bytes, void* stream);
 
+/* --------------------------------------------------------------- MFCC statistics (NEXT-3, drift-classifier front end) */
+/* validation/classifier/trainer.py:50-52: mfcc = librosa.feature.mfcc(y=y, sr=16000, n_mfcc=13); mean and std over the
+ * frames, for n clips of 16 kHz audio (e.g. the output of rho_b200_resample3to2).  librosa >= 0.10 semantics: stft 2048 /
+ * hop 512, periodic hann, centred with zero padding, |X|^2, 128 slaney mel bands, 10 log10(max(1e-10, .)) clamped at
+ * (clip maximum - 80), orthonormal DCT-II, first 13.  out[s] = 13 means then 13 population standard deviations.
+ * librosa is absent from the authoring image: the oracle is pinned on transformers' port of these steps and on scipy's
+ * DCT (oracle/mfcc.py).  Clips must not be empty.  workspace: rho_b200_mfcc_workspace_bytes(n, max_len), 256-byte
+ * aligned. */
+size_t rho_b200_mfcc_workspace_bytes(int n, int64_t max_len);
+int rho_b200_mfcc_stats(rho_handle* h, const float* x16, const int64_t* off, const int32_t* len, int len_stride_bytes,
+                        int n, int64_t max_len, float* out, void* workspace, size_t ws_bytes, void* stream);
+
 /* --------------------------------------------------------------- batched decay check on finished audio (a5) */
 /* _validate_sound_decay (base_tts.py:297-323) for n clips that are already final, e.g. after the Qwen loudness hook,
  * which the pipeline runs between the join and the decay check (base_tts.py:911-926).  Rewrites first_rms, last_rms,

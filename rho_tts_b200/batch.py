@@ -172,6 +172,25 @@ def pitch_shift_batch(rb: RaggedBatch, sample_rate: int, n_steps: float,
     return out
 
 
+def mfcc_stats_batch(rb16: RaggedBatch, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[n, 26] fp32: mean and std over the frames of librosa.feature.mfcc(y, sr=16000, n_mfcc=13) per 16 kHz clip -- the
+    MFCC part of the drift classifier's feature vector (validation/classifier/trainer.py:50-52)."""
+    dev = _dev_index(rb16.data)
+    h = Handle.get(dev)
+    n = rb16.n
+    out = torch.empty((n, 26), dtype=torch.float32, device=rb16.device)
+    if n == 0:
+        return out
+    if lengths is None and int(min(rb16.h_lengths)) < 1:
+        raise RuntimeError("rho_tts_b200.mfcc_stats_batch: empty clip")
+    need = int(h.lib.rho_b200_mfcc_workspace_bytes(n, rb16.max_len))
+    ws = torch.empty(max(need, 256), dtype=torch.uint8, device=rb16.device)
+    lens = rb16.lengths if lengths is None else lengths
+    _lib.check(h.lib.rho_b200_mfcc_stats(h.ptr, _ptr(rb16.data), _ptr(rb16.offsets), _ptr(lens), 4, n, rb16.max_len,
+                                         _ptr(out), _ptr(ws), ws.numel(), _stream(dev)), "mfcc_stats")
+    return out
+
+
 def logmel_batch(rb16: RaggedBatch, n_mels: int = 80, pad_to_30s: bool = True,
                  lengths: Optional[torch.Tensor] = None):
     """WhisperFeatureExtractor features.  Returns (mel [n, n_mels, T], n_frames int32 [n]) on the device;

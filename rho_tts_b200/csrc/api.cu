@@ -49,7 +49,7 @@ const char* const kKernelNames[KID_COUNT] = {
   "k_init", "k_scan", "k_finalize_segs", "k_plan_items", "k_gather", "k_finalize_items",
   "k_resample3to2", "k_logmel_init", "k_logmel_frames", "k_logmel_norm", "k_cosine", "k_single_clip_helpers",
   "k_fused_features", "k_mel_gemm", "k_qwen_moments", "k_qwen_plan", "k_qwen_apply", "k_resample_general",
-  "k_pv_stft", "k_pv_phase", "k_pv_cumsum", "k_pv_istft", "k_resample_windowed"};
+  "k_pv_stft", "k_pv_phase", "k_pv_cumsum", "k_pv_istft", "k_resample_windowed", "k_mfcc_frames", "k_mfcc_stats"};
 }
 
 struct rho_handle {
@@ -68,6 +68,8 @@ struct rho_handle {
   // rho_b200_pitch_shift: FFT / window / phase-advance tables (built on first use) and windowed tap tables per ratio
   PitchTables pitch_tb{};
   bool pitch_tb_ok = false;
+  MfccTables mfcc_tb{};
+  bool mfcc_tb_ok = false;
   struct WinTaps { float* taps; int* ilo; };
   std::map<uint64_t, WinTaps> windowed_taps;
 };
@@ -452,6 +454,56 @@ int rho_b200_pitch_shift(rho_handle* h, const float* x, const int64_t* off, cons
   cudaError_t e = launch_pitch_shift(h->pitch_tb, x, off, len, len_stride_bytes, n, max_len, rate, arange_vec, orig, nw,
                                      width, W, wt.taps, wt.ilo, y, y_off, workspace, (cudaStream_t)stream, &h->lc);
   return e == cudaSuccess ? RHO_OK : cuda_fail(e, "pitch_shift");
+}
+
+size_t rho_b200_mfcc_workspace_bytes(int n, int64_t max_len) { return mfcc_workspace_bytes(n, max_len); }
+
+int rho_b200_mfcc_stats(rho_handle* h, const float* x16, const int64_t* off, const int32_t* len, int len_stride_bytes,
+                        int n, int64_t max_len, float* out, void* workspace, size_t ws_bytes, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  if (n < 0 || max_len < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (n == 0) return RHO_OK;
+  if (n > 65535) return fail(RHO_ERR_INVALID, "at most 65535 clips per call");
+  if (!x16 || !off || !len || !out) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  const size_t need = mfcc_workspace_bytes(n, max_len);
+  if (!workspace || ws_bytes < need) return fail(RHO_ERR_WORKSPACE, "workspace too small: have %zu, need %zu", ws_bytes, need);
+  if (((uintptr_t)workspace) & 255u) return fail(RHO_ERR_INVALID, "workspace must be 256-byte aligned");
+  {
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!h->mfcc_tb_ok) {
+      std::vector<float> hn(2048), w1(2048), w2(2050), dct(13 * 128), w256(512), w512(514), hn512(512), pv(257);
+      host_mfcc_tables(hn.data(), w1.data(), w2.data(), dct.data());
+      host_pitch_tables(w256.data(), w512.data(), hn512.data(), pv.data());
+      std::vector<float> dense((size_t)128 * 1025);
+      host_mel_filterbank_bins(128, 1025, dense.data());
+      std::vector<int> lo(128), cnt(128), wofs(128);
+      std::vector<float> w;
+      for (int m = 0; m < 128; ++m) {
+        int a = 0, b = 1025;
+        while (a < 1025 && dense[(size_t)m * 1025 + a] == 0.f) ++a;
+        while (b > a && dense[(size_t)m * 1025 + b - 1] == 0.f) --b;
+        lo[m] = a; cnt[m] = b - a; wofs[m] = (int)w.size();
+        for (int k = a; k < b; ++k) w.push_back(dense[(size_t)m * 1025 + k]);
+      }
+      if (w.empty()) w.push_back(0.f);
+      MfccTables& t = h->mfcc_tb;
+      cudaError_t e;
+      if ((e = dev_upload(h, (float**)&t.w256, w256.data(), w256.size())) != cudaSuccess ||
+          (e = dev_upload(h, (float**)&t.w1024, w1.data(), w1.size())) != cudaSuccess ||
+          (e = dev_upload(h, (float**)&t.w2048, w2.data(), w2.size())) != cudaSuccess ||
+          (e = dev_upload(h, &t.hann, hn.data(), hn.size())) != cudaSuccess ||
+          (e = dev_upload(h, &t.mel_lo, lo.data(), lo.size())) != cudaSuccess ||
+          (e = dev_upload(h, &t.mel_cnt, cnt.data(), cnt.size())) != cudaSuccess ||
+          (e = dev_upload(h, &t.mel_wofs, wofs.data(), wofs.size())) != cudaSuccess ||
+          (e = dev_upload(h, &t.mel_w, w.data(), w.size())) != cudaSuccess ||
+          (e = dev_upload(h, &t.dct, dct.data(), dct.size())) != cudaSuccess)
+        return cuda_fail(e, "mfcc tables");
+      h->mfcc_tb_ok = true;
+    }
+  }
+  cudaError_t e = launch_mfcc_stats(h->mfcc_tb, x16, off, len, len_stride_bytes, n, max_len, out, workspace,
+                                    (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "mfcc_stats");
 }
 
 int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const int32_t* len16, int n,

@@ -47,7 +47,7 @@ struct Tables {
 enum KernelId {
   KID_INIT = 0, KID_SCAN, KID_FINALIZE_SEGS, KID_PLAN, KID_GATHER, KID_FINALIZE_ITEMS,
   KID_RESAMPLE, KID_LOGMEL_INIT, KID_LOGMEL_FRAMES, KID_LOGMEL_NORM, KID_COSINE, KID_SINGLE, KID_FUSED, KID_MEL_GEMM, KID_QWEN_MOMENTS, KID_QWEN_PLAN, KID_QWEN_APPLY, KID_RESAMPLE_GENERAL,
-  KID_PV_STFT, KID_PV_PHASE, KID_PV_CUMSUM, KID_PV_ISTFT, KID_PV_RESAMPLE, KID_COUNT
+  KID_PV_STFT, KID_PV_PHASE, KID_PV_CUMSUM, KID_PV_ISTFT, KID_PV_RESAMPLE, KID_MFCC_FRAMES, KID_MFCC_STATS, KID_COUNT
 };
 extern const char* const kKernelNames[KID_COUNT];
 
@@ -145,6 +145,23 @@ cudaError_t launch_pitch_shift(const PitchTables& tb, const float* x, const int6
                                int nw, int width, int W, const float* taps, const int* ilo, float* y,
                                const int64_t* y_off, void* workspace, cudaStream_t st, LaunchCtx* lc);
 
+// mfcc.cu: librosa.feature.mfcc(sr=16000, n_mfcc=13) mean / std per clip (drift-classifier front end)
+struct MfccTables {
+  float2* w256;    // [256]  exp(-2 pi i k / 256)
+  float2* w1024;   // [1024] exp(-2 pi i k / 1024)
+  float2* w2048;   // [1025] exp(-2 pi i k / 2048)
+  float* hann;     // [2048]
+  int* mel_lo;     // [128] sparse slaney filterbank over 1025 bins
+  int* mel_cnt;
+  int* mel_wofs;
+  float* mel_w;
+  float* dct;      // [13][128]
+};
+size_t mfcc_workspace_bytes(int n, int64_t max_len);
+cudaError_t launch_mfcc_stats(const MfccTables& tb, const float* x, const int64_t* off, const int32_t* len,
+                              int len_stride_bytes, int n, int64_t max_len, float* out, void* workspace,
+                              cudaStream_t st, LaunchCtx* lc);
+
 // cosine.cu
 cudaError_t launch_cosine(const float* emb, const float* ref, int n, int dim, float* out, int out_stride_bytes,
                           cudaStream_t st, LaunchCtx* lc);
@@ -157,6 +174,8 @@ void host_resample_taps_windowed(int orig, int nw, int width, int W, float* taps
 void host_pitch_tables(float* w256 /* [256][2] */, float* w512 /* [257][2] */, float* hann512, float* padv /* [257] */);
 void host_hann(float* out /* [400] */);
 void host_mel_filterbank(int n_mels, float* out /* [n_mels][201] */);
+void host_mel_filterbank_bins(int n_mels, int n_bins, float* out /* [n_mels][n_bins] */);
+void host_mfcc_tables(float* hann2048, float* w1024 /* [1024][2] */, float* w2048 /* [1025][2] */, float* dct /* [13][128] */);
 void host_twiddles(float* out /* [400][2] */);
 
 }  // namespace rho

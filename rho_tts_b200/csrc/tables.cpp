@@ -151,7 +151,10 @@ static double mel_to_hz(double m) {
 
 // transformers/audio_utils.py:453-544 with mel_scale="slaney", norm="slaney", 0..8000 Hz, 201 bins
 // of a 16 kHz / 400-point FFT; float64 then cast to fp32 (feature_extraction_whisper.py:152).
-void host_mel_filterbank(int n_mels, float* out) {
+void host_mel_filterbank(int n_mels, float* out) { host_mel_filterbank_bins(n_mels, N_BINS, out); }
+
+// the same triangles over n_bins = n_fft / 2 + 1 bins of a 16 kHz signal (librosa.filters.mel(sr=16000, n_fft, n_mels))
+void host_mel_filterbank_bins(int n_mels, int n_bins, float* out) {
   const double m_lo = hz_to_mel(0.0), m_hi = hz_to_mel(8000.0);
   std::vector<double> centres(n_mels + 2);
   for (int i = 0; i < n_mels + 2; ++i) {
@@ -160,17 +163,37 @@ void host_mel_filterbank(int n_mels, float* out) {
     const double m = (i == n_mels + 1) ? m_hi : m_lo + i * step;
     centres[i] = mel_to_hz(m);
   }
-  for (int k = 0; k < N_BINS; ++k) {
-    const double step = 8000.0 / (N_BINS - 1);
-    const double f = (k == N_BINS - 1) ? 8000.0 : 0.0 + k * step;
+  for (int k = 0; k < n_bins; ++k) {
+    const double step = 8000.0 / (n_bins - 1);
+    const double f = (k == n_bins - 1) ? 8000.0 : 0.0 + k * step;
     for (int m = 0; m < n_mels; ++m) {
       const double down = -(centres[m] - f) / (centres[m + 1] - centres[m]);
       const double up = (centres[m + 2] - f) / (centres[m + 2] - centres[m + 1]);
       double v = std::max(0.0, std::min(down, up));
       v *= 2.0 / (centres[m + 2] - centres[m]);
-      out[m * N_BINS + k] = (float)v;
+      out[m * n_bins + k] = (float)v;
     }
   }
+}
+
+// Tables of the MFCC front end: torch / scipy periodic hann(2048), W1024 and W2048 twiddles, and the first 13 rows of the
+// orthonormal DCT-II over 128 inputs (scipy.fftpack.dct(type=2, norm="ortho")).
+void host_mfcc_tables(float* hann2048, float* w1024, float* w2048, float* dct) {
+  for (int n = 0; n < 2048; ++n) hann2048[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * n / 2048));
+  for (int k = 0; k < 1024; ++k) {
+    w1024[2 * k] = (float)std::cos(2.0 * M_PI * k / 1024);
+    w1024[2 * k + 1] = (float)(-std::sin(2.0 * M_PI * k / 1024));
+  }
+  for (int k = 0; k <= 1024; ++k) {
+    w2048[2 * k] = (float)std::cos(2.0 * M_PI * k / 2048);
+    w2048[2 * k + 1] = (float)(-std::sin(2.0 * M_PI * k / 2048));
+  }
+  for (int k = 0; k < 13; ++k)
+    for (int m = 0; m < 128; ++m) {
+      double v = std::cos(M_PI * k * (2.0 * m + 1.0) / 256.0) * std::sqrt(2.0 / 128.0);
+      if (k == 0) v *= std::sqrt(0.5);
+      dct[k * 128 + m] = (float)v;
+    }
 }
 
 }  // namespace rho

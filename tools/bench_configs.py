@@ -130,6 +130,16 @@ for cfg in args:
         line(cfg, f"{n} x 10 s clips, torchaudio.functional.pitch_shift n_steps={n_steps:+g} "
              "(stft 512/128 -> phase vocoder -> istft -> resample -> crop)", n * 10.0, ms, prof, alg)
         del x, rb, out
+    elif cfg == "mfcc":
+        n = 1000
+        x = synth.make_clip_block(n, 160000, 0xB200, device=dev)          # 10 s at 16 kHz
+        rb = R.RaggedBatch.from_dense(x)
+        out, ms, prof = timed(lambda: R.mfcc_stats_batch(rb), steps)
+        T = 1 + 160000 // 512
+        alg = {"k_mfcc_frames": 4.0 * n * 160000 + 4.0 * 128 * T * n, "k_mfcc_stats": 4.0 * 128 * T * n}
+        line(cfg, f"{n} x 10 s clips at 16 kHz, mean / std of librosa.feature.mfcc(n_mfcc=13) (stft 2048/512 -> mel 128 -> dB -> DCT)",
+             n * 10.0, ms, prof, alg)
+        del x, rb, out
     elif cfg in ("c3", "c3v"):
         rb, first = ragged_c3()
         audio_s = rb.total_samples / SR
