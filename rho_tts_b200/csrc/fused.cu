@@ -116,6 +116,7 @@ struct FzNext {
   long long y_off;
   int u, c, start, end;
   float dc;
+  int tile;
   int prefetched;                   // the unit's first span is a bulk copy already issued on FzHalf::bar
 };
 
@@ -128,6 +129,7 @@ struct alignas(1024) FzHalf {
   uint64_t bar;                     // mbarrier the TMA copy of the span completes on
   uint64_t mma_bar;                 // mbarrier the tensor-core mel projection of a batch commits to
   int last;                         // "this half finished its clip last" broadcast
+  int fill_max;                     // ... and the clip maximum it read (ordered-int form)
   int next_unit;                    // the tile this half works on next (claimed one tile ahead)
   FzNext nd;
 };
@@ -334,9 +336,10 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   // thread 0 of the half only: resolve unit `un` into H.nd
   auto fill_desc = [&](int un) {
     FzNext d;
-    d.u = un; d.c = 0; d.start = 0; d.end = 0; d.dc = 0.f; d.prefetched = 0; d.x_off = 0; d.y_off = 0;
+    d.u = un; d.c = 0; d.start = 0; d.end = 0; d.dc = 0.f; d.tile = 0; d.prefetched = 0; d.x_off = 0; d.y_off = 0;
     if (un < n_units) {
-      d.c = un % n_items;
+      d.tile = un / n_items;                             // tile-major: the last (short) tiles of the clips come at the end
+      d.c = un - d.tile * n_items;
       const int sn = item_first_seg[d.c];
       const SegState sn_st = seg[sn];
       d.start = sn_st.start; d.end = sn_st.end; d.dc = sn_st.dc;
@@ -353,7 +356,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     const int nn16 = nn > 0 ? (int)((2LL * nn + 2) / 3) : 0;
     int Tn, Tn_real, Nn, nvn;
     lm_frame_counts(nn16, pad_frames, &Tn, &Tn_real, &Nn, &nvn);
-    const int tt0 = sched.start[d.u / n_items] * LM_BF;
+    const int tt0 = sched.start[d.tile] * LM_BF;
     if (tt0 >= max(Tn_real, (nn + 239) / 240)) return;
     const float* xsn = x + d.x_off;
     const long long j0 = 240LL * tt0 - FZ_LEAD;
@@ -372,7 +375,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   if (u >= n_units) break;
   if (tid == 0) H.next_unit = atomicAdd(work_counter, 1);
   const int c = nd.c;
-  const int tile = u / n_items;
+  const int tile = nd.tile;
   SegState st;
   st.start = nd.start; st.end = nd.end; st.dc = nd.dc;
   const int n = st.end - st.start;                   // samples of y
@@ -755,7 +758,8 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     double a = tid < NW ? H.redd[0][tid] : 0.0, bq = tid < NW ? H.redd[1][tid] : 0.0;
     m = warp_max(m); a = warp_sum(a); bq = warp_sum(bq);
     if (tid == 0) {
-      if (m > -INFINITY) atomicMax(&clip_max[c], float_to_ordered(m));
+      int seen = 0;
+      if (m > -INFINITY) seen = atomicMax(&clip_max[c], float_to_ordered(m));
       if (a != 0.0) atomicAdd(&item[c].s_first, a);
       if (bq != 0.0) atomicAdd(&item[c].s_last, bq);
       // The half that finishes its clip last knows the clip maximum: it writes the constant that fills the
@@ -763,21 +767,23 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       // for; the frames with signal are clamped / scaled by k_logmel_norm, which then moves 1/3 of the bytes.
       // (Normalising them here too was measured and is NOT a gain: the loads expose L2 latency on a half that
       //  has nothing else to do, profiles/README.md.)
+      // No fence: the count is incremented by an atomic whose operand depends on the RETURN value of this half's
+      // atomicMax, so it is issued after that one has been performed at L2; whoever sees the full count reads the
+      // maximum with another atomic at the same point of coherence.
       int last = 0;
       if (FZ_INLINE_NORM && tiles_done) {
-        // barrier (CTA scope) -> fence (GPU scope) -> atomic: the grid-sync idiom
-        __threadfence();
         int clip_tiles = 0;                          // tiles of the schedule that start inside this clip
         while (clip_tiles < sched.n_tiles && sched.start[clip_tiles] * LM_BF < t_cover) ++clip_tiles;
-        last = (atomicAdd(&tiles_done[c], 1) == clip_tiles - 1);
-        if (last) __threadfence();                   // acquire side: the other halves' maxima
+        const int inc = (seen == 0x7fffffff) ? 2 : 1;            // never 2: no clip maximum is a NaN pattern
+        last = (atomicAdd(&tiles_done[c], inc) == clip_tiles - 1);
+        if (last) H.fill_max = atomicMax(&clip_max[c], (int)0x80000000);
       }
       H.last = last;
     }
   }
   half_sync(half);
   if (H.last && T > T_real) {
-    const float mx = ordered_to_float(__ldcg(&clip_max[c]));
+    const float mx = ordered_to_float(H.fill_max);
     const float fill = __fmul_rn(__fadd_rn(fmaxf(-10.0f, __fsub_rn(mx, 8.0f)), 4.0f), 0.25f);
     const int t_lo = (T_real + 3) & ~3;              // whole 128-bit pieces from here; [T_real, t_lo) is k_logmel_norm's
     const bool vec = (mel_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);

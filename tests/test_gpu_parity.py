@@ -331,6 +331,9 @@ def test_full_size_properties(R, cuda_device):
     # frames that only see zero padding are one constant per clip: (max(-10, m-8)+4)/4
     tail = mel[:, :, 1010:]
     assert torch.equal(tail.amax(dim=(1, 2)), tail.amin(dim=(1, 2)))
+    # ... and it is the constant of the FINAL clip maximum (the half that finishes a clip last must have seen the maxima
+    # of all the other tiles): with m the clip maximum, the features peak at (m+4)/4 and the padding sits at (m-8+4)/4
+    assert float((mel.amax(dim=(1, 2)) - 2.0 - tail[:, 0, 0]).abs().max()) <= 1e-6
     # the Whisper clamp: per clip, max - min <= 8/4
     assert float((mel.amax(dim=(1, 2)) - mel.amin(dim=(1, 2))).max()) <= 2.0 + 1e-6
     # idempotence of the trim: the processed clip starts and ends loud, so a second scan trims at most
