@@ -311,7 +311,9 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
         "k_gather": 8 * sum_out,
         "k_resample3to2": 4 * sum_out + 4 * sum16,
         "k_logmel_frames": 4 * sum16 + 4 * sum_mel_real,
-        "k_logmel_norm": 8 * sum_mel_real if fused_fills else 4 * sum_mel_real + 4.0 * N_MELS * PAD_FRAMES * n,
+        # the normaliser reads every frame with signal and writes back only what the clamp changes (data-dependent, a few
+        # per cent: not counted) -- plus the padding constant when the fused kernel does not write it
+        "k_logmel_norm": 4 * sum_mel_real if fused_fills else 4.0 * N_MELS * PAD_FRAMES * n,
         # fused apply + resample + log-mel: x[start:end] in, y out, raw log-mel frames out (+ the padding constant)
         "k_fused_features": 8 * sum_out + 4 * sum_mel_real + (fill_bytes if fused_fills else 0.0),
     }

@@ -217,14 +217,14 @@ __device__ __noinline__ void fz_tc_epilogue(uint64_t* mma_bar, unsigned parity, 
       v.z = __log2f(fmaxf(__uint_as_float(r[4 * j + 2]), 1e-10f)) * 0.30102999566398120f;
       v.w = __log2f(fmaxf(__uint_as_float(r[4 * j + 3]), 1e-10f)) * 0.30102999566398120f;
       mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-      *reinterpret_cast<float4*>(row + 4 * j) = v;
+      *reinterpret_cast<float4*>(row + 4 * j) = make_float4(lm_scaled(v.x), lm_scaled(v.y), lm_scaled(v.z), lm_scaled(v.w));
     }
   } else {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       if (t0p + j < T_real) {
         const float ls = __log2f(fmaxf(__uint_as_float(r[j]), 1e-10f)) * 0.30102999566398120f;
-        row[j] = ls;
+        row[j] = lm_scaled(ls);
         mx = fmaxf(mx, ls);
       }
     }
@@ -730,7 +730,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       auto emit = [&](int m, float acc) {
         const float ls = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
         if (live) {
-          o[(long long)m * mel_stride] = ls;
+          o[(long long)m * mel_stride] = lm_scaled(ls);
           lmax = fmaxf(lmax, ls);
         }
       };

@@ -91,6 +91,11 @@ __device__ __forceinline__ float lm_sample(const float* __restrict__ xs, long lo
 }
 
 // number of frames of clip with n16 samples, and how many of them see any signal
+// (x + 4) / 4 of the Whisper normalisation (x / 4 == x * 0.25 bit for bit).  The frame kernels store log-mel values
+// already scaled: the scaling is monotone, so max(x, m - 8) followed by it equals max(scaled x, scaled (m - 8)) bit for
+// bit, and k_logmel_norm only has to WRITE the values the clamp changes.
+__device__ __forceinline__ float lm_scaled(float x) { return __fmul_rn(__fadd_rn(x, 4.0f), 0.25f); }
+
 __device__ __forceinline__ void lm_frame_counts(int n16, int pad_frames, int* T, int* T_real, int* N, int* n_valid) {
   if (pad_frames > 0) {
     *N = pad_frames * HOP16;

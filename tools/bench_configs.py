@@ -99,7 +99,7 @@ for cfg in args:
         fills = bool(R._lib.load().rho_b200_build_flags() & 1) and pad
         fill_b = 4.0 * nm * float((3000 - np.minimum(3000, (t_real + 3) // 4 * 4)).sum()) if pad else 0.0
         alg = {"k_scan": s_in, "k_fused_features": 2 * s_out + mel_real + (fill_b if fills else 0.0),
-               "k_logmel_norm": 2 * mel_real if fills else mel_real + mel_full}
+               "k_logmel_norm": mel_real if fills else mel_full}   # reads; writes only what the clamp changes
         line(cfg, f"{n} x 10 s clips, post-process + log-mel {nm} ({'30 s pad' if pad else 'unpadded'}) + cosine",
              n * 10.0, ms, prof, alg)
         del x, rb, plan, out
@@ -159,7 +159,7 @@ for cfg in args:
             len16 = (2 * rec["out_len"].astype(np.int64) + 2) // 3
             mel_b = 4.0 * 80 * float((len16 // 160).sum())
             alg = {"k_scan": s_in, "k_gather": s_in + s_out, "k_resample3to2": s_out + s_out * 2 / 3,
-                   "k_logmel_frames": s_out * 2 / 3 + mel_b, "k_logmel_norm": 2 * mel_b}
+                   "k_logmel_frames": s_out * 2 / 3 + mel_b, "k_logmel_norm": mel_b}
             line(cfg, f"{rb.n} ragged clips in {len(first) - 1} joined items -> resample -> log-mel 80 (unpadded) -> cosine",
                  audio_s, ms, prof, alg)
             del plan
