@@ -614,21 +614,19 @@ int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, con
   cudaError_t e;
   const bool fused = (flags & RHO_V_ONE_SEGMENT_ITEMS) && !(flags & RHO_V_NO_FUSION) && n_segments == n_items;
   if (fused) {
-    // init -> scan -> bounds/DC -> plan -> ONE kernel for apply + resample + log-mel -> records (decay decision +
-    // cosine) -> clamp / scale: seven launches per batch
+    // init -> scan -> bounds / DC / plan -> ONE kernel for apply + resample + log-mel -> clamp + records (decay
+    // decision, cosine): five launches per batch
     e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,
-                    rec, nullptr, ws, st, &h->lc, JOIN_PREPARE | JOIN_INIT_FEATURES);
+                    rec, nullptr, ws, st, &h->lc, JOIN_PREPARE | JOIN_INIT_FEATURES | JOIN_ONE_SEG_ITEMS);
     if (e != cudaSuccess) return cuda_fail(e, "join prepare");
     e = launch_fused_features(h->tb, x, seg_off, ws, item_first_seg, n_items, max_item_len, d, y, y_off, n_mels,
                               pad_frames, mel, mel_stride_frames, st, &h->lc);
     if (e != cudaSuccess) return cuda_fail(e, "fused features");
-    e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,
-                    rec, nullptr, ws, st, &h->lc, JOIN_FINISH, emb, ref_emb, emb_dim);
-    if (e != cudaSuccess) return cuda_fail(e, "join finish");
-    // clamp / scale of the frames with signal and the constant fill of the zero-padding frames (fill_done: the
-    // fused kernel wrote the fill itself, an option that is off by default)
+    // the Whisper clamp of the frames with signal (and the constant of the zero-padding frames unless the fused kernel
+    // wrote it: fill_done); its first warp per clip assembles the record
+    const FinalizeArgs fin{ws.seg, ws.item, item_first_seg, d.decay_thr, rec, emb, ref_emb, emb_dim};
     e = launch_logmel_norm(ws.len16, n_items, n_mels, pad_frames, mel, mel_stride_frames, ws.clip_max, st, &h->lc,
-                           fused_inline_norm());
+                           fused_inline_norm(), &fin);
     if (e != cudaSuccess) return cuda_fail(e, "logmel norm");
   } else {
     if (!scratch16) return fail(RHO_ERR_INVALID, "scratch16 is NULL (needed by the unfused path)");

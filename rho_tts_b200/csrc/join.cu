@@ -10,6 +10,7 @@
 // (never contracted into an FMA) so `sqrt(sum/window) > thr` is the same predicate.
 #include "common.cuh"
 #include "kernels.h"
+#include "records_dev.cuh"
 
 namespace rho {
 
@@ -200,7 +201,7 @@ __global__ void k_finalize_segs(const float* __restrict__ x, const int64_t* __re
                                 const int32_t* __restrict__ len, SegState* __restrict__ seg,
                                 const float* __restrict__ block_sum, int blocks_per_seg,
                                 int n_seg, int window, int hop, int trim_enabled,
-                                rho_seg_info* __restrict__ info_out) {
+                                rho_seg_info* __restrict__ info_out, ItemState* __restrict__ one_seg_item) {
   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (s >= n_seg) return;
@@ -251,6 +252,10 @@ __global__ void k_finalize_segs(const float* __restrict__ x, const int64_t* __re
     st.dc = n > 0 ? (float)(acc / (double)n) : 0.f;
     st.flags = (st.flags & 0xffffff00u) | flags;
     seg[s] = st;
+    if (one_seg_item) {                                  // item s IS segment s (base_tts.py:447-452): k_plan_items' n == 1 case
+      one_seg_item[s].out_len = end - start;
+      one_seg_item[s].flags = (flags & RHO_F_ALL_SILENT) ? (RHO_F_ALL_SILENT | RHO_F_TWO_D) : (flags & RHO_F_UNTOUCHED);
+    }
     if (info_out) {
       rho_seg_info o; o.start = start; o.end = end; o.dc = st.dc; o.flags = flags;
       info_out[s] = o;
@@ -499,22 +504,7 @@ k_gather(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const
 }
 
 // ------------------------------------------------------------------ per-item finalize (decay)
-__device__ __forceinline__ void decay_decide(double s_first, double s_last, int n, double thr,
-                                             float* first_rms, float* last_rms, double* ratio, int* ok) {
-  // _validate_sound_decay :304-323
-  *first_rms = 0.f; *last_rms = 0.f; *ratio = 1.0; *ok = 1;
-  const int third = n / 3;
-  if (n <= 0 || third < 1) return;
-  const float fr = __fsqrt_rn((float)(s_first / (double)third));
-  const float lr = __fsqrt_rn((float)(s_last / (double)third));
-  *first_rms = fr; *last_rms = lr;
-  if ((double)fr < 1e-8) return;
-  const double r = (double)lr / (double)fr;
-  *ratio = r; *ok = (r >= thr) ? 1 : 0;
-}
-
-// One warp per item: lane 0 assembles the record; when embeddings are given the warp also computes the speaker
-// cosine (base_tts.py:341-344) so the validate path needs no separate k_cosine launch.
+// decay_decide() and finalize_item() live in records_dev.cuh: the fused path runs them inside k_logmel_norm.
 __global__ void __launch_bounds__(256)
 k_finalize_items(const SegState* __restrict__ seg, const ItemState* __restrict__ item,
                  const int32_t* __restrict__ item_first_seg, int n_items, double decay_thr,
@@ -522,36 +512,7 @@ k_finalize_items(const SegState* __restrict__ seg, const ItemState* __restrict__
   const int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (it >= n_items) return;
-  float cosv = 0.f;
-  if (emb && ref) {
-    const float* __restrict__ e = emb + (size_t)it * dim;
-    float dot = 0.f, ne = 0.f, nr = 0.f;
-    if ((dim & 3) == 0 && ((((uintptr_t)e) | ((uintptr_t)ref)) & 15u) == 0) {
-      for (int i = 4 * lane; i < dim; i += 128) {
-        const float4 a = *reinterpret_cast<const float4*>(e + i);
-        const float4 r = __ldg(reinterpret_cast<const float4*>(ref + i));
-        dot += a.x * r.x + a.y * r.y + a.z * r.z + a.w * r.w;
-        ne += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
-        nr += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
-      }
-    } else {
-      for (int i = lane; i < dim; i += 32) {
-        const float a = e[i], r = __ldg(ref + i);
-        dot += a * r; ne += a * a; nr += r * r;
-      }
-    }
-    dot = warp_sum(dot); ne = warp_sum(ne); nr = warp_sum(nr);
-    cosv = __fdiv_rn(dot, __fmul_rn(__fsqrt_rn(nr), __fsqrt_rn(ne)));
-  }
-  if (lane != 0) return;
-  const ItemState is = item[it];
-  const int s0 = item_first_seg[it], n = item_first_seg[it + 1] - s0;
-  rho_record r;
-  r.start = 0; r.end = 0; r.dc = 0.f;
-  if (n > 0) { const SegState st = seg[s0]; r.start = st.start; r.end = st.end; r.dc = st.dc; }
-  r.out_len = is.out_len; r.flags = is.flags; r.cosine = cosv; r.n_segments = n;
-  decay_decide(is.s_first, is.s_last, is.out_len, decay_thr, &r.first_rms, &r.last_rms, &r.decay_ratio, &r.ok);
-  rec[it] = r;
+  finalize_item(seg, item, item_first_seg, it, lane, decay_thr, rec, emb, ref, dim);
 }
 
 // ------------------------------------------------------------------ single-clip helpers (method shim)
@@ -719,7 +680,7 @@ cudaError_t launch_trim_scan(const float* x, const int64_t* off, const int32_t* 
   if (e != cudaSuccess) return e;
   lc->begin(KID_FINALIZE_SEGS, st);
   k_finalize_segs<<<(n_seg * 32 + 255) / 256, 256, 0, st>>>(x, off, len, ws.seg, ws.block_sum, ws.blocks_per_seg,
-                                                          n_seg, d.window, d.hop, d.trim_enabled, info);
+                                                          n_seg, d.window, d.hop, d.trim_enabled, info, nullptr);
   lc->end(st);
   return cudaGetLastError();
 }
@@ -744,13 +705,16 @@ cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* s
       lc->begin(KID_FINALIZE_SEGS, st);
       k_finalize_segs<<<(n_seg * 32 + 255) / 256, 256, 0, st>>>(x, seg_off, seg_len, ws.seg, ws.block_sum,
                                                               ws.blocks_per_seg, n_seg, d.window, d.hop,
-                                                              d.trim_enabled, seg_info);
+                                                              d.trim_enabled, seg_info,
+                                                              (stages & JOIN_ONE_SEG_ITEMS) ? ws.item : nullptr);
       lc->end(st);
     }
-    lc->begin(KID_PLAN, st);
-    k_plan_items<<<(n_items + 127) / 128, 128, 0, st>>>(ws.seg, seg_len, ws.span, ws.item, item_first_seg, n_items,
-                                                       d.cf, d.pause, d.pause_on, seg_off, y_off);
-    lc->end(st);
+    if (!(stages & JOIN_ONE_SEG_ITEMS)) {                // one-segment items were planned by k_finalize_segs
+      lc->begin(KID_PLAN, st);
+      k_plan_items<<<(n_items + 127) / 128, 128, 0, st>>>(ws.seg, seg_len, ws.span, ws.item, item_first_seg, n_items,
+                                                         d.cf, d.pause, d.pause_on, seg_off, y_off);
+      lc->end(st);
+    }
   }
   if ((stages & JOIN_GATHER) && n_seg > 0) {
     // a segment's span is at most its own length plus one pause

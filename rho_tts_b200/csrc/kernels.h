@@ -71,7 +71,8 @@ struct LaunchCtx {
 
 // join.cu
 enum { JOIN_PREPARE = 1, JOIN_GATHER = 2, JOIN_FINISH = 4, JOIN_ALL = 7,     // stages of launch_join
-       JOIN_INIT_FEATURES = 8 };   // with JOIN_PREPARE: also reset the log-mel clip maxima / tile counters
+       JOIN_INIT_FEATURES = 8,     // with JOIN_PREPARE: also reset the log-mel clip maxima / tile counters
+       JOIN_ONE_SEG_ITEMS = 16 };  // with JOIN_PREPARE: item i is segment i -- k_finalize_segs plans it, no k_plan_items
 cudaError_t launch_trim_scan(const float* x, const int64_t* off, const int32_t* len, const uint8_t* trim_flags,
                              int n_seg, int64_t max_len, const Derived& d, const Workspace& ws,
                              rho_seg_info* info, cudaStream_t st, LaunchCtx* lc);
@@ -105,9 +106,20 @@ cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off
                           cudaStream_t st, LaunchCtx* lc);
 
 cudaError_t launch_logmel_init(int* clip_max, int n, cudaStream_t st, LaunchCtx* lc, int* tiles_done = nullptr);
+// what k_logmel_norm needs to assemble the records itself (fused path: saves the k_finalize_items launch)
+struct FinalizeArgs {
+  const SegState* seg;
+  const ItemState* item;
+  const int32_t* item_first_seg;
+  double decay_thr;
+  rho_record* rec;
+  const float* emb;
+  const float* ref;
+  int dim;
+};
 cudaError_t launch_logmel_norm(const int32_t* len16, int n, int n_mels, int pad_frames, float* mel,
                                int64_t mel_stride_frames, const int* clip_max, cudaStream_t st, LaunchCtx* lc,
-                               bool fill_done = false);
+                               bool fill_done = false, const FinalizeArgs* fin = nullptr);
 
 // fused.cu
 bool fused_inline_norm();   // the fused kernel writes the constant fill of the zero-padding frames itself

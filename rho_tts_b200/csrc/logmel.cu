@@ -14,6 +14,7 @@
 // Kernel 2 (k_logmel_norm): max(x, clipmax-8), (x+4)/4 -- on values kernel 1 stored already scaled, so only the
 // clamped ones are written back -- and the constant fill of the frames that only see zero padding.
 #include "logmel_dev.cuh"
+#include "records_dev.cuh"
 
 namespace rho {
 
@@ -191,8 +192,11 @@ constexpr int NORM_ROWS = 8;
 constexpr int NORM_BATCH = 4;     // rows in flight per thread: 48 registers -> 5 CTAs per SM (8 in flight needed 78 -> 3 CTAs)
 __global__ void __launch_bounds__(256, 5)
 k_logmel_norm(const int32_t* __restrict__ len16, int n_mels, int pad_frames, float* __restrict__ mel,
-              long long mel_stride, const int* __restrict__ clip_max, int fill_done) {
+              long long mel_stride, const int* __restrict__ clip_max, int fill_done, FinalizeArgs fin) {
   const int c = blockIdx.x;
+  // fused path: the first warp of the clip's first CTA also assembles the clip's record (decay decision, cosine)
+  if (fin.rec && blockIdx.y == 0 && threadIdx.x < 32)
+    finalize_item(fin.seg, fin.item, fin.item_first_seg, c, threadIdx.x, fin.decay_thr, fin.rec, fin.emb, fin.ref, fin.dim);
   int T, T_real, N, n_valid;
   lm_frame_counts(len16[c], pad_frames, &T, &T_real, &N, &n_valid);
   if (T <= 0) return;
@@ -298,11 +302,13 @@ cudaError_t launch_logmel_init(int* clip_max, int n, cudaStream_t st, LaunchCtx*
 
 cudaError_t launch_logmel_norm(const int32_t* len16, int n, int n_mels, int pad_frames, float* mel,
                                int64_t mel_stride_frames, const int* clip_max, cudaStream_t st, LaunchCtx* lc,
-                               bool fill_done) {
+                               bool fill_done, const FinalizeArgs* fin) {
   if (n <= 0) return cudaSuccess;
   dim3 g2((unsigned)n, (unsigned)((n_mels + NORM_ROWS - 1) / NORM_ROWS));
+  FinalizeArgs fa{};
+  if (fin) fa = *fin;
   lc->begin(KID_LOGMEL_NORM, st);
-  k_logmel_norm<<<g2, 256, 0, st>>>(len16, n_mels, pad_frames, mel, mel_stride_frames, clip_max, fill_done ? 1 : 0);
+  k_logmel_norm<<<g2, 256, 0, st>>>(len16, n_mels, pad_frames, mel, mel_stride_frames, clip_max, fill_done ? 1 : 0, fa);
   lc->end(st);
   return cudaGetLastError();
 }
