@@ -328,7 +328,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   const bool epi_warp = tid < 128 && 32 * ((threadIdx.x >> 5) & 3) < NM;   // first four warps of the half: one TMEM lane quarter each
 #endif
 
-  // Persistent CTA: one per SM.  Every half claims its own 128-frame tiles from a global counter (tile-major
+  // Persistent CTA: one per SM.  Every half claims its own tiles (sched: length chosen per call) from a global counter (tile-major
   // order: the short last tiles of the clips come at the end) and runs at its own pace -- a half never waits
   // for its partner, and no SM is left with one tile more than the others.  The next claim is issued at the
   // start of a tile and consumed at its end, so the atomic's round trip is never exposed.
