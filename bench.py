@@ -240,6 +240,9 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
         raise RuntimeError("bench.py: no CUDA device; the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one process per GPU: run on the CPUs of the GPU's NUMA node, so that the pinned host buffers of the e2e leg
+    # (first touch) and the copies to / from them stay on the GPU's side of the host
+    numa_cpus = R.dist.bind_to_gpu_numa(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -369,7 +372,9 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
                "steps": e2e_steps, "api": "rho_b200_validate_host (pinned host buffers, chunked copy/compute overlap)",
                "timer": "host perf_counter around the synchronous C call, max over ranks",
                "value_features_stay_in_hbm": res["features stay in HBM"],
-               "d2h_bytes_per_step_features_stay_in_hbm": yh.numel() * 4 + rech.numel()}
+               "d2h_bytes_per_step_features_stay_in_hbm": yh.numel() * 4 + rech.numel(),
+               "host_numa_binding": (f"rank 0 bound to {len(numa_cpus)} CPUs local to its GPU (NVML)" if numa_cpus
+                                     else "none")}
         # the host path must agree with the device path
         rh = rech.numpy().view(R.REC_DTYPE).reshape(-1)
         assert np.array_equal(rh["out_len"], rec["out_len"]) and np.array_equal(rh["ok"], rec["ok"])

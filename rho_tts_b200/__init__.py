@@ -12,5 +12,6 @@ from .batch import (make_params, params_from_tts, trim_scan_batch, join_batch, p
                     ValidatePlan, JoinOutput, ValidateOutput, REC_DTYPE, SEG_DTYPE)
 from .mixin import B200AudioMixin, B200QwenAudioMixin, make_b200_provider, register_b200_providers   # noqa: F401
 from . import _lib                                                         # noqa: F401
+from . import dist                                                         # noqa: F401  (sharding, record gather, NUMA binding)
 
 __version__ = "0.1.0"

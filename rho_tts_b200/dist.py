@@ -69,3 +69,27 @@ def gather_records_ragged(records: torch.Tensor, counts: Sequence[int], group=No
     pad[:records.shape[0]] = records
     allr = gather_records(pad, group=group).reshape(len(counts), mx, *records.shape[1:])
     return torch.cat([allr[r, :int(c)] for r, c in enumerate(counts)], dim=0)
+
+
+def bind_to_gpu_numa(local_rank: int) -> Optional[list]:
+    """Pin this process (one process per GPU) to the CPUs NVML reports as local to GPU `local_rank`, BEFORE it
+    allocates pinned host buffers: first-touch then places them on the GPU's NUMA node, and the host <-> device copies
+    of rho_b200_validate_host do not cross the socket interconnect.  With 8 ranks on a two-socket box this is the
+    difference between every rank sharing one socket's memory controllers and each GPU using its own.
+    Returns the CPU list, or None when NVML / the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+        n_cpus = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpus + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:                   # noqa: BLE001  (no NVML, no permission: keep the default placement)
+        return None
