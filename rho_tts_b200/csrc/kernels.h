@@ -7,7 +7,7 @@
 namespace rho {
 
 #ifndef RHO_SCAN_FR
-#define RHO_SCAN_FR 64               // measured on B200: 64 -> 0.207 ms, 128 -> 0.210 ms, 256 -> 0.304 ms (C2 scan)
+#define RHO_SCAN_FR 32               // measured on B200 (C2 scan, dense rows): 32 -> 0.165 ms, 64 -> 0.170, 96 -> 0.184, 128 -> 0.194
 #endif
 #ifndef RHO_GATHER_CHUNKS
 #define RHO_GATHER_CHUNKS 1          // passes per gather CTA
