@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include "kernels.h"
@@ -669,7 +670,9 @@ int rho_b200_validate_host(rho_handle* h, const float* x, int n, int32_t clip_le
     h->streams_ok = true;
   }
   // chunking: CH clips per chunk, 3 chunk slots so copy-in(k+1), compute(k) and copy-out(k-1) overlap
-  const int CH = n < 64 ? n : 64;
+  static const int env_chunk = [] { const char* v = getenv("RHO_HOST_CHUNK"); return v ? atoi(v) : 0; }();   // A/B tool
+  const int chunk_clips = env_chunk > 0 ? env_chunk : 64;
+  const int CH = n < chunk_clips ? n : chunk_clips;
   const int SLOTS = 3;
   const size_t stride = align_up((size_t)clip_len, 32);                 // samples per clip slot
   const size_t b_x = align_up(stride * CH * sizeof(float), 256);

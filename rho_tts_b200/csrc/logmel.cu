@@ -188,7 +188,10 @@ k_logmel_frames(const float* __restrict__ x16, const int64_t* __restrict__ off, 
 // grid (n clips, groups of 8 rows); normalises the frames with signal and fills the zero-padding frames.
 // One 128-bit column piece per thread and pass, all 8 rows of the group: the 8 loads of a piece with signal
 // are issued before the first store (the kernel used to wait for every load: long-scoreboard bound).
-constexpr int NORM_ROWS = 8;
+#ifndef RHO_NORM_ROWS
+#define RHO_NORM_ROWS 8
+#endif
+constexpr int NORM_ROWS = RHO_NORM_ROWS;   // mel rows per CTA
 constexpr int NORM_BATCH = 4;     // rows in flight per thread: 48 registers -> 5 CTAs per SM (8 in flight needed 78 -> 3 CTAs)
 __global__ void __launch_bounds__(256, 5)
 k_logmel_norm(const int32_t* __restrict__ len16, int n_mels, int pad_frames, float* __restrict__ mel,
