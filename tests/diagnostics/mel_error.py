@@ -1,7 +1,7 @@
 """Developer diagnostic: worst log-mel error of the fused and the unfused GPU paths against the fp64 oracle
 chain, and against each other (40 clips x 5 s)."""
 import numpy as np, torch, sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle
 import rho_tts_b200 as R
 from rho_tts_b200 import synth

@@ -1,6 +1,6 @@
 """Error of the GPU pitch shift against (a) the oracle (fp32, torch's roundings) and (b) torchaudio on the same box,
 in fp32 and in fp64 -- how much of the distance is the reference's own fp32 noise.  GPU box only (torchaudio is in
-the image; /root/reference is not needed).    python tools/pitch_error.py"""
+the image; /root/reference is not needed).    python tests/diagnostics/pitch_error.py"""
 import os
 import sys
 import time
@@ -9,8 +9,8 @@ import numpy as np
 import torch
 import torchaudio
 
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests", "golden"))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "golden"))
 import rho_tts_b200 as R  # noqa: E402
 from oracle import pitch as OP  # noqa: E402
 from pitch_inputs import pitch_input  # noqa: E402

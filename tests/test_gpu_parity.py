@@ -288,7 +288,7 @@ def test_fused_and_unfused_paths_agree(R, cuda_device):
         assert torch.equal(a.audio.clip(i, L), b.audio.clip(i, L)) or \
             torch.equal(ya[a.audio.h_offsets[i]:a.audio.h_offsets[i] + L], b.audio.clip(i, L))
     # two fp32 evaluation orders of the same FIR / FFT: they differ by rounding only, amplified on the
-    # -70 dB bins exactly like the reference's own fp32 noise (tools/mel_error.py: each path is
+    # -70 dB bins exactly like the reference's own fp32 noise (tests/diagnostics/mel_error.py: each path is
     # 4e-5 .. 7e-5 from the fp64 value, as is the numpy oracle)
     d = float((ma - b.mel).abs().max())
     assert d < 1e-4, d

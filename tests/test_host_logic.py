@@ -138,3 +138,19 @@ def test_mixin_registers_with_reference_factory(reference_basetts):
         assert getattr(type(tts), name) is getattr(R.B200AudioMixin, name)
     with pytest.raises(TypeError):
         TTSFactory.register_provider("bad", R.B200AudioMixin)
+
+
+def test_only_tests_bench_and_smoke_touch_the_oracle():
+    """oracle/ is test infrastructure: only tests/, bench.py (its CPU baseline / reference arm) and
+    __graft_entry__.py (smoke) may import it -- not the package, not tools/."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(import oracle|from oracle)", re.M)
+    offenders = []
+    for sub in ("rho_tts_b200", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(root, sub)):
+            for f in files:
+                if f.endswith(".py") and pat.search(open(os.path.join(dirpath, f)).read()):
+                    offenders.append(os.path.join(sub, f))
+    assert offenders == []
