@@ -178,6 +178,13 @@ int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const i
 int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,
                          float* mel, int64_t ld_mel, int64_t frames_per_item, int64_t item_stride, void* stream);
 
+/* --------------------------------------------------------------- 16-bit PCM payload (the caller after the path) */
+/* BaseTTS._save_wav's in-tree WAV writer (base_tts.py:661-667; the fallback it takes when torchaudio.save has no
+ * backend): (np.clip(audio, -1, 1) * 32767).astype(np.int16), i.e. an fp32 product truncated toward zero.  out[s] has
+ * the length of clip s; with it a clip leaves the device as 2 bytes per sample instead of 4. */
+int rho_b200_pcm16(rho_handle* h, const float* y, const int64_t* off, const int32_t* len, int len_stride_bytes, int n,
+                   int64_t max_len, int16_t* out, const int64_t* out_off, void* stream);
+
 /* --------------------------------------------------------------- pitch shift (NEXT-4, the pitch half) */
 /* The pitch branch of BaseTTS._apply_speed_pitch (base_tts.py:639-648): torchaudio.functional.pitch_shift(audio,
  * sample_rate, n_steps) = stft(512, hop 128) -> phase_vocoder(rate = 2^(-n_steps / 12)) -> istft(round(L / rate)) ->

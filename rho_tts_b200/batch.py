@@ -172,6 +172,35 @@ def pitch_shift_batch(rb: RaggedBatch, sample_rate: int, n_steps: float,
     return out
 
 
+def pcm16_batch(rb: RaggedBatch, lengths: Optional[torch.Tensor] = None, len_stride: int = 4) -> torch.Tensor:
+    """int16 samples of every clip at the clip's offsets (one int16 tensor as long as rb.data): the payload
+    BaseTTS._save_wav's in-tree writer puts into the WAV file (base_tts.py:661-667)."""
+    dev = _dev_index(rb.data)
+    h = Handle.get(dev)
+    out = torch.zeros(rb.data.numel(), dtype=torch.int16, device=rb.device)
+    if rb.n == 0:
+        return out
+    lens = rb.lengths if lengths is None else lengths
+    _lib.check(h.lib.rho_b200_pcm16(h.ptr, _ptr(rb.data), _ptr(rb.offsets), _ptr(lens), int(len_stride), rb.n, rb.max_len,
+                                    _ptr(out), _ptr(rb.offsets), _stream(dev)), "pcm16")
+    return out
+
+
+def write_wav(path: str, audio: torch.Tensor, sample_rate: int, device=None) -> None:
+    """The file BaseTTS._save_wav's in-tree writer produces (mono 16-bit PCM, base_tts.py:661-667), with the
+    float -> int16 conversion on the B200 and half the bytes crossing PCIe."""
+    import wave
+    flat = audio.detach().reshape(-1)
+    dev = flat.device if flat.is_cuda else torch.device("cuda", 0 if device is None else int(device))
+    rb = RaggedBatch.from_list([flat.to(dev, torch.float32)], dev)
+    pcm = pcm16_batch(rb)[int(rb.h_offsets[0]):int(rb.h_offsets[0]) + flat.numel()].cpu().numpy()
+    with wave.open(path, "wb") as wf:
+        wf.setnchannels(1)
+        wf.setsampwidth(2)
+        wf.setframerate(int(sample_rate))
+        wf.writeframes(pcm.tobytes())
+
+
 def mfcc_stats_batch(rb16: RaggedBatch, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[n, 26] fp32: mean and std over the frames of librosa.feature.mfcc(y, sr=16000, n_mfcc=13) per 16 kHz clip -- the
     MFCC part of the drift classifier's feature vector (validation/classifier/trainer.py:50-52)."""

@@ -562,6 +562,17 @@ int rho_b200_sound_decay_batch(rho_handle* h, const float* y, const int64_t* off
   return e == cudaSuccess ? RHO_OK : cuda_fail(e, "sound_decay_batch");
 }
 
+int rho_b200_pcm16(rho_handle* h, const float* y, const int64_t* off, const int32_t* len, int len_stride_bytes, int n,
+                   int64_t max_len, int16_t* out, const int64_t* out_off, void* stream) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  if (n < 0 || max_len < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (n == 0 || max_len == 0) return RHO_OK;
+  if (n > 65535) return fail(RHO_ERR_INVALID, "at most 65535 clips per call");
+  if (!y || !off || !len || !out || !out_off) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  cudaError_t e = launch_pcm16(y, off, len, len_stride_bytes, n, max_len, out, out_off, (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "pcm16");
+}
+
 size_t rho_b200_qwen_workspace_bytes(int n, int64_t max_len, int sr) { return qwen_workspace_bytes(n, max_len, sr); }
 
 int rho_b200_qwen_postprocess(rho_handle* h, const float* x, const int64_t* off, const int32_t* len,

@@ -624,6 +624,44 @@ cudaError_t launch_sound_decay_batch(const float* y, const int64_t* off, const i
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ 16-bit PCM payload of _save_wav
+// The in-tree WAV writer (base_tts.py:661-667): (np.clip(x, -1, 1) * 32767).astype(np.int16) -- an fp32 product,
+// truncated toward zero.  8 samples per thread: two 128-bit loads, one 128-bit store.
+__global__ void __launch_bounds__(256)
+k_pcm16(const float* __restrict__ y, const int64_t* __restrict__ off, const char* __restrict__ len_base, int len_stride,
+        int16_t* __restrict__ out, const int64_t* __restrict__ out_off) {
+  const int c = blockIdx.y;
+  const long long n = *reinterpret_cast<const int32_t*>(len_base + (size_t)c * len_stride);
+  const float* __restrict__ src = y + off[c];
+  int16_t* __restrict__ dst = out + out_off[c];
+  auto q = [](float v) { return (int16_t)__float2int_rz(__fmul_rn(fminf(fmaxf(v, -1.0f), 1.0f), 32767.0f)); };
+  const long long i0 = ((long long)blockIdx.x * 256 + threadIdx.x) * 8;
+  if (i0 >= n) return;
+  const bool vec = i0 + 8 <= n && ((reinterpret_cast<uintptr_t>(src + i0) & 15u) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dst + i0) & 15u) == 0);
+  if (vec) {
+    const float4 a = *reinterpret_cast<const float4*>(src + i0), b = *reinterpret_cast<const float4*>(src + i0 + 4);
+    union { int16_t h[8]; uint4 u; } p;
+    p.h[0] = q(a.x); p.h[1] = q(a.y); p.h[2] = q(a.z); p.h[3] = q(a.w);
+    p.h[4] = q(b.x); p.h[5] = q(b.y); p.h[6] = q(b.z); p.h[7] = q(b.w);
+    *reinterpret_cast<uint4*>(dst + i0) = p.u;
+  } else {
+    for (long long i = i0; i < n && i < i0 + 8; ++i) dst[i] = q(src[i]);
+  }
+}
+
+cudaError_t launch_pcm16(const float* y, const int64_t* off, const int32_t* len, int len_stride_bytes, int n,
+                         int64_t max_len, int16_t* out, const int64_t* out_off, cudaStream_t st, LaunchCtx* lc) {
+  if (n <= 0 || max_len <= 0) return cudaSuccess;
+  if (n > 65535) return cudaErrorInvalidValue;
+  const unsigned gx = (unsigned)((max_len + 2047) / 2048);
+  lc->begin(KID_SINGLE, st);
+  k_pcm16<<<dim3(gx, (unsigned)n), 256, 0, st>>>(y, off, reinterpret_cast<const char*>(len),
+                                                len_stride_bytes ? len_stride_bytes : (int)sizeof(int32_t), out, out_off);
+  lc->end(st);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ host launchers
 #ifndef RHO_SCAN_DENSE
 #define RHO_SCAN_DENSE 1

@@ -89,6 +89,9 @@ cudaError_t launch_sound_decay_batch(const float* y, const int64_t* off, const i
                                      int n, int64_t max_len, double thr, rho_record* rec, double* sums,
                                      cudaStream_t st, LaunchCtx* lc);
 
+cudaError_t launch_pcm16(const float* y, const int64_t* off, const int32_t* len, int len_stride_bytes, int n,
+                         int64_t max_len, int16_t* out, const int64_t* out_off, cudaStream_t st, LaunchCtx* lc);
+
 // resample.cu
 cudaError_t upload_resample_taps(const float* taps /* [2][23] */);
 cudaError_t launch_resample3to2(const float* x, const int64_t* off, const int32_t* len, int len_stride_bytes,
