@@ -99,6 +99,11 @@ const char* rho_b200_last_error(void);
  *   kind 1: periodic Hann(400), out[400]           (feature_extraction_whisper.py:141)
  *   kind 2: mel filterbank, arg = n_mels, out[n_mels*201] row-major [mel][bin]
  *                                                   (transformers audio_utils.py:453-544)
+ *   kind 3: pitch shift phase_advance = torch.linspace(0, pi*128, 257) as torch's fp32 kernel makes it, out[257]
+ *   kind 4: MFCC DCT-II rows (orthonormal), out[13*128]
+ *   kind 5: MFCC slaney filterbank, 128 bands over the 1025 bins of a 2048-point FFT at 16 kHz, out[128*1025]
+ *   kind 6: windowed resample taps of arg -> 24000 Hz (reduced ratio orig:new), out[new * W], W = 2*width+2 rounded
+ *           up to a multiple of 4                  (torchaudio functional.py:1305-1405, taps inside the Hann window)
  * Returns the number of floats written, or a negative status. */
 int rho_b200_host_table(int kind, int arg, float* out, size_t out_capacity);
 

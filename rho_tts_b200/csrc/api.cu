@@ -152,6 +152,8 @@ int rho_b200_abi_version(void) { return RHO_B200_ABI_VERSION; }
 
 const char* rho_b200_last_error(void) { return g_err; }
 
+static long long gcd_ll(long long a, long long b);
+
 int rho_b200_host_table(int kind, int arg, float* out, size_t cap) {
   if (!out) return fail(RHO_ERR_INVALID, "out is NULL");
   switch (kind) {
@@ -165,6 +167,32 @@ int rho_b200_host_table(int kind, int arg, float* out, size_t cap) {
       if (arg != 80 && arg != 128) return fail(RHO_ERR_INVALID, "n_mels must be 80 or 128");
       if (cap < (size_t)arg * N_BINS) return fail(RHO_ERR_INVALID, "capacity");
       host_mel_filterbank(arg, out); return arg * N_BINS;
+    case 3: {                                          // pitch shift: phase_advance = torch.linspace(0, pi * 128, 257)
+      if (cap < 257) return fail(RHO_ERR_INVALID, "capacity");
+      std::vector<float> w256(512), w512(514), hn(512);
+      host_pitch_tables(w256.data(), w512.data(), hn.data(), out);
+      return 257;
+    }
+    case 4: {                                          // MFCC: 13 x 128 orthonormal DCT-II rows
+      if (cap < 13 * 128) return fail(RHO_ERR_INVALID, "capacity");
+      std::vector<float> hn(2048), w1(2048), w2(2050);
+      host_mfcc_tables(hn.data(), w1.data(), w2.data(), out);
+      return 13 * 128;
+    }
+    case 5:                                            // MFCC: slaney filterbank, 128 bands over 1025 bins
+      if (cap < (size_t)128 * 1025) return fail(RHO_ERR_INVALID, "capacity");
+      host_mel_filterbank_bins(128, 1025, out); return 128 * 1025;
+    case 6: {                                          // windowed resample taps of ratio arg : 24000 (reduced), [nw][W]
+      if (arg <= 0 || arg == 24000) return fail(RHO_ERR_INVALID, "orig_freq");
+      const long long g = gcd_ll(arg, 24000);
+      const int orig = (int)(arg / g), nw = (int)(24000 / g);
+      const int width = host_resample_width(orig, nw);
+      const int W = (2 * width + 2 + 3) / 4 * 4;
+      if (cap < (size_t)nw * W) return fail(RHO_ERR_INVALID, "capacity: need %zu", (size_t)nw * W);
+      std::vector<int> lo((size_t)nw);
+      host_resample_taps_windowed(orig, nw, width, W, out, lo.data());
+      return nw * W;
+    }
     default:
       return fail(RHO_ERR_INVALID, "unknown table kind %d", kind);
   }

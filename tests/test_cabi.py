@@ -113,3 +113,32 @@ def test_baked_mel_weights_match_runtime_table(lib):
             for hx, k in re.findall(r"__uint_as_float\((0x[0-9a-f]{8})u\), p\[(\d+)\]", taps):
                 seen[int(m), int(k)] = np.array([int(hx, 16)], dtype=np.uint32).view(np.float32)[0]
         assert np.array_equal(seen.view(np.uint32), table.view(np.uint32))
+
+
+def test_pitch_and_mfcc_host_tables(lib):
+    """The tables the pitch-shift / MFCC kernels get from the host, against torch / the oracle (no GPU needed)."""
+    import math
+    from oracle import mfcc as OM
+    from oracle import pitch as OP
+    padv = _table(lib, 3, 0, 257)
+    assert np.array_equal(padv, torch.linspace(0, math.pi * 128, 257).numpy())       # bit for bit: the phases depend on it
+    assert np.array_equal(padv, OP.linspace_f32(math.pi * 128, 257))
+    dct = _table(lib, 4, 0, 13 * 128).reshape(13, 128)
+    assert float(np.abs(dct - OM.dct_matrix()).max()) <= 1e-7
+    fb = _table(lib, 5, 0, 128 * 1025).reshape(128, 1025)
+    assert float(np.abs(fb - OM.mel_filterbank()).max()) <= 1e-8
+    # windowed taps of 26939 -> 24000 (pitch +2 semitones): every tap torchaudio's dense fp32 kernel holds above 1e-20
+    # is in the window, with the same value to an ulp
+    ta = pytest.importorskip("torchaudio")
+    orig, new = 11, 10                                                                 # 26400 -> 24000: small dense kernel
+    taps = _table(lib, 6, 26400, new * 16).reshape(new, 16)
+    kt, width = ta.functional.functional._get_sinc_resample_kernel(26400, 24000, 2400, dtype=torch.float32)
+    dense = kt.numpy()[:, 0, :]
+    assert width == 7
+    for p in range(new):
+        lo = max(0, int(math.floor(p * orig / new + width - 6 * orig / (min(orig, new) * 0.99))))
+        row = np.zeros(dense.shape[1] + 16, np.float32)
+        row[:dense.shape[1]] = dense[p]
+        assert float(np.abs(taps[p] - row[lo:lo + 16]).max()) <= 1.2e-7
+        outside = np.delete(dense[p], np.arange(lo, min(lo + 16, dense.shape[1])))
+        assert float(np.abs(outside).max(initial=0.0)) < 1e-20
