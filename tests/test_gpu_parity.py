@@ -397,3 +397,57 @@ def test_mel_project_batched_layout(R, cuda_device):
         nt = min(T, n_frames - i * T)
         np.testing.assert_allclose(got[i, :, :nt], want[:, i * T:i * T + nt], rtol=2e-6)
         assert np.all(got[i, :, nt:] == -1.0)                                                 # nothing else is touched
+
+
+def test_full_size_ragged_joins_properties(R, cuda_device):
+    """BASELINE config C3 size: 4000 ragged clips of 1..30 s (6 GB) joined into ~1000 items of 2..6 segments.
+    Size-independent checks, plus three items against the oracle."""
+    from rho_tts_b200 import synth
+    n = 4000
+    lens = synth.make_ragged_lengths(n, 1234 + 3)
+    rb = R.RaggedBatch.empty_like_lengths(lens, cuda_device)
+    order = np.argsort(lens)
+    for g0 in range(0, n, 50):                                   # groups of similar length share one generator call
+        idx = order[g0:g0 + 50]
+        blk = synth.make_clip_block(len(idx), int(lens[idx].max()), 7919 * 1237 + g0, device=cuda_device)
+        for j, i in enumerate(idx):
+            rb.clip(int(i)).copy_(blk[j, :int(lens[i])])
+    first = synth.make_item_partition(n, 1234 + 3)
+    p = R.make_params()
+    out = R.join_batch(rb, first, p, want_seg_info=True)
+    rec, seg = out.records_host(), out.seg_info_host()
+    n_items = len(first) - 1
+    assert rec.shape[0] == n_items and np.array_equal(rec["n_segments"], np.diff(first))
+    # trim bounds: hop-aligned starts, ends hop-aligned or at the clip end, inside the clip
+    assert np.all(seg["start"] % 120 == 0) and np.all((seg["end"] % 120 == 0) | (seg["end"] == lens))
+    assert np.all((0 <= seg["start"]) & (seg["start"] <= seg["end"]) & (seg["end"] <= lens))
+    # length bookkeeping of base_tts.py:481-523 for regular items (every segment longer than the crossfade): the kept
+    # samples, minus one crossfade overlap per joint, plus one pause after every middle segment
+    kept = (seg["end"] - seg["start"]).astype(np.int64)
+    csum = np.concatenate([[0], np.cumsum(kept)])
+    k = np.diff(first).astype(np.int64)
+    regular = np.array([kept[first[i]:first[i + 1]].min() > 2400 for i in range(n_items)]) & ((rec["flags"] & 0x3) == 0)
+    want_len = (csum[first[1:]] - csum[first[:-1]]) - (k - 1) * 1200 + np.maximum(0, k - 2) * 2400
+    assert regular.mean() > 0.9
+    assert np.array_equal(rec["out_len"][regular], want_len[regular])
+    # the decay decision equals the one recomputed from the joined audio itself
+    for i in range(0, n_items, 97):
+        y = out.audio.clip(i, int(rec["out_len"][i])).double()
+        third = y.numel() // 3
+        if third < 1:
+            continue
+        fr, lr = float(y[:third].pow(2).mean().sqrt()), float(y[-third:].pow(2).mean().sqrt())
+        if fr >= 1e-8:
+            assert abs(lr / fr - rec["decay_ratio"][i]) <= 1e-4 * max(1.0, lr / fr)
+            assert bool(rec["ok"][i]) == (lr / fr >= 0.3) or abs(lr / fr - 0.3) < 1e-4
+    # determinism: the same call again gives the same bytes
+    out2 = R.join_batch(rb, first, p, want_seg_info=False)
+    assert torch.equal(out.records, out2.records)
+    # three items against the oracle
+    c = oracle.derive_constants()
+    for i in (0, n_items // 2, n_items - 1):
+        segs = [rb.clip(s).cpu().numpy() for s in range(first[i], first[i + 1])]
+        o = oracle.smooth_segment_join(segs, c)
+        L = int(rec["out_len"][i])
+        assert L == o.audio.size
+        assert_close(out.audio.clip(i, L).cpu().numpy(), o.audio, what=f"item {i}")
