@@ -451,3 +451,27 @@ def test_full_size_ragged_joins_properties(R, cuda_device):
         L = int(rec["out_len"][i])
         assert L == o.audio.size
         assert_close(out.audio.clip(i, L).cpu().numpy(), o.audio, what=f"item {i}")
+
+
+def test_full_size_c4_shard_128_bins(R, cuda_device):
+    """One GPU's shard of BASELINE config C4: 8000 x 10 s clips, 128-bin log-mel (30 s pad), cosine: 28 GB resident."""
+    from rho_tts_b200 import synth
+    n = 8000
+    x = synth.make_clip_block(n, 240000, 0xC4, device=cuda_device)
+    emb, ref = synth.make_embeddings(n, device=cuda_device)
+    out = R.validate_batch(R.RaggedBatch.from_dense(x), R.make_params(), emb, ref, n_mels=128)
+    rec = out.records_host()
+    mel = out.mel
+    assert mel.shape == (n, 128, 3000)
+    assert np.all(rec["out_len"] == rec["end"] - rec["start"]) and np.all(np.abs(rec["cosine"]) <= 1.0 + 1e-6)
+    mx = mel.amax(dim=(1, 2))
+    tail = mel[:, :, 1010:]
+    assert torch.equal(tail.amax(dim=(1, 2)), tail.amin(dim=(1, 2)))
+    assert float((mx - 2.0 - tail[:, 0, 0]).abs().max()) <= 1e-6          # padding constant of the final clip maximum
+    assert float((mx - mel.amin(dim=(1, 2))).max()) <= 2.0 + 1e-6         # the Whisper clamp
+    c = oracle.derive_constants()
+    for i in (17, n - 1):
+        o, m, cs = _oracle_pipeline(x[i].cpu().numpy(), c, 128, emb[i].cpu().numpy(), ref.cpu().numpy())
+        assert (rec["start"][i], rec["end"][i], bool(rec["ok"][i])) == (o["start"], o["end"], o["ok"])
+        assert_close(mel[i].cpu().numpy(), m, what=f"mel clip {i}")
+        assert abs(rec["cosine"][i] - cs) <= 1e-5
