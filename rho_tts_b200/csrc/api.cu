@@ -1,5 +1,6 @@
 // C ABI of librho_b200.so (see include/rho_b200.h).  Host-side glue only: argument checks,
 // constants derived the way the reference derives them, workspace carving, launches.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -470,7 +471,15 @@ int rho_b200_pitch_shift(rho_handle* h, const float* x, const int64_t* off, cons
     if (it == h->windowed_taps.end()) {
       std::vector<float> t((size_t)nw * W);
       std::vector<int> lo((size_t)nw);
-      host_resample_taps_windowed(orig, nw, width, W, t.data(), lo.data());
+      if (orig == nw) {
+        // int(sample_rate / rate) == sample_rate (a shift of a few thousandths of a semitone): torchaudio's resample
+        // returns its input unchanged (functional.py:1417-1418) -- an identity tap, not the 0.99-rolloff low-pass
+        std::fill(t.begin(), t.end(), 0.f);
+        t[0] = 1.f;
+        lo[0] = width;
+      } else {
+        host_resample_taps_windowed(orig, nw, width, W, t.data(), lo.data());
+      }
       cudaError_t e;
       if ((e = dev_upload(h, &wt.taps, t.data(), t.size())) != cudaSuccess ||
           (e = dev_upload(h, &wt.ilo, lo.data(), lo.size())) != cudaSuccess)

@@ -137,6 +137,18 @@ def test_gpu_long_tonal_clip_within_reference_noise(cuda_device):
 
 
 @pytest.mark.gpu
+def test_gpu_pitch_tiny_step_skips_the_resample(cuda_device):
+    """int(sr / rate) == sr for |n_steps| < ~7e-4: torchaudio's resample returns its input, so only the vocoder acts."""
+    import rho_tts_b200 as R
+    x = pitch_input(9000, 90)
+    for steps in (3e-4, -2e-4):                       # -2e-4: 23999 -> 24000, a ratio with 24000 phases
+        assert int(SR / OP.pitch_rate(steps)) == (SR if steps > 0 else SR - 1)
+        rb = R.RaggedBatch.from_list([torch.from_numpy(x)], cuda_device)
+        y = R.pitch_shift_batch(rb, SR, steps).clip(0).cpu().numpy()
+        assert_close(y, OP.pitch_shift(x, SR, steps), tol=TOL, what=f"n_steps {steps}")
+
+
+@pytest.mark.gpu
 def test_gpu_pitch_errors(cuda_device):
     import rho_tts_b200 as R
     rb = R.RaggedBatch.from_list([torch.from_numpy(pitch_input(256, 1)), torch.from_numpy(pitch_input(4000, 2))], cuda_device)
