@@ -154,3 +154,13 @@ def test_only_tests_bench_and_smoke_touch_the_oracle():
                 if f.endswith(".py") and pat.search(open(os.path.join(dirpath, f)).read()):
                     offenders.append(os.path.join(sub, f))
     assert offenders == []
+
+
+def test_bind_to_gpu_numa_is_harmless_without_nvml():
+    """No GPU / NVML here: the helper must leave the affinity alone and say so."""
+    import os
+    import rho_tts_b200 as R
+    before = os.sched_getaffinity(0)
+    assert R.dist.bind_to_gpu_numa(0) is None or isinstance(R.dist.bind_to_gpu_numa(0), list)
+    if not __import__("torch").cuda.is_available():
+        assert os.sched_getaffinity(0) == before
