@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RHO_B200_ABI_VERSION 1
+#define RHO_B200_ABI_VERSION 2
 
 typedef struct rho_handle rho_handle;
 
@@ -257,29 +257,67 @@ int rho_b200_cosine(rho_handle* h, const float* emb, const float* ref, int n, in
                     float* out, int out_stride_bytes, void* stream);
 
 /* ------------------------------------------------ whole validation front end */
-/* join/post-process -> resample 24k->16k -> log-mel -> cosine, device resident.
- * scratch16 holds the 16 kHz intermediate (same offsets as y, 2/3 the length).
- * flags: RHO_V_ONE_SEGMENT_ITEMS -- the caller asserts every item is exactly one segment
- *        (item_first_seg = 0,1,2,...): enables the fused kernel that applies DC/fades, resamples and
- *        computes the log-mel frames in one pass over each clip (scratch16 is then unused, may be NULL).
- *        RHO_V_NO_FUSION -- force the kernel-per-stage path (for A/B measurements). */
+/* join/post-process -> resample 24k->16k -> log-mel -> cosine, device resident: what every generated item passes
+ * through between generation and the accept / retry decision (base_tts.py:912-926 followed by the validation front
+ * end, stt_validator.py:78-107 -> feature_extraction_whisper.py:135-164, and the speaker cosine base_tts.py:341-344).
+ *   one-segment items (RHO_V_ONE_SEGMENT_ITEMS: the caller asserts item_first_seg = 0,1,2,...): ONE kernel applies
+ *     DC / fades, resamples and computes the log-mel frames in one pass over each clip;
+ *   joined items: the join writes y, the same kernel then reads the finished y (resample + log-mel).
+ *   Either way the 16 kHz signal never leaves shared memory; scratch16 is only used with RHO_V_NO_FUSION (the
+ *   kernel-per-stage path kept for A/B measurements: same offsets as y, 2/3 the length) and may be NULL otherwise.
+ * Features: mel + i*n_mels*mel_stride_frames, rows of mel_stride_frames floats.
+ *   pad_frames = 3000, default: mel_stride_frames >= 3000, every row complete (feature_extraction_whisper.py:296-303).
+ *   pad_frames = 3000, RHO_V_COMPACT_PAD: rows of mel_stride_frames < 3000 frames (a multiple of 4, at least
+ *     rho_b200_compact_frames(max_item_len, 3000)): only the frames that can see signal are materialised; every frame
+ *     t >= mel_stride_frames of item i equals pad_value[i] (the 30 s window of a 10 s clip is 2/3 such frames).
+ *   pad_value (device, n_items floats, may be NULL): the constant of item i's zero-padding frames, in either layout.
+ * Records: rec[i]; when record peers are set (rho_b200_set_record_peers) the same record is also stored to every
+ * peer sink by the kernel that assembles it. */
 #define RHO_V_ONE_SEGMENT_ITEMS 1u
 #define RHO_V_NO_FUSION 2u
+#define RHO_V_COMPACT_PAD 4u
 int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, const int32_t* seg_len,
                       int n_segments, int64_t max_seg_len,
                       const int32_t* item_first_seg, int n_items, int64_t max_item_len,
                       const rho_params* p, float* y, const int64_t* y_off,
-                      int n_mels, int pad_frames, float* mel, int64_t mel_stride_frames,
+                      int n_mels, int pad_frames, float* mel, int64_t mel_stride_frames, float* pad_value,
                       const float* emb, const float* ref_emb, int emb_dim,
                       rho_record* rec, float* scratch16, uint32_t flags,
                       void* workspace, size_t ws_bytes, void* stream);
+/* Frames per row a compact feature tensor needs for items of at most max_item_len 24 kHz samples (pad_frames = 3000:
+ * ceil((min(ceil(2L/3), 480000) + 200) / 160) rounded up to a multiple of 4, at most 3000; pad_frames = 0: the
+ * unpadded frame count ceil(2L/3) / 160). */
+int64_t rho_b200_compact_frames(int64_t max_item_len, int pad_frames);
 
-/* HOST entry point: the call a non-torch embedder makes.  All pointers are HOST
- * buffers (pinned for full speed).  Copies clips in, runs rho_b200_validate in
- * chunks on internal streams (H2D, compute and D2H overlapped), copies processed
- * audio, records and (if mel != NULL) features back, and returns after the last
- * copy finished.  Fixed-length layout: n clips of `clip_len` samples each, every
- * item is one clip. */
+/* Multi-GPU record exchange fused into the record assembly (the one exchange of the path is the
+ * gather of the 48-byte records).  sinks[r], r < n_sinks: DEVICE pointers valid on this handle's device -- rank r's
+ * gathered-record buffer mapped into this process over NVLink peer memory (cudaIpcOpenMemHandle / symmetric memory;
+ * sinks[own rank] is the local buffer).  From now on every record rho_b200_validate / rho_b200_join assembles is also
+ * stored to sinks[r][slot + i] for all r, by the kernel that writes rec[i]: no collective call on the critical path.
+ * Readers order themselves after the writers with their own barrier / flag (rho_tts_b200.dist.RecordExchange).
+ * n_sinks = 0 switches it off.  At most 16 sinks. */
+int rho_b200_set_record_peers(rho_handle* h, void* const* sinks, int n_sinks, int64_t slot);
+
+/* HOST entry points: the calls a non-torch embedder makes.  All pointers are HOST buffers (pinned for full speed).
+ * Segments are copied in, rho_b200_validate (or rho_b200_join when mel == NULL: no features) runs in chunks of whole
+ * items on internal streams (H2D, kernels and D2H overlapped), processed audio, records and features are copied back;
+ * the call returns after the last copy.  Re-entrant: concurrent callers on one handle get their own streams / arena.
+ *   x, seg_off, seg_len, item_first_seg: the ragged layout of rho_b200_join, in host memory; segments in increasing,
+ *     non-overlapping order.  y, y_off: item i is written at y + y_off[i], the caller reserves sum(len) + pauses as
+ *     for rho_b200_join, items in increasing order; host samples BETWEEN the items of a chunk are clobbered.
+ *     Offsets that are all multiples of 4 give one copy per chunk and direction (else one per segment / item).
+ *   mel (may be NULL), mel_stride_frames, pad_value (may be NULL): as rho_b200_validate with the layouts
+ *     mel_stride_frames >= 3000 (complete rows) or < 3000 (compact rows + pad_value).  Only the frames that can see
+ *     signal cross PCIe in either case: complete rows get their constant tail written by host threads from pad_value
+ *     (RHO_HOST_FILL_THREADS, default min(8, cores / 4)), overlapped with the copies of the following chunks.
+ *   emb [n_items][emb_dim], ref_emb [emb_dim] (may be NULL): speaker cosine into rec[i].cosine. */
+int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* seg_off, const int32_t* seg_len,
+                                  int n_segments, const int32_t* item_first_seg, int n_items, const rho_params* p,
+                                  float* y, const int64_t* y_off, int n_mels, int pad_frames, float* mel,
+                                  int64_t mel_stride_frames, float* pad_value, const float* emb,
+                                  const float* ref_emb, int emb_dim, rho_record* rec);
+/* Fixed-length layout: n clips of clip_len samples each, every item is one clip; complete feature rows
+ * [n][n_mels][3000] (mel may be NULL).  A wrapper of rho_b200_validate_host_ragged. */
 int rho_b200_validate_host(rho_handle* h, const float* x, int n, int32_t clip_len,
                            const rho_params* p, float* y /* n*clip_len */, int n_mels, int pad_frames,
                            float* mel /* n*n_mels*pad_frames or NULL */,

@@ -224,7 +224,9 @@ def join_plan(seg_lens: Sequence[int], trims: Sequence[TrimResult], c: Consts) -
     cf = c.cf
     # segment 0 (:484-488)
     if Ls[0] > cf:
-        emit(P_COPY, Ls[0] - cf, seg=0, src=0, two_d=dims2[0])
+        # current_segment[..., :-crossfade_samples]: with crossfade_samples == 0 this is [..., :0], an EMPTY slice --
+        # the reference drops segment 0 when the crossfade is disabled (kept bug for bug)
+        emit(P_COPY, Ls[0] - cf if cf > 0 else 0, seg=0, src=0, two_d=dims2[0])
     else:
         emit(P_COPY, Ls[0], seg=0, src=0, two_d=dims2[0])
     for i in range(1, n):

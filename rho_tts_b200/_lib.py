@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # RHO_B200_LIB: developer override used by tools/ab_fused.sh to A/B kernel variants
 LIB_PATH = os.environ.get("RHO_B200_LIB") or os.path.join(_HERE, "librho_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # flags (include/rho_b200.h)
 F_ALL_SILENT = 1
@@ -25,13 +25,15 @@ F_TWO_D = 4
 F_UNTOUCHED = 8
 V_ONE_SEGMENT_ITEMS = 1
 V_NO_FUSION = 2
+V_COMPACT_PAD = 4
 
 EXPORTS = (
     "rho_b200_abi_version", "rho_b200_create", "rho_b200_destroy", "rho_b200_last_error",
     "rho_b200_host_table", "rho_b200_workspace_bytes", "rho_b200_trim_scan", "rho_b200_join",
     "rho_b200_remove_dc", "rho_b200_apply_fades", "rho_b200_sound_decay", "rho_b200_sound_decay_batch", "rho_b200_resample3to2",
     "rho_b200_resample_out_len", "rho_b200_resample", "rho_b200_pitch_workspace_bytes", "rho_b200_pitch_shift", "rho_b200_mfcc_workspace_bytes", "rho_b200_mfcc_stats", "rho_b200_pcm16", "rho_b200_logmel", "rho_b200_mel_project", "rho_b200_qwen_workspace_bytes", "rho_b200_qwen_postprocess",
-    "rho_b200_cosine", "rho_b200_validate", "rho_b200_validate_host",
+    "rho_b200_cosine", "rho_b200_validate", "rho_b200_compact_frames", "rho_b200_set_record_peers",
+    "rho_b200_validate_host", "rho_b200_validate_host_ragged",
     "rho_b200_build_flags", "rho_b200_launch_count", "rho_b200_profile_begin", "rho_b200_profile_end", "rho_b200_kernel_name",
 )
 
@@ -102,8 +104,12 @@ def load():
             "rho_b200_qwen_workspace_bytes": (c_size_t, [c_int, i64, c_int]),
             "rho_b200_qwen_postprocess": (c_int, [vp, vp, vp, vp, c_int, c_int, i64, c_int, vp, vp, vp, c_size_t, vp]),
             "rho_b200_cosine": (c_int, [vp, vp, vp, i32, c_int, vp, c_int, vp]),
-            "rho_b200_validate": (c_int, [vp, vp, vp, vp, i32, i64, vp, i32, i64, P, vp, vp, c_int, c_int, vp, i64,
+            "rho_b200_validate": (c_int, [vp, vp, vp, vp, i32, i64, vp, i32, i64, P, vp, vp, c_int, c_int, vp, i64, vp,
                                           vp, vp, c_int, vp, vp, c_uint32, vp, c_size_t, vp]),
+            "rho_b200_compact_frames": (c_int64, [i64, c_int]),
+            "rho_b200_set_record_peers": (c_int, [vp, vp, c_int, i64]),
+            "rho_b200_validate_host_ragged": (c_int, [vp, vp, vp, vp, c_int, vp, c_int, P, vp, vp, c_int, c_int, vp, i64,
+                                                      vp, vp, vp, c_int, vp]),
             "rho_b200_validate_host": (c_int, [vp, vp, c_int, c_int32, P, vp, c_int, c_int, vp, vp, vp, c_int, vp]),
             "rho_b200_build_flags": (c_int, []),
             "rho_b200_launch_count": (c_int64, [vp]),

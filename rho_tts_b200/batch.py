@@ -340,8 +340,9 @@ def cosine_batch(emb: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
 @dataclass
 class ValidateOutput:
     audio: RaggedBatch
-    mel: torch.Tensor
+    mel: torch.Tensor           # [n, n_mels, T]: T = 3000, the unpadded frame count, or the compact row length
     records: torch.Tensor
+    pad_value: Optional[torch.Tensor] = None    # [n] fp32 (30 s padding): the value of every frame past the signal
 
     def records_host(self) -> np.ndarray:
         return self.records.cpu().numpy().view(REC_DTYPE).reshape(-1)
@@ -352,7 +353,7 @@ class ValidatePlan:
     (the benchmark's steady state: allocation is not part of the hot path)."""
 
     def __init__(self, rb: RaggedBatch, item_first_seg: Sequence[int], p: RhoParams, n_mels: int = 80,
-                 pad_to_30s: bool = True, fuse: bool = True):
+                 pad_to_30s: bool = True, fuse: bool = True, compact: bool = False):
         self.dev = _dev_index(rb.data)
         self.h = Handle.get(self.dev)
         self.p = p
@@ -363,14 +364,22 @@ class ValidatePlan:
         self.n_seg = rb.n
         self.max_seg_len = rb.max_len
         one_seg = self.n_items == self.n_seg and bool(np.all(np.diff(first) == 1))
-        self.flags = (_lib.V_ONE_SEGMENT_ITEMS if one_seg else 0) | (0 if fuse else _lib.V_NO_FUSION)
+        # compact (30 s padding only): rows hold just the frames that can see signal; every later frame of item i is
+        # pad_value[i] (RHO_V_COMPACT_PAD) -- a third of the bytes for 10 s clips
+        self.compact = bool(compact and pad_to_30s)
+        self.flags = (_lib.V_ONE_SEGMENT_ITEMS if one_seg else 0) | (0 if fuse else _lib.V_NO_FUSION) | \
+            (_lib.V_COMPACT_PAD if self.compact else 0)
         pause = int(p.sr * p.pause_sec) if p.pause_sec > 0 else 0
         seg_tot = np.concatenate([[0], np.cumsum(rb.h_lengths.astype(np.int64))])
         cap = (seg_tot[first[1:]] - seg_tot[first[:-1]]) + np.maximum(0, np.diff(first) - 2) * pause
         self.max_item_len = int(cap.max()) if self.n_items else 0
         self.out = RaggedBatch.empty_like_lengths(cap.astype(np.int32), rb.device)
-        self.scratch16 = torch.empty_like(self.out.data)
+        # the 16 kHz intermediate exists only on the kernel-per-stage path (fuse=False)
+        self.scratch16 = torch.empty_like(self.out.data) if not fuse else None
         self.T = 3000 if pad_to_30s else max(((2 * self.max_item_len + 2) // 3) // 160, 1)
+        if self.compact:
+            self.T = int(self.h.lib.rho_b200_compact_frames(self.max_item_len, 3000))
+        self.pad_value = torch.empty(self.n_items, dtype=torch.float32, device=rb.device) if pad_to_30s else None
         self.T_alloc = (self.T + 3) // 4 * 4      # rows 16-byte aligned: the normaliser's 128-bit path
         self.mel_buf = torch.empty((self.n_items, self.n_mels, self.T_alloc), dtype=torch.float32, device=rb.device)
         self.mel = self.mel_buf[:, :, :self.T]
@@ -384,17 +393,18 @@ class ValidatePlan:
             h.ptr, _ptr(rb.data), _ptr(rb.offsets), _ptr(rb.lengths), self.n_seg, self.max_seg_len,
             _ptr(self.d_first), self.n_items, self.max_item_len, ctypes.byref(self.p),
             _ptr(self.out.data), _ptr(self.out.offsets), self.n_mels, self.pad_frames, _ptr(self.mel_buf), self.T_alloc,
-            _ptr(emb), _ptr(ref), int(emb.shape[1]) if emb is not None else 0, _ptr(self.rec),
+            _ptr(self.pad_value), _ptr(emb), _ptr(ref), int(emb.shape[1]) if emb is not None else 0, _ptr(self.rec),
             _ptr(self.scratch16), self.flags, _ptr(self.ws), self.ws.numel(), _stream(self.dev)), "validate")
-        return ValidateOutput(self.out, self.mel, self.rec)
+        return ValidateOutput(self.out, self.mel, self.rec, self.pad_value)
 
 
 def validate_batch(rb: RaggedBatch, p: RhoParams, emb: Optional[torch.Tensor] = None,
                    ref: Optional[torch.Tensor] = None, n_mels: int = 80, pad_to_30s: bool = True,
-                   item_first_seg: Optional[Sequence[int]] = None, fuse: bool = True) -> ValidateOutput:
+                   item_first_seg: Optional[Sequence[int]] = None, fuse: bool = True,
+                   compact: bool = False) -> ValidateOutput:
     """post-process/join -> resample 24k->16k -> log-mel -> cosine, all on the device."""
     first = np.arange(rb.n + 1, dtype=np.int32) if item_first_seg is None else item_first_seg
-    return ValidatePlan(rb, first, p, n_mels, pad_to_30s, fuse).run(rb, emb, ref)
+    return ValidatePlan(rb, first, p, n_mels, pad_to_30s, fuse, compact).run(rb, emb, ref)
 
 
 def validate_host(x: torch.Tensor, p: RhoParams, emb: Optional[torch.Tensor], ref: Optional[torch.Tensor],
@@ -413,3 +423,66 @@ def validate_host(x: torch.Tensor, p: RhoParams, emb: Optional[torch.Tensor], re
     _lib.check(h.lib.rho_b200_validate_host(h.ptr, _ptr(x), n, L, ctypes.byref(p), _ptr(y), int(n_mels), 3000,
                                             _ptr(mel), _ptr(emb), _ptr(ref), dim, _ptr(rec)), "validate_host")
     return y, mel, rec
+
+
+@dataclass
+class HostRaggedOutput:
+    audio: torch.Tensor         # flat CPU fp32; item i at y_offsets[i], valid length records["out_len"][i]
+    y_offsets: np.ndarray       # int64 [n_items]
+    records: np.ndarray         # REC_DTYPE [n_items]
+    mel: Optional[torch.Tensor]         # [n_items, n_mels, T] CPU (None: no features were asked for)
+    pad_value: Optional[torch.Tensor]   # [n_items] CPU fp32: the value of every frame past the signal (30 s padding)
+
+
+def host_item_layout(seg_lengths: np.ndarray, item_first_seg: np.ndarray, p: RhoParams, align: int = ALIGN):
+    """Output offsets (aligned) and capacities for the items of a ragged host batch, as rho_b200_join wants them:
+    sum of the item's segment lengths + max(0, n - 2) pauses."""
+    first = np.asarray(item_first_seg, dtype=np.int64)
+    pause = int(p.sr * p.pause_sec) if p.pause_sec > 0 else 0
+    tot = np.concatenate([[0], np.cumsum(np.asarray(seg_lengths, dtype=np.int64))])
+    cap = (tot[first[1:]] - tot[first[:-1]]) + np.maximum(0, np.diff(first) - 2) * pause
+    padded = (cap + align - 1) // align * align
+    off = np.concatenate([[0], np.cumsum(padded)])[:-1].astype(np.int64)
+    return off, cap.astype(np.int64), int(padded.sum())
+
+
+def validate_host_ragged(x: torch.Tensor, seg_offsets: np.ndarray, seg_lengths: np.ndarray,
+                         item_first_seg: Sequence[int], p: RhoParams, emb: Optional[torch.Tensor] = None,
+                         ref: Optional[torch.Tensor] = None, n_mels: int = 80, features: bool = True,
+                         pad_to_30s: bool = True, compact: bool = False, y: Optional[torch.Tensor] = None,
+                         mel: Optional[torch.Tensor] = None, device: int = 0) -> HostRaggedOutput:
+    """rho_b200_validate_host_ragged: ragged segments / items in HOST memory (x flat CPU fp32, pinned for full speed)
+    -> _smooth_segment_join + _validate_sound_decay per item (base_tts.py:435-536, 297-323) and, with features, the
+    16 kHz resample + Whisper log-mel + cosine.  Everything comes back in host memory."""
+    assert not x.is_cuda and x.dim() == 1 and x.dtype == torch.float32 and x.is_contiguous()
+    h = Handle.get(device)
+    seg_off = np.ascontiguousarray(seg_offsets, dtype=np.int64)
+    seg_len = np.ascontiguousarray(seg_lengths, dtype=np.int32)
+    first = np.ascontiguousarray(item_first_seg, dtype=np.int32)
+    n_items, n_seg = len(first) - 1, len(seg_len)
+    y_off, cap, y_total = host_item_layout(seg_len, first, p)
+    if y is None:
+        y = torch.empty(max(y_total, 1), dtype=torch.float32).pin_memory()
+    assert y.numel() >= y_total
+    rec = np.zeros(n_items, dtype=REC_DTYPE)
+    pad_frames = 3000 if pad_to_30s else 0
+    pad_value = None
+    T = 0
+    if features:
+        max_cap = int(cap.max()) if n_items else 0
+        T_need = int(h.lib.rho_b200_compact_frames(max_cap, pad_frames))
+        T = 3000 if (pad_to_30s and not compact) else max((T_need + 3) // 4 * 4, 4)
+        if mel is None:
+            mel = torch.empty((n_items, n_mels, T), dtype=torch.float32).pin_memory()
+        assert mel.shape == (n_items, n_mels, T) and mel.is_contiguous()
+        if pad_to_30s:
+            pad_value = torch.empty(n_items, dtype=torch.float32)
+    else:
+        mel = None
+    dim = int(emb.shape[1]) if emb is not None else 0
+    _lib.check(h.lib.rho_b200_validate_host_ragged(
+        h.ptr, _ptr(x), ctypes.c_void_p(seg_off.ctypes.data), ctypes.c_void_p(seg_len.ctypes.data), n_seg,
+        ctypes.c_void_p(first.ctypes.data), n_items, ctypes.byref(p), _ptr(y), ctypes.c_void_p(y_off.ctypes.data),
+        int(n_mels), pad_frames, _ptr(mel), int(T), _ptr(pad_value), _ptr(emb), _ptr(ref), dim,
+        ctypes.c_void_p(rec.ctypes.data)), "validate_host_ragged")
+    return HostRaggedOutput(y, y_off, rec, mel, pad_value)

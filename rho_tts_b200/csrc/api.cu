@@ -9,20 +9,20 @@
 #include <cstdlib>
 #include <map>
 #include <mutex>
-#include "kernels.h"
+#include "handle.h"
 
 namespace rho {
 
-static thread_local char g_err[512] = "";
+thread_local char g_err[512] = "";
 
-static int fail(int code, const char* fmt, ...) {
+int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
 }
-static int cuda_fail(cudaError_t e, const char* where) {
+int cuda_fail(cudaError_t e, const char* where) {
   return fail(RHO_ERR_CUDA, "%s: %s", where, cudaGetErrorString(e));
 }
 
@@ -54,36 +54,19 @@ const char* const kKernelNames[KID_COUNT] = {
   "k_pv_stft", "k_pv_phase", "k_pv_cumsum", "k_pv_istft", "k_resample_windowed", "k_mfcc_frames", "k_mfcc_stats"};
 }
 
-struct rho_handle {
-  int device;
-  Tables tb;
-  std::vector<void*> allocs;
-  LaunchCtx lc;
-  // arena for the HOST entry point
-  void* arena;
-  size_t arena_bytes;
-  cudaStream_t s_copy_in, s_compute, s_copy_out;
-  bool streams_ok;
-  std::mutex mu;
-  // tap tables of rho_b200_resample, one per reduced ratio seen so far: key = (orig << 32) | new
-  std::map<uint64_t, float*> resample_taps;
-  // rho_b200_pitch_shift: FFT / window / phase-advance tables (built on first use) and windowed tap tables per ratio
-  PitchTables pitch_tb{};
-  bool pitch_tb_ok = false;
-  MfccTables mfcc_tb{};
-  bool mfcc_tb_ok = false;
-  struct WinTaps { float* taps; int* ilo; };
-  std::map<uint64_t, WinTaps> windowed_taps;
-};
-
 namespace {
 
+// Lazily built tables: the copy from the (pageable) host vector is synchronous with respect to the host, but the
+// kernel that reads the table is launched on the CALLER's stream, which need not be ordered after the legacy default
+// stream (torch side streams are non-blocking).  Waiting for the device here orders the two; it happens once per table.
 template <typename T>
 cudaError_t dev_upload(rho_handle* h, T** dst, const T* src, size_t n) {
   cudaError_t e = cudaMalloc((void**)dst, n * sizeof(T));
   if (e != cudaSuccess) return e;
   h->allocs.push_back(*dst);
-  return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+  e = cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return e;
+  return cudaDeviceSynchronize();
 }
 
 struct WsPlan {
@@ -213,11 +196,11 @@ int rho_b200_create(rho_handle** out, int device) {
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
   if (prop.major != 10)
     return fail(RHO_ERR_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-  e = cudaSetDevice(device);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  DeviceGuard guard(device);                         // the caller's current device is restored on every return path
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
 
   rho_handle* h = new rho_handle();
-  h->device = device; h->arena = nullptr; h->arena_bytes = 0; h->streams_ok = false;
+  h->device = device; h->sm_count = prop.multiProcessorCount;
   memset(&h->tb, 0, sizeof(h->tb));
 
   std::vector<float> taps(2 * RS_TAPS), hann(N_FFT), tw(2 * N_FFT);
@@ -254,12 +237,9 @@ int rho_b200_create(rho_handle** out, int device) {
 
 int rho_b200_destroy(rho_handle* h) {
   if (!h) return RHO_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   for (void* p : h->allocs) cudaFree(p);
-  if (h->arena) cudaFree(h->arena);
-  if (h->streams_ok) {
-    cudaStreamDestroy(h->s_copy_in); cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy_out);
-  }
+  for (HostCtx* c : h->host_ctx_free) host_ctx_destroy(c);
   delete h;
   return RHO_OK;
 }
@@ -267,7 +247,7 @@ int rho_b200_destroy(rho_handle* h) {
 int64_t rho_b200_launch_count(rho_handle* h) { return h ? h->lc.launches.load() : (int64_t)0; }
 
 int rho_b200_profile_begin(rho_handle* h) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   for (auto& sp : h->lc.spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   h->lc.spans.clear();
   h->lc.profiling = true;
@@ -275,7 +255,7 @@ int rho_b200_profile_begin(rho_handle* h) {
 }
 
 int rho_b200_profile_end(rho_handle* h, double* ms_per_kernel, int64_t* launches_per_kernel, int capacity) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   if (capacity < KID_COUNT || !ms_per_kernel || !launches_per_kernel) return fail(RHO_ERR_INVALID, "capacity < %d", (int)KID_COUNT);
   h->lc.profiling = false;
   for (int i = 0; i < KID_COUNT; ++i) { ms_per_kernel[i] = 0.0; launches_per_kernel[i] = 0; }
@@ -303,7 +283,7 @@ size_t rho_b200_workspace_bytes(int n_segments, int n_items, int64_t max_seg_len
 int rho_b200_trim_scan(rho_handle* h, const float* x, const int64_t* off, const int32_t* len,
                        const uint8_t* trim_flags, int n_segments, int64_t max_seg_len,
                        const rho_params* p, rho_seg_info* info, void* workspace, size_t ws_bytes, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   int rc = check_params(p); if (rc) return rc;
   if (n_segments < 0 || max_seg_len < 0) return fail(RHO_ERR_INVALID, "negative size");
   if (n_segments == 0) return RHO_OK;
@@ -320,7 +300,7 @@ int rho_b200_join(rho_handle* h, const float* x, const int64_t* seg_off, const i
                   int n_segments, int64_t max_seg_len, const int32_t* item_first_seg, int n_items,
                   int64_t max_item_len, const rho_params* p, float* y, const int64_t* y_off,
                   rho_record* rec, rho_seg_info* seg_info, void* workspace, size_t ws_bytes, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   int rc = check_params(p); if (rc) return rc;
   if (n_segments < 0 || n_items < 0 || max_seg_len < 0) return fail(RHO_ERR_INVALID, "negative size");
   if (n_items == 0) return RHO_OK;
@@ -335,7 +315,7 @@ int rho_b200_join(rho_handle* h, const float* x, const int64_t* seg_off, const i
 }
 
 int rho_b200_remove_dc(rho_handle* h, float* x, int64_t n, float* dc_out, void* workspace, size_t ws_bytes, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   if (n < 0) return fail(RHO_ERR_INVALID, "negative size");
   if (n == 0) return RHO_OK;                       // base_tts.py:396-397
   if (!x) return fail(RHO_ERR_INVALID, "NULL device pointer");
@@ -345,7 +325,7 @@ int rho_b200_remove_dc(rho_handle* h, float* x, int64_t n, float* dc_out, void* 
 }
 
 int rho_b200_apply_fades(rho_handle* h, float* x, int64_t n, int fade_in, int fade_out, const rho_params* p, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   int rc = check_params(p); if (rc) return rc;
   if (n < 0) return fail(RHO_ERR_INVALID, "negative size");
   if (n == 0) return RHO_OK;
@@ -357,7 +337,7 @@ int rho_b200_apply_fades(rho_handle* h, float* x, int64_t n, int fade_in, int fa
 
 int rho_b200_sound_decay(rho_handle* h, const float* x, int64_t n, const rho_params* p, rho_record* rec,
                          void* workspace, size_t ws_bytes, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   int rc = check_params(p); if (rc) return rc;
   if (n < 0 || n > INT32_MAX) return fail(RHO_ERR_INVALID, "size out of range");
   if (!rec || (n > 0 && !x)) return fail(RHO_ERR_INVALID, "NULL device pointer");
@@ -369,7 +349,7 @@ int rho_b200_sound_decay(rho_handle* h, const float* x, int64_t n, const rho_par
 int rho_b200_resample3to2(rho_handle* h, const float* x, const int64_t* off, const int32_t* len,
                           int len_stride_bytes, int n, int64_t max_len, float* y, const int64_t* y_off,
                           int32_t* y_len, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   if (n < 0 || max_len < 0) return fail(RHO_ERR_INVALID, "negative size");
   if (n == 0) return RHO_OK;
   if (!x || !off || !len || !y || !y_off) return fail(RHO_ERR_INVALID, "NULL device pointer");
@@ -390,7 +370,7 @@ int64_t rho_b200_resample_out_len(int64_t len, int orig_freq, int new_freq) {
 int rho_b200_resample(rho_handle* h, const float* x, const int64_t* off, const int32_t* len, int len_stride_bytes,
                       int n, int64_t max_len, int orig_freq, int new_freq, float* y, const int64_t* y_off,
                       int32_t* y_len, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   if (n < 0 || max_len < 0) return fail(RHO_ERR_INVALID, "negative size");
   if (orig_freq <= 0 || new_freq <= 0) return fail(RHO_ERR_INVALID, "sample rates must be positive");
   if (orig_freq == new_freq) return fail(RHO_ERR_INVALID, "orig_freq == new_freq: torchaudio returns the input unchanged, so does the caller");
@@ -432,7 +412,7 @@ size_t rho_b200_pitch_workspace_bytes(int n, int64_t max_len, double n_steps) {
 int rho_b200_pitch_shift(rho_handle* h, const float* x, const int64_t* off, const int32_t* len, int len_stride_bytes,
                          int n, int64_t min_len, int64_t max_len, int sample_rate, double n_steps, int arange_vec,
                          float* y, const int64_t* y_off, void* workspace, size_t ws_bytes, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   if (n < 0 || max_len < 0 || min_len > max_len) return fail(RHO_ERR_INVALID, "bad sizes");
   if (sample_rate <= 0) return fail(RHO_ERR_INVALID, "sample_rate must be positive");
   if (!(std::fabs(n_steps) <= 48.0)) return fail(RHO_ERR_INVALID, "n_steps must be within +-48 semitones, got %g", n_steps);
@@ -498,7 +478,7 @@ size_t rho_b200_mfcc_workspace_bytes(int n, int64_t max_len) { return mfcc_works
 
 int rho_b200_mfcc_stats(rho_handle* h, const float* x16, const int64_t* off, const int32_t* len, int len_stride_bytes,
                         int n, int64_t max_len, float* out, void* workspace, size_t ws_bytes, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   if (n < 0 || max_len < 0) return fail(RHO_ERR_INVALID, "negative size");
   if (n == 0) return RHO_OK;
   if (n > 65535) return fail(RHO_ERR_INVALID, "at most 65535 clips per call");
@@ -547,7 +527,7 @@ int rho_b200_mfcc_stats(rho_handle* h, const float* x16, const int64_t* off, con
 int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const int32_t* len16, int n,
                     int64_t max_len16, int n_mels, int pad_frames, float* mel, int64_t mel_stride_frames,
                     int32_t* n_frames, void* workspace, size_t ws_bytes, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   if (n_mels != 80 && n_mels != 128) return fail(RHO_ERR_INVALID, "n_mels must be 80 or 128, got %d", n_mels);
   if (pad_frames != 0 && pad_frames != MEL_PAD_FRAMES) return fail(RHO_ERR_INVALID, "pad_frames must be 0 or 3000");
   if (n < 0 || max_len16 < 0) return fail(RHO_ERR_INVALID, "negative size");
@@ -564,7 +544,7 @@ int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const i
 
 int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,
                          float* mel, int64_t ld_mel, int64_t frames_per_item, int64_t item_stride, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   if (n_mels != 80 && n_mels != 128) return fail(RHO_ERR_INVALID, "n_mels must be 80 or 128, got %d", n_mels);
   if (n_frames < 0) return fail(RHO_ERR_INVALID, "negative size");
   if (n_frames == 0) return RHO_OK;
@@ -574,10 +554,7 @@ int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, in
   if (frames_per_item <= 0) { frames_per_item = n_frames; item_stride = 0; }
   if (ld_mel < frames_per_item) return fail(RHO_ERR_INVALID, "ld_mel too small");
   if (frames_per_item < n_frames && item_stride < (int64_t)n_mels * ld_mel) return fail(RHO_ERR_INVALID, "item_stride too small");
-  int sms = 0;
-  cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-  if (e != cudaSuccess) return cuda_fail(e, "device attribute");
-  e = launch_mel_gemm(h->tb, power, n_frames, ld_power, n_mels, mel, ld_mel, frames_per_item, item_stride, sms,
+  cudaError_t e = launch_mel_gemm(h->tb, power, n_frames, ld_power, n_mels, mel, ld_mel, frames_per_item, item_stride, h->sm_count,
                       (cudaStream_t)stream, &h->lc);
   return e == cudaSuccess ? RHO_OK : cuda_fail(e, "mel_gemm");
 }
@@ -585,7 +562,7 @@ int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, in
 int rho_b200_sound_decay_batch(rho_handle* h, const float* y, const int64_t* off, const int32_t* len,
                                int len_stride_bytes, int n, int64_t max_len, const rho_params* p, rho_record* rec,
                                void* workspace, size_t ws_bytes, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   int rc = check_params(p); if (rc) return rc;
   if (n < 0 || max_len < 0) return fail(RHO_ERR_INVALID, "negative size");
   if (n == 0) return RHO_OK;
@@ -601,7 +578,7 @@ int rho_b200_sound_decay_batch(rho_handle* h, const float* y, const int64_t* off
 
 int rho_b200_pcm16(rho_handle* h, const float* y, const int64_t* off, const int32_t* len, int len_stride_bytes, int n,
                    int64_t max_len, int16_t* out, const int64_t* out_off, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   if (n < 0 || max_len < 0) return fail(RHO_ERR_INVALID, "negative size");
   if (n == 0 || max_len == 0) return RHO_OK;
   if (n > 65535) return fail(RHO_ERR_INVALID, "at most 65535 clips per call");
@@ -615,7 +592,7 @@ size_t rho_b200_qwen_workspace_bytes(int n, int64_t max_len, int sr) { return qw
 int rho_b200_qwen_postprocess(rho_handle* h, const float* x, const int64_t* off, const int32_t* len,
                               int len_stride_bytes, int n, int64_t max_len, int sr, float* y, const int64_t* y_off,
                               void* workspace, size_t ws_bytes, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   if (n < 0 || max_len < 0) return fail(RHO_ERR_INVALID, "negative size");
   if (sr <= 0) return fail(RHO_ERR_INVALID, "sample rate must be positive, got %d", sr);
   if (n == 0 || max_len == 0) return RHO_OK;
@@ -630,7 +607,7 @@ int rho_b200_qwen_postprocess(rho_handle* h, const float* x, const int64_t* off,
 
 int rho_b200_cosine(rho_handle* h, const float* emb, const float* ref, int n, int dim, float* out,
                     int out_stride_bytes, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   if (n < 0 || dim <= 0) return fail(RHO_ERR_INVALID, "bad size");
   if (n == 0) return RHO_OK;
   if (!emb || !ref || !out) return fail(RHO_ERR_INVALID, "NULL device pointer");
@@ -638,13 +615,43 @@ int rho_b200_cosine(rho_handle* h, const float* emb, const float* ref, int n, in
   return e == cudaSuccess ? RHO_OK : cuda_fail(e, "cosine");
 }
 
+// frames of the 30 s (pad_frames) window that can see signal for an item of at most max_item_len 24 kHz samples,
+// rounded up to whole 128-bit pieces: the shortest row a compact feature tensor may have
+static int64_t compact_frames(int64_t max_item_len, int pad_frames) {
+  const int64_t n16 = (2 * max_item_len + 2) / 3;
+  const int64_t nv = std::min<int64_t>(n16, (int64_t)pad_frames * HOP16);
+  int64_t t = (nv + N_FFT / 2 + HOP16 - 1) / HOP16;
+  t = std::max<int64_t>(t, 2);
+  t = std::min<int64_t>((t + 3) / 4 * 4, pad_frames);
+  return t;
+}
+
+int64_t rho_b200_compact_frames(int64_t max_item_len, int pad_frames) {
+  return pad_frames > 0 ? compact_frames(max_item_len, pad_frames) : ((2 * max_item_len + 2) / 3) / HOP16;
+}
+
+int rho_b200_set_record_peers(rho_handle* h, void* const* sinks, int n_sinks, int64_t slot) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  if (n_sinks < 0 || n_sinks > MAX_RECORD_PEERS) return fail(RHO_ERR_INVALID, "at most %d record sinks", MAX_RECORD_PEERS);
+  if (n_sinks > 0 && (!sinks || slot < 0)) return fail(RHO_ERR_INVALID, "sinks is NULL or slot negative");
+  std::lock_guard<std::mutex> lock(h->mu);
+  h->peers = RecordPeers{};
+  h->peers.n = n_sinks;
+  h->peers.slot = slot;
+  for (int i = 0; i < n_sinks; ++i) {
+    if (!sinks[i] || (((uintptr_t)sinks[i]) & 7u)) return fail(RHO_ERR_INVALID, "sink %d is NULL or misaligned", i);
+    h->peers.sink[i] = (rho_record*)sinks[i];
+  }
+  return RHO_OK;
+}
+
 int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, const int32_t* seg_len,
                       int n_segments, int64_t max_seg_len, const int32_t* item_first_seg, int n_items,
                       int64_t max_item_len, const rho_params* p, float* y, const int64_t* y_off,
-                      int n_mels, int pad_frames, float* mel, int64_t mel_stride_frames,
+                      int n_mels, int pad_frames, float* mel, int64_t mel_stride_frames, float* pad_value,
                       const float* emb, const float* ref_emb, int emb_dim, rho_record* rec, float* scratch16,
                       uint32_t flags, void* workspace, size_t ws_bytes, void* stream) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  RHO_ON_DEVICE(h);
   int rc = check_params(p); if (rc) return rc;
   if (p->sr != 24000) return fail(RHO_ERR_INVALID, "validate needs 24 kHz input (3:2 resampler), got %d", p->sr);
   if (n_mels != 80 && n_mels != 128) return fail(RHO_ERR_INVALID, "n_mels must be 80 or 128, got %d", n_mels);
@@ -654,169 +661,62 @@ int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, con
   if (!mel || !rec || !item_first_seg || !y_off || (n_segments > 0 && (!x || !seg_off || !seg_len || !y)))
     return fail(RHO_ERR_INVALID, "NULL device pointer");
   const int64_t max16 = (2 * max_item_len + 2) / 3;
+  const bool compact = (flags & RHO_V_COMPACT_PAD) && pad_frames > 0;
+  int fill_to = pad_frames;
   if (pad_frames == 0 && mel_stride_frames < max16 / HOP16) return fail(RHO_ERR_INVALID, "mel_stride_frames too small");
-  if (pad_frames > 0 && mel_stride_frames < pad_frames) return fail(RHO_ERR_INVALID, "mel_stride_frames too small");
+  if (compact) {
+    const int64_t need = compact_frames(max_item_len, pad_frames);
+    if (mel_stride_frames < need || mel_stride_frames % 4 != 0)
+      return fail(RHO_ERR_INVALID, "compact rows need mel_stride_frames >= %lld and a multiple of 4, got %lld",
+                  (long long)need, (long long)mel_stride_frames);
+    fill_to = (int)std::min<int64_t>(mel_stride_frames, pad_frames);
+  } else if (pad_frames > 0 && mel_stride_frames < pad_frames) {
+    return fail(RHO_ERR_INVALID, "mel_stride_frames too small");
+  }
   const Derived d = derive(*p);
   Workspace ws;
   rc = carve(workspace, ws_bytes, n_segments, n_items, max_seg_len, d, &ws, nullptr); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
-  const bool fused = (flags & RHO_V_ONE_SEGMENT_ITEMS) && !(flags & RHO_V_NO_FUSION) && n_segments == n_items;
-  if (fused) {
-    // init -> scan -> bounds / DC / plan -> ONE kernel for apply + resample + log-mel -> clamp + records (decay
-    // decision, cosine): five launches per batch
+  RecordPeers peers;
+  { std::lock_guard<std::mutex> lock(h->mu); peers = h->peers; }
+  const bool one_seg = (flags & RHO_V_ONE_SEGMENT_ITEMS) && n_segments == n_items;
+  if (!(flags & RHO_V_NO_FUSION)) {
+    // one-segment items:  init -> scan -> bounds / DC / plan -> ONE kernel for apply + resample + log-mel -> clamp +
+    //                     records (decay decision, cosine): five launches per batch
+    // joined items:       init -> scan -> bounds / DC -> plan -> gather (y) -> the same kernel reading the finished y
+    //                     (resample + log-mel; the 16 kHz signal never leaves shared memory) -> clamp + records
     e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,
-                    rec, nullptr, ws, st, &h->lc, JOIN_PREPARE | JOIN_INIT_FEATURES | JOIN_ONE_SEG_ITEMS);
+                    rec, nullptr, ws, st, &h->lc,
+                    one_seg ? (JOIN_PREPARE | JOIN_INIT_FEATURES | JOIN_ONE_SEG_ITEMS)
+                            : (JOIN_PREPARE | JOIN_GATHER | JOIN_INIT_FEATURES));
     if (e != cudaSuccess) return cuda_fail(e, "join prepare");
     e = launch_fused_features(h->tb, x, seg_off, ws, item_first_seg, n_items, max_item_len, d, y, y_off, n_mels,
-                              pad_frames, mel, mel_stride_frames, st, &h->lc);
+                              pad_frames, mel, mel_stride_frames, h->sm_count, st, &h->lc, !one_seg, fill_to);
     if (e != cudaSuccess) return cuda_fail(e, "fused features");
     // the Whisper clamp of the frames with signal (and the constant of the zero-padding frames unless the fused kernel
     // wrote it: fill_done); its first warp per clip assembles the record
-    const FinalizeArgs fin{ws.seg, ws.item, item_first_seg, d.decay_thr, rec, emb, ref_emb, emb_dim};
+    const FinalizeArgs fin{ws.seg, ws.item, item_first_seg, d.decay_thr, rec, emb, ref_emb, emb_dim, peers};
     e = launch_logmel_norm(ws.len16, n_items, n_mels, pad_frames, mel, mel_stride_frames, ws.clip_max, st, &h->lc,
-                           fused_inline_norm(), &fin);
+                           fused_inline_norm(), &fin, fill_to, pad_value);
     if (e != cudaSuccess) return cuda_fail(e, "logmel norm");
   } else {
-    if (!scratch16) return fail(RHO_ERR_INVALID, "scratch16 is NULL (needed by the unfused path)");
+    if (!scratch16) return fail(RHO_ERR_INVALID, "scratch16 is NULL (needed by the kernel-per-stage path)");
     e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,
-                    rec, nullptr, ws, st, &h->lc, JOIN_ALL);
+                    rec, nullptr, ws, st, &h->lc, JOIN_ALL, nullptr, nullptr, 0, &peers);
     if (e != cudaSuccess) return cuda_fail(e, "join");
     // 16 kHz intermediate lives at the same offsets as y (it is 2/3 as long)
     e = launch_resample3to2(y, y_off, &rec[0].out_len, (int)sizeof(rho_record), n_items, max_item_len,
                             scratch16, y_off, ws.len16, st, &h->lc);
     if (e != cudaSuccess) return cuda_fail(e, "resample3to2");
     e = launch_logmel(h->tb, scratch16, y_off, ws.len16, n_items, max16, n_mels, pad_frames, mel, mel_stride_frames,
-                      nullptr, ws.clip_max, st, &h->lc);
+                      nullptr, ws.clip_max, st, &h->lc, fill_to, pad_value);
     if (e != cudaSuccess) return cuda_fail(e, "logmel");
-  }
-  if (emb && ref_emb && !fused) {
-    e = launch_cosine(emb, ref_emb, n_items, emb_dim, &rec[0].cosine, (int)sizeof(rho_record), st, &h->lc);
-    if (e != cudaSuccess) return cuda_fail(e, "cosine");
-  }
-  return RHO_OK;
-}
-
-// ----------------------------------------------------------------------------- HOST entry point
-int rho_b200_validate_host(rho_handle* h, const float* x, int n, int32_t clip_len, const rho_params* p,
-                           float* y, int n_mels, int pad_frames, float* mel, const float* emb,
-                           const float* ref_emb, int emb_dim, rho_record* rec) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
-  int rc = check_params(p); if (rc) return rc;
-  if (n < 0 || clip_len <= 0) return fail(RHO_ERR_INVALID, "bad size");
-  if (n == 0) return RHO_OK;
-  if (!x || !y || !rec) return fail(RHO_ERR_INVALID, "NULL host pointer");
-  if (pad_frames != MEL_PAD_FRAMES) return fail(RHO_ERR_INVALID, "host entry point supports pad_frames=3000 only");
-  std::lock_guard<std::mutex> lock(h->mu);
-  cudaError_t e = cudaSetDevice(h->device);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-  if (!h->streams_ok) {
-    if ((e = cudaStreamCreateWithFlags(&h->s_copy_in, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&h->s_copy_out, cudaStreamNonBlocking)) != cudaSuccess)
-      return cuda_fail(e, "cudaStreamCreate");
-    h->streams_ok = true;
-  }
-  // chunking: CH clips per chunk, 3 chunk slots so copy-in(k+1), compute(k) and copy-out(k-1) overlap
-  static const int env_chunk = [] { const char* v = getenv("RHO_HOST_CHUNK"); return v ? atoi(v) : 0; }();   // A/B tool
-  const int chunk_clips = env_chunk > 0 ? env_chunk : 64;
-  const int CH = n < chunk_clips ? n : chunk_clips;
-  const int SLOTS = 3;
-  const size_t stride = align_up((size_t)clip_len, 32);                 // samples per clip slot
-  const size_t b_x = align_up(stride * CH * sizeof(float), 256);
-  const size_t b_mel = align_up((size_t)CH * n_mels * pad_frames * sizeof(float), 256);
-  const size_t b_rec = align_up(sizeof(rho_record) * CH, 256);
-  const size_t b_emb = align_up(sizeof(float) * (size_t)CH * (emb_dim > 0 ? emb_dim : 1), 256);
-  const size_t b_meta = align_up((sizeof(int64_t) * 2 + sizeof(int32_t) * 2) * (size_t)(CH + 1), 256);
-  const size_t b_ws = align_up(rho_b200_workspace_bytes(CH, CH, clip_len), 256);
-  const size_t per_slot = 3 * b_x + b_mel + b_rec + b_emb + b_ws;
-  const size_t total = SLOTS * per_slot + b_meta + align_up(sizeof(float) * (emb_dim > 0 ? emb_dim : 1), 256);
-  if (h->arena_bytes < total) {
-    if (h->arena) cudaFree(h->arena);
-    h->arena = nullptr; h->arena_bytes = 0;
-    if ((e = cudaMalloc(&h->arena, total)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(arena)");
-    h->arena_bytes = total;
-  }
-  char* base = (char*)h->arena;
-  // metadata (identical for every chunk): offsets, lengths, item_first_seg
-  std::vector<int64_t> offs(CH + 1);
-  std::vector<int32_t> lens(CH + 1), first(CH + 1);
-  for (int i = 0; i <= CH; ++i) { offs[i] = (int64_t)i * stride; lens[i] = clip_len; first[i] = i; }
-  int64_t* d_off = (int64_t*)base;
-  int32_t* d_len = (int32_t*)(base + sizeof(int64_t) * (CH + 1));
-  int32_t* d_first = (int32_t*)(base + (sizeof(int64_t) + sizeof(int32_t)) * (CH + 1));
-  float* d_ref = (float*)(base + b_meta);
-  cudaStream_t sc = h->s_compute;
-  if ((e = cudaMemcpyAsync(d_off, offs.data(), sizeof(int64_t) * (CH + 1), cudaMemcpyHostToDevice, sc)) != cudaSuccess ||
-      (e = cudaMemcpyAsync(d_len, lens.data(), sizeof(int32_t) * (CH + 1), cudaMemcpyHostToDevice, sc)) != cudaSuccess ||
-      (e = cudaMemcpyAsync(d_first, first.data(), sizeof(int32_t) * (CH + 1), cudaMemcpyHostToDevice, sc)) != cudaSuccess)
-    return cuda_fail(e, "metadata upload");
-  const bool have_emb = emb && ref_emb && emb_dim > 0;
-  if (have_emb && (e = cudaMemcpyAsync(d_ref, ref_emb, sizeof(float) * emb_dim, cudaMemcpyHostToDevice, sc)) != cudaSuccess)
-    return cuda_fail(e, "ref upload");
-  if ((e = cudaStreamSynchronize(sc)) != cudaSuccess) return cuda_fail(e, "metadata sync");  // vectors go out of scope later
-
-  char* slots = base + b_meta + align_up(sizeof(float) * (emb_dim > 0 ? emb_dim : 1), 256);
-  cudaEvent_t ev_in[SLOTS], ev_done[SLOTS], ev_out[SLOTS];
-  for (int s = 0; s < SLOTS; ++s) {
-    cudaEventCreateWithFlags(&ev_in[s], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_done[s], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_out[s], cudaEventDisableTiming);
-  }
-  int status = RHO_OK;
-  const int n_chunks = (n + CH - 1) / CH;
-  for (int k = 0; k < n_chunks && status == RHO_OK; ++k) {
-    const int s = k % SLOTS;
-    const int c0 = k * CH, cn = (n - c0 < CH) ? n - c0 : CH;
-    char* sb = slots + (size_t)s * per_slot;
-    float* d_x = (float*)sb;
-    float* d_y = (float*)(sb + b_x);
-    float* d_16 = (float*)(sb + 2 * b_x);
-    float* d_mel = (float*)(sb + 3 * b_x);
-    rho_record* d_rec = (rho_record*)(sb + 3 * b_x + b_mel);
-    float* d_emb = (float*)(sb + 3 * b_x + b_mel + b_rec);
-    void* d_ws = sb + 3 * b_x + b_mel + b_rec + b_emb;
-    // slot reuse: wait until chunk k-SLOTS has been copied out
-    if (k >= SLOTS) cudaStreamWaitEvent(h->s_copy_in, ev_out[s], 0);
-    if (stride == (size_t)clip_len) {
-      e = cudaMemcpyAsync(d_x, x + (size_t)c0 * clip_len, sizeof(float) * (size_t)cn * clip_len, cudaMemcpyHostToDevice, h->s_copy_in);
-    } else {
-      e = cudaMemcpy2DAsync(d_x, stride * sizeof(float), x + (size_t)c0 * clip_len, (size_t)clip_len * sizeof(float),
-                            (size_t)clip_len * sizeof(float), cn, cudaMemcpyHostToDevice, h->s_copy_in);
+    if (emb && ref_emb) {
+      e = launch_cosine(emb, ref_emb, n_items, emb_dim, &rec[0].cosine, (int)sizeof(rho_record), st, &h->lc);
+      if (e != cudaSuccess) return cuda_fail(e, "cosine");
     }
-    if (e == cudaSuccess && have_emb)
-      e = cudaMemcpyAsync(d_emb, emb + (size_t)c0 * emb_dim, sizeof(float) * (size_t)cn * emb_dim, cudaMemcpyHostToDevice, h->s_copy_in);
-    if (e != cudaSuccess) { status = cuda_fail(e, "H2D"); break; }
-    cudaEventRecord(ev_in[s], h->s_copy_in);
-    cudaStreamWaitEvent(sc, ev_in[s], 0);
-    status = rho_b200_validate(h, d_x, d_off, d_len, cn, clip_len, d_first, cn, clip_len, p, d_y, d_off,
-                               n_mels, pad_frames, d_mel, pad_frames, have_emb ? d_emb : nullptr,
-                               have_emb ? d_ref : nullptr, emb_dim, d_rec, d_16, RHO_V_ONE_SEGMENT_ITEMS, d_ws, b_ws, sc);
-    if (status != RHO_OK) break;
-    cudaEventRecord(ev_done[s], sc);
-    cudaStreamWaitEvent(h->s_copy_out, ev_done[s], 0);
-    if (stride == (size_t)clip_len) {
-      e = cudaMemcpyAsync(y + (size_t)c0 * clip_len, d_y, sizeof(float) * (size_t)cn * clip_len, cudaMemcpyDeviceToHost, h->s_copy_out);
-    } else {
-      e = cudaMemcpy2DAsync(y + (size_t)c0 * clip_len, (size_t)clip_len * sizeof(float), d_y, stride * sizeof(float),
-                            (size_t)clip_len * sizeof(float), cn, cudaMemcpyDeviceToHost, h->s_copy_out);
-    }
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(rec + c0, d_rec, sizeof(rho_record) * cn, cudaMemcpyDeviceToHost, h->s_copy_out);
-    if (e == cudaSuccess && mel)
-      e = cudaMemcpyAsync(mel + (size_t)c0 * n_mels * pad_frames, d_mel, sizeof(float) * (size_t)cn * n_mels * pad_frames,
-                          cudaMemcpyDeviceToHost, h->s_copy_out);
-    if (e != cudaSuccess) { status = cuda_fail(e, "D2H"); break; }
-    cudaEventRecord(ev_out[s], h->s_copy_out);
   }
-  cudaError_t e1 = cudaStreamSynchronize(h->s_copy_in);
-  cudaError_t e2 = cudaStreamSynchronize(sc);
-  cudaError_t e3 = cudaStreamSynchronize(h->s_copy_out);
-  for (int s = 0; s < SLOTS; ++s) { cudaEventDestroy(ev_in[s]); cudaEventDestroy(ev_done[s]); cudaEventDestroy(ev_out[s]); }
-  if (status != RHO_OK) return status;
-  if (e1 != cudaSuccess) return cuda_fail(e1, "sync copy-in");
-  if (e2 != cudaSuccess) return cuda_fail(e2, "sync compute");
-  if (e3 != cudaSuccess) return cuda_fail(e3, "sync copy-out");
   return RHO_OK;
 }
 

@@ -263,7 +263,13 @@ __device__ __noinline__ void fz_apply_edge(float* e, int o, int n, int fade, boo
   }
 }
 
-template <int NM>
+// FROM_Y = false: one-segment items, everything above in one pass over x.
+// FROM_Y = true : the features of FINISHED items (the output of k_gather: joined, faded audio at y + y_off[c], length
+//                 item[c].out_len): the span is read from y, nothing is applied or written back, the 16 kHz signal still
+//                 never leaves shared memory -- the path of base_tts.py:912-926 items that have several segments.
+// fill_to: the constant of the zero-padding frames is written for frames < fill_to only (3000, or the row length of a
+//          compact feature tensor, RHO_V_COMPACT_PAD).
+template <int NM, bool FROM_Y>
 __global__ void __launch_bounds__(FZ_THREADS, 1)
 k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const SegState* __restrict__ seg,
                  ItemState* __restrict__ item, const int32_t* __restrict__ item_first_seg,
@@ -271,7 +277,8 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
                  const float* __restrict__ g_hann, const float2* __restrict__ g_tw, int pad_frames,
                  float* __restrict__ mel, long long mel_stride, int* __restrict__ clip_max,
                  int32_t* __restrict__ len16_out, int* __restrict__ tiles_done, int* __restrict__ work_counter,
-                 const __grid_constant__ FzSched sched, int n_items, const float* __restrict__ mel_dense) {
+                 const __grid_constant__ FzSched sched, int n_items, const float* __restrict__ mel_dense,
+                 int fill_to) {
   extern __shared__ unsigned char smem_raw[];
   FzSmem& S = *reinterpret_cast<FzSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   for (int i = threadIdx.x; i < N_FFT; i += FZ_THREADS) {
@@ -340,11 +347,16 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     if (un < n_units) {
       d.tile = un / n_items;                             // tile-major: the last (short) tiles of the clips come at the end
       d.c = un - d.tile * n_items;
-      const int sn = item_first_seg[d.c];
-      const SegState sn_st = seg[sn];
-      d.start = sn_st.start; d.end = sn_st.end; d.dc = sn_st.dc;
-      d.x_off = seg_off[sn] + sn_st.start;
       d.y_off = y_off[d.c];
+      if (FROM_Y) {
+        d.start = 0; d.end = item[d.c].out_len; d.dc = 0.f;
+        d.x_off = d.y_off;
+      } else {
+        const int sn = item_first_seg[d.c];
+        const SegState sn_st = seg[sn];
+        d.start = sn_st.start; d.end = sn_st.end; d.dc = sn_st.dc;
+        d.x_off = seg_off[sn] + sn_st.start;
+      }
     }
     H.nd = d;
   };
@@ -357,8 +369,8 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     int Tn, Tn_real, Nn, nvn;
     lm_frame_counts(nn16, pad_frames, &Tn, &Tn_real, &Nn, &nvn);
     const int tt0 = sched.start[d.tile] * LM_BF;
-    if (tt0 >= max(Tn_real, (nn + 239) / 240)) return;
-    const float* xsn = x + d.x_off;
+    if (tt0 >= (FROM_Y ? Tn_real : max(Tn_real, (nn + 239) / 240))) return;
+    const float* xsn = (FROM_Y ? y : x) + d.x_off;
     const long long j0 = 240LL * tt0 - FZ_LEAD;
     if ((reinterpret_cast<uintptr_t>(xsn) & 15u) != 0 || j0 < 0 || j0 + FZ_SPAN > nn) return;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -384,12 +396,12 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   int T, T_real, N, n_valid;
   lm_frame_counts(n16, pad_frames, &T, &T_real, &N, &n_valid);
   if (tile == 0 && tid == 0) len16_out[c] = n16;
-  const int t_cover = max(T_real, (n + 239) / 240);  // batches needed for the features AND to write all of y
+  const int t_cover = FROM_Y ? T_real : max(T_real, (n + 239) / 240);  // batches needed for the features AND to write all of y
   const int tile_t0 = sched.start[tile] * LM_BF;
   const int tile_batches = sched.start[tile + 1] - sched.start[tile];
   if (tile_t0 >= t_cover) { if (tid == 0) fill_desc(H.next_unit); continue; }
 
-  const float* __restrict__ xs = x + nd.x_off;
+  const float* __restrict__ xs = (FROM_Y ? y : x) + nd.x_off;
   float* __restrict__ ys = y + nd.y_off;
   float* __restrict__ out = mel + (long long)c * NM * mel_stride;
   const int third = n / 3;
@@ -446,9 +458,11 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     const int own_lo = 240 * t0, own_hi = own_lo + FZ_OWN;
     // interior batch: every sample of the span is plain x - dc, and the owned range lies in ONE decay zone
     const bool in_first = own_hi <= third, in_last = own_lo >= n - third;
-    const bool fast = FZ_FAST_APPLY && j0 >= edge_lo && j0 + FZ_SPAN <= edge_hi &&
-                      (in_first || own_lo >= third) && (in_last || own_hi <= n - third);
-    if (fast) {
+    const bool fast = FROM_Y || (FZ_FAST_APPLY && j0 >= edge_lo && j0 + FZ_SPAN <= edge_hi &&
+                                 (in_first || own_lo >= third) && (in_last || own_hi <= n - third));
+    if (FROM_Y) {
+      // finished audio: nothing to apply, nothing to write back; samples outside the item were zero-filled by the staging
+    } else if (fast) {
       // ---- apply, interior: 6 pieces per thread, registers -> HBM; the span keeps the raw x
       float ss = 0.f;
       const float2 ndc = make_float2(-dc, -dc);
@@ -758,8 +772,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     double a = tid < NW ? H.redd[0][tid] : 0.0, bq = tid < NW ? H.redd[1][tid] : 0.0;
     m = warp_max(m); a = warp_sum(a); bq = warp_sum(bq);
     if (tid == 0) {
-      int seen = 0;
-      if (m > -INFINITY) seen = atomicMax(&clip_max[c], float_to_ordered(m));
+      if (m > -INFINITY) atomicMax(&clip_max[c], float_to_ordered(m));
       if (a != 0.0) atomicAdd(&item[c].s_first, a);
       if (bq != 0.0) atomicAdd(&item[c].s_last, bq);
       // The half that finishes its clip last knows the clip maximum: it writes the constant that fills the
@@ -767,22 +780,27 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       // for; the frames with signal are clamped / scaled by k_logmel_norm, which then moves 1/3 of the bytes.
       // (Normalising them here too was measured and is NOT a gain: the loads expose L2 latency on a half that
       //  has nothing else to do, profiles/README.md.)
-      // No fence: the count is incremented by an atomic whose operand depends on the RETURN value of this half's
-      // atomicMax, so it is issued after that one has been performed at L2; whoever sees the full count reads the
-      // maximum with another atomic at the same point of coherence.
+      // Ordering: the count is incremented with an acquire-release atomic at GPU scope.  Its release half orders this
+      // half's atomicMax (and decay sums) before the increment; its acquire half makes the maxima of the halves that
+      // incremented earlier visible to whoever sees the full count, so the last finisher's read of the clip maximum
+      // (which decides the constant of 2/3 of the clip's features) is ordered by the PTX memory model, not by where
+      // the L2 happens to resolve atomics.  (Round 1 relied on a data dependency between relaxed atomics: 1.7 % faster,
+      // not guaranteed.)
       int last = 0;
       if (FZ_INLINE_NORM && tiles_done) {
         int clip_tiles = 0;                          // tiles of the schedule that start inside this clip
         while (clip_tiles < sched.n_tiles && sched.start[clip_tiles] * LM_BF < t_cover) ++clip_tiles;
-        const int inc = (seen == 0x7fffffff) ? 2 : 1;            // never 2: no clip maximum is a NaN pattern
-        last = (atomicAdd(&tiles_done[c], inc) == clip_tiles - 1);
+        int before;
+        asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(before) : "l"(tiles_done + c) : "memory");
+        last = (before == clip_tiles - 1);
         if (last) H.fill_max = atomicMax(&clip_max[c], (int)0x80000000);
       }
       H.last = last;
     }
   }
   half_sync(half);
-  if (H.last && T > T_real) {
+  if (H.last && min(T, fill_to) > T_real) {
+    T = min(T, fill_to);
     const float mx = ordered_to_float(H.fill_max);
     const float fill = __fmul_rn(__fadd_rn(fmaxf(-10.0f, __fsub_rn(mx, 8.0f)), 4.0f), 0.25f);
     const int t_lo = (T_real + 3) & ~3;              // whole 128-bit pieces from here; [T_real, t_lo) is k_logmel_norm's
@@ -818,8 +836,10 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
 cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_t* seg_off, const Workspace& ws,
                                   const int32_t* item_first_seg, int n_items, int64_t max_len,
                                   const Derived& d, float* y, const int64_t* y_off, int n_mels, int pad_frames,
-                                  float* mel, int64_t mel_stride_frames, cudaStream_t st, LaunchCtx* lc) {
+                                  float* mel, int64_t mel_stride_frames, int sm_count, cudaStream_t st, LaunchCtx* lc,
+                                  bool from_y, int fill_to) {
   if (n_items <= 0) return cudaSuccess;
+  if (fill_to <= 0) fill_to = pad_frames;
   // frames to cover: the features' frames and, for clips the 30 s window truncates, the rest of y
   const int64_t max16 = (2 * max_len + 2) / 3;
   int64_t max_real;
@@ -831,11 +851,8 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
   } else {
     max_real = max16 / HOP16;
   }
-  const int64_t cover = std::max<int64_t>(max_real, (max_len + 239) / 240);
-  int dev = 0, sm_count = 0;                         // per call: a process may drive several devices
-  cudaError_t e;
-  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-  if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  const int64_t cover = from_y ? max_real : std::max<int64_t>(max_real, (max_len + 239) / 240);
+  cudaError_t e;                                     // sm_count: of the handle's device (a process may drive several)
   // Unit = (clip, tile).  Every tile ends with a reduction, three atomics and a fence and starts with an empty
   // pipeline (~3 us together), so tiles should be long -- but the halves draw units from one counter, and whoever draws
   // a long tile last finishes last.  Measured on 1000 x 10 s (32 batches per clip), k_fused_features in ms:
@@ -868,7 +885,8 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
   }
   const int64_t tiles = sched.n_tiles;
   const size_t smem = sizeof(FzSmem) + 1024;      // slack to align the halves to 1024 bytes (swizzle atoms)
-  auto kern = (n_mels == 80) ? k_fused_features<80> : k_fused_features<128>;
+  auto kern = from_y ? ((n_mels == 80) ? k_fused_features<80, true> : k_fused_features<128, true>)
+                     : ((n_mels == 80) ? k_fused_features<80, false> : k_fused_features<128, false>);
   if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
   const uint64_t n_units = (uint64_t)n_items * (uint64_t)tiles;
   if (n_units > 0x7fffffffull) return cudaErrorInvalidValue;
@@ -878,7 +896,7 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
   kern<<<grid, FZ_THREADS, smem, st>>>(x, seg_off, ws.seg, ws.item, item_first_seg, y, y_off, d.fade, tb.hann,
                                        tb.twiddle, pad_frames, mel, mel_stride_frames, ws.clip_max, ws.len16,
                                        ws.tiles_done, ws.work_counter, sched, n_items,
-                                       tb.mel_dense[n_mels == 80 ? 0 : 1]);
+                                       tb.mel_dense[n_mels == 80 ? 0 : 1], fill_to);
   lc->end(st);
   return cudaGetLastError();
 }

@@ -1,0 +1,65 @@
+// The library handle and the helpers shared by the translation units that implement the C ABI (api.cu, host_api.cu).
+#pragma once
+#include <map>
+#include <mutex>
+#include <vector>
+#include "kernels.h"
+
+namespace rho {
+
+extern thread_local char g_err[512];
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* where);
+
+// Every entry point runs on the handle's device, whatever the caller's current device is, and leaves the caller's
+// current device as it found it (one process may drive several GPUs; torch keeps its own notion of "current").
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) {
+      err = cudaSetDevice(device);
+      switched = (err == cudaSuccess);
+    }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define RHO_ON_DEVICE(h)                                            \
+  if (!(h)) return rho::fail(RHO_ERR_INVALID, "handle is NULL");    \
+  rho::DeviceGuard _guard((h)->device);                             \
+  if (_guard.err != cudaSuccess) return rho::cuda_fail(_guard.err, "cudaSetDevice")
+
+struct HostCtx;   // host_api.cu: streams, device arena and pinned staging of one in-flight host call
+
+}  // namespace rho
+
+struct rho_handle {
+  int device;
+  int sm_count;            // of `device` (grids of the persistent kernels)
+  rho::Tables tb;
+  std::vector<void*> allocs;
+  rho::LaunchCtx lc;
+  std::mutex mu;
+  // HOST entry points: one context per concurrent caller, recycled (a handle may be shared by concurrent sessions,
+  // ui/state.py:85-87 of the reference: callers do not serialise on each other)
+  std::vector<rho::HostCtx*> host_ctx_free;
+  // tap tables of rho_b200_resample, one per reduced ratio seen so far: key = (orig << 32) | new
+  std::map<uint64_t, float*> resample_taps;
+  // rho_b200_pitch_shift: FFT / window / phase-advance tables (built on first use) and windowed tap tables per ratio
+  rho::PitchTables pitch_tb{};
+  bool pitch_tb_ok = false;
+  rho::MfccTables mfcc_tb{};
+  bool mfcc_tb_ok = false;
+  struct WinTaps { float* taps; int* ilo; };
+  std::map<uint64_t, WinTaps> windowed_taps;
+  // records of rho_b200_validate are also stored into these peer buffers (NVLink P2P), see rho_b200_set_record_peers
+  rho::RecordPeers peers{};
+};
+
+namespace rho {
+void host_ctx_destroy(HostCtx* c);   // host_api.cu
+}

@@ -321,7 +321,8 @@ __global__ void k_plan_items(const SegState* __restrict__ seg, const int32_t* __
     const bool di = (st.flags & RHO_F_ALL_SILENT) != 0;
     SegSpan sp = z; sp.dst = pos;
     if (i == 0) {
-      sp.body = (Li > cf) ? Li - cf : Li;              // :484-488
+      // :484-488 -- with crossfade_samples == 0 the reference's slice [..., :-0] is EMPTY: segment 0 is dropped
+      sp.body = (Li > cf) ? (cf > 0 ? Li - cf : 0) : Li;
       mark(di, sp.body);
     } else {
       int ov = cf < Lprev ? cf : Lprev; if (Li < ov) ov = Li;   // :491
@@ -508,11 +509,12 @@ k_gather(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const
 __global__ void __launch_bounds__(256)
 k_finalize_items(const SegState* __restrict__ seg, const ItemState* __restrict__ item,
                  const int32_t* __restrict__ item_first_seg, int n_items, double decay_thr,
-                 rho_record* __restrict__ rec, const float* __restrict__ emb, const float* __restrict__ ref, int dim) {
+                 rho_record* __restrict__ rec, const float* __restrict__ emb, const float* __restrict__ ref, int dim,
+                 const RecordPeers peers) {
   const int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (it >= n_items) return;
-  finalize_item(seg, item, item_first_seg, it, lane, decay_thr, rec, emb, ref, dim);
+  finalize_item(seg, item, item_first_seg, it, lane, decay_thr, rec, emb, ref, dim, peers);
 }
 
 // ------------------------------------------------------------------ single-clip helpers (method shim)
@@ -727,7 +729,7 @@ cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* s
                         const int32_t* item_first_seg, int n_items, int64_t max_item_len,
                         const Derived& d, float* y, const int64_t* y_off, rho_record* rec, rho_seg_info* seg_info,
                         const Workspace& ws, cudaStream_t st, LaunchCtx* lc, int stages,
-                        const float* emb, const float* ref_emb, int emb_dim) {
+                        const float* emb, const float* ref_emb, int emb_dim, const RecordPeers* peers) {
   if (n_items <= 0) return cudaSuccess;
   cudaError_t e = cudaSuccess;
   if (stages & JOIN_PREPARE) {
@@ -769,7 +771,7 @@ cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* s
   if (stages & JOIN_FINISH) {
     lc->begin(KID_FINALIZE_ITEMS, st);
     k_finalize_items<<<(n_items * 32 + 255) / 256, 256, 0, st>>>(ws.seg, ws.item, item_first_seg, n_items, d.decay_thr,
-                                                            rec, emb, ref_emb, emb_dim);
+                                                            rec, emb, ref_emb, emb_dim, peers ? *peers : RecordPeers{});
     lc->end(st);
   }
   return cudaGetLastError();

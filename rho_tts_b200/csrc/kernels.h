@@ -80,7 +80,8 @@ cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* s
                         const int32_t* item_first_seg, int n_items, int64_t max_item_len,
                         const Derived& d, float* y, const int64_t* y_off, rho_record* rec, rho_seg_info* seg_info,
                         const Workspace& ws, cudaStream_t st, LaunchCtx* lc, int stages = JOIN_ALL,
-                        const float* emb = nullptr, const float* ref_emb = nullptr, int emb_dim = 0);
+                        const float* emb = nullptr, const float* ref_emb = nullptr, int emb_dim = 0,
+                        const struct RecordPeers* peers = nullptr);
 cudaError_t launch_remove_dc(float* x, int64_t n, float* dc_out, double* scratch, cudaStream_t st, LaunchCtx* lc);
 cudaError_t launch_apply_fades(float* x, int64_t n, int fade, int fade_in, int fade_out, cudaStream_t st, LaunchCtx* lc);
 cudaError_t launch_sound_decay(const float* x, int64_t n, double thr, rho_record* rec, double* scratch,
@@ -106,10 +107,21 @@ cudaError_t launch_resample_general(const float* x, const int64_t* off, const in
 cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off, const int32_t* len16,
                           int n, int64_t max_len16, int n_mels, int pad_frames, float* mel,
                           int64_t mel_stride_frames, int32_t* n_frames, int* clip_max,
-                          cudaStream_t st, LaunchCtx* lc);
+                          cudaStream_t st, LaunchCtx* lc, int fill_to = 0, float* pad_value = nullptr);
 
 cudaError_t launch_logmel_init(int* clip_max, int n, cudaStream_t st, LaunchCtx* lc, int* tiles_done = nullptr);
 // what k_logmel_norm needs to assemble the records itself (fused path: saves the k_finalize_items launch)
+// The record "gather" of the multi-GPU path as part of the kernel that assembles the records (no collective call on
+// the critical path): besides rec[it] the record of item `it` is stored to sink[r][slot + it] for every r < n, where
+// sink[r] is rank r's gathered-record buffer mapped into this process (CUDA IPC over NVLink / NVSwitch peer memory;
+// sink[own rank] is the local buffer).  rho_b200_set_record_peers / rho_tts_b200.dist.RecordExchange.
+constexpr int MAX_RECORD_PEERS = 16;
+struct RecordPeers {
+  int n;                                 // 0: no peer stores
+  int pad;
+  long long slot;                        // index of this rank's first record in every gathered buffer
+  rho_record* sink[MAX_RECORD_PEERS];
+};
 struct FinalizeArgs {
   const SegState* seg;
   const ItemState* item;
@@ -119,10 +131,14 @@ struct FinalizeArgs {
   const float* emb;
   const float* ref;
   int dim;
+  RecordPeers peers;
 };
+// fill_to (0 = pad_frames): frames >= fill_to are not materialised (compact feature rows); pad_value[c] (optional)
+// receives the constant every frame >= T_real of clip c holds
 cudaError_t launch_logmel_norm(const int32_t* len16, int n, int n_mels, int pad_frames, float* mel,
                                int64_t mel_stride_frames, const int* clip_max, cudaStream_t st, LaunchCtx* lc,
-                               bool fill_done = false, const FinalizeArgs* fin = nullptr);
+                               bool fill_done = false, const FinalizeArgs* fin = nullptr, int fill_to = 0,
+                               float* pad_value = nullptr);
 
 // fused.cu
 bool fused_inline_norm();   // the fused kernel writes the constant fill of the zero-padding frames itself
@@ -130,7 +146,8 @@ cudaError_t upload_fused_taps(const float* taps /* [2][23] */);
 cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_t* seg_off, const Workspace& ws,
                                   const int32_t* item_first_seg, int n_items, int64_t max_len,
                                   const Derived& d, float* y, const int64_t* y_off, int n_mels, int pad_frames,
-                                  float* mel, int64_t mel_stride_frames, cudaStream_t st, LaunchCtx* lc);
+                                  float* mel, int64_t mel_stride_frames, int sm_count, cudaStream_t st, LaunchCtx* lc,
+                                  bool from_y = false, int fill_to = 0);
 
 // mel_gemm.cu: the mel projection as a tcgen05 / TMEM / TMA GEMM (3xTF32), in isolation
 cudaError_t launch_mel_gemm(const Tables& tb, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,

@@ -195,19 +195,23 @@ constexpr int NORM_ROWS = RHO_NORM_ROWS;   // mel rows per CTA
 constexpr int NORM_BATCH = 4;     // rows in flight per thread: 48 registers -> 5 CTAs per SM (8 in flight needed 78 -> 3 CTAs)
 __global__ void __launch_bounds__(256, 5)
 k_logmel_norm(const int32_t* __restrict__ len16, int n_mels, int pad_frames, float* __restrict__ mel,
-              long long mel_stride, const int* __restrict__ clip_max, int fill_done, FinalizeArgs fin) {
+              long long mel_stride, const int* __restrict__ clip_max, int fill_done, FinalizeArgs fin, int fill_to,
+              float* __restrict__ pad_value) {
   const int c = blockIdx.x;
   // fused path: the first warp of the clip's first CTA also assembles the clip's record (decay decision, cosine)
   if (fin.rec && blockIdx.y == 0 && threadIdx.x < 32)
-    finalize_item(fin.seg, fin.item, fin.item_first_seg, c, threadIdx.x, fin.decay_thr, fin.rec, fin.emb, fin.ref, fin.dim);
+    finalize_item(fin.seg, fin.item, fin.item_first_seg, c, threadIdx.x, fin.decay_thr, fin.rec, fin.emb, fin.ref, fin.dim,
+                  fin.peers);
   int T, T_real, N, n_valid;
   lm_frame_counts(len16[c], pad_frames, &T, &T_real, &N, &n_valid);
   if (T <= 0) return;
+  if (pad_frames > 0) T = min(T, max(fill_to, T_real));   // compact rows: frames >= fill_to are not materialised
   // fill_done: the fused kernel has already written the constant for the columns >= round_up(T_real, 4)
   if (fill_done && T > T_real) T = min(T, (T_real + 3) & ~3);
   const float mx = ordered_to_float(clip_max[c]);
   const float floor_v = __fsub_rn(mx, 8.0f);
   const float fill = __fmul_rn(__fadd_rn(fmaxf(-10.0f, floor_v), 4.0f), 0.25f);   // x / 4 == x * 0.25 bit for bit
+  if (pad_value && blockIdx.y == 0 && threadIdx.x == 32) pad_value[c] = fill;
   // the stored values are lm_scaled(x): the reference's (max(x, floor) + 4) / 4 is max(stored, lm_scaled(floor)) bit for bit
   const float floor_s = lm_scaled(floor_v);
   auto nrm = [&](float v) { return fmaxf(v, floor_s); };
@@ -268,7 +272,7 @@ k_logmel_norm(const int32_t* __restrict__ len16, int n_mels, int pad_frames, flo
 cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off, const int32_t* len16,
                           int n, int64_t max_len16, int n_mels, int pad_frames, float* mel,
                           int64_t mel_stride_frames, int32_t* n_frames, int* clip_max,
-                          cudaStream_t st, LaunchCtx* lc) {
+                          cudaStream_t st, LaunchCtx* lc, int fill_to, float* pad_value) {
   if (n <= 0) return cudaSuccess;
   cudaError_t e0 = launch_logmel_init(clip_max, n, st, lc);
   if (e0 != cudaSuccess) return e0;
@@ -292,7 +296,8 @@ cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off
   kern<<<grid, LM_THREADS, smem, st>>>(x16, off, len16, tb.hann, tb.twiddle, n_mels, pad_frames, mel,
                                        mel_stride_frames, clip_max, n_frames);
   lc->end(st);
-  return launch_logmel_norm(len16, n, n_mels, pad_frames, mel, mel_stride_frames, clip_max, st, lc);
+  return launch_logmel_norm(len16, n, n_mels, pad_frames, mel, mel_stride_frames, clip_max, st, lc, false, nullptr,
+                            fill_to, pad_value);
 }
 
 cudaError_t launch_logmel_init(int* clip_max, int n, cudaStream_t st, LaunchCtx* lc, int* tiles_done) {
@@ -305,13 +310,15 @@ cudaError_t launch_logmel_init(int* clip_max, int n, cudaStream_t st, LaunchCtx*
 
 cudaError_t launch_logmel_norm(const int32_t* len16, int n, int n_mels, int pad_frames, float* mel,
                                int64_t mel_stride_frames, const int* clip_max, cudaStream_t st, LaunchCtx* lc,
-                               bool fill_done, const FinalizeArgs* fin) {
+                               bool fill_done, const FinalizeArgs* fin, int fill_to, float* pad_value) {
   if (n <= 0) return cudaSuccess;
+  if (fill_to <= 0) fill_to = pad_frames;
   dim3 g2((unsigned)n, (unsigned)((n_mels + NORM_ROWS - 1) / NORM_ROWS));
   FinalizeArgs fa{};
   if (fin) fa = *fin;
   lc->begin(KID_LOGMEL_NORM, st);
-  k_logmel_norm<<<g2, 256, 0, st>>>(len16, n_mels, pad_frames, mel, mel_stride_frames, clip_max, fill_done ? 1 : 0, fa);
+  k_logmel_norm<<<g2, 256, 0, st>>>(len16, n_mels, pad_frames, mel, mel_stride_frames, clip_max, fill_done ? 1 : 0, fa,
+                                    fill_to, pad_value);
   lc->end(st);
   return cudaGetLastError();
 }

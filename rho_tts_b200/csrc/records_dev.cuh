@@ -1,6 +1,7 @@
 // Record assembly shared by k_finalize_items (join.cu) and k_logmel_norm (logmel.cu, fused path).
 #pragma once
 #include "common.cuh"
+#include "kernels.h"
 
 namespace rho {
 
@@ -23,7 +24,8 @@ __device__ __forceinline__ void decay_decide(double s_first, double s_last, int 
 __device__ __forceinline__ void finalize_item(const SegState* __restrict__ seg, const ItemState* __restrict__ item,
                                               const int32_t* __restrict__ item_first_seg, int it, int lane,
                                               double decay_thr, rho_record* __restrict__ rec,
-                                              const float* __restrict__ emb, const float* __restrict__ ref, int dim) {
+                                              const float* __restrict__ emb, const float* __restrict__ ref, int dim,
+                                              const RecordPeers& peers) {
   float cosv = 0.f;
   if (emb && ref) {
     const float* __restrict__ e = emb + (size_t)it * dim;
@@ -54,6 +56,9 @@ __device__ __forceinline__ void finalize_item(const SegState* __restrict__ seg, 
   r.out_len = is.out_len; r.flags = is.flags; r.cosine = cosv; r.n_segments = n;
   decay_decide(is.s_first, is.s_last, is.out_len, decay_thr, &r.first_rms, &r.last_rms, &r.decay_ratio, &r.ok);
   rec[it] = r;
+  // multi-GPU: the same 48 bytes go straight into every rank's gathered buffer (peer-mapped memory, NVLink stores);
+  // the stores are ordered for the readers by the end of this kernel + the flag kernel that follows it in the stream
+  for (int q = 0; q < peers.n; ++q) peers.sink[q][peers.slot + it] = r;
 }
 
 }  // namespace rho

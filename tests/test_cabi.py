@@ -37,7 +37,7 @@ def test_header_symbols_all_exported(lib):
 
 
 def test_abi_version_and_struct_sizes(lib):
-    assert lib.rho_b200_abi_version() == 1
+    assert lib.rho_b200_abi_version() == 2 == _lib.ABI_VERSION
     assert ctypes.sizeof(_lib.RhoRecord) == 48 and ctypes.sizeof(_lib.RhoSegInfo) == 16
     assert ctypes.sizeof(_lib.RhoParams) == 48
     from rho_tts_b200 import REC_DTYPE, SEG_DTYPE
@@ -80,6 +80,31 @@ def test_hann_and_mel_tables(lib):
         assert np.array_equal(m, WhisperFeatureExtractor(feature_size=nm).mel_filters.astype(np.float32).T)
     assert lib.rho_b200_host_table(2, 64, h.ctypes.data, 400) < 0
     assert b"n_mels" in lib.rho_b200_last_error()
+
+
+def test_compact_frames(lib):
+    """Row length of a compact feature tensor: the frames of the 30 s window that can see signal (SURVEY App. A.9:
+    t < ceil((L16 + 200) / 160)), rounded up to whole 128-bit pieces; the unpadded frame count with pad_frames = 0."""
+    for L in (1, 100, 24000, 240000, 240001, 719999, 720000, 2000000):
+        L16 = -(-2 * L // 3)
+        t_real = min(3000, max(2, -(-(min(L16, 480000) + 200) // 160)))
+        assert lib.rho_b200_compact_frames(L, 3000) == min(3000, (t_real + 3) // 4 * 4), L
+        assert lib.rho_b200_compact_frames(L, 0) == L16 // 160
+    assert lib.rho_b200_compact_frames(240000, 3000) == 1004
+
+
+def test_host_entry_points_reject_bad_layouts_without_a_gpu(lib):
+    """Argument / layout checks of the host entry points run before anything touches the device."""
+    x = np.zeros(1000, np.float32)
+    off = np.array([0, 400], np.int64); ln = np.array([500, 400], np.int32)          # overlapping segments
+    first = np.array([0, 1, 2], np.int32); yoff = np.array([0, 512], np.int64)
+    rec = np.zeros(2 * 48, np.uint8)
+    p = _lib.RhoParams(24000, 1, -50.0, 0.02, 0.05, 0.1, 0.3)
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)     # noqa: E731
+    assert lib.rho_b200_validate_host_ragged(None, vp(x), vp(off), vp(ln), 2, vp(first), 2, ctypes.byref(p), vp(x), vp(yoff),
+                                             80, 3000, None, 3000, None, None, None, 0, vp(rec)) == -1
+    assert b"handle is NULL" in lib.rho_b200_last_error()
+    assert lib.rho_b200_set_record_peers(None, None, 0, 0) == -1
 
 
 def test_workspace_bytes_monotone(lib):

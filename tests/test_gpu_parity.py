@@ -152,6 +152,34 @@ def test_join_batch_vs_oracle(R, cuda_device, pause_sec):
     assert n_fb > 10
 
 
+@pytest.mark.parametrize("xfade_sec", [0.0, 0.0004])
+def test_join_with_crossfade_disabled(R, cuda_device, xfade_sec):
+    """crossfade_samples == 0 drops segment 0 like the reference's [..., :-0] slice (base_tts.py:485); <= 10 samples:
+    no crossfade.  Golden vectors from the reference (tests/golden/make_golden_cf0.py) and the oracle on random items."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
+    GCF = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_cf0_v1.npz"))
+    v = [float(x) for x in GCF["xfade_secs"]].index(xfade_sec)
+    rng = np.random.default_rng(77)
+    items = [[G[f"clip{j}"] for j in GCF[f"v{v}_item{k}_idx"]] for k in range(int(GCF["n_items"]))]
+    n_golden = len(items)
+    items += [_join_case(rng) for _ in range(60)]
+    segs = [s for it in items for s in it]
+    first = np.concatenate([[0], np.cumsum([len(it) for it in items])]).astype(np.int32)
+    p = R.make_params(crossfade_duration_sec=xfade_sec)
+    out = R.join_batch(_rb(R, segs, cuda_device), first, p)
+    rec = out.records_host()
+    c = oracle.derive_constants(xfade_sec=xfade_sec)
+    for i, it in enumerate(items):
+        o = oracle.smooth_segment_join(it, c)
+        assert int(rec["out_len"][i]) == o.audio.size, (i, [len(s) for s in it], rec[i], o.fallback)
+        assert bool(rec["flags"][i] & 2) == o.fallback and bool(rec["flags"][i] & 4) == o.two_d, i
+        got = out.audio.clip(i, o.audio.size).cpu().numpy()
+        assert_close(got, o.audio, what=f"item {i}")
+        if i < n_golden:
+            assert_close(got, GCF[f"v{v}_item{i}"], what=f"golden item {i}")
+
+
 # ----------------------------------------------------------------------------- resample
 def test_resample_vs_oracle(R, cuda_device):
     rng = np.random.default_rng(5)

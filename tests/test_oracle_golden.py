@@ -82,3 +82,22 @@ def test_cosine():
     e = G["emb"]
     got = np.asarray([oracle.cosine_similarity(e[0], g) for g in e[1:]], dtype=np.float32)
     assert_close(got, G["cos"], tol=1e-6, what="cosine")
+
+
+# ----------------------------------------------------------------------------- crossfade disabled (cf == 0, cf <= 10)
+GCF = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_cf0_v1.npz"))
+
+
+@pytest.mark.parametrize("v", range(2))
+def test_join_with_crossfade_disabled(v):
+    """crossfade_duration_sec = 0: the reference's [..., :-0] slice drops segment 0 (base_tts.py:485); 0.0004 s gives
+    9 samples <= 10, so no crossfade but segment 0 loses its last 9 samples.  Vectors from the reference itself."""
+    c = oracle.derive_constants(xfade_sec=float(GCF["xfade_secs"][v]))
+    assert c.cf == (0, 9)[v]
+    for k in range(int(GCF["n_items"])):
+        segs = [G[f"clip{j}"] for j in GCF[f"v{v}_item{k}_idx"]]
+        o = oracle.smooth_segment_join(segs, c)
+        want = GCF[f"v{v}_item{k}"]
+        assert o.audio.size == want.size, (v, k, o.fallback)
+        assert (2 if o.two_d else 1) == int(GCF[f"v{v}_item_dim{k}"])
+        assert_close(o.audio, want, tol=1e-6, what=f"cf0 v{v} item {k}")

@@ -84,6 +84,25 @@ def test_join_without_pause_and_custom_threshold(reference_basetts):
     assert ref._validate_sound_decay(torch.from_numpy(x))[1] == oracle.sound_decay(x, 0.8)[1]
 
 
+@pytest.mark.parametrize("xfade_sec", [0.0, 0.0004, 0.001])
+def test_join_with_crossfade_disabled_matches_reference(reference_basetts, xfade_sec):
+    """crossfade_samples == 0: `current_segment[..., :-0]` (base_tts.py:485) is empty, the reference drops segment 0;
+    crossfade_samples <= 10: no crossfade is made but segment 0 still loses its tail."""
+    rng = np.random.default_rng(31)
+    ref = _ref_obj(reference_basetts, crossfade_duration_sec=xfade_sec)
+    c = oracle.derive_constants(xfade_sec=xfade_sec)
+    for _ in range(40):
+        segs = []
+        for _ in range(int(rng.integers(2, 5))):
+            L = int(rng.choice([0, 5, 20, 600, 5000, 20000]))
+            segs.append(rng.normal(0, 1e-4, L).astype(np.float32) if rng.integers(0, 5) == 0
+                        else tone_clip(rng, L, min(L // 4, 2000), min(L // 5, 2000)))
+        r = ref._smooth_segment_join([torch.from_numpy(s.copy()) for s in segs])
+        o = oracle.smooth_segment_join(segs, c)
+        assert r.numel() == o.audio.size and (r.dim() == 2) == o.two_d, ([s.size for s in segs], o.fallback)
+        assert_close(o.audio, r.numpy().reshape(-1), tol=1e-6, what="join, crossfade disabled")
+
+
 def test_resample_matches_torchaudio():
     ta = pytest.importorskip("torchaudio")
     rng = np.random.default_rng(2)
