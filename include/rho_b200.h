@@ -271,8 +271,8 @@ int rho_b200_cosine(rho_handle* h, const float* emb, const float* ref, int n, in
  *     rho_b200_compact_frames(max_item_len, 3000)): only the frames that can see signal are materialised; every frame
  *     t >= mel_stride_frames of item i equals pad_value[i] (the 30 s window of a 10 s clip is 2/3 such frames).
  *   pad_value (device, n_items floats, may be NULL): the constant of item i's zero-padding frames, in either layout.
- * Records: rec[i]; when record peers are set (rho_b200_set_record_peers) the same record is also stored to every
- * peer sink by the kernel that assembles it. */
+ * Records: rec[i]; with a connected record exchange (rho_b200_exchange_*) the same record is also stored into every
+ * rank's gathered buffer by the kernel that assembles it. */
 #define RHO_V_ONE_SEGMENT_ITEMS 1u
 #define RHO_V_NO_FUSION 2u
 #define RHO_V_COMPACT_PAD 4u
@@ -289,14 +289,33 @@ int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, con
  * unpadded frame count ceil(2L/3) / 160). */
 int64_t rho_b200_compact_frames(int64_t max_item_len, int pad_frames);
 
-/* Multi-GPU record exchange fused into the record assembly (the one exchange of the path is the
- * gather of the 48-byte records).  sinks[r], r < n_sinks: DEVICE pointers valid on this handle's device -- rank r's
- * gathered-record buffer mapped into this process over NVLink peer memory (cudaIpcOpenMemHandle / symmetric memory;
- * sinks[own rank] is the local buffer).  From now on every record rho_b200_validate / rho_b200_join assembles is also
- * stored to sinks[r][slot + i] for all r, by the kernel that writes rec[i]: no collective call on the critical path.
- * Readers order themselves after the writers with their own barrier / flag (rho_tts_b200.dist.RecordExchange).
- * n_sinks = 0 switches it off.  At most 16 sinks. */
-int rho_b200_set_record_peers(rho_handle* h, void* const* sinks, int n_sinks, int64_t slot);
+/* ------------------------------------------------ multi-GPU record exchange */
+/* The one exchange of the path is the gather of the 48-byte records (one process per GPU, clips sharded with no
+ * data-path collective).  It is fused into the record assembly instead of being a collective call on the critical path:
+ *   create : allocates this rank's gathered buffer ([2 parities][world][n_per_rank] records + one flag word per source
+ *            rank) and exports it as a 64-byte CUDA IPC handle (ipc_handle_out).  The caller all-gathers the handles
+ *            (any transport: torch.distributed object collective, a file, MPI).
+ *   connect: maps every peer's buffer into this process (cudaIpcOpenMemHandle, NVLink / NVSwitch peer memory);
+ *            all_handles = world x 64 bytes in rank order.  From then on the kernel of rho_b200_validate that writes
+ *            rec[i] also stores the record to EVERY rank's buffer at [epoch & 1][rank][i], and the last record of the
+ *            call publishes flag[rank] = epoch on every rank (system-scope fence + release store); epoch counts the
+ *            rho_b200_validate calls on this handle since connect (rho_b200_exchange_epoch).  Every rank must make the
+ *            same sequence of calls.
+ *   wait   : enqueues a one-warp kernel on `stream` that waits until all ranks' flags have reached `epoch` (bounded
+ *            spin: after ~2 s it records a time-out instead of hanging the GPU).  Work enqueued behind it may read
+ *            the gathered block of that epoch.  Two parities: epoch e's block is overwritten by epoch e + 2, so a rank
+ *            waits for epoch e before it starts call e + 2 (rho_tts_b200.dist.RecordExchange does).
+ *   read   : copies the gathered block of `epoch` (world * n_per_rank records, rank-major) to dst (device) on `stream`;
+ *            with timed_out != NULL it also synchronises the stream and reports whether any wait so far ran into its
+ *            time-out (1 + the rank that was missing).
+ * Failure to map a peer (no IPC in this container, no P2P path) is an error of connect; the caller then keeps using
+ * an NCCL all-gather of the records (rho_tts_b200.dist.gather_records). */
+int rho_b200_exchange_create(rho_handle* h, int world, int rank, int64_t n_per_rank, void* ipc_handle_out /* 64 B */);
+int rho_b200_exchange_connect(rho_handle* h, const void* all_handles /* world * 64 B */);
+int rho_b200_exchange_wait(rho_handle* h, int64_t epoch, void* stream);
+int64_t rho_b200_exchange_epoch(rho_handle* h);
+int rho_b200_exchange_read(rho_handle* h, int64_t epoch, void* dst, int* timed_out, void* stream);
+int rho_b200_exchange_destroy(rho_handle* h);
 
 /* HOST entry points: the calls a non-torch embedder makes.  All pointers are HOST buffers (pinned for full speed).
  * Segments are copied in, rho_b200_validate (or rho_b200_join when mel == NULL: no features) runs in chunks of whole

@@ -32,7 +32,8 @@ EXPORTS = (
     "rho_b200_host_table", "rho_b200_workspace_bytes", "rho_b200_trim_scan", "rho_b200_join",
     "rho_b200_remove_dc", "rho_b200_apply_fades", "rho_b200_sound_decay", "rho_b200_sound_decay_batch", "rho_b200_resample3to2",
     "rho_b200_resample_out_len", "rho_b200_resample", "rho_b200_pitch_workspace_bytes", "rho_b200_pitch_shift", "rho_b200_mfcc_workspace_bytes", "rho_b200_mfcc_stats", "rho_b200_pcm16", "rho_b200_logmel", "rho_b200_mel_project", "rho_b200_qwen_workspace_bytes", "rho_b200_qwen_postprocess",
-    "rho_b200_cosine", "rho_b200_validate", "rho_b200_compact_frames", "rho_b200_set_record_peers",
+    "rho_b200_cosine", "rho_b200_validate", "rho_b200_compact_frames", "rho_b200_exchange_create", "rho_b200_exchange_connect",
+    "rho_b200_exchange_wait", "rho_b200_exchange_epoch", "rho_b200_exchange_read", "rho_b200_exchange_destroy",
     "rho_b200_validate_host", "rho_b200_validate_host_ragged",
     "rho_b200_build_flags", "rho_b200_launch_count", "rho_b200_profile_begin", "rho_b200_profile_end", "rho_b200_kernel_name",
 )
@@ -107,7 +108,12 @@ def load():
             "rho_b200_validate": (c_int, [vp, vp, vp, vp, i32, i64, vp, i32, i64, P, vp, vp, c_int, c_int, vp, i64, vp,
                                           vp, vp, c_int, vp, vp, c_uint32, vp, c_size_t, vp]),
             "rho_b200_compact_frames": (c_int64, [i64, c_int]),
-            "rho_b200_set_record_peers": (c_int, [vp, vp, c_int, i64]),
+            "rho_b200_exchange_create": (c_int, [vp, c_int, c_int, i64, vp]),
+            "rho_b200_exchange_connect": (c_int, [vp, vp]),
+            "rho_b200_exchange_wait": (c_int, [vp, i64, vp]),
+            "rho_b200_exchange_epoch": (c_int64, [vp]),
+            "rho_b200_exchange_read": (c_int, [vp, i64, POINTER(c_void_p), POINTER(c_int)]),
+            "rho_b200_exchange_destroy": (c_int, [vp]),
             "rho_b200_validate_host_ragged": (c_int, [vp, vp, vp, vp, c_int, vp, c_int, P, vp, vp, c_int, c_int, vp, i64,
                                                       vp, vp, vp, c_int, vp]),
             "rho_b200_validate_host": (c_int, [vp, vp, c_int, c_int32, P, vp, c_int, c_int, vp, vp, vp, c_int, vp]),

@@ -51,7 +51,8 @@ const char* const kKernelNames[KID_COUNT] = {
   "k_init", "k_scan", "k_finalize_segs", "k_plan_items", "k_gather", "k_finalize_items",
   "k_resample3to2", "k_logmel_init", "k_logmel_frames", "k_logmel_norm", "k_cosine", "k_single_clip_helpers",
   "k_fused_features", "k_mel_gemm", "k_qwen_moments", "k_qwen_plan", "k_qwen_apply", "k_resample_general",
-  "k_pv_stft", "k_pv_phase", "k_pv_cumsum", "k_pv_istft", "k_resample_windowed", "k_mfcc_frames", "k_mfcc_stats"};
+  "k_pv_stft", "k_pv_phase", "k_pv_cumsum", "k_pv_istft", "k_resample_windowed", "k_mfcc_frames", "k_mfcc_stats",
+  "k_wait_flags"};
 }
 
 namespace {
@@ -630,21 +631,6 @@ int64_t rho_b200_compact_frames(int64_t max_item_len, int pad_frames) {
   return pad_frames > 0 ? compact_frames(max_item_len, pad_frames) : ((2 * max_item_len + 2) / 3) / HOP16;
 }
 
-int rho_b200_set_record_peers(rho_handle* h, void* const* sinks, int n_sinks, int64_t slot) {
-  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
-  if (n_sinks < 0 || n_sinks > MAX_RECORD_PEERS) return fail(RHO_ERR_INVALID, "at most %d record sinks", MAX_RECORD_PEERS);
-  if (n_sinks > 0 && (!sinks || slot < 0)) return fail(RHO_ERR_INVALID, "sinks is NULL or slot negative");
-  std::lock_guard<std::mutex> lock(h->mu);
-  h->peers = RecordPeers{};
-  h->peers.n = n_sinks;
-  h->peers.slot = slot;
-  for (int i = 0; i < n_sinks; ++i) {
-    if (!sinks[i] || (((uintptr_t)sinks[i]) & 7u)) return fail(RHO_ERR_INVALID, "sink %d is NULL or misaligned", i);
-    h->peers.sink[i] = (rho_record*)sinks[i];
-  }
-  return RHO_OK;
-}
-
 int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, const int32_t* seg_len,
                       int n_segments, int64_t max_seg_len, const int32_t* item_first_seg, int n_items,
                       int64_t max_item_len, const rho_params* p, float* y, const int64_t* y_off,
@@ -678,8 +664,24 @@ int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, con
   rc = carve(workspace, ws_bytes, n_segments, n_items, max_seg_len, d, &ws, nullptr); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
-  RecordPeers peers;
-  { std::lock_guard<std::mutex> lock(h->mu); peers = h->peers; }
+  // multi-GPU: this call's records also go to every rank's gathered buffer, parity = epoch & 1 (exchange.cu)
+  RecordPeers peers{};
+  {
+    std::lock_guard<std::mutex> lock(h->mu);
+    Exchange& X = h->xch;
+    if (X.connected && !(flags & RHO_V_NO_FUSION)) {
+      if (n_items > X.n_per_rank) return fail(RHO_ERR_INVALID, "exchange sized for %lld items per rank, call has %d", (long long)X.n_per_rank, n_items);
+      ++X.epoch;
+      peers.n = X.world; peers.rank = X.rank; peers.epoch = (unsigned)X.epoch; peers.n_items = n_items;
+      peers.slot = ((long long)(X.epoch & 1) * X.world + X.rank) * X.n_per_rank;
+      char* fl = (char*)X.buf + align_up(X.rec_bytes, 256);
+      peers.done = (int*)(fl + 192);
+      for (int q = 0; q < X.world; ++q) {
+        peers.sink[q] = (rho_record*)X.peer[q];
+        peers.flag[q] = (unsigned*)((char*)X.peer[q] + align_up(X.rec_bytes, 256));
+      }
+    }
+  }
   const bool one_seg = (flags & RHO_V_ONE_SEGMENT_ITEMS) && n_segments == n_items;
   if (!(flags & RHO_V_NO_FUSION)) {
     // one-segment items:  init -> scan -> bounds / DC / plan -> ONE kernel for apply + resample + log-mel -> clamp +
@@ -703,7 +705,7 @@ int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, con
   } else {
     if (!scratch16) return fail(RHO_ERR_INVALID, "scratch16 is NULL (needed by the kernel-per-stage path)");
     e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,
-                    rec, nullptr, ws, st, &h->lc, JOIN_ALL, nullptr, nullptr, 0, &peers);
+                    rec, nullptr, ws, st, &h->lc, JOIN_ALL);
     if (e != cudaSuccess) return cuda_fail(e, "join");
     // 16 kHz intermediate lives at the same offsets as y (it is 2/3 as long)
     e = launch_resample3to2(y, y_off, &rec[0].out_len, (int)sizeof(rho_record), n_items, max_item_len,

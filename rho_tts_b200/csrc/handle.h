@@ -33,6 +33,17 @@ struct DeviceGuard {
   rho::DeviceGuard _guard((h)->device);                             \
   if (_guard.err != cudaSuccess) return rho::cuda_fail(_guard.err, "cudaSetDevice")
 
+// exchange.cu: this rank's gathered-record buffer and the peer mappings of everybody else's
+struct Exchange {
+  void* buf = nullptr;                   // [2 parities][world][n_per_rank] records | 32 flag words | error word | done counter
+  size_t bytes = 0, rec_bytes = 0;
+  int world = 0, rank = 0;
+  int64_t n_per_rank = 0;
+  uint64_t epoch = 0;                    // calls of rho_b200_validate since the exchange was connected
+  bool connected = false;
+  void* peer[MAX_RECORD_PEERS] = {};     // peer[q]: rank q's buffer in this process's address space
+};
+
 struct HostCtx;   // host_api.cu: streams, device arena and pinned staging of one in-flight host call
 
 }  // namespace rho
@@ -56,8 +67,8 @@ struct rho_handle {
   bool mfcc_tb_ok = false;
   struct WinTaps { float* taps; int* ilo; };
   std::map<uint64_t, WinTaps> windowed_taps;
-  // records of rho_b200_validate are also stored into these peer buffers (NVLink P2P), see rho_b200_set_record_peers
-  rho::RecordPeers peers{};
+  // multi-GPU: records of rho_b200_validate are also stored into every rank's gathered buffer (rho_b200_exchange_*)
+  rho::Exchange xch;
 };
 
 namespace rho {

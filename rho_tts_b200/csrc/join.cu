@@ -509,12 +509,11 @@ k_gather(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const
 __global__ void __launch_bounds__(256)
 k_finalize_items(const SegState* __restrict__ seg, const ItemState* __restrict__ item,
                  const int32_t* __restrict__ item_first_seg, int n_items, double decay_thr,
-                 rho_record* __restrict__ rec, const float* __restrict__ emb, const float* __restrict__ ref, int dim,
-                 const RecordPeers peers) {
+                 rho_record* __restrict__ rec, const float* __restrict__ emb, const float* __restrict__ ref, int dim) {
   const int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (it >= n_items) return;
-  finalize_item(seg, item, item_first_seg, it, lane, decay_thr, rec, emb, ref, dim, peers);
+  finalize_item(seg, item, item_first_seg, it, lane, decay_thr, rec, emb, ref, dim, RecordPeers{});
 }
 
 // ------------------------------------------------------------------ single-clip helpers (method shim)
@@ -729,7 +728,7 @@ cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* s
                         const int32_t* item_first_seg, int n_items, int64_t max_item_len,
                         const Derived& d, float* y, const int64_t* y_off, rho_record* rec, rho_seg_info* seg_info,
                         const Workspace& ws, cudaStream_t st, LaunchCtx* lc, int stages,
-                        const float* emb, const float* ref_emb, int emb_dim, const RecordPeers* peers) {
+                        const float* emb, const float* ref_emb, int emb_dim) {
   if (n_items <= 0) return cudaSuccess;
   cudaError_t e = cudaSuccess;
   if (stages & JOIN_PREPARE) {
@@ -771,7 +770,7 @@ cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* s
   if (stages & JOIN_FINISH) {
     lc->begin(KID_FINALIZE_ITEMS, st);
     k_finalize_items<<<(n_items * 32 + 255) / 256, 256, 0, st>>>(ws.seg, ws.item, item_first_seg, n_items, d.decay_thr,
-                                                            rec, emb, ref_emb, emb_dim, peers ? *peers : RecordPeers{});
+                                                            rec, emb, ref_emb, emb_dim);
     lc->end(st);
   }
   return cudaGetLastError();

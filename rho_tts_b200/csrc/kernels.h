@@ -47,7 +47,7 @@ struct Tables {
 enum KernelId {
   KID_INIT = 0, KID_SCAN, KID_FINALIZE_SEGS, KID_PLAN, KID_GATHER, KID_FINALIZE_ITEMS,
   KID_RESAMPLE, KID_LOGMEL_INIT, KID_LOGMEL_FRAMES, KID_LOGMEL_NORM, KID_COSINE, KID_SINGLE, KID_FUSED, KID_MEL_GEMM, KID_QWEN_MOMENTS, KID_QWEN_PLAN, KID_QWEN_APPLY, KID_RESAMPLE_GENERAL,
-  KID_PV_STFT, KID_PV_PHASE, KID_PV_CUMSUM, KID_PV_ISTFT, KID_PV_RESAMPLE, KID_MFCC_FRAMES, KID_MFCC_STATS, KID_COUNT
+  KID_PV_STFT, KID_PV_PHASE, KID_PV_CUMSUM, KID_PV_ISTFT, KID_PV_RESAMPLE, KID_MFCC_FRAMES, KID_MFCC_STATS, KID_XCH_WAIT, KID_COUNT
 };
 extern const char* const kKernelNames[KID_COUNT];
 
@@ -80,8 +80,7 @@ cudaError_t launch_join(const float* x, const int64_t* seg_off, const int32_t* s
                         const int32_t* item_first_seg, int n_items, int64_t max_item_len,
                         const Derived& d, float* y, const int64_t* y_off, rho_record* rec, rho_seg_info* seg_info,
                         const Workspace& ws, cudaStream_t st, LaunchCtx* lc, int stages = JOIN_ALL,
-                        const float* emb = nullptr, const float* ref_emb = nullptr, int emb_dim = 0,
-                        const struct RecordPeers* peers = nullptr);
+                        const float* emb = nullptr, const float* ref_emb = nullptr, int emb_dim = 0);
 cudaError_t launch_remove_dc(float* x, int64_t n, float* dc_out, double* scratch, cudaStream_t st, LaunchCtx* lc);
 cudaError_t launch_apply_fades(float* x, int64_t n, int fade, int fade_in, int fade_out, cudaStream_t st, LaunchCtx* lc);
 cudaError_t launch_sound_decay(const float* x, int64_t n, double thr, rho_record* rec, double* scratch,
@@ -111,16 +110,21 @@ cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off
 
 cudaError_t launch_logmel_init(int* clip_max, int n, cudaStream_t st, LaunchCtx* lc, int* tiles_done = nullptr);
 // what k_logmel_norm needs to assemble the records itself (fused path: saves the k_finalize_items launch)
-// The record "gather" of the multi-GPU path as part of the kernel that assembles the records (no collective call on
-// the critical path): besides rec[it] the record of item `it` is stored to sink[r][slot + it] for every r < n, where
-// sink[r] is rank r's gathered-record buffer mapped into this process (CUDA IPC over NVLink / NVSwitch peer memory;
-// sink[own rank] is the local buffer).  rho_b200_set_record_peers / rho_tts_b200.dist.RecordExchange.
+// The record "gather" of the multi-GPU path, fused into the kernel that assembles the records (no collective call on
+// the critical path; exchange.cu, rho_b200_exchange_*).  Besides rec[it], the record of item `it` is stored to
+// sink[q][slot + it] for every rank q < n: sink[q] is rank q's gathered-record buffer mapped into this process (CUDA IPC
+// over NVLink / NVSwitch peer memory; sink[own rank] is the local buffer).  The CTA that finishes last publishes
+// flag[q][rank] = epoch with a system-scope release after a system-scope fence: rank q's readers wait for that value.
 constexpr int MAX_RECORD_PEERS = 16;
 struct RecordPeers {
   int n;                                 // 0: no peer stores
-  int pad;
-  long long slot;                        // index of this rank's first record in every gathered buffer
+  int rank;
+  long long slot;                        // index of this rank's first record in every gathered buffer (this epoch's parity)
+  unsigned epoch;
+  int n_items;                           // records this call produces (the last of them publishes the flags)
+  int* done;                             // local counter of records stored (reset by the publisher)
   rho_record* sink[MAX_RECORD_PEERS];
+  unsigned* flag[MAX_RECORD_PEERS];
 };
 struct FinalizeArgs {
   const SegState* seg;

@@ -204,7 +204,8 @@ k_logmel_norm(const int32_t* __restrict__ len16, int n_mels, int pad_frames, flo
                   fin.peers);
   int T, T_real, N, n_valid;
   lm_frame_counts(len16[c], pad_frames, &T, &T_real, &N, &n_valid);
-  if (T <= 0) return;
+  const bool publisher = fin.rec && blockIdx.y == 0 && threadIdx.x == 0;      // the thread that stored this clip's record
+  if (T <= 0) { if (publisher) publish_records(fin.peers); return; }
   if (pad_frames > 0) T = min(T, max(fill_to, T_real));   // compact rows: frames >= fill_to are not materialised
   // fill_done: the fused kernel has already written the constant for the columns >= round_up(T_real, 4)
   if (fill_done && T > T_real) T = min(T, (T_real + 3) & ~3);
@@ -267,6 +268,7 @@ k_logmel_norm(const int32_t* __restrict__ len16, int n_mels, int pad_frames, flo
       }
     }
   }
+  if (publisher) publish_records(fin.peers);
 }
 
 cudaError_t launch_logmel(const Tables& tb, const float* x16, const int64_t* off, const int32_t* len16,

@@ -61,4 +61,18 @@ __device__ __forceinline__ void finalize_item(const SegState* __restrict__ seg, 
   for (int q = 0; q < peers.n; ++q) peers.sink[q][peers.slot + it] = r;
 }
 
+// Called by the thread that stored item records (finalize_item's lane 0) once its CTA has nothing else to do: makes its
+// peer stores visible system-wide, counts the record, and -- if it was the last one of this call -- tells every rank
+// that this rank's block of epoch `epoch` is complete.
+__device__ __forceinline__ void publish_records(const RecordPeers& peers) {
+  if (peers.n <= 0) return;
+  __threadfence_system();
+  if (atomicAdd(peers.done, 1) == peers.n_items - 1) {
+    *peers.done = 0;                                     // ready for the next call (stream order)
+    __threadfence_system();                              // acquire side of the count: every other CTA's fence happened before
+    for (int q = 0; q < peers.n; ++q)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(peers.flag[q] + peers.rank), "r"(peers.epoch) : "memory");
+  }
+}
+
 }  // namespace rho

@@ -104,7 +104,7 @@ def test_host_entry_points_reject_bad_layouts_without_a_gpu(lib):
     assert lib.rho_b200_validate_host_ragged(None, vp(x), vp(off), vp(ln), 2, vp(first), 2, ctypes.byref(p), vp(x), vp(yoff),
                                              80, 3000, None, 3000, None, None, None, 0, vp(rec)) == -1
     assert b"handle is NULL" in lib.rho_b200_last_error()
-    assert lib.rho_b200_set_record_peers(None, None, 0, 0) == -1
+    assert lib.rho_b200_exchange_wait(None, 1, None) == -1 and lib.rho_b200_exchange_epoch(None) == -1
 
 
 def test_workspace_bytes_monotone(lib):

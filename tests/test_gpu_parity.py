@@ -20,6 +20,15 @@ def R():
     return r
 
 
+def _records_match(a, b):
+    """Records of two runs of the same items: integers, flags and the cosine bit for bit; the decay sums are fp32 partial
+    sums whose grouping follows the tile schedule (which depends on the batch), so RMS / ratio agree to rounding only."""
+    for f in ("start", "end", "out_len", "flags", "ok", "n_segments", "cosine", "dc"):
+        assert np.array_equal(a[f], b[f]), f
+    for f in ("first_rms", "last_rms", "decay_ratio"):
+        assert np.allclose(a[f], b[f], rtol=1e-6, atol=0), f
+
+
 def _rb(R, clips, dev):
     return R.RaggedBatch.from_list([torch.from_numpy(np.ascontiguousarray(c)) for c in clips], dev)
 
@@ -323,21 +332,188 @@ def test_fused_and_unfused_paths_agree(R, cuda_device):
 
 
 def test_validate_host_matches_device_path(R, cuda_device):
+    """The host-buffer entry point against the device-resident path, byte for byte: only the frames that can see signal
+    cross PCIe, the constant tail of every row is written on the host (include/rho_b200.h)."""
     from rho_tts_b200 import synth
     n = 150                                   # > 2 chunks of 64, last one ragged
     x = synth.make_clip_block(n, 48000, 77).pin_memory()
     emb, ref = synth.make_embeddings(n)
     p = R.make_params()
-    mel_h = torch.empty((n, 80, 3000), dtype=torch.float32).pin_memory()
+    mel_h = torch.full((n, 80, 3000), float("nan"), dtype=torch.float32).pin_memory()
     y, mel_h, rec_h = R.validate_host(x, p, emb.pin_memory(), ref.pin_memory(), 80, mel=mel_h)
     out = R.validate_batch(R.RaggedBatch.from_dense(x.to(cuda_device)), p, emb.to(cuda_device), ref.to(cuda_device))
     rec_d = out.records_host(); rec_h = rec_h.numpy().view(R.REC_DTYPE).reshape(-1)
-    assert np.array_equal(rec_d["out_len"], rec_h["out_len"]) and np.array_equal(rec_d["ok"], rec_h["ok"])
-    assert np.array_equal(rec_d["cosine"], rec_h["cosine"])
+    _records_match(rec_d, rec_h)
     assert torch.equal(out.mel.cpu(), mel_h)
-    for i in range(0, n, 7):
+    for i in range(n):
         L = int(rec_d["out_len"][i])
         assert torch.equal(out.audio.clip(i, L).cpu(), y[i, :L])
+    # the per-clip constant on the device is the tail of the full rows
+    assert torch.equal(out.pad_value.cpu(), mel_h[:, 0, 2999])
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_compact_feature_rows(R, cuda_device, n_mels):
+    """RHO_V_COMPACT_PAD: rows of rho_b200_compact_frames(L) frames + pad_value[i] == the head and the constant tail
+    of the complete [n_mels][3000] rows, bit for bit (feature_extraction_whisper.py:296-303)."""
+    from rho_tts_b200 import synth
+    lens = [240000, 200001, 100, 24000, 730000, 7680]
+    clips = [synth.make_clip_block(1, L, 900 + i)[0].numpy() for i, L in enumerate(lens)]
+    for group in (clips[:4], clips):                     # 10 s rows (1004 frames) and rows that hit the 3000-frame window
+        rb = _rb(R, group, cuda_device)
+        full = R.validate_batch(rb, R.make_params(), n_mels=n_mels)
+        mel_full, rec_full = full.mel.clone(), full.records.clone()
+        comp = R.validate_batch(rb, R.make_params(), n_mels=n_mels, compact=True)
+        T = comp.mel.shape[2]
+        assert T == int(R._lib.load().rho_b200_compact_frames(max(len(c) for c in group), 3000))
+        assert torch.equal(comp.records, rec_full)
+        assert torch.equal(comp.mel, mel_full[:, :, :T])
+        if T < 3000:
+            tail = mel_full[:, :, T:]
+            assert torch.equal(tail, comp.pad_value[:, None, None].expand_as(tail))
+
+
+@pytest.mark.parametrize("pad", [True, False])
+def test_validate_joined_items_vs_oracle(R, cuda_device, pad):
+    """Items of several segments through the whole front end (base_tts.py:912-926 then the features): join -> y, then the
+    fused kernel reads the finished y (resample + log-mel).  Against the oracle chain and against the kernel-per-stage path."""
+    from rho_tts_b200 import synth
+    rng = np.random.default_rng(4242)
+    items = []
+    for k in range(14):
+        n = int(rng.integers(1, 5))
+        segs = []
+        for _ in range(n):
+            L = int(rng.choice([300, 5000, 24000, 48017, 100001, 250000]))
+            if rng.integers(0, 7) == 0:
+                segs.append(rng.normal(0, 1e-4, L).astype(np.float32))           # all-silent segment -> fallback items
+            else:
+                segs.append(synth.make_clip_block(1, L, 3000 + 17 * k + len(segs))[0].numpy())
+        items.append(segs)
+    if pad:
+        items.append([synth.make_clip_block(1, 400000, 3900 + j)[0].numpy() for j in range(2)])   # > 30 s: truncated features
+    segs = [s for it in items for s in it]
+    first = np.concatenate([[0], np.cumsum([len(it) for it in items])]).astype(np.int32)
+    emb, ref = synth.make_embeddings(len(items))
+    rb = _rb(R, segs, cuda_device)
+    p = R.make_params()
+    out = R.validate_batch(rb, p, emb.to(cuda_device), ref.to(cuda_device), n_mels=80, pad_to_30s=pad, item_first_seg=first)
+    rec = out.records_host(); mel = out.mel.cpu().numpy()
+    audio = [out.audio.clip(i, int(rec["out_len"][i])).cpu().numpy() for i in range(len(items))]
+    c = oracle.derive_constants()
+    for i, it in enumerate(items):
+        o = oracle.smooth_segment_join(it, c)
+        assert int(rec["out_len"][i]) == o.audio.size and bool(rec["flags"][i] & 2) == o.fallback, i
+        assert_close(audio[i], o.audio, what=f"item {i} audio")
+        ratio, ok, fr, _ = oracle.sound_decay(o.audio, 0.3)
+        if fr > 1e-6:
+            assert bool(rec["ok"][i]) == ok
+        assert_close(rec["cosine"][i], oracle.cosine_similarity(ref.numpy(), emb[i].numpy()), what="cosine")
+        w16 = oracle.resample(o.audio)
+        if not pad and w16.size <= 200:
+            continue
+        m = oracle.log_mel(w16, 80, pad)
+        assert_close(mel[i][:, :m.shape[1]], m, what=f"mel item {i}")
+    stage = R.validate_batch(rb, p, emb.to(cuda_device), ref.to(cuda_device), n_mels=80, pad_to_30s=pad,
+                             item_first_seg=first, fuse=False)
+    rs = stage.records_host()
+    for f in ("start", "end", "out_len", "ok", "flags", "cosine", "n_segments"):
+        assert np.array_equal(rec[f], rs[f]), f
+    assert float((out.mel - stage.mel).abs().max()) < 1e-4
+
+
+def test_validate_host_ragged_joins(R, cuda_device):
+    """rho_b200_validate_host_ragged: ragged segments and items in host memory (BASELINE config C3's shape, small), several
+    chunks, with and without features, aligned and unaligned offsets -- against the device-resident calls, byte for byte."""
+    from rho_tts_b200 import synth
+    rng = np.random.default_rng(99)
+    seg_lens = rng.integers(2400, 260000, size=220).astype(np.int32)     # 29 M samples: two chunks
+    first = [0]
+    while first[-1] < len(seg_lens):
+        first.append(min(len(seg_lens), first[-1] + int(rng.integers(1, 5))))
+    first = np.asarray(first, np.int32)
+    n_items = len(first) - 1
+    p = R.make_params()
+    emb, ref = synth.make_embeddings(n_items)
+    for align in (32, 1):
+        padded = (seg_lens.astype(np.int64) + align - 1) // align * align + (0 if align > 1 else 3)
+        seg_off = np.concatenate([[0], np.cumsum(padded)])[:-1].astype(np.int64)
+        x = torch.zeros(int(seg_off[-1] + padded[-1]), dtype=torch.float32)
+        for s, L in enumerate(seg_lens):
+            x[seg_off[s]:seg_off[s] + L] = synth.make_clip_block(1, int(L), 5000 + s)[0]
+        x = x.pin_memory()
+        rb = R.RaggedBatch.from_list([x[seg_off[s]:seg_off[s] + int(L)] for s, L in enumerate(seg_lens)], cuda_device)
+        # (a) join + decay only (mel is NULL): what config C3 asks for
+        h = R.validate_host_ragged(x, seg_off, seg_lens, first, p, features=False)
+        d = R.join_batch(rb, first, p, want_seg_info=False)
+        rd = d.records_host()
+        _records_match(rd, h.records)
+        for i in range(n_items):
+            L = int(rd["out_len"][i])
+            assert torch.equal(d.audio.clip(i, L).cpu(), h.audio[h.y_offsets[i]:h.y_offsets[i] + L]), i
+        # (b) with features, complete rows and compact rows
+        dv = R.validate_batch(rb, p, emb.to(cuda_device), ref.to(cuda_device), item_first_seg=first)
+        rdv = dv.records_host()
+        hv = R.validate_host_ragged(x, seg_off, seg_lens, first, p, emb.pin_memory(), ref.pin_memory())
+        _records_match(rdv, hv.records)
+        assert torch.equal(dv.mel.cpu(), hv.mel) and torch.equal(dv.pad_value.cpu(), hv.pad_value)
+        hc = R.validate_host_ragged(x, seg_off, seg_lens, first, p, emb.pin_memory(), ref.pin_memory(), compact=True)
+        T = hc.mel.shape[2]
+        assert torch.equal(hc.mel, hv.mel[:, :, :T]) and torch.equal(hc.pad_value, hv.pad_value)
+        for i in range(0, n_items, 3):
+            L = int(rdv["out_len"][i])
+            assert torch.equal(dv.audio.clip(i, L).cpu(), hv.audio[hv.y_offsets[i]:hv.y_offsets[i] + L]), i
+
+
+def test_validate_host_odd_clip_length_and_unpadded_errors(R, cuda_device):
+    """clip_len % 4 != 0: the host rows are not 16-byte aligned, the entry point falls back to one copy per clip."""
+    from rho_tts_b200 import synth
+    n, L = 9, 30001
+    x = synth.make_clip_block(n, L, 13).pin_memory()
+    p = R.make_params()
+    y, _, rec_h = R.validate_host(x, p, None, None, 80)
+    out = R.post_process_batch(R.RaggedBatch.from_dense(x.to(cuda_device)), p)
+    rec_d = out.records_host(); rec_h = rec_h.numpy().view(R.REC_DTYPE).reshape(-1)
+    for f in ("start", "end", "out_len", "ok"):
+        assert np.array_equal(rec_d[f], rec_h[f]), f
+    for i in range(n):
+        k = int(rec_d["out_len"][i])
+        assert torch.equal(out.audio.clip(i, k).cpu(), y[i, :k])
+
+
+def test_host_calls_from_concurrent_threads(R, cuda_device):
+    """One shared handle, four threads in the host entry point at once (a provider instance is shared by concurrent
+    sessions, ui/state.py:85-87 of the reference): every caller gets its own streams / arena, results are unaffected."""
+    import threading
+    from rho_tts_b200 import synth
+    p = R.make_params()
+    xs = [synth.make_clip_block(40, 36000, 600 + t).pin_memory() for t in range(4)]
+    want = []
+    for x in xs:
+        y, mel, rec = R.validate_host(x, p, None, None, 80, mel=torch.empty((40, 80, 3000)).pin_memory())
+        want.append((y.clone(), mel.clone(), rec.clone()))
+    got = [None] * 4
+    errs = []
+
+    def work(t):
+        try:
+            for _ in range(3):
+                y, mel, rec = R.validate_host(xs[t], p, None, None, 80, mel=torch.empty((40, 80, 3000)).pin_memory())
+            got[t] = (y, mel, rec)
+        except Exception as e:          # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for t in range(4):
+        rw = want[t][2].numpy().view(R.REC_DTYPE).reshape(-1); rg = got[t][2].numpy().view(R.REC_DTYPE).reshape(-1)
+        _records_match(rw, rg)
+        assert torch.equal(want[t][1], got[t][1])
+        for i in range(40):
+            k = int(rw["out_len"][i])
+            assert torch.equal(want[t][0][i, :k], got[t][0][i, :k])
 
 
 # ----------------------------------------------------------------------------- size-independent properties
