@@ -5,19 +5,23 @@ Contract (driver):  python bench.py --gpus N --steps K --warmup W        (N > 1:
 One JSON line on rank 0.  A "step" is one pass of the hot path (post-process -> resample 24k->16k ->
 80-bin Whisper log-mel -> cosine) over one batch of synthetic clips per GPU.
 
-Workload at every N: BASELINE.json configs[1] per GPU -- 1000 synthetic 10 s 24 kHz clips, full
-post-process + 80-bin log-mel (30 s Whisper padding) + cosine vs a reference embedding.  Clips shard
-across GPUs with no data-path collective; each step ends with the one NCCL all-gather of the 48-byte
-per-clip records (weak scaling).
+Headline workload at every N: BASELINE.json configs[1] per GPU -- 1000 synthetic 10 s 24 kHz clips, full
+post-process + 80-bin log-mel (30 s Whisper padding) + cosine vs a reference embedding.  Clips shard across GPUs
+with no data-path collective; the 48-byte per-clip records of every step are gathered on all ranks by peer stores
+issued from the kernel that assembles them (rho_tts_b200.dist.RecordExchange; NCCL all-gather on a side stream where
+peer mapping is unavailable) -- weak scaling.
 
   value    : whole-job audio-seconds / second, inputs resident in HBM, device-timed (CUDA events, max over ranks)
   e2e      : the same through the host-buffer C-ABI call (rho_b200_validate_host): pinned host clips in,
-             processed audio + records + features back to pinned host memory, copies inside the timed region
+             processed audio + records + complete [80][3000] feature rows back in pinned host memory, copies inside
+             the timed region; next to it the copy-only ceiling of the box's host link measured in the same run
   roofline : dominant kernel, algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json
-  cpu_baseline : the numpy oracle (a port of the reference's torch/numpy path) on the host cores, bounded sample
+  configs  : the other BASELINE configurations in the same run -- C3 (ragged joins, 1 GPU), C4 (8000 clips per GPU,
+             128-bin, record gather), C5 (256 k clips split over the ranks, device-resident waves, strong scaling)
+  cpu_baseline : the reference's own CPU path on the host cores (baseline/_ref when it is installed, else the numpy
+             oracle port), bounded sample
 
---impl reference times that CPU oracle alone, on all host cores (the reference is pure Python: there is
-no oracle/_ref binary).
+--impl reference times that CPU path alone, on all host cores.
 """
 from __future__ import annotations
 
@@ -40,20 +44,60 @@ PAD_FRAMES = 3000
 EMB_DIM = 256
 METRIC = "audio-seconds processed/sec (postproc+log-mel+cosine)"
 UNIT = "audio-s/s"
+REF_INSTALL = os.path.join(ROOT, "baseline", "_ref")
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
 _CPU_CLIPS = None
 _CPU_EMB = None
+_CPU_REF = None          # (Ref object with the reference's unbound methods, WhisperFeatureExtractor, torchaudio) or None
+
+
+def _load_reference():
+    """The UNMODIFIED reference (baseline/_ref: `pip install --target` of /root/reference) plus the two
+    third-party functions its validation front end calls.  None when any of it is missing on this box."""
+    if not os.path.isdir(os.path.join(REF_INSTALL, "rho_tts")):
+        return None
+    try:
+        import logging
+        if REF_INSTALL not in sys.path:
+            sys.path.insert(0, REF_INSTALL)
+        import torch
+        import torchaudio
+        from transformers import WhisperFeatureExtractor
+        from rho_tts.base_tts import BaseTTS
+        logging.getLogger("rho_tts").setLevel(logging.ERROR)
+        logging.getLogger("rho_tts.base_tts").setLevel(logging.ERROR)
+
+        class Ref:      # the reference's own test idiom (tests/test_audio_processing.py:7-29): unbound methods on a plain object
+            device = "cpu"; silence_threshold_db = -50.0; crossfade_duration_sec = 0.05; trim_silence = True
+            fade_duration_sec = 0.02; force_sentence_split = True; inter_sentence_pause_sec = 0.1
+            sound_decay_threshold = 0.3; sample_rate = SR
+
+        for n in ("_trim_silence", "_remove_dc_offset", "_apply_fades", "_smooth_segment_join", "_validate_sound_decay",
+                  "_post_process_audio"):
+            setattr(Ref, n, getattr(BaseTTS, n))
+        return Ref(), WhisperFeatureExtractor(feature_size=N_MELS), torchaudio, torch
+    except Exception:       # noqa: BLE001
+        return None
 
 
 def _cpu_one(i: int):
-    """The oracle pipeline for one clip: what the reference does per clip on the CPU
-    (_smooth_segment_join([c]) -> _post_process_audio -> _validate_sound_decay, then the 16 kHz resample,
-    Whisper log-mel and the embedding cosine of the validation front end)."""
-    import oracle
+    """One clip through the CPU path, the way the reference handles it (base_tts.py:912-926, then the 16 kHz resample,
+    Whisper features and the embedding cosine of the validation front end)."""
     x = _CPU_CLIPS[i]
     emb, ref = _CPU_EMB
+    if _CPU_REF is not None:
+        import numpy as np
+        R, fe, torchaudio, torch = _CPU_REF
+        y = R._smooth_segment_join([torch.from_numpy(x.copy())])
+        y = R._post_process_audio(y)
+        ratio, ok = R._validate_sound_decay(y)
+        w16 = torchaudio.functional.resample(y.reshape(1, -1), SR, 16000)[0]
+        mel = fe(w16.numpy(), sampling_rate=16000, return_tensors="np")["input_features"][0]
+        cs = np.dot(ref, emb[i]) / (np.linalg.norm(ref) * np.linalg.norm(emb[i]))       # base_tts.py:341-344
+        return float(mel[0, 0]) + float(cs) + float(ratio) + y.shape[-1]
+    import oracle
     c = oracle.derive_constants()
     o = oracle.post_process_clip(x, c)
     w16 = oracle.resample(o["audio"])
@@ -66,20 +110,27 @@ def _cpu_worker_init():
     try:
         from threadpoolctl import threadpool_limits
         threadpool_limits(1)
-    except Exception:
+    except Exception:       # noqa: BLE001
         pass
     os.environ["OMP_NUM_THREADS"] = "1"
+    if _CPU_REF is not None:
+        _CPU_REF[3].set_num_threads(1)
 
 
 class CpuArm:
-    """Bounded-sample CPU timing of the oracle on all host cores (fork pool, one BLAS thread each)."""
+    """Bounded-sample CPU timing on all host cores (fork pool, one thread per worker): the reference's own
+    implementation when baseline/_ref is present (`kind: reference`), else the numpy oracle port (`kind: port`)."""
 
     def __init__(self, n_clips: int):
-        global _CPU_CLIPS, _CPU_EMB
+        global _CPU_CLIPS, _CPU_EMB, _CPU_REF
         import multiprocessing as mp
+        import torch
+        torch.set_num_threads(1)        # no OpenMP pool in the parent before the fork
         from rho_tts_b200 import synth
         self.cores = os.cpu_count() or 1
         self.n_clips = n_clips
+        _CPU_REF = None if os.environ.get("RHO_BENCH_CPU_PORT") else _load_reference()
+        self.kind = "reference" if _CPU_REF is not None else "port"
         x = synth.make_clip_block(n_clips, CLIP_LEN, 1234 + 1)           # CPU generator, config C2's seed
         emb, ref = synth.make_embeddings(n_clips)
         _CPU_CLIPS = [x[i].numpy() for i in range(n_clips)]
@@ -97,27 +148,30 @@ class CpuArm:
 
     @property
     def sample(self) -> str:
-        return (f"{self.n_clips} x {CLIP_SECONDS:.0f} s clips of the C2 workload per step "
-                f"(numpy oracle: post-process+decay, resample 24k->16k, 80-bin log-mel 30 s pad, cosine)")
+        what = ("rho_tts BaseTTS._smooth_segment_join -> _post_process_audio -> _validate_sound_decay, torchaudio resample "
+                "24k->16k, transformers WhisperFeatureExtractor(80, 30 s pad), numpy cosine" if self.kind == "reference" else
+                "numpy oracle port: post-process+decay, resample 24k->16k, 80-bin log-mel 30 s pad, cosine")
+        return f"{self.n_clips} x {CLIP_SECONDS:.0f} s clips of the C2 workload per step, one worker per core ({what})"
 
 
 def run_reference_arm(args, rank: int, world: int) -> None:
     if rank != 0:
         return
-    n_clips = max(2 * (os.cpu_count() or 1), 32)
+    n_clips = max(4 * (os.cpu_count() or 1), 64)
     arm = CpuArm(n_clips)
     for _ in range(max(args.warmup, 1)):
         arm.step()
-    times = [arm.step() for _ in range(args.steps)]
+    steps = max(1, min(args.steps, 20))
+    times = [arm.step() for _ in range(steps)]
     arm.close()
     total = sum(times)
-    value = n_clips * CLIP_SECONDS * args.steps / total
+    value = n_clips * CLIP_SECONDS * steps / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": arm.sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -130,8 +184,7 @@ def workload_config(n_gpus: int, clips: int = 1000) -> dict:
                     f"log-mel (30 s pad) + cosine vs reference embedding",
         "clips_per_gpu": clips, "clip_seconds": CLIP_SECONDS, "sample_rate": SR, "n_mels": N_MELS,
         "pad_frames": PAD_FRAMES, "emb_dim": EMB_DIM,
-        "parallelism": f"clip-sharded x{n_gpus}, one NCCL all-gather of 48 B records per step" if n_gpus > 1
-        else "single GPU",
+        "parallelism": f"clip-sharded x{n_gpus}, per-step gather of the 48 B records" if n_gpus > 1 else "single GPU",
         "l2_policy": "inputs larger than L2 (0.96 GB of clips per step vs 126 MB L2)",
     }
 
@@ -216,11 +269,120 @@ def load_traffic(kernel: str):
         return None
 
 
+def fused_alg_bytes(rec, n_mels: int, pad: bool, fused_fills: bool) -> dict:
+    """Algorithmic HBM bytes per launch of the kernels of the one-segment-item path:
+    4 B per input sample read by the scan; x[start:end] read + y written + the log-mel frames that see signal written by
+    the fused kernel (+ the constant of the zero-padding frames when this build lets it write them); the normaliser
+    reads the frames with signal (its writes are data dependent, a few per cent: not counted)."""
+    import numpy as np
+    out_len = rec["out_len"].astype(np.int64)
+    len16 = (2 * out_len + 2) // 3
+    n = len(out_len)
+    if pad:
+        t_real = np.minimum(PAD_FRAMES, np.maximum(2, (np.minimum(len16, PAD_FRAMES * 160) + 200 + 159) // 160))
+        t_lo = np.minimum(PAD_FRAMES, (t_real + 3) // 4 * 4)
+        fill = 4.0 * n_mels * float((PAD_FRAMES - t_lo).sum())
+        full = 4.0 * n_mels * PAD_FRAMES * n
+    else:
+        t_real = np.where(len16 > 200, len16 // 160, 0)
+        fill, full = 0.0, 4.0 * n_mels * float(t_real.sum())
+    mel_real = 4.0 * n_mels * float(t_real.sum())
+    s_out = 4.0 * float(out_len.sum())
+    return {"k_fused_features": 2 * s_out + mel_real + (fill if fused_fills else 0.0),
+            "k_logmel_norm": mel_real if (fused_fills or not pad) else full,
+            "_mel_full": full, "_s_out": s_out}
+
+
+def kernel_table(prof: dict, alg: dict, prof_steps: int, peak: float) -> dict:
+    kernels = {}
+    for name, (tot_ms, cnt) in prof.items():
+        per = tot_ms / cnt
+        k = {"ms_per_launch": per, "launches_per_step": cnt / prof_steps}
+        if name in alg:
+            k["algorithmic_bytes"] = alg[name]
+            k["achieved_gbs"] = alg[name] / (per * 1e-3) / 1e9
+            k["frac"] = k["achieved_gbs"] / peak
+        kernels[name] = k
+    return kernels
+
+
+def dominant_roofline(kernels: dict, alg: dict, peak: float, peak_src: str) -> dict:
+    dominant = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches_per_step"])
+    dk = kernels[dominant]
+    return {"kernel": dominant, "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s",
+            "frac": dk["frac"], "traffic": load_traffic(dominant), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": dk["algorithmic_bytes"], "ms_per_launch": dk["ms_per_launch"],
+            "share_of_step": dk["ms_per_launch"] * dk["launches_per_step"] /
+            sum(v["ms_per_launch"] * v["launches_per_step"] for v in kernels.values())}
+
+
+class DeviceTimer:
+    """K steps bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks."""
+
+    def __init__(self, dev, dist):
+        self.dev, self.dist = dev, dist
+
+    def run(self, step, steps: int, warmup: int, finish=None):
+        import torch
+        for _ in range(warmup):
+            step()
+        if finish:
+            finish()
+        torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(steps):
+            step()
+        if finish:
+            finish()                        # e.g. the wait for the last step's gathered records
+        ev1.record()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if self.dist is not None:
+            self.dist.barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item()), t0, t1
+
+
+def make_fixed_clips(n: int, seed: int, dev):
+    """n x 10 s clips generated on the owning GPU in blocks of 1000 (the generator's temporaries stay small)."""
+    import torch
+    from rho_tts_b200 import synth
+    if n <= 1000:
+        return synth.make_clip_block(n, CLIP_LEN, seed, device=dev)
+    x = torch.empty((n, CLIP_LEN), dtype=torch.float32, device=dev)
+    for b0 in range(0, n, 1000):
+        nb = min(1000, n - b0)
+        x[b0:b0 + nb] = synth.make_clip_block(nb, CLIP_LEN, seed + 977 * (b0 // 1000), device=dev)
+    return x
+
+
+def make_ragged_c3(n: int, seed: int, dev, R):
+    """C3: n clips with lengths U[1, 30] s, the C2 clip model; groups of similar length share one generator call."""
+    import numpy as np
+    from rho_tts_b200 import synth
+    lens = synth.make_ragged_lengths(n, seed)
+    rb = R.RaggedBatch.empty_like_lengths(lens, dev)
+    order = np.argsort(lens)
+    for g0 in range(0, n, 50):
+        idx = order[g0:g0 + 50]
+        blk = synth.make_clip_block(len(idx), int(lens[idx].max()), seed * 7919 + g0, device=dev)
+        for j, i in enumerate(idx):
+            rb.clip(int(i)).copy_(blk[j, :int(lens[i])])
+    return rb, synth.make_item_partition(n, seed)
+
+
 def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # CPU leg first, before CUDA is initialised in this process (fork pool)
-        arm = CpuArm(max(2 * (os.cpu_count() or 1), 32))
+        arm = CpuArm(max(4 * (os.cpu_count() or 1), 64))
         arm.step()
         reps = 0
         t_total = 0.0
@@ -229,12 +391,13 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
             reps += 1
         arm.close()
         cpu_baseline = {"value": arm.n_clips * CLIP_SECONDS * reps / t_total, "unit": UNIT, "cores": arm.cores,
-                        "kind": "port", "sample": f"{reps} passes over " + arm.sample}
+                        "kind": arm.kind, "sample": f"{reps} passes over " + arm.sample}
 
     import numpy as np
     import torch
     import rho_tts_b200 as R
     from rho_tts_b200 import synth
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device; the B200 path has no CPU fallback")
@@ -249,135 +412,295 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
         # NCCL's version / debug banner goes to stderr: stdout carries the one JSON line only
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+    timer = DeviceTimer(dev, dist)
+    peak, peak_src = load_peaks()
+    handle = R._lib.Handle.get(local_rank)
+    fused_fills = bool(R._lib.load().rho_b200_build_flags() & 1)   # who writes the zero-padding frames' constant
+    p = R.make_params()
+    configs = {}
+    want = set(args.configs.split(",")) if args.configs else set()
 
+    # =================================================================== C2 (headline): 1000 x 10 s per GPU, 80 bins
     n = args.clips
-    x = synth.make_clip_block(n, CLIP_LEN, 0xB200 + rank, device=dev)           # generated on the owning GPU
+    x = make_fixed_clips(n, 0xB200 + rank, dev)                                  # generated on the owning GPU
     emb, ref = synth.make_embeddings(n, EMB_DIM, 4321 + rank, device=dev)
     rb = R.RaggedBatch.from_dense(x)
-    p = R.make_params()
     plan = R.ValidatePlan(rb, np.arange(n + 1, dtype=np.int32), p, N_MELS, True)
-    handle = R._lib.Handle.get(local_rank)
-    gathered = torch.empty((world * n, 48), dtype=torch.uint8, device=dev) if world > 1 else None
+    ex = R.dist.RecordExchange(local_rank, n, force_nccl=bool(os.environ.get("RHO_BENCH_NCCL_GATHER"))) if world > 1 else None
+    gather_mode = ex.mode if ex else "none"
+    gather_why = ex.why if ex else ""
 
     def step():
         out = plan.run(rb, emb, ref)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out.records)      # the path's only collective
+        if ex:
+            ex.after_step(out.records)              # p2p: flow control only (the stores are in the kernel); nccl: side stream
         return out
+
+    gathered_last = {}
+
+    def finish():
+        if ex:
+            gathered_last["rec"] = ex.gathered()    # every step's gather completes inside the timed region
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    l0 = None
+
+    def step_counted():
+        return step()
+
     for _ in range(max(args.warmup, 3)):
-        out = step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+        step()
+    finish()
     torch.cuda.synchronize()
     l0 = handle.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_host0 = time.perf_counter()
-    ev0.record()
-    for _ in range(args.steps):
-        out = step()
-    ev1.record()
-    torch.cuda.synchronize()
-    t_host1 = time.perf_counter()
-    if world > 1:
-        dist.barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total, t_host0, t_host1 = timer.run(step_counted, args.steps, 0, finish)
     launches = handle.launch_count - l0
-
+    out = plan.run(rb, emb, ref) if ex is None else step()
+    if ex:
+        finish()
+    torch.cuda.synchronize()
+    rec = out.records_host()
+    gather_ok = None
+    if ex:
+        g = gathered_last["rec"].cpu().numpy().view(R.REC_DTYPE).reshape(world, n)
+        gather_ok = bool(g[rank].tobytes() == rec.tobytes())
+        cnt = torch.tensor([int(g["out_len"].astype(np.int64).sum())], dtype=torch.int64, device=dev)
+        lo, hi = cnt.clone(), cnt.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        gather_ok = gather_ok and int(lo.item()) == int(hi.item())      # every rank holds the same gathered block
+        ex.close()                                  # the profiling / e2e passes below do not exchange records
+        ex = None
     audio_s_per_rank_step = n * CLIP_SECONDS
     value = world * audio_s_per_rank_step * args.steps / (ms_total * 1e-3)
 
     # ---- per-kernel device time (separate pass, events around every kernel on the launching stream)
-    rec = out.records_host()
     prof_steps = max(1, min(args.steps, 20))
     handle.profile_begin()
     for _ in range(prof_steps):
         plan.run(rb, emb, ref)
     prof = handle.profile_end()
-    sum_in = float(n) * CLIP_LEN
-    sum_out = float(rec["out_len"].astype(np.int64).sum())
-    len16 = (2 * rec["out_len"].astype(np.int64) + 2) // 3
-    sum16 = float(len16.sum())
-    t_real = np.minimum(PAD_FRAMES, np.maximum(2, (len16 + 200 + 159) // 160))
-    sum_mel_real = float(t_real.sum()) * N_MELS
-    fused_fills = bool(R._lib.load().rho_b200_build_flags() & 1)   # who writes the zero-padding frames' constant
-    t_lo = np.minimum(PAD_FRAMES, (t_real + 3) // 4 * 4)
-    fill_bytes = 4.0 * N_MELS * float((PAD_FRAMES - t_lo).sum())
-    alg = {
-        "k_scan": 4 * sum_in,
-        "k_gather": 8 * sum_out,
-        "k_resample3to2": 4 * sum_out + 4 * sum16,
-        "k_logmel_frames": 4 * sum16 + 4 * sum_mel_real,
-        # the normaliser reads every frame with signal and writes back only what the clamp changes (data-dependent, a few
-        # per cent: not counted) -- plus the padding constant when the fused kernel does not write it
-        "k_logmel_norm": 4 * sum_mel_real if fused_fills else 4.0 * N_MELS * PAD_FRAMES * n,
-        # fused apply + resample + log-mel: x[start:end] in, y out, raw log-mel frames out (+ the padding constant)
-        "k_fused_features": 8 * sum_out + 4 * sum_mel_real + (fill_bytes if fused_fills else 0.0),
-    }
-    peak, peak_src = load_peaks()
-    kernels = {}
-    for name, (tot_ms, cnt) in prof.items():
-        per = tot_ms / cnt
-        k = {"ms_per_launch": per, "launches_per_step": cnt / prof_steps}
-        if name in alg:
-            k["algorithmic_bytes"] = alg[name]
-            k["achieved_gbs"] = alg[name] / (per * 1e-3) / 1e9
-            k["frac"] = k["achieved_gbs"] / peak
-        kernels[name] = k
-    dominant = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["ms_per_launch"])
-    dk = kernels[dominant]
-    roofline = {"kernel": dominant, "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": dk["frac"], "traffic": load_traffic(dominant), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": dk["algorithmic_bytes"], "ms_per_launch": dk["ms_per_launch"],
-                "share_of_step": dk["ms_per_launch"] * dk["launches_per_step"] /
-                sum(v["ms_per_launch"] * v["launches_per_step"] for v in kernels.values())}
-    pipeline_bytes = 4 * sum_in + 4 * sum_out + 4.0 * N_MELS * PAD_FRAMES * n + 48 * n + 4 * EMB_DIM * n
+    alg = fused_alg_bytes(rec, N_MELS, True, fused_fills)
+    alg["k_scan"] = 4.0 * n * CLIP_LEN
+    kernels = kernel_table(prof, alg, prof_steps, peak)
+    roofline = dominant_roofline(kernels, alg, peak, peak_src)
+    pipeline_bytes = 4.0 * n * CLIP_LEN + alg["_s_out"] + alg["_mel_full"] + 48 * n + 4 * EMB_DIM * n
     pipeline = {"algorithmic_bytes_per_step": pipeline_bytes,
                 "achieved_gbs": pipeline_bytes / (ms_total / args.steps * 1e-3) / 1e9,
                 "frac_of_hbm_peak": pipeline_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak}
+    # compact feature rows (RHO_V_COMPACT_PAD): the frames that can see signal + one constant per clip
+    plan_c = R.ValidatePlan(rb, np.arange(n + 1, dtype=np.int32), p, N_MELS, True, compact=True)
+    ms_c, _, _ = timer.run(lambda: plan_c.run(rb, emb, ref), max(5, args.steps // 4), 3)
+    compact = {"value": world * audio_s_per_rank_step * max(5, args.steps // 4) / (ms_c * 1e-3), "unit": UNIT,
+               "frames_per_row": int(plan_c.T), "note": "rows of the frames that can see signal + pad_value per clip"}
+    del plan_c
 
-    # ---- end to end through the HOST-buffer C ABI (pinned host memory, copies inside the timed region)
+    # =================================================================== e2e: HOST buffers through the C ABI
     e2e = None
     if not args.no_e2e:
+        from tools.link_ceiling import measure as link_measure
         xh = x.cpu().pin_memory()
         embh, refh = emb.cpu().pin_memory(), ref.cpu().pin_memory()
         yh = torch.empty_like(xh).pin_memory()
         melh = torch.empty((n, N_MELS, PAD_FRAMES), dtype=torch.float32).pin_memory()
         rech = torch.empty((n, 48), dtype=torch.uint8).pin_memory()
         e2e_steps = max(1, min(args.steps, 10))
-        res = {}
-        for label, mel_buf in (("all results to host", melh), ("features stay in HBM", None)):
+
+        def host_timed(fn):
             for _ in range(2):
-                R.validate_host(xh, p, embh, refh, N_MELS, y=yh, mel=mel_buf, rec=rech, device=local_rank)
+                fn()
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
-                R.validate_host(xh, p, embh, refh, N_MELS, y=yh, mel=mel_buf, rec=rech, device=local_rank)
+                fn()
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            res[label] = world * audio_s_per_rank_step * e2e_steps / float(dt.item())
-        h2d = xh.numel() * 4 + embh.numel() * 4 + refh.numel() * 4
-        d2h = yh.numel() * 4 + rech.numel() + melh.numel() * 4
-        e2e = {"value": res["all results to host"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": e2e_steps, "api": "rho_b200_validate_host (pinned host buffers, chunked copy/compute overlap)",
-               "timer": "host perf_counter around the synchronous C call, max over ranks",
-               "value_features_stay_in_hbm": res["features stay in HBM"],
-               "d2h_bytes_per_step_features_stay_in_hbm": yh.numel() * 4 + rech.numel(),
-               "host_numa_binding": (f"rank 0 bound to {len(numa_cpus)} CPUs local to its GPU (NVML)" if numa_cpus
-                                     else "none")}
+            return float(dt.item())
+
+        dt_full = host_timed(lambda: R.validate_host(xh, p, embh, refh, N_MELS, y=yh, mel=melh, rec=rech, device=local_rank))
         # the host path must agree with the device path
         rh = rech.numpy().view(R.REC_DTYPE).reshape(-1)
         assert np.array_equal(rh["out_len"], rec["out_len"]) and np.array_equal(rh["ok"], rec["ok"])
+        assert torch.equal(melh[::97], out.mel[::97].cpu()), "host feature rows differ from the device path"
+        # compact rows on the host as well (what an embedder that feeds its own encoder input buffer would take)
+        seg_off = np.arange(n, dtype=np.int64) * CLIP_LEN
+        seg_len = np.full(n, CLIP_LEN, dtype=np.int32)
+        first = np.arange(n + 1, dtype=np.int32)
+        T_c = int(R._lib.load().rho_b200_compact_frames(CLIP_LEN, PAD_FRAMES))
+        melc = torch.empty((n, N_MELS, T_c), dtype=torch.float32).pin_memory()
+        dt_comp = host_timed(lambda: R.validate_host_ragged(xh.reshape(-1), seg_off, seg_len, first, p, embh, refh, N_MELS,
+                                                            compact=True, y=yh.reshape(-1), mel=melc, device=local_rank))
+        h2d = xh.numel() * 4 + embh.numel() * 4 + refh.numel() * 4
+        d2h_link = yh.numel() * 4 + rech.numel() + melc.numel() * 4 + 4 * n     # what crosses the link
+        link = link_measure(dev, h2d, d2h_link, reps=3, dist=dist)
+        ceiling = world * audio_s_per_rank_step / link["seconds_per_step_copy_only"]
+        e2e_value = world * audio_s_per_rank_step * e2e_steps / dt_full
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_link,
+               "steps": e2e_steps,
+               "api": "rho_b200_validate_host: pinned host clips in; processed audio, records and complete [80][3000] "
+                      "feature rows back in pinned host memory (only the frames that can see signal cross the link, the "
+                      "constant tail of every row is written by host threads from the per-clip value)",
+               "result_bytes_in_host_memory_per_step": yh.numel() * 4 + rech.numel() + melh.numel() * 4,
+               "timer": "host perf_counter around the synchronous C call, max over ranks",
+               "value_compact_rows": world * audio_s_per_rank_step * e2e_steps / dt_comp,
+               "link_ceiling_gbs": {"h2d": link["h2d_gbs_concurrent"], "d2h": link["d2h_gbs_concurrent"],
+                                    "h2d_alone": link["h2d_gbs_alone"], "d2h_alone": link["d2h_gbs_alone"]},
+               "link_ceiling_value": ceiling, "frac_of_link_ceiling": e2e_value / ceiling,
+               "link_ceiling_note": "copy-only run of the same bytes per step on this box in this run (tools/link_ceiling.py): "
+                                    "per rank, all ranks at once, max over ranks",
+               "host_numa_binding": (f"rank 0 bound to {len(numa_cpus)} CPUs local to its GPU (NVML)" if numa_cpus
+                                     else "none")}
+        del xh, yh, melh, melc
+    del plan, rb, x, out
+    torch.cuda.empty_cache()
+
+    # =================================================================== C4 / C5: 8000 clips per GPU
+    if "c4" in want or "c5" in want:
+        n4 = 8000
+        x4 = make_fixed_clips(n4, 0xC400 + 31 * rank, dev)
+        emb4, ref4 = synth.make_embeddings(n4, EMB_DIM, 99 + rank, device=dev)
+        rb4 = R.RaggedBatch.from_dense(x4)
+        first4 = np.arange(n4 + 1, dtype=np.int32)
+        if "c4" in want:
+            plan4 = R.ValidatePlan(rb4, first4, p, 128, True)
+            ex4 = R.dist.RecordExchange(local_rank, n4) if world > 1 else None
+
+            def step4():
+                o = plan4.run(rb4, emb4, ref4)
+                if ex4:
+                    ex4.after_step(o.records)
+                return o
+
+            g4 = {}
+
+            def fin4():
+                if ex4:
+                    g4["rec"] = ex4.gathered()
+            k4 = 5
+            ms4, _, _ = timer.run(step4, k4, 2, fin4)
+            o4 = step4(); fin4(); torch.cuda.synchronize()
+            rec4 = o4.records_host()
+            if ex4:
+                gg = g4["rec"].cpu().numpy().view(R.REC_DTYPE).reshape(world, n4)
+                assert gg[rank].tobytes() == rec4.tobytes(), "C4: gathered records differ from the local ones"
+                ex4.close()
+            handle.profile_begin()
+            plan4.run(rb4, emb4, ref4)
+            prof4 = handle.profile_end()
+            alg4 = fused_alg_bytes(rec4, 128, True, fused_fills)
+            alg4["k_scan"] = 4.0 * n4 * CLIP_LEN
+            kern4 = kernel_table(prof4, alg4, 1, peak)
+            configs["C4"] = {
+                "workload": f"{world} x {n4} x 10 s clips ({world * n4} clips), post-process + 128-bin log-mel (30 s pad) + "
+                            f"cosine, per-step gather of all records on every rank ({ex4.mode if ex4 else 'single GPU'})"
+                            + (" -- BASELINE configs[3] at N = 8" if world == 8 else ""),
+                "value": world * n4 * CLIP_SECONDS * k4 / (ms4 * 1e-3), "unit": UNIT, "ms_per_step": ms4 / k4, "steps": k4,
+                "scaling": "weak", "clips_per_gpu": n4, "roofline": dominant_roofline(kern4, alg4, peak, peak_src),
+                "kernels_ms": {k: round(v["ms_per_launch"] * v["launches_per_step"], 4) for k, v in kern4.items()},
+                "accept_rate": float(rec4["ok"].mean())}
+            del plan4, o4
+            torch.cuda.empty_cache()
+        if "c5" in want:
+            total5 = 256000
+            lo5, hi5 = R.dist.shard_range(total5, rank, world)
+            mine = hi5 - lo5
+            waves = [(w0, min(n4, mine - w0)) for w0 in range(0, mine, n4)]
+            plan5 = R.ValidatePlan(rb4, first4, p, N_MELS, True)
+            plans_tail = {}
+            ex5 = R.dist.RecordExchange(local_rank, n4) if world > 1 else None
+
+            def run_waves():
+                for _, cnt in waves:
+                    if cnt == n4:
+                        o = plan5.run(rb4, emb4, ref4)
+                    else:                       # the ragged last wave of this rank
+                        if cnt not in plans_tail:
+                            sub = R.RaggedBatch.from_dense(x4[:cnt])
+                            plans_tail[cnt] = (sub, R.ValidatePlan(sub, np.arange(cnt + 1, dtype=np.int32), p, N_MELS, True))
+                        sub, pl = plans_tail[cnt]
+                        o = pl.run(sub, emb4[:cnt], ref4)
+                    if ex5:
+                        ex5.after_step(o.records)
+
+            def fin5():
+                if ex5:
+                    ex5.gathered()
+            ms5, _, _ = timer.run(run_waves, 1, 1, fin5)
+            if ex5:
+                ex5.close()
+            configs["C5"] = {
+                "workload": f"{total5} x 10 s clips (2.56 M audio-s, ~711 h) split over {world} rank(s) with dist.shard_range, "
+                            f"processed in device-resident waves of {n4} clips (each wave re-reads this rank's resident 7.7 GB "
+                            f"wave buffer, 60x L2), post-process + 80-bin log-mel (30 s pad) + cosine, records gathered per wave",
+                "value": total5 * CLIP_SECONDS / (ms5 * 1e-3), "unit": UNIT, "seconds": ms5 * 1e-3, "scaling": "strong",
+                "clips_per_rank": mine, "waves_per_rank": len(waves)}
+            del plan5, plans_tail
+        del rb4, x4
+        torch.cuda.empty_cache()
+
+    # =================================================================== C3: ragged joins, one GPU
+    if "c3" in want and world == 1:
+        rb3, first3 = make_ragged_c3(4000, 1234 + 3, dev, R)
+        n_items3 = len(first3) - 1
+        audio3 = rb3.total_samples / SR
+        emb3, ref3 = synth.make_embeddings(n_items3, EMB_DIM, 7, device=dev)
+        k3 = 5
+        msj, _, _ = timer.run(lambda: R.join_batch(rb3, first3, p, want_seg_info=False), k3, 2)
+        oj = R.join_batch(rb3, first3, p, want_seg_info=False)
+        recj = oj.records_host()
+        handle.profile_begin()
+        R.join_batch(rb3, first3, p, want_seg_info=False)
+        profj = handle.profile_end()
+        s_in3, s_out3 = 4.0 * rb3.total_samples, 4.0 * float(recj["out_len"].astype(np.int64).sum())
+        kernj = kernel_table(profj, {"k_scan": s_in3, "k_gather": s_in3 + s_out3}, 1, peak)
+        del oj
+        plan3 = R.ValidatePlan(rb3, first3, p, N_MELS, False)
+        msv, _, _ = timer.run(lambda: plan3.run(rb3, emb3, ref3), k3, 2)
+        handle.profile_begin()
+        plan3.run(rb3, emb3, ref3)
+        profv = handle.profile_end()
+        len16 = (2 * recj["out_len"].astype(np.int64) + 2) // 3
+        mel3 = 4.0 * N_MELS * float((len16 // 160).sum())
+        kernv = kernel_table(profv, {"k_scan": s_in3, "k_gather": s_in3 + s_out3, "k_fused_features": s_out3 + mel3,
+                                     "k_logmel_norm": mel3}, 1, peak)
+        c3 = {"workload": f"4000 ragged clips of 1..30 s ({rb3.total_samples * 4 / 1e9:.2f} GB, {audio3:.0f} audio-s) in "
+                          f"{n_items3} items of 2..6 segments",
+              "join": {"what": "trim + DC + crossfade joins + pauses + fades + decay check into batch outputs (BASELINE configs[2])",
+                       "value": audio3 * k3 / (msj * 1e-3), "unit": UNIT, "ms_per_step": msj / k3,
+                       "roofline": dominant_roofline(kernj, {"k_scan": 1, "k_gather": 1}, peak, peak_src)},
+              "join_and_features": {"what": "the same items through the whole front end: join -> resample + 80-bin log-mel "
+                                            "(unpadded) read straight from the joined audio -> cosine",
+                                    "value": audio3 * k3 / (msv * 1e-3), "unit": UNIT, "ms_per_step": msv / k3,
+                                    "kernels_ms": {k: round(v["ms_per_launch"] * v["launches_per_step"], 4) for k, v in kernv.items()},
+                                    "frac": {k: round(v["frac"], 3) for k, v in kernv.items() if "frac" in v}}}
+        del plan3
+        torch.cuda.empty_cache()
+        if not args.no_e2e:
+            # C3 end to end: ragged segments in pinned host memory -> joined items + records back in host memory
+            lens3 = rb3.h_lengths.astype(np.int32)
+            off3 = rb3.h_offsets.astype(np.int64)
+            xh3 = rb3.data.cpu().pin_memory()
+            y_off3, cap3, y_total3 = R.host_item_layout(lens3, first3, p)
+            yh3 = torch.empty(y_total3, dtype=torch.float32).pin_memory()
+            R.validate_host_ragged(xh3, off3, lens3, first3, p, features=False, y=yh3, device=local_rank)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps3 = 2
+            for _ in range(reps3):
+                h3 = R.validate_host_ragged(xh3, off3, lens3, first3, p, features=False, y=yh3, device=local_rank)
+            dt3 = (time.perf_counter() - t0) / reps3
+            assert np.array_equal(h3.records["out_len"], recj["out_len"]) and np.array_equal(h3.records["ok"], recj["ok"])
+            c3["join"]["e2e"] = {"value": audio3 / dt3, "unit": UNIT, "h2d_bytes_per_step": int(xh3.numel() * 4),
+                                 "d2h_bytes_per_step": int(y_total3 * 4 + 48 * n_items3),
+                                 "api": "rho_b200_validate_host_ragged (mel = NULL)"}
+            del xh3, yh3
+        configs["C3"] = c3
+        del rb3
+        torch.cuda.empty_cache()
 
     sampler.stop()
     sampler.join(timeout=1.0)
@@ -392,6 +715,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
             "roofline": roofline, "pipeline_roofline": pipeline, "kernels": kernels,
             "cpu_baseline": cpu_baseline, "impl": "rho_tts_b200",
             "accept_rate": float(rec["ok"].mean()),
+            "record_gather": {"mode": gather_mode, "verified": gather_ok, "fallback_reason": gather_why or None},
+            "value_compact_rows": compact, "configs": configs,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -405,6 +730,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips", type=int, default=1000, help="clips per GPU per step (C2: 1000)")
+    ap.add_argument("--configs", default="c3,c4,c5", help="other BASELINE configurations to run in the same job ('' = none)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -464,7 +464,9 @@ def validate_host_ragged(x: torch.Tensor, seg_offsets: np.ndarray, seg_lengths: 
     if y is None:
         y = torch.empty(max(y_total, 1), dtype=torch.float32).pin_memory()
     assert y.numel() >= y_total
-    rec = np.zeros(n_items, dtype=REC_DTYPE)
+    # pinned: a device -> pageable-host copy would block the enqueuing thread and serialise the chunk pipeline
+    rec_t = torch.zeros((max(n_items, 1), 48), dtype=torch.uint8).pin_memory()
+    rec = rec_t.numpy().view(REC_DTYPE).reshape(-1)[:n_items]
     pad_frames = 3000 if pad_to_30s else 0
     pad_value = None
     T = 0
@@ -484,5 +486,5 @@ def validate_host_ragged(x: torch.Tensor, seg_offsets: np.ndarray, seg_lengths: 
         h.ptr, _ptr(x), ctypes.c_void_p(seg_off.ctypes.data), ctypes.c_void_p(seg_len.ctypes.data), n_seg,
         ctypes.c_void_p(first.ctypes.data), n_items, ctypes.byref(p), _ptr(y), ctypes.c_void_p(y_off.ctypes.data),
         int(n_mels), pad_frames, _ptr(mel), int(T), _ptr(pad_value), _ptr(emb), _ptr(ref), dim,
-        ctypes.c_void_p(rec.ctypes.data)), "validate_host_ragged")
+        _ptr(rec_t)), "validate_host_ragged")
     return HostRaggedOutput(y, y_off, rec, mel, pad_value)
