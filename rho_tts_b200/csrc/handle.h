@@ -3,6 +3,7 @@
 #include <map>
 #include <mutex>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX 3: a no-op unless a tool (ncu --nvtx, nsys) injects itself
 #include "kernels.h"
 
 namespace rho {
@@ -28,7 +29,16 @@ struct DeviceGuard {
   DeviceGuard(const DeviceGuard&) = delete;
   DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
+// NVTX range named after the entry point, open for the duration of the call (tracing is a net-new
+// deliverable).  Kernel launches get a nested range named after the kernel (LaunchCtx::begin / end).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 #define RHO_ON_DEVICE(h)                                            \
+  rho::NvtxRange _nvtx(__func__);                                   \
   if (!(h)) return rho::fail(RHO_ERR_INVALID, "handle is NULL");    \
   rho::DeviceGuard _guard((h)->device);                             \
   if (_guard.err != cudaSuccess) return rho::cuda_fail(_guard.err, "cudaSetDevice")

@@ -32,7 +32,9 @@ struct HostCtx {
   cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
   void* arena = nullptr;      size_t arena_bytes = 0;      // device
   void* pinned = nullptr;     size_t pinned_bytes = 0;     // host staging: per-chunk metadata in, pad values out
-  std::vector<cudaEvent_t> ev_out;                          // one per chunk (blocking-sync: fill threads sleep on them)
+  std::vector<cudaEvent_t> ev_out;                          // one per chunk: everything of the chunk is in host memory
+  std::vector<cudaEvent_t> ev_small;                        // one per chunk: its records and pad values are (blocking-sync:
+                                                            // the fill threads sleep on them)
   cudaEvent_t ev_in[HC_SLOTS] = {}, ev_done[HC_SLOTS] = {};
   bool ok = false;
 };
@@ -45,6 +47,7 @@ void host_ctx_destroy(HostCtx* c) {
   if (c->arena) cudaFree(c->arena);
   if (c->pinned) cudaFreeHost(c->pinned);
   for (cudaEvent_t e : c->ev_out) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_small) cudaEventDestroy(e);
   for (int s = 0; s < HC_SLOTS; ++s) {
     if (c->ev_in[s]) cudaEventDestroy(c->ev_in[s]);
     if (c->ev_done[s]) cudaEventDestroy(c->ev_done[s]);
@@ -113,6 +116,9 @@ void fill_f32(float* p, int64_t n, float v) {
 #endif
 }
 
+// developer switches for tools/e2e_sweep.py (timing experiments only)
+bool debug_skip_fill() { static const bool v = getenv("RHO_HOST_DEBUG_SKIP_FILL") != nullptr; return v; }
+
 int fill_threads() {
   static const int n = [] {
     if (const char* v = getenv("RHO_HOST_FILL_THREADS")) return std::max(1, atoi(v));
@@ -125,7 +131,7 @@ int fill_threads() {
 int64_t chunk_budget_samples() {
   static const int64_t n = [] {
     if (const char* v = getenv("RHO_HOST_CHUNK_SAMPLES")) return std::max<int64_t>(1, atoll(v));
-    return (int64_t)64 * 240000;              // 61 MB of fp32 samples (e2e is link-bound at every chunk size measured)
+    return (int64_t)128 * 240000;             // 123 MB of fp32 samples in the steady state (the ramps start at 1/16 of it)
   }();
   return n;
 }
@@ -180,11 +186,19 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
       return fail(RHO_ERR_LAYOUT, "outputs must be laid out in increasing order with room for sum(len) + pauses (item %d)", i);
     if (y_off[i] & 3) contig = false;
   }
-  const int64_t budget = chunk_budget_samples();
+  // Chunk sizes ramp up from 1/16 of the budget (doubling) and down again at the end (halving): the pipeline fills
+  // and drains with small chunks -- the first copy-out starts after ~0.1 ms instead of after a whole 120 MB chunk has
+  // come in and been processed -- while the steady state runs on large ones (fewer launches and copy calls).
+  const int64_t budget_max = chunk_budget_samples();
+  const int64_t budget_min = std::max<int64_t>(1, budget_max / 16);
+  int64_t total_samples = 0, done_samples = 0;
+  for (int s = 0; s < n_segments; ++s) total_samples += seg_len[s];
   std::vector<Chunk> chunks;
   for (int i = 0; i < n_items;) {
     Chunk c{};
     c.i0 = i; c.s0 = item_first_seg[i];
+    const int64_t budget = std::min(budget_max, std::max(budget_min, std::min(done_samples + budget_min,
+                                                                              (total_samples - done_samples) / 2)));
     int64_t samples = 0;
     int j = i;
     while (j < n_items) {
@@ -194,6 +208,7 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
       samples += it; ++j;
       if (j - i >= 65535) break;
     }
+    done_samples += samples;
     c.i1 = j; c.s1 = item_first_seg[j];
     for (int s = c.s0; s < c.s1; ++s) c.max_seg_len = std::max<int64_t>(c.max_seg_len, seg_len[s]);
     for (int q = c.i0; q < c.i1; ++q) c.max_item_cap = std::max(c.max_item_cap, cap[q]);
@@ -256,10 +271,12 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
     C.pinned_bytes = pin_total;
   }
   while ((int)C.ev_out.size() < n_chunks) {
-    cudaEvent_t ev;
-    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess)
+    cudaEvent_t ev, ev2;
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess)
       return cuda_fail(e, "cudaEventCreate");
     C.ev_out.push_back(ev);
+    C.ev_small.push_back(ev2);
   }
   char* base = (char*)C.arena;
   float* d_ref = (float*)base;
@@ -281,12 +298,14 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
         if (abort_fill.load(std::memory_order_relaxed)) return;
         std::this_thread::yield();
       }
-      if (cudaEventSynchronize(C.ev_out[k]) != cudaSuccess) { fill_err.store(1); return; }
+      // the constant tail of a row only needs the chunk's pad values: it is written while the chunk's frames with
+      // signal (a disjoint part of the same rows) are still crossing the link
+      if (cudaEventSynchronize(C.ev_small[k]) != cudaSuccess) { fill_err.store(1); return; }
       const Chunk& c = chunks[k];
       const int64_t t0 = std::min<int64_t>(c.t_dev, mel_stride_frames), t1 = std::min<int64_t>(mel_stride_frames, pad_frames);
       const int64_t rows = (int64_t)(c.i1 - c.i0) * n_mels;
       if (pad_value && w == 0) memcpy(pad_value + c.i0, h_pad + c.i0, sizeof(float) * (size_t)(c.i1 - c.i0));
-      if (t1 <= t0) continue;
+      if (t1 <= t0 || debug_skip_fill()) continue;
       for (int64_t r = w; r < rows; r += W) {
         const int64_t it = c.i0 + r / n_mels;
         fill_f32(mel + ((int64_t)c.i0 * n_mels + r) * mel_stride_frames + t0, t1 - t0, h_pad[it]);
@@ -373,27 +392,34 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
     if (status != RHO_OK) break;
     cudaEventRecord(C.ev_done[s], sc);
     cudaStreamWaitEvent(C.s_out, C.ev_done[s], 0);
-    if (contig) {
-      e = cudaMemcpyAsync(y + c.y_lo, d_y, sizeof(float) * (size_t)(c.y_hi - c.y_lo), cudaMemcpyDeviceToHost, C.s_out);
-    } else {
-      for (int q = 0; q < ni && e == cudaSuccess; ++q)
-        if (cap[c.i0 + q] > 0)
-          e = cudaMemcpyAsync(y + y_off[c.i0 + q], d_y + m_yoff[q], sizeof(float) * (size_t)cap[c.i0 + q],
-                              cudaMemcpyDeviceToHost, C.s_out);
+    // small results first: the records and the per-item pad values (the host fill of this chunk starts on them)
+    e = cudaMemcpyAsync(rec + c.i0, d_rec, sizeof(rho_record) * (size_t)ni, cudaMemcpyDeviceToHost, C.s_out);
+    if (e == cudaSuccess && features && pad_frames > 0)
+      e = cudaMemcpyAsync(h_pad + c.i0, d_pad, sizeof(float) * (size_t)ni, cudaMemcpyDeviceToHost, C.s_out);
+    if (e == cudaSuccess) e = cudaEventRecord(C.ev_small[k], C.s_out);
+    issued.store(k + 1, std::memory_order_release);
+    if (e == cudaSuccess) {
+      if (contig) {
+        e = cudaMemcpyAsync(y + c.y_lo, d_y, sizeof(float) * (size_t)(c.y_hi - c.y_lo), cudaMemcpyDeviceToHost, C.s_out);
+      } else {
+        for (int q = 0; q < ni && e == cudaSuccess; ++q)
+          if (cap[c.i0 + q] > 0)
+            e = cudaMemcpyAsync(y + y_off[c.i0 + q], d_y + m_yoff[q], sizeof(float) * (size_t)cap[c.i0 + q],
+                                cudaMemcpyDeviceToHost, C.s_out);
+      }
     }
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(rec + c.i0, d_rec, sizeof(rho_record) * (size_t)ni, cudaMemcpyDeviceToHost, C.s_out);
     if (e == cudaSuccess && features) {
       // compact device rows -> the caller's rows: only the frames that can see signal cross the link
-      const size_t w = sizeof(float) * (size_t)std::min<int64_t>(c.t_dev, mel_stride_frames);
-      e = cudaMemcpy2DAsync(mel + (size_t)c.i0 * n_mels * mel_stride_frames, sizeof(float) * (size_t)mel_stride_frames,
-                            d_mel, sizeof(float) * (size_t)c.t_dev, w, (size_t)ni * n_mels, cudaMemcpyDeviceToHost, C.s_out);
-      if (e == cudaSuccess && pad_frames > 0)
-        e = cudaMemcpyAsync(h_pad + c.i0, d_pad, sizeof(float) * (size_t)ni, cudaMemcpyDeviceToHost, C.s_out);
+      const int64_t wf = std::min<int64_t>(c.t_dev, mel_stride_frames);
+      float* dst = mel + (size_t)c.i0 * n_mels * mel_stride_frames;
+      if (wf == c.t_dev && wf == mel_stride_frames)      // the caller's rows are the device's rows: one linear copy
+        e = cudaMemcpyAsync(dst, d_mel, sizeof(float) * (size_t)wf * ni * n_mels, cudaMemcpyDeviceToHost, C.s_out);
+      else
+        e = cudaMemcpy2DAsync(dst, sizeof(float) * (size_t)mel_stride_frames, d_mel, sizeof(float) * (size_t)c.t_dev,
+                              sizeof(float) * (size_t)wf, (size_t)ni * n_mels, cudaMemcpyDeviceToHost, C.s_out);
     }
     if (e != cudaSuccess) { status = cuda_fail(e, "D2H"); break; }
     cudaEventRecord(C.ev_out[k], C.s_out);
-    issued.store(k + 1, std::memory_order_release);
   }
   if (status != RHO_OK) abort_fill.store(1);
   if (host_fill && status == RHO_OK) fill_worker(0, W);     // the calling thread is worker 0

@@ -2,6 +2,7 @@
 #pragma once
 #include <atomic>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 #include "common.cuh"
 
 namespace rho {
@@ -57,6 +58,7 @@ struct LaunchCtx {
   struct Span { int id; cudaEvent_t a, b; };
   std::vector<Span> spans;
   void begin(int id, cudaStream_t st) {
+    nvtxRangePushA(kKernelNames[id]);       // closed by end(): one NVTX range per kernel launch, nested in the entry point's
     if (!profiling) return;
     Span sp; sp.id = id;
     cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
@@ -64,6 +66,7 @@ struct LaunchCtx {
     spans.push_back(sp);
   }
   void end(cudaStream_t st) {
+    nvtxRangePop();
     ++launches;
     if (profiling && !spans.empty()) cudaEventRecord(spans.back().b, st);
   }

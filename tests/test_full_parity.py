@@ -1,0 +1,150 @@
+"""GPU: parity at the FULL sizes of the BASELINE configurations, not spot checks.
+
+Every clip's integer outputs (trim bounds, output length, flags, accept / reject decision) are compared with the oracle
+-- 1000 (C2) + 8000 (C4 shard, 128 bins) + 4000 segments in 1017 items (C3) = 13 000 clips -- and 64 clips / 16 items
+per configuration also in audio and log-mel.  The oracle runs on a fork pool over the host cores (numpy only in the
+children).  Plus a reduced run of the randomised soak (tests/diagnostics/soak.py).
+"""
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.util import TOL, assert_close
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_X = None          # inputs of the running test, inherited by the forked workers
+_ITEMS = None
+_NM = 80
+
+
+def _w_post(i):
+    o = oracle.post_process_clip(_X[i], oracle.derive_constants())
+    return (o["start"], o["end"], o["out_len"], bool(o["all_silent"]), bool(o["ok"]), float(o["first_rms"]),
+            float(o["last_rms"]), float(o["decay_ratio"]))
+
+
+def _w_full(i):
+    o = oracle.post_process_clip(_X[i], oracle.derive_constants())
+    return o["audio"], oracle.log_mel(oracle.resample(o["audio"]), _NM, True)
+
+
+def _w_join(i):
+    s0, s1 = _ITEMS[i]
+    o = oracle.smooth_segment_join([_X[s] for s in range(s0, s1)], oracle.derive_constants())
+    ratio, ok, fr, lr = oracle.sound_decay(o.audio, 0.3)
+    return (int(o.audio.size), bool(o.fallback), bool(o.two_d), [(t.start, t.end, bool(t.all_silent)) for t in o.plan.trims],
+            float(ratio), bool(ok), float(fr))
+
+
+def _w_join_audio(i):
+    s0, s1 = _ITEMS[i]
+    return oracle.smooth_segment_join([_X[s] for s in range(s0, s1)], oracle.derive_constants()).audio
+
+
+def _pool_map(fn, idx):
+    with mp.get_context("fork").Pool(min(os.cpu_count() or 1, 32)) as pool:
+        return pool.map(fn, list(idx), chunksize=max(1, len(list(idx)) // 256))
+
+
+def _check_fixed(R, dev, n, seed_blocks, n_mels, n_full=64):
+    global _X, _NM
+    from rho_tts_b200 import synth
+    x = torch.cat([synth.make_clip_block(min(1000, n - b), 240000, s, device=dev)
+                   for b, s in zip(range(0, n, 1000), seed_blocks)])
+    emb, ref = synth.make_embeddings(n, device=dev)
+    out = R.validate_batch(R.RaggedBatch.from_dense(x), R.make_params(), emb, ref, n_mels=n_mels)
+    rec = out.records_host()
+    xh = x.cpu().numpy()
+    _X, _NM = xh, n_mels
+    want = _pool_map(_w_post, range(n))
+    w = np.array([t[:3] for t in want], dtype=np.int64)
+    assert np.array_equal(rec["start"], w[:, 0]) and np.array_equal(rec["end"], w[:, 1])
+    assert np.array_equal(rec["out_len"], w[:, 2])
+    assert np.array_equal((rec["flags"] & 4) != 0, np.array([t[3] for t in want]))
+    ok_w = np.array([t[4] for t in want]); ratio_w = np.array([t[7] for t in want]); fr_w = np.array([t[5] for t in want])
+    decided = fr_w > 1e-6
+    assert np.array_equal(rec["ok"][decided] != 0, ok_w[decided])                  # EVERY accept / reject decision
+    assert np.allclose(rec["decay_ratio"][decided], ratio_w[decided], rtol=TOL, atol=0)
+    assert np.allclose(rec["first_rms"], fr_w, rtol=TOL, atol=1e-9)
+    assert np.allclose(rec["last_rms"], np.array([t[6] for t in want]), rtol=TOL, atol=1e-9)
+    assert 0.02 < 1.0 - ok_w.mean() < 0.5
+    pick = np.linspace(0, n - 1, n_full).astype(int)
+    full = _pool_map(_w_full, pick)
+    worst = 0.0
+    for i, (audio, mel) in zip(pick, full):
+        assert_close(out.audio.clip(int(i), audio.size).cpu().numpy(), audio, what=f"audio {i}")
+        worst = max(worst, assert_close(out.mel[int(i)].cpu().numpy(), mel, what=f"mel {i}"))
+    _X = None
+    return n, worst
+
+
+def test_c2_every_clip(cuda_device):
+    """BASELINE configs[1]: 1000 x 10 s, 80 bins -- all integer outputs and decisions, 64 clips in audio + log-mel."""
+    import rho_tts_b200 as R
+    n, worst = _check_fixed(R, cuda_device, 1000, [0xB200], 80)
+    print(f"C2: {n} clips exact in bounds / lengths / decisions; worst log-mel error on 64 clips {worst:.2e}")
+
+
+def test_c4_shard_every_clip(cuda_device):
+    """One GPU's shard of BASELINE configs[3]: 8000 x 10 s, 128 bins."""
+    import rho_tts_b200 as R
+    n, worst = _check_fixed(R, cuda_device, 8000, [0xC400 + 977 * b for b in range(8)], 128)
+    print(f"C4 shard: {n} clips exact in bounds / lengths / decisions; worst 128-bin log-mel error on 64 clips {worst:.2e}")
+
+
+def test_c3_every_segment_and_item(cuda_device):
+    """BASELINE configs[2]: 4000 ragged clips of 1..30 s in ~1000 items: every segment's trim bounds, every item's
+    length / fallback / rank / decision, 16 items in audio."""
+    global _X, _ITEMS
+    import rho_tts_b200 as R
+    from rho_tts_b200 import synth
+    n = 4000
+    lens = synth.make_ragged_lengths(n, 1234 + 3)
+    rb = R.RaggedBatch.empty_like_lengths(lens, cuda_device)
+    order = np.argsort(lens)
+    for g0 in range(0, n, 50):
+        idx = order[g0:g0 + 50]
+        blk = synth.make_clip_block(len(idx), int(lens[idx].max()), 7919 * 1237 + g0, device=cuda_device)
+        for j, i in enumerate(idx):
+            rb.clip(int(i)).copy_(blk[j, :int(lens[i])])
+    first = synth.make_item_partition(n, 1234 + 3)
+    n_items = len(first) - 1
+    out = R.join_batch(rb, first, R.make_params(), want_seg_info=True)
+    rec, seg = out.records_host(), out.seg_info_host()
+    flat = rb.data.cpu().numpy()
+    _X = [flat[int(o):int(o) + int(L)] for o, L in zip(rb.h_offsets, lens)]
+    _ITEMS = [(int(first[i]), int(first[i + 1])) for i in range(n_items)]
+    want = _pool_map(_w_join, range(n_items))
+    n_seg_checked = 0
+    for i, (L, fb, two_d, trims, ratio, ok, fr) in enumerate(want):
+        assert int(rec["out_len"][i]) == L and bool(rec["flags"][i] & 2) == fb and bool(rec["flags"][i] & 4) == two_d, i
+        for k, (s, e, silent) in enumerate(trims):
+            sg = seg[first[i] + k]
+            assert (int(sg["start"]), int(sg["end"]), bool(sg["flags"] & 1)) == (s, e, silent), (i, k)
+            n_seg_checked += 1
+        if fr > 1e-6:
+            assert bool(rec["ok"][i]) == ok, i
+            assert abs(rec["decay_ratio"][i] - ratio) <= TOL * max(1.0, abs(ratio))
+    assert n_seg_checked == n
+    pick = np.linspace(0, n_items - 1, 16).astype(int)
+    for i, audio in zip(pick, _pool_map(_w_join_audio, pick)):
+        assert_close(out.audio.clip(int(i), audio.size).cpu().numpy(), audio, what=f"item {i}")
+    _X = _ITEMS = None
+    print(f"C3: {n} segments and {n_items} items exact in bounds / lengths / fallback / decisions")
+
+
+def test_randomised_soak_reduced():
+    """40 random ragged batches (joins of random partitions, the fused path with 80 / 128 bins, padded / unpadded) against
+    the oracle: tests/diagnostics/soak.py exits non-zero on any mismatch."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "diagnostics", "soak.py"), "40"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    print(r.stdout.strip().splitlines()[-1])

@@ -419,7 +419,10 @@ def test_validate_joined_items_vs_oracle(R, cuda_device, pad):
     rs = stage.records_host()
     for f in ("start", "end", "out_len", "ok", "flags", "cosine", "n_segments"):
         assert np.array_equal(rec[f], rs[f]), f
-    assert float((out.mel - stage.mel).abs().max()) < 1e-4
+    for i in range(len(items)):                      # the frames each item has (rows are not written past them when unpadded)
+        T_i = 3000 if pad else ((2 * int(rec["out_len"][i]) + 2) // 3) // 160
+        if T_i > 0 and (pad or (2 * int(rec["out_len"][i]) + 2) // 3 > 200):
+            assert float((out.mel[i, :, :T_i] - stage.mel[i, :, :T_i]).abs().max()) < 1e-4, i
 
 
 def test_validate_host_ragged_joins(R, cuda_device):
