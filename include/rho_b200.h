@@ -183,6 +183,18 @@ int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const i
 int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,
                          float* mel, int64_t ld_mel, int64_t frames_per_item, int64_t item_stride, void* stream);
 
+/* --------------------------------------------------------------- windowed DFT as tensor-core GEMMs (a8, north_star) */
+/* P[row][k] = |STFT|^2 of feature_extraction_whisper.py:149-158 (torch.stft n_fft 400 / hop 160 / periodic Hann /
+ * centre + reflect, then magnitude squared), k <= 200, on the tensor cores: the DFT is factored 400 = 25 x 16 into two
+ * tcgen05.mma.kind::tf32 GEMMs (3xTF32 split) with the twiddle between them (csrc/stft_tc.cu).  This is the
+ * "windowed-DFT contraction" of BASELINE.json's north_star measured on its own, like rho_b200_mel_project; together
+ * they are the log-mel front end on tensor cores only.  The product path keeps the shared-memory FFT.
+ * x16 / off / len16 / pad_frames: as rho_b200_logmel.  tiles (device, 16-byte aligned, n_tiles x 4 int32): clip,
+ * first frame, number of frames (1..8), first output row -- frame t of the tile goes to power + (row + t) * ld_power.
+ * Only columns 0..200 of a row are written. */
+int rho_b200_stft_power_tc(rho_handle* h, const float* x16, const int64_t* off, const int32_t* len16, int pad_frames,
+                           const int32_t* tiles, int n_tiles, float* power, int64_t ld_power, void* stream);
+
 /* --------------------------------------------------------------- 16-bit PCM payload (the caller after the path) */
 /* BaseTTS._save_wav's in-tree WAV writer (base_tts.py:661-667; the fallback it takes when torchaudio.save has no
  * backend): (np.clip(audio, -1, 1) * 32767).astype(np.int16), i.e. an fp32 product truncated toward zero.  out[s] has
@@ -328,7 +340,7 @@ int rho_b200_exchange_destroy(rho_handle* h);
  *   mel (may be NULL), mel_stride_frames, pad_value (may be NULL): as rho_b200_validate with the layouts
  *     mel_stride_frames >= 3000 (complete rows) or < 3000 (compact rows + pad_value).  Only the frames that can see
  *     signal cross PCIe in either case: complete rows get their constant tail written by host threads from pad_value
- *     (RHO_HOST_FILL_THREADS, default min(8, cores / 4)), overlapped with the copies of the following chunks.
+ *     (RHO_HOST_FILL_THREADS, default 2), overlapped with the copies of the following chunks.
  *   emb [n_items][emb_dim], ref_emb [emb_dim] (may be NULL): speaker cosine into rec[i].cosine. */
 int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* seg_off, const int32_t* seg_len,
                                   int n_segments, const int32_t* item_first_seg, int n_items, const rho_params* p,

@@ -42,4 +42,4 @@ from .dsp import (  # noqa: F401
     post_process_clip,
 )
 from .resample import sinc_resample_kernel, resample  # noqa: F401
-from .logmel import slaney_mel_filterbank, hann_periodic, stft_power, log_mel  # noqa: F401
+from .logmel import slaney_mel_filterbank, hann_periodic, stft_power, log_mel, log_mel_truth64  # noqa: F401

@@ -105,3 +105,29 @@ def log_mel(w16: np.ndarray, n_mels: int = 80, pad_to_30s: bool = True) -> np.nd
     ls = np.log10(np.maximum(mel, F32(1e-10))).astype(F32)
     ls = np.maximum(ls, ls.max() - F32(8.0))
     return ((ls + F32(4.0)) / F32(4.0)).astype(F32)
+
+
+def log_mel_truth64(y24: np.ndarray, n_mels: int = 80) -> np.ndarray:
+    """What the reference chain resample(24k -> 16k) -> WhisperFeatureExtractor(30 s pad) computes, evaluated in float64
+    with the SAME fp32 tables (taps, window, filterbank): the value every fp32 implementation -- torch / MKL in the
+    reference, pocketfft in this oracle, the GPU kernels -- approximates.  On bins 70..80 dB below a frame's peak an fp32
+    FFT is itself up to ~1e-4 (after the log) from this value, so parity tests at the 1e-4 level judge the GPU against
+    this truth and allow its distance to another fp32 implementation to exceed 1e-4 only by that implementation's own
+    distance to the truth (tests/test_full_parity.py)."""
+    from .resample import sinc_resample_kernel
+    taps, width, orig, new = sinc_resample_kernel(24000, 16000)
+    y = np.asarray(y24, dtype=np.float64).reshape(-1)
+    L = y.size
+    xp = np.zeros(L + 2 * width + orig)
+    xp[width:width + L] = y
+    fr = np.lib.stride_tricks.sliding_window_view(xp, taps.shape[1])[::orig]
+    w = (fr @ taps.astype(np.float64).T).reshape(-1)[:-(-new * L // orig)]
+    buf = np.zeros(N_SAMPLES_30S)
+    buf[:min(w.size, N_SAMPLES_30S)] = w[:N_SAMPLES_30S]
+    p = np.concatenate([buf[200:0:-1], buf, buf[-2:-202:-1]])
+    frames = np.lib.stride_tricks.sliding_window_view(p, 400)[::160][:3000]
+    power = np.abs(np.fft.rfft(frames * hann_periodic().astype(np.float64)[None, :], axis=1)) ** 2
+    mel = slaney_mel_filterbank(n_mels).astype(F32).astype(np.float64).T @ power.T
+    ls = np.log10(np.maximum(mel, 1e-10))
+    ls = np.maximum(ls, ls.max() - 8.0)
+    return (ls + 4.0) / 4.0

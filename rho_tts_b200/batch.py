@@ -268,6 +268,34 @@ def mel_project(power: torch.Tensor, n_mels: int = 80, frames_per_item: int = 0,
     return out
 
 
+def stft_power_tc(rb16: RaggedBatch, pad_to_30s: bool = True):
+    """|STFT|^2 of the Whisper front end (feature_extraction_whisper.py:149-158) on the tensor cores: the windowed DFT
+    factored 400 = 25 x 16 into two tcgen05 GEMMs (rho_b200_stft_power_tc).  Returns (power [n_frames_total, 208] fp32
+    on the device -- columns 0..200 are the bins, the layout rho_b200_mel_project reads --, frame_base int64 [n + 1]:
+    clip i owns rows frame_base[i] .. frame_base[i + 1]).  Padded: the frames of the 30 s window that see signal."""
+    dev = _dev_index(rb16.data)
+    h = Handle.get(dev)
+    n16 = rb16.h_lengths.astype(np.int64)
+    if pad_to_30s:
+        nv = np.minimum(n16, 480000)
+        T = np.minimum(3000, np.maximum(2, (nv + 200 + 159) // 160))
+    else:
+        T = np.where(n16 > 200, n16 // 160, 0)
+    base = np.concatenate([[0], np.cumsum(T)]).astype(np.int64)
+    tiles = []
+    for c in range(rb16.n):
+        t0 = np.arange(0, int(T[c]), 8, dtype=np.int64)
+        if t0.size:
+            tiles.append(np.stack([np.full_like(t0, c), t0, np.minimum(8, int(T[c]) - t0), base[c] + t0], axis=1))
+    power = torch.zeros((max(int(base[-1]), 1), 208), dtype=torch.float32, device=rb16.device)
+    if tiles:
+        tl = torch.from_numpy(np.concatenate(tiles).astype(np.int32)).to(rb16.device)
+        _lib.check(h.lib.rho_b200_stft_power_tc(h.ptr, _ptr(rb16.data), _ptr(rb16.offsets), _ptr(rb16.lengths),
+                                                3000 if pad_to_30s else 0, _ptr(tl), int(tl.shape[0]), _ptr(power), 208,
+                                                _stream(dev)), "stft_power_tc")
+    return power[:int(base[-1])], base
+
+
 def qwen_post_process_batch(rb: RaggedBatch, sr: int = 24000, lengths: Optional[torch.Tensor] = None,
                             len_stride: int = 4, in_place: bool = False) -> RaggedBatch:
     """QwenTTS._post_process_audio (providers/qwen.py:268-378) for every clip of the batch: windowed decay

@@ -52,7 +52,7 @@ const char* const kKernelNames[KID_COUNT] = {
   "k_resample3to2", "k_logmel_init", "k_logmel_frames", "k_logmel_norm", "k_cosine", "k_single_clip_helpers",
   "k_fused_features", "k_mel_gemm", "k_qwen_moments", "k_qwen_plan", "k_qwen_apply", "k_resample_general",
   "k_pv_stft", "k_pv_phase", "k_pv_cumsum", "k_pv_istft", "k_resample_windowed", "k_mfcc_frames", "k_mfcc_stats",
-  "k_wait_flags"};
+  "k_wait_flags", "k_stft_tc"};
 }
 
 namespace {
@@ -558,6 +558,29 @@ int rho_b200_mel_project(rho_handle* h, const float* power, int64_t n_frames, in
   cudaError_t e = launch_mel_gemm(h->tb, power, n_frames, ld_power, n_mels, mel, ld_mel, frames_per_item, item_stride, h->sm_count,
                       (cudaStream_t)stream, &h->lc);
   return e == cudaSuccess ? RHO_OK : cuda_fail(e, "mel_gemm");
+}
+
+int rho_b200_stft_power_tc(rho_handle* h, const float* x16, const int64_t* off, const int32_t* len16, int pad_frames,
+                           const int32_t* tiles, int n_tiles, float* power, int64_t ld_power, void* stream) {
+  RHO_ON_DEVICE(h);
+  if (pad_frames != 0 && pad_frames != MEL_PAD_FRAMES) return fail(RHO_ERR_INVALID, "pad_frames must be 0 or 3000");
+  if (n_tiles < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (n_tiles == 0) return RHO_OK;
+  if (!x16 || !off || !len16 || !tiles || !power) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  if (ld_power < N_BINS) return fail(RHO_ERR_INVALID, "ld_power must be >= 201");
+  if (((uintptr_t)tiles) & 15u) return fail(RHO_ERR_INVALID, "tiles must be 16-byte aligned");
+  {
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!h->stft_tc_tables) {
+      std::vector<unsigned char> t(stft_tc_table_bytes());
+      host_stft_tc_tables(t.data());
+      cudaError_t e = dev_upload(h, &h->stft_tc_tables, t.data(), t.size());
+      if (e != cudaSuccess) { h->stft_tc_tables = nullptr; return cuda_fail(e, "stft tables"); }
+    }
+  }
+  cudaError_t e = launch_stft_tc(h->stft_tc_tables, x16, off, len16, pad_frames, tiles, n_tiles, power, ld_power,
+                                 h->sm_count, (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "stft_power_tc");
 }
 
 int rho_b200_sound_decay_batch(rho_handle* h, const float* y, const int64_t* off, const int32_t* len,

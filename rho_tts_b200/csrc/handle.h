@@ -77,6 +77,7 @@ struct rho_handle {
   bool mfcc_tb_ok = false;
   struct WinTaps { float* taps; int* ilo; };
   std::map<uint64_t, WinTaps> windowed_taps;
+  unsigned char* stft_tc_tables = nullptr;   // rho_b200_stft_power_tc: DFT matrices (hi / lo), window, twiddles
   // multi-GPU: records of rho_b200_validate are also stored into every rank's gathered buffer (rho_b200_exchange_*)
   rho::Exchange xch;
 };

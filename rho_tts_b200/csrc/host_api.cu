@@ -122,8 +122,9 @@ bool debug_skip_fill() { static const bool v = getenv("RHO_HOST_DEBUG_SKIP_FILL"
 int fill_threads() {
   static const int n = [] {
     if (const char* v = getenv("RHO_HOST_FILL_THREADS")) return std::max(1, atoi(v));
-    const unsigned hw = std::thread::hardware_concurrency();
-    return (int)std::min(8u, std::max(2u, hw / 4));
+    // measured on a 16-core B200 host (tools/e2e_sweep.py, profiles/e2e_sweep_r02.log): 2 threads keep up with the
+    // link (0.64 GB of constants per 1.28 GB of copy-out) and disturb the DMA traffic least; 4 and 8 are slower
+    return 2;
   }();
   return n;
 }

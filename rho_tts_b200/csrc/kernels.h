@@ -48,7 +48,7 @@ struct Tables {
 enum KernelId {
   KID_INIT = 0, KID_SCAN, KID_FINALIZE_SEGS, KID_PLAN, KID_GATHER, KID_FINALIZE_ITEMS,
   KID_RESAMPLE, KID_LOGMEL_INIT, KID_LOGMEL_FRAMES, KID_LOGMEL_NORM, KID_COSINE, KID_SINGLE, KID_FUSED, KID_MEL_GEMM, KID_QWEN_MOMENTS, KID_QWEN_PLAN, KID_QWEN_APPLY, KID_RESAMPLE_GENERAL,
-  KID_PV_STFT, KID_PV_PHASE, KID_PV_CUMSUM, KID_PV_ISTFT, KID_PV_RESAMPLE, KID_MFCC_FRAMES, KID_MFCC_STATS, KID_XCH_WAIT, KID_COUNT
+  KID_PV_STFT, KID_PV_PHASE, KID_PV_CUMSUM, KID_PV_ISTFT, KID_PV_RESAMPLE, KID_MFCC_FRAMES, KID_MFCC_STATS, KID_XCH_WAIT, KID_STFT_TC, KID_COUNT
 };
 extern const char* const kKernelNames[KID_COUNT];
 
@@ -160,6 +160,13 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
 cudaError_t launch_mel_gemm(const Tables& tb, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,
                             float* mel, int64_t ld_mel, int64_t frames_per_item, int64_t item_stride, int sm_count,
                             cudaStream_t st, LaunchCtx* lc);
+
+// stft_tc.cu: the windowed DFT as two tcgen05 GEMMs (400 = 25 x 16), in isolation
+size_t stft_tc_table_bytes();
+void host_stft_tc_tables(unsigned char* out /* stft_tc_table_bytes() */);
+cudaError_t launch_stft_tc(const unsigned char* tables, const float* x16, const int64_t* off, const int32_t* len16,
+                           int pad_frames, const int32_t* tiles, int n_tiles, float* power, int64_t ld_power, int sm_count,
+                           cudaStream_t st, LaunchCtx* lc);
 
 // qwen.cu: QwenTTS._post_process_audio (windowed decay correction, -23 dBFS, tanh soft clip)
 size_t qwen_workspace_bytes(int n, int64_t max_len, int sr);

@@ -33,7 +33,7 @@ def _w_post(i):
 
 def _w_full(i):
     o = oracle.post_process_clip(_X[i], oracle.derive_constants())
-    return o["audio"], oracle.log_mel(oracle.resample(o["audio"]), _NM, True)
+    return o["audio"], oracle.log_mel(oracle.resample(o["audio"]), _NM, True), oracle.log_mel_truth64(o["audio"], _NM)
 
 
 def _w_join(i):
@@ -78,26 +78,38 @@ def _check_fixed(R, dev, n, seed_blocks, n_mels, n_full=64):
     assert 0.02 < 1.0 - ok_w.mean() < 0.5
     pick = np.linspace(0, n - 1, n_full).astype(int)
     full = _pool_map(_w_full, pick)
-    worst = 0.0
-    for i, (audio, mel) in zip(pick, full):
+    # log-mel: the fp32 contract is 1e-4 against the value the reference algorithm defines (float64 evaluation with the
+    # same fp32 tables, oracle.log_mel_truth64).  Two fp32 implementations may sit on opposite sides of it on the bins
+    # 70..80 dB below a frame's peak, so against the fp32 numpy oracle the bound is 1e-4 + that oracle's own distance to
+    # the truth on the same clip (at 128 bins the numpy oracle alone reaches ~7e-5, the reference's MKL FFT 9e-5).
+    worst = worst_oracle = worst_vs = 0.0
+    for i, (audio, mel, truth) in zip(pick, full):
         assert_close(out.audio.clip(int(i), audio.size).cpu().numpy(), audio, what=f"audio {i}")
-        worst = max(worst, assert_close(out.mel[int(i)].cpu().numpy(), mel, what=f"mel {i}"))
+        got = out.mel[int(i)].cpu().numpy().astype(np.float64)
+        e_gpu = float(np.max(np.abs(got - truth) / np.maximum(1.0, np.abs(truth))))
+        e_orc = float(np.max(np.abs(mel - truth) / np.maximum(1.0, np.abs(truth))))
+        e_vs = float(np.max(np.abs(got - mel) / np.maximum(1.0, np.abs(mel))))
+        assert e_gpu <= TOL, f"mel {i}: {e_gpu:.3e} from the float64 value of the reference algorithm"
+        assert e_vs <= TOL + e_orc, f"mel {i}: {e_vs:.3e} from the fp32 oracle, whose own error is {e_orc:.3e}"
+        worst, worst_oracle, worst_vs = max(worst, e_gpu), max(worst_oracle, e_orc), max(worst_vs, e_vs)
     _X = None
-    return n, worst
+    return n, (worst, worst_oracle, worst_vs)
 
 
 def test_c2_every_clip(cuda_device):
     """BASELINE configs[1]: 1000 x 10 s, 80 bins -- all integer outputs and decisions, 64 clips in audio + log-mel."""
     import rho_tts_b200 as R
     n, worst = _check_fixed(R, cuda_device, 1000, [0xB200], 80)
-    print(f"C2: {n} clips exact in bounds / lengths / decisions; worst log-mel error on 64 clips {worst:.2e}")
+    print(f"C2: {n} clips exact in bounds / lengths / decisions; 64 clips log-mel: GPU vs float64 {worst[0]:.2e}, "
+          f"numpy oracle vs float64 {worst[1]:.2e}, GPU vs numpy oracle {worst[2]:.2e}")
 
 
 def test_c4_shard_every_clip(cuda_device):
     """One GPU's shard of BASELINE configs[3]: 8000 x 10 s, 128 bins."""
     import rho_tts_b200 as R
     n, worst = _check_fixed(R, cuda_device, 8000, [0xC400 + 977 * b for b in range(8)], 128)
-    print(f"C4 shard: {n} clips exact in bounds / lengths / decisions; worst 128-bin log-mel error on 64 clips {worst:.2e}")
+    print(f"C4 shard: {n} clips exact in bounds / lengths / decisions; 64 clips 128-bin log-mel: GPU vs float64 "
+          f"{worst[0]:.2e}, numpy oracle vs float64 {worst[1]:.2e}, GPU vs numpy oracle {worst[2]:.2e}")
 
 
 def test_c3_every_segment_and_item(cuda_device):

@@ -682,3 +682,63 @@ def test_full_size_c4_shard_128_bins(R, cuda_device):
         assert (rec["start"][i], rec["end"][i], bool(rec["ok"][i])) == (o["start"], o["end"], o["ok"])
         assert_close(mel[i].cpu().numpy(), m, what=f"mel clip {i}")
         assert abs(rec["cosine"][i] - cs) <= 1e-5
+
+
+# ----------------------------------------------------------------------------- windowed DFT on the tensor cores
+def _frames64(w16, pad):
+    """The frames torch.stft(center=True, reflect) cuts out of the (padded) 16 kHz clip, float64."""
+    w = np.asarray(w16, np.float64)
+    if pad:
+        buf = np.zeros(480000); buf[:min(w.size, 480000)] = w[:480000]; w = buf
+    p = np.concatenate([w[200:0:-1], w, w[-2:-202:-1]])
+    return np.lib.stride_tricks.sliding_window_view(p, 400)[::160][:w.size // 160]
+
+
+@pytest.mark.parametrize("pad", [True, False])
+def test_stft_power_tensor_core_vs_fp64(R, cuda_device, pad):
+    """rho_b200_stft_power_tc (the windowed DFT factored 400 = 25 x 16 into two tcgen05 GEMMs, 3xTF32) against the
+    float64 DFT of the same windowed frames: fp32-FFT-class accuracy, i.e. an error that is small against the frame's
+    strongest bin (an fp32 FFT is no better on the weak bins)."""
+    from rho_tts_b200 import synth
+    lens = [160000, 16000, 4001, 100001, 481000 if pad else 1000, 201 if not pad else 37]
+    clips = [oracle.resample(synth.make_clip_block(1, (3 * L + 1) // 2, 70 + i)[0].numpy())[:L] for i, L in enumerate(lens)]
+    rb = _rb(R, clips, cuda_device)
+    power, base = R.stft_power_tc(rb, pad_to_30s=pad)
+    power = power.cpu().numpy()
+    hann = oracle.hann_periodic().astype(np.float64)
+    worst_rel_peak, worst_amp = 0.0, 0.0
+    for i, w in enumerate(clips):
+        T = int(base[i + 1] - base[i])
+        fr = _frames64(w, pad)[:T]
+        assert fr.shape[0] == T, (i, len(w), T, fr.shape)
+        if T == 0:
+            continue
+        X = np.fft.rfft(fr * hann[None, :], axis=1)
+        want = np.abs(X) ** 2                                                        # (T, 201)
+        got = power[base[i]:base[i + 1], :201].astype(np.float64)
+        peak = np.maximum(want.max(axis=1, keepdims=True), 1e-30)
+        worst_rel_peak = max(worst_rel_peak, float((np.abs(got - want) / peak).max()))
+        worst_amp = max(worst_amp, float((np.abs(np.sqrt(got) - np.abs(X)) / np.sqrt(peak)).max()))
+    print(f"stft_power_tc pad={pad}: worst |P - P64| / max_k P64 = {worst_rel_peak:.2e}, amplitude error / peak amplitude {worst_amp:.2e}")
+    assert worst_rel_peak < 2e-6 and worst_amp < 2e-6
+
+
+def test_log_mel_on_tensor_cores_only(R, cuda_device):
+    """The whole Whisper front end of a clip on the tensor cores: rho_b200_stft_power_tc -> rho_b200_mel_project ->
+    log10 / clamp / scale, against the float64 value of the reference algorithm and the product (FFT) path."""
+    from rho_tts_b200 import synth
+    x = synth.make_clip_block(3, 240000, 11)
+    clips16 = [oracle.resample(x[i].numpy()) for i in range(3)]
+    rb = _rb(R, clips16, cuda_device)
+    power, base = R.stft_power_tc(rb, pad_to_30s=False)
+    prod, _ = R.logmel_batch(rb, 80, False)
+    for i, w in enumerate(clips16):
+        mel = R.mel_project(power[base[i]:base[i + 1]].contiguous(), 80).cpu().numpy()
+        ls = np.log10(np.maximum(mel, 1e-10)); ls = np.maximum(ls, ls.max() - 8.0)
+        got = (ls + 4.0) / 4.0
+        want = oracle.log_mel(w, 80, pad_to_30s=False)
+        T = want.shape[1]
+        e_or = float(np.abs(got[:, :T] - want).max())
+        e_pr = float(np.abs(got[:, :T] - prod[i, :, :T].cpu().numpy()).max())
+        print(f"tensor-core-only log-mel, clip {i}: {e_or:.2e} from the numpy oracle, {e_pr:.2e} from the product path")
+        assert e_or < 2e-4 and e_pr < 2e-4
