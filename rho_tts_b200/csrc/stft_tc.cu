@@ -20,9 +20,9 @@
 //   stage 2: rows (frame, k1) = 13 per frame -> 104 of 128 rows,            K = 32 (n2 re/im), N = 32 (k2 re/im)
 // 24 MMAs per 8 frames (the mel projection: 78 per 32 frames).
 //
-// One persistent CTA per SM: two groups of four worker warps (one TMEM lane quarter each), each group owns every other
+// One persistent CTA per SM: six groups of four worker warps (one TMEM lane quarter each), every group owns every sixth
 // tile -- build A1 -> [MMA stage 1] -> read D1, twiddle, build A2 -> [MMA stage 2] -> read D2, |.|^2, store -- plus one
-// MMA-issuing warp; while one group waits for the tensor core the other does its CUDA-core part.
+// MMA-issuing warp; while a group waits for the tensor core (or for its next samples) the others do their CUDA-core part.
 #include <cmath>
 #include <vector>
 #include "logmel_dev.cuh"
@@ -30,18 +30,22 @@
 namespace rho {
 
 constexpr int ST_FR = 8;                         // frames per tile
-constexpr int ST_GROUPS = 2;
+constexpr int ST_GROUPS = 6;                     // tiles in flight per SM: the stages are tiny (12 MMAs), what has to be
+                                                 // covered is the latency of the two hand-offs per tile (2 groups: 8.2 ms
+                                                 // per 1 M frames, tensor pipe 2 % active)
 constexpr int ST_WORKERS = 128;                  // threads per group
 constexpr int ST_THREADS = ST_GROUPS * ST_WORKERS + 32;
 constexpr int ST_K1 = 13;                        // k1 = 0..12
 constexpr uint32_t ST_A_BYTES = 128 * 128;       // 128 rows x 32 floats: [K-block of 16 floats][row][64 B]
 constexpr uint32_t ST_B_BYTES = 32 * 128;        // 32 rows (N) x 32 floats
-constexpr uint32_t ST_TMEM_COLS = 128;           // D1 / D2 of two groups, 32 columns each
+constexpr uint32_t ST_TMEM_COLS = 512;           // D1 / D2 of six groups, 32 columns each (384 used)
 constexpr uint32_t ST_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t ST_DHI = (512u >> 4) | (1u << 14) | (4u << 29);   // SBO 512 B (8 rows x 64 B), version 1, SWIZZLE_64B
 
+// One operand buffer per group: A1 (stage 1) is dead once stage 1 has been committed, A2 (stage 2) is written into the
+// same bytes.  Rows 104..127 keep A1 values during stage 2: finite, and nobody reads those rows of D2.
 struct StGroup {
-  unsigned char a1_hi[ST_A_BYTES], a1_lo[ST_A_BYTES], a2_hi[ST_A_BYTES], a2_lo[ST_A_BYTES];
+  unsigned char a_hi[ST_A_BYTES], a_lo[ST_A_BYTES];
 };
 struct alignas(1024) StSmem {
   StGroup g[ST_GROUPS];
@@ -52,13 +56,16 @@ struct alignas(1024) StSmem {
   uint32_t tmem_base;
 };
 constexpr size_t ST_TABLE_BYTES = 4 * ST_B_BYTES + sizeof(float) * N_FFT + sizeof(float2) * 16 * ST_K1;
+static_assert(sizeof(StSmem) + 1024 <= 232448, "shared memory budget");
 
 // byte offset of element (row r, column k) of a K-major operand with `rows` rows, 64-byte swizzle: K-blocks of 16 floats,
 // 64-byte rows, the 16-byte chunk index XORed with bits [7, 9) of the address
 __host__ __device__ __forceinline__ uint32_t st_off(uint32_t rows, uint32_t r, uint32_t k) {
   return (k >> 4) * rows * 64u + r * 64u + ((((k >> 2) ^ (r >> 1)) & 3u) << 4) + (k & 3u) * 4u;
 }
-__device__ __forceinline__ float st_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+// nearest TF32 value (10 explicit mantissa bits): with hi rounded to nearest, |v - hi| <= 2^-12 |v| and the two halves
+// together carry 23 bits (truncation: 22)
+__device__ __forceinline__ float st_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void st_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void st_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void st_arrive(uint64_t* bar) {
@@ -80,15 +87,17 @@ __device__ __forceinline__ uint32_t st_elect() {
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
   return pred;
 }
-__device__ __forceinline__ void st_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-#pragma unroll
-  for (int j = 0; j < 2; ++j)
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(r[16 * j + 0]), "=r"(r[16 * j + 1]), "=r"(r[16 * j + 2]), "=r"(r[16 * j + 3]),
-                   "=r"(r[16 * j + 4]), "=r"(r[16 * j + 5]), "=r"(r[16 * j + 6]), "=r"(r[16 * j + 7]),
-                   "=r"(r[16 * j + 8]), "=r"(r[16 * j + 9]), "=r"(r[16 * j + 10]), "=r"(r[16 * j + 11]),
-                   "=r"(r[16 * j + 12]), "=r"(r[16 * j + 13]), "=r"(r[16 * j + 14]), "=r"(r[16 * j + 15])
-                 : "r"(taddr + 16 * j) : "memory");
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {
+  unsigned done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void st_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
@@ -100,12 +109,9 @@ k_stft_tc(const float* __restrict__ x16, const int64_t* __restrict__ off, const 
   StSmem& S = *reinterpret_cast<StSmem*>(st_raw + ((1024u - (smem_u32(st_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5;
 
-  // constant operands and tables: one copy per CTA; the rows of A2 that no (frame, k1) owns stay zero
+  // constant operands and tables: one copy per CTA
   for (uint32_t i = threadIdx.x; i < ST_TABLE_BYTES / 16; i += ST_THREADS)
     reinterpret_cast<uint4*>(S.b1_hi)[i] = reinterpret_cast<const uint4*>(tables)[i];
-  for (int g = 0; g < ST_GROUPS; ++g)
-    for (uint32_t i = threadIdx.x; i < 2 * ST_A_BYTES / 16; i += ST_THREADS)
-      reinterpret_cast<uint4*>(S.g[g].a2_hi)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     for (int g = 0; g < ST_GROUPS; ++g) {
       mbar_init(&S.a1_ready[g], ST_WORKERS); mbar_init(&S.a2_ready[g], ST_WORKERS);
@@ -113,7 +119,8 @@ k_stft_tc(const float* __restrict__ x16, const int64_t* __restrict__ off, const 
     }
     mbar_fence_init();
   }
-  if (warp == 2 * 4) {
+  constexpr int MMA_WARP = ST_GROUPS * 4;
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&S.tmem_base)), "r"(ST_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -124,12 +131,12 @@ k_stft_tc(const float* __restrict__ x16, const int64_t* __restrict__ off, const 
   const uint32_t tmem = S.tmem_base;
   const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  if (warp == 2 * 4) {
-    // ================================ MMA issuer: stage 1 of tile `it`, then stage 2 of tile `it - 1`
+  if (warp == MMA_WARP) {
+    // ================================ MMA issuer
     auto stage = [&](int g, int which) {
       StGroup& G = S.g[g];
       const uint32_t d = tmem + (uint32_t)(64 * g + 32 * which);
-      const uint32_t a_hi = smem_u32(which ? G.a2_hi : G.a1_hi), a_lo = smem_u32(which ? G.a2_lo : G.a1_lo);
+      const uint32_t a_hi = smem_u32(G.a_hi), a_lo = smem_u32(G.a_lo);
       const uint32_t b_hi = smem_u32(which ? S.b2_hi : S.b1_hi), b_lo = smem_u32(which ? S.b2_lo : S.b1_lo);
       if (st_elect()) {
 #pragma unroll
@@ -143,18 +150,28 @@ k_stft_tc(const float* __restrict__ x16, const int64_t* __restrict__ off, const 
       }
       __syncwarp();
     };
-    for (int it = 0; it <= my_tiles; ++it) {
-      if (it < my_tiles) {
-        const int g = it & 1;
-        mbar_wait(&S.a1_ready[g], (unsigned)(it >> 1) & 1u);
-        st_fence_after();
-        stage(g, 0);
-      }
-      if (it >= 1) {
-        const int g = (it - 1) & 1;
-        mbar_wait(&S.a2_ready[g], (unsigned)((it - 1) >> 1) & 1u);
-        st_fence_after();
-        stage(g, 1);
+    // Out-of-order service: whichever group has an operand ready gets its stage next (polling the groups' barriers in
+    // turn); a group alternates stage 1 / stage 2, so `done[g]` stages of it have been issued and the barrier it waits
+    // on and its phase follow from that count.
+    int done[ST_GROUPS], need[ST_GROUPS], left = 0;
+#pragma unroll
+    for (int g = 0; g < ST_GROUPS; ++g) {
+      done[g] = 0;
+      need[g] = 2 * ((my_tiles > g) ? (my_tiles - g + ST_GROUPS - 1) / ST_GROUPS : 0);
+      left += need[g];
+    }
+    while (left > 0) {
+#pragma unroll
+      for (int g = 0; g < ST_GROUPS; ++g) {
+        if (done[g] < need[g]) {
+          const int which = done[g] & 1;
+          const unsigned parity = (unsigned)(done[g] >> 1) & 1u;
+          if (mbar_test(which ? &S.a2_ready[g] : &S.a1_ready[g], parity)) {
+            st_fence_after();
+            stage(g, which);
+            ++done[g]; --left;
+          }
+        }
       }
     }
   } else {
@@ -164,47 +181,58 @@ k_stft_tc(const float* __restrict__ x16, const int64_t* __restrict__ off, const 
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * g);
     const int f1 = w >> 4, n2 = w & 15;                       // stage-1 row: (frame, n2)
     const int f2 = w / ST_K1, k1 = w - f2 * ST_K1;            // stage-2 row: (frame, k1), valid for w < 104
-    for (int it = g; it < my_tiles; it += ST_GROUPS) {
-      const unsigned parity = (unsigned)(it >> 1) & 1u;
-      const int4 td = tiles[blockIdx.x + (long long)it * gridDim.x];     // clip, t0, frames, first output row
+    // the samples of this thread's row of a tile (the 25 loads are independent: one round trip to HBM)
+    auto load_row = [&](const int4 td, float (&v)[25]) {
       const float* __restrict__ xs = x16 + off[td.x];
       int T, T_real, N, n_valid;
       lm_frame_counts(len16[td.x], pad_frames, &T, &T_real, &N, &n_valid);
-      // ---- A1: the windowed samples of row (frame, n2), n1 = 0..24, as hi / lo TF32 halves
-      {
-        float v[32];
-        const long long s0 = (long long)HOP16 * (td.y + f1) - N_FFT / 2 + n2;
+      const long long s0 = (long long)HOP16 * (td.y + f1) - N_FFT / 2 + n2;
 #pragma unroll
-        for (int n1 = 0; n1 < 25; ++n1)
-          v[n1] = (f1 < td.z) ? lm_sample(xs, s0 + 16 * n1, n_valid, N) * S.win[16 * n1 + n2] : 0.f;
+      for (int n1 = 0; n1 < 25; ++n1) v[n1] = (f1 < td.z) ? lm_sample(xs, s0 + 16 * n1, n_valid, N) : 0.f;
+    };
+    float v[25];
+    int4 td = make_int4(0, 0, 0, 0);
+    if (g < my_tiles) { td = tiles[blockIdx.x + (long long)g * gridDim.x]; load_row(td, v); }
+    for (int it = g; it < my_tiles; it += ST_GROUPS) {
+      const unsigned parity = (unsigned)(it / ST_GROUPS) & 1u;
+      const int4 cur = td;
+      // ---- A1: the windowed samples of row (frame, n2), n1 = 0..24 (+ 7 zero columns), as hi / lo TF32 halves
 #pragma unroll
-        for (int n1 = 25; n1 < 32; ++n1) v[n1] = 0.f;
+      for (int j = 0; j < 8; ++j) {
+        float e[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 h = make_float4(st_hi(v[4 * j]), st_hi(v[4 * j + 1]), st_hi(v[4 * j + 2]), st_hi(v[4 * j + 3]));
-          const uint32_t o = st_off(128, (uint32_t)w, (uint32_t)(4 * j));
-          *reinterpret_cast<float4*>(G.a1_hi + o) = h;
-          *reinterpret_cast<float4*>(G.a1_lo + o) = make_float4(v[4 * j] - h.x, v[4 * j + 1] - h.y, v[4 * j + 2] - h.z, v[4 * j + 3] - h.w);
-        }
+        for (int c = 0; c < 4; ++c) e[c] = (4 * j + c < 25) ? v[4 * j + c] * S.win[16 * (4 * j + c) + n2] : 0.f;
+        const float4 h = make_float4(st_hi(e[0]), st_hi(e[1]), st_hi(e[2]), st_hi(e[3]));
+        const uint32_t o = st_off(128, (uint32_t)w, (uint32_t)(4 * j));
+        *reinterpret_cast<float4*>(G.a_hi + o) = h;
+        *reinterpret_cast<float4*>(G.a_lo + o) = make_float4(st_hi(e[0] - h.x), st_hi(e[1] - h.y), st_hi(e[2] - h.z), st_hi(e[3] - h.w));
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       st_arrive(&S.a1_ready[g]);
+      // the next tile's samples travel while the tensor core and the twiddle step work on this one
+      if (it + ST_GROUPS < my_tiles) { td = tiles[blockIdx.x + (long long)(it + ST_GROUPS) * gridDim.x]; load_row(td, v); }
       // ---- twiddle: D1 row (frame, n2) holds Y[k1] as (re, im) pairs -> Y' -> A2[(frame, k1)][(n2, re / im)]
       mbar_wait(&S.d1_full[g], parity);
       st_fence_after();
       {
-        uint32_t r[32];
-        st_ld32(lane_addr, r);
         const float2* __restrict__ tw = S.tw + n2 * ST_K1;
 #pragma unroll
-        for (int k = 0; k < ST_K1; ++k) {
-          const float2 y = make_float2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
-          const float2 t = tw[k];
-          const float2 z = make_float2(y.x * t.x - y.y * t.y, y.x * t.y + y.y * t.x);
-          const float2 h = make_float2(st_hi(z.x), st_hi(z.y));
-          const uint32_t o = st_off(128, (uint32_t)(f1 * ST_K1 + k), (uint32_t)(2 * n2));
-          *reinterpret_cast<float2*>(G.a2_hi + o) = h;
-          *reinterpret_cast<float2*>(G.a2_lo + o) = make_float2(z.x - h.x, z.y - h.y);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[16];
+          st_ld16(lane_addr + 16 * half, r);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const int k = 8 * half + kk;
+            if (k < ST_K1) {
+              const float2 y = make_float2(__uint_as_float(r[2 * kk]), __uint_as_float(r[2 * kk + 1]));
+              const float2 t = tw[k];
+              const float2 z = make_float2(y.x * t.x - y.y * t.y, y.x * t.y + y.y * t.x);
+              const float2 h = make_float2(st_hi(z.x), st_hi(z.y));
+              const uint32_t o = st_off(128, (uint32_t)(f1 * ST_K1 + k), (uint32_t)(2 * n2));
+              *reinterpret_cast<float2*>(G.a_hi + o) = h;
+              *reinterpret_cast<float2*>(G.a_lo + o) = make_float2(st_hi(z.x - h.x), st_hi(z.y - h.y));
+            }
+          }
         }
       }
       st_fence_before();
@@ -213,14 +241,16 @@ k_stft_tc(const float* __restrict__ x16, const int64_t* __restrict__ off, const 
       // ---- epilogue: D2 row (frame, k1) holds X[k1 + 25 k2] -> |.|^2 -> P[frame][bin]; bins 25 - k1 + ... by symmetry
       mbar_wait(&S.d2_full[g], parity);
       st_fence_after();
-      {
-        uint32_t r[32];
-        st_ld32(lane_addr + 32, r);
-        if (w < ST_FR * ST_K1 && f2 < td.z) {
-          float* __restrict__ row = power + (long long)(td.w + f2) * ld_power;
 #pragma unroll
-          for (int k2 = 0; k2 < 16; ++k2) {
-            const float re = __uint_as_float(r[2 * k2]), im = __uint_as_float(r[2 * k2 + 1]);
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[16];
+        st_ld16(lane_addr + 32 + 16 * half, r);
+        if (w < ST_FR * ST_K1 && f2 < cur.z) {
+          float* __restrict__ row = power + (long long)(cur.w + f2) * ld_power;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const int k2 = 8 * half + kk;
+            const float re = __uint_as_float(r[2 * kk]), im = __uint_as_float(r[2 * kk + 1]);
             const float p = re * re + im * im;
             const int k = k1 + 25 * k2;
             if (k <= 200) row[k] = p;
@@ -233,7 +263,7 @@ k_stft_tc(const float* __restrict__ x16, const int64_t* __restrict__ off, const 
   }
   st_fence_before();
   __syncthreads();
-  if (warp == 2 * 4) {
+  if (warp == MMA_WARP) {
     st_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(ST_TMEM_COLS) : "memory");
   }
@@ -252,13 +282,13 @@ void host_stft_tc_tables(unsigned char* out) {
     const float v = (float)val;
     uint32_t b;
     memcpy(&b, &v, 4);
-    b &= 0xffffe000u;
+    b = (b + 0x1000u) & 0xffffe000u;              // nearest TF32, like st_hi on the device
     float h;
     memcpy(&h, &b, 4);
     const float r = v - h;
     uint32_t bl;
     memcpy(&bl, &r, 4);
-    bl &= 0xffffe000u;
+    bl = (bl + 0x1000u) & 0xffffe000u;
     float l;
     memcpy(&l, &bl, 4);
     const uint32_t o = st_off(32, n, k);
