@@ -407,9 +407,14 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
     # (first touch) and the copies to / from them stay on the GPU's side of the host
     numa_cpus = R.dist.bind_to_gpu_numa(local_rank) if world > 1 else None
     dist = None
+    saved_stdout = None
     if world > 1:
         import torch.distributed as dist
-        # NCCL's version / debug banner goes to stderr: stdout carries the one JSON line only
+        # stdout carries the one JSON line only: NCCL prints its version banner there on some boxes, so the file
+        # descriptor is pointed at stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     timer = DeviceTimer(dev, dist)
@@ -718,6 +723,9 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
             "record_gather": {"mode": gather_mode, "verified": gather_ok, "fallback_reason": gather_why or None},
             "value_compact_rows": compact, "configs": configs,
         }
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -113,7 +113,7 @@ def load():
             "rho_b200_exchange_connect": (c_int, [vp, vp]),
             "rho_b200_exchange_wait": (c_int, [vp, i64, vp]),
             "rho_b200_exchange_epoch": (c_int64, [vp]),
-            "rho_b200_exchange_read": (c_int, [vp, i64, POINTER(c_void_p), POINTER(c_int)]),
+            "rho_b200_exchange_read": (c_int, [vp, i64, vp, POINTER(c_int), vp]),
             "rho_b200_exchange_destroy": (c_int, [vp]),
             "rho_b200_validate_host_ragged": (c_int, [vp, vp, vp, vp, c_int, vp, c_int, P, vp, vp, c_int, c_int, vp, i64,
                                                       vp, vp, vp, c_int, vp]),

@@ -95,12 +95,14 @@ int rho_b200_exchange_read(rho_handle* h, int64_t epoch, void* dst, int* timed_o
   const size_t block = sizeof(rho_record) * (size_t)X.world * (size_t)X.n_per_rank;
   cudaError_t e = cudaMemcpyAsync(dst, (char*)X.buf + block * (size_t)(epoch & 1), block, cudaMemcpyDeviceToDevice,
                                   (cudaStream_t)stream);
-  if (e != cudaSuccess) return cuda_fail(e, "exchange read");
+  if (e != cudaSuccess)
+    return fail(RHO_ERR_CUDA, "exchange read (records, %zu bytes from %p to %p): %s", block,
+                (void*)((char*)X.buf + block * (size_t)(epoch & 1)), dst, cudaGetErrorString(e));
   if (timed_out) {
     unsigned v = 0;
-    e = cudaMemcpyAsync(&v, (char*)X.buf + align_up(X.rec_bytes, 256) + 128, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
-    if (e != cudaSuccess) return cuda_fail(e, "exchange read");
+    if ((e = cudaStreamSynchronize((cudaStream_t)stream)) != cudaSuccess) return cuda_fail(e, "exchange read (sync)");
+    e = cudaMemcpy(&v, (char*)X.buf + align_up(X.rec_bytes, 256) + 128, 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return cuda_fail(e, "exchange read (time-out word)");
     *timed_out = (int)v;
   }
   return RHO_OK;

@@ -108,3 +108,32 @@ def test_record_exchange_two_ranks(force_nccl):
     print(f"record exchange mode: {modes.pop()} (fallback reason: {res[0][3] or 'none'})")
     if force_nccl:
         assert res[0][2] == "nccl"
+
+
+def test_record_exchange_single_rank(cuda_device):
+    """World size 1 (runs on a one-GPU box): the exchange with only the local sink -- records stored by the assembling
+    kernel into the gathered buffer, epoch flag, wait kernel, read-back -- against the records themselves."""
+    import torch.distributed as dist
+    import rho_tts_b200 as R
+    from rho_tts_b200 import synth
+    if dist.is_initialized():
+        pytest.skip("a process group is already initialised in this process")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()), RANK="0", WORLD_SIZE="1")
+    dist.init_process_group("nccl", device_id=cuda_device)
+    try:
+        n = 64
+        x = synth.make_clip_block(n, 60000, 3, device=cuda_device)
+        rb = R.RaggedBatch.from_dense(x)
+        plan = R.ValidatePlan(rb, np.arange(n + 1, dtype=np.int32), R.make_params(), 80, True)
+        ex = R.dist.RecordExchange(0, n)
+        assert ex.mode == "p2p", ex.why
+        for step in range(4):
+            x.mul_(0.9)
+            out = plan.run(rb, None, None)
+            ex.after_step(out.records)
+            got = ex.gathered()
+            torch.cuda.synchronize()
+            assert torch.equal(got, out.records), step
+        ex.close()
+    finally:
+        dist.destroy_process_group()
