@@ -719,18 +719,20 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       float2 wp[10];                                         // all ten partner reads in flight before the first use
 #pragma unroll
       for (int k2 = 0; k2 < 10; ++k2) wp[k2] = part[20 * (9 - k2)];   // partner's k2' = 19 - k2, stored at 20 * (k2' - 10)
+      // 4 |A|^2 and 4 |B|^2 (the factor 1/4 of A = (Z + conj Z')/2 is applied once per mel row, where it is exact:
+      // scaling by a power of two commutes with every rounding of the projection).  Packed: S = Z + W = (ar, bi),
+      // D = Z - W = (br, ai); |A|^2 = ar^2 + ai^2 = S.x^2 + D.y^2, |B|^2 = br^2 + bi^2 = D.x^2 + S.y^2.
 #pragma unroll
       for (int k2 = 0; k2 < 10; ++k2) {
-        const float2 w = wp[k2];
-        const float2 z = v[k2];
-        const float ar = z.x + w.x, ai = z.y - w.y, br = z.x - w.x, bi = z.y + w.y;
-        pa[20 * k2] = 0.25f * (ar * ar + ai * ai);
-        pb[20 * k2] = 0.25f * (br * br + bi * bi);
+        const float2 sm = cadd(v[k2], wp[k2]), df = csub(v[k2], wp[k2]);
+        const float2 s2 = __fmul2_rn(sm, sm), d2 = __fmul2_rn(df, df);
+        pa[20 * k2] = s2.x + d2.y;
+        pb[20 * k2] = d2.x + s2.y;
       }
       if (lane == 0) {                                       // k = 200: Z[200] pairs with itself
         const float2 z = v[10];
-        pa[200] = z.x * z.x;
-        pb[200] = z.y * z.y;
+        pa[200] = 4.f * (z.x * z.x);
+        pb[200] = 4.f * (z.y * z.y);
       }
     }
     half_sync(half);
@@ -742,7 +744,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       const float* p = power + f * LM_PS;
       float* __restrict__ o = out + t;
       auto emit = [&](int m, float acc) {
-        const float ls = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
+        const float ls = __log2f(fmaxf(0.25f * acc, 1e-10f)) * 0.30102999566398120f;   // the spectra are 4 |.|^2
         if (live) {
           o[(long long)m * mel_stride] = lm_scaled(ls);
           lmax = fmaxf(lmax, ls);
