@@ -90,6 +90,11 @@ cudaError_t upload_fused_taps(const float* taps) {
 // 32 frames keep the accumulator busy well into the next batch (profiles/ab_r01_tc_mel.log).
 #define FZ_TC_MEL 0
 #endif
+#ifndef FZ_DEFER_TILE_END
+#define FZ_DEFER_TILE_END 1   // the tile-end atomics are issued and NOT waited for: their results (am I the half that finished
+                              // this clip last?) are consumed in the first batch of the half's next tile, where the fill of the
+                              // padding constant then happens; two barriers and the atomic round trip leave every tile end
+#endif
 bool fused_inline_norm() { return FZ_INLINE_NORM != 0; }
 constexpr int FZ_HALVES = 2;
 constexpr int FZ_THREADS = LM_THREADS * FZ_HALVES;          // 640
@@ -131,6 +136,8 @@ struct alignas(1024) FzHalf {
   int last;                         // "this half finished its clip last" broadcast
   int fill_max;                     // ... and the clip maximum it read (ordered-int form)
   int next_unit;                    // the tile this half works on next (claimed one tile ahead)
+  int pend_c, pend_tiles, pend_T_real, pend_T;   // FZ_DEFER_TILE_END: the clip whose tile-end count is in flight
+  int fill_c;                       // ... and the clip whose padding constant this half writes next (-1: none)
   FzNext nd;
 };
 static_assert(LM_SLAB_SM <= LM_BF * LM_PS, "the slab must fit in the pw region");
@@ -378,7 +385,42 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     bulk_g2s(H.span, xsn + j0, FZ_SPAN * 4, &H.bar);
     H.nd.prefetched = 1;
   };
-  if (tid == 0) fill_desc(atomicAdd(work_counter, 1));
+  // The constant of the frames that only see zero padding, for clip fc (2/3 of a 10 s clip's features): pure stores.
+  auto do_fill = [&](int fc, int fT_real, int fT, int fmax_ordered) {
+    float* __restrict__ fout = mel + (long long)fc * NM * mel_stride;
+    const float mx = ordered_to_float(fmax_ordered);
+    const float fill = __fmul_rn(__fadd_rn(fmaxf(-10.0f, __fsub_rn(mx, 8.0f)), 4.0f), 0.25f);
+    const int t_lo = (fT_real + 3) & ~3;             // whole 128-bit pieces from here; [T_real, t_lo) is k_logmel_norm's
+    const bool vec = (mel_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(fout) & 15u) == 0);
+    if (vec) {
+      const int T4 = (fT - t_lo) >> 2;
+      const float4 f4 = make_float4(fill, fill, fill, fill);
+      for (int cp = tid; cp < T4; cp += LM_THREADS) {
+        float* col = fout + t_lo + 4 * cp;
+#pragma unroll 8
+        for (int m = 0; m < NM; ++m) stg_stream4(col + (long long)m * mel_stride, f4);
+      }
+      for (int i = tid; i < NM * ((fT - t_lo) & 3); i += LM_THREADS) {
+        const int rem = (fT - t_lo) & 3, m = i / rem;
+        fout[(long long)m * mel_stride + t_lo + 4 * T4 + (i - m * rem)] = fill;
+      }
+    } else {
+      for (int m = 0; m < NM; ++m)
+        for (int t = t_lo + tid; t < fT; t += LM_THREADS) fout[(long long)m * mel_stride + t] = fill;
+    }
+  };
+  int pend_before = 0;                               // thread 0: the in-flight result of the tile-end count (FZ_DEFER_TILE_END)
+  bool pend = false;
+  // thread 0, at a point where the previous tile end is at least one FIR old: was this half the last finisher of that clip?
+  auto resolve_pending = [&]() {
+    int fc = -1;
+    if (pend) {
+      if (pend_before == H.pend_tiles - 1) { H.fill_max = atomicMax(&clip_max[H.pend_c], (int)0x80000000); fc = H.pend_c; }
+      pend = false;
+    }
+    H.fill_c = fc;
+  };
+  if (tid == 0) { H.fill_c = -1; fill_desc(atomicAdd(work_counter, 1)); }
   for (;;) {
   half_sync(half);                                   // the descriptor written by tid 0 is visible
   const FzNext nd = H.nd;
@@ -503,11 +545,13 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       half_sync(half);
     }
     if (t0 >= T_real) {                                      // a batch that only had output samples left to write
+      if (FZ_DEFER_TILE_END && FZ_INLINE_NORM && b == 0 && tid == 0) resolve_pending();
       if (next) { half_sync(half); stage_span(t0 + LM_BF); }
       else {
         half_sync(half);
         if (tid == 0) { if (b == 0) fill_desc(H.next_unit); prefetch_next_tile(); }
       }
+      if (FZ_DEFER_TILE_END && FZ_INLINE_NORM && b == 0 && H.fill_c >= 0) do_fill(H.fill_c, H.pend_T_real, H.pend_T, H.fill_max);
       continue;
     }
     // ---- FIR 24k -> 16k: slab position i holds w16[w0 + i], w0 = 160*t0 - 200;
@@ -571,6 +615,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     }
 #endif
     half_sync(half);
+    if (FZ_DEFER_TILE_END && FZ_INLINE_NORM && b == 0 && tid == 0) resolve_pending();   // the previous tile end is a FIR old
     // ---- reflect padding of torch.stft(center=True): indices < 0 and >= N mirror the computed ones
     const bool left = w0 < 0, right = (long long)w0 + LM_SLAB > N;
     if (left || right) {
@@ -631,6 +676,8 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     half_sync(half);
     if (next) stage_span(t0 + LM_BF);                        // span and slab are dead: prefetch under stage 2 / mel
     else if (tid == 0) { if (b == 0) fill_desc(H.next_unit); prefetch_next_tile(); }
+    // the padding constant of the clip this half finished last a tile ago (decided by thread 0 after the FIR barrier)
+    if (FZ_DEFER_TILE_END && FZ_INLINE_NORM && b == 0 && H.fill_c >= 0) do_fill(H.fill_c, H.pend_T_real, H.pend_T, H.fill_max);
     // ---- FFT stage 2: lane = k1, 20-point DFT over n2 -> Z[k1 + 20*k2] in v[k2]
 #pragma unroll
     for (int n2 = 0; n2 < 20; ++n2) v[n2] = fb[lane * 21 + n2];
@@ -765,7 +812,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   // ---- per-half reductions: clip max (ordered-int atomicMax), decay sums (double atomics)
   lmax = warp_max(lmax);
   const double df = warp_sum((double)a_first), dl = warp_sum((double)a_last);
-  half_sync(half);
+  if (!FZ_DEFER_TILE_END) half_sync(half);           // (deferred: warp 0 read these right after the barrier below, a tile ago)
   if ((tid & 31) == 0) { H.redf[tid >> 5] = lmax; H.redd[0][tid >> 5] = df; H.redd[1][tid >> 5] = dl; }
   half_sync(half);
   if (tid < 32) {
@@ -792,39 +839,31 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       if (FZ_INLINE_NORM && tiles_done) {
         int clip_tiles = 0;                          // tiles of the schedule that start inside this clip
         while (clip_tiles < sched.n_tiles && sched.start[clip_tiles] * LM_BF < t_cover) ++clip_tiles;
-        int before;
-        asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(before) : "l"(tiles_done + c) : "memory");
-        last = (before == clip_tiles - 1);
-        if (last) H.fill_max = atomicMax(&clip_max[c], (int)0x80000000);
+        if (FZ_DEFER_TILE_END) {
+          // issued, not waited for: every tile runs resolve_pending() in its first batch, so no older count is in flight
+          asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(pend_before) : "l"(tiles_done + c) : "memory");
+          H.pend_c = c; H.pend_tiles = clip_tiles; H.pend_T_real = T_real; H.pend_T = min(T, fill_to);
+          pend = min(T, fill_to) > T_real;           // nothing to fill: nobody needs the answer
+        } else {
+          int before;
+          asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(before) : "l"(tiles_done + c) : "memory");
+          last = (before == clip_tiles - 1);
+          if (last) H.fill_max = atomicMax(&clip_max[c], (int)0x80000000);
+        }
       }
       H.last = last;
     }
   }
-  half_sync(half);
-  if (H.last && min(T, fill_to) > T_real) {
-    T = min(T, fill_to);
-    const float mx = ordered_to_float(H.fill_max);
-    const float fill = __fmul_rn(__fadd_rn(fmaxf(-10.0f, __fsub_rn(mx, 8.0f)), 4.0f), 0.25f);
-    const int t_lo = (T_real + 3) & ~3;              // whole 128-bit pieces from here; [T_real, t_lo) is k_logmel_norm's
-    const bool vec = (mel_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
-    if (vec) {
-      const int T4 = (T - t_lo) >> 2;
-      const float4 f4 = make_float4(fill, fill, fill, fill);
-      for (int cp = tid; cp < T4; cp += LM_THREADS) {
-        float* col = out + t_lo + 4 * cp;
-#pragma unroll 8
-        for (int m = 0; m < NM; ++m) stg_stream4(col + (long long)m * mel_stride, f4);
-      }
-      for (int i = tid; i < NM * ((T - t_lo) & 3); i += LM_THREADS) {
-        const int rem = (T - t_lo) & 3, m = i / rem;
-        out[(long long)m * mel_stride + t_lo + 4 * T4 + (i - m * rem)] = fill;
-      }
-    } else {
-      for (int m = 0; m < NM; ++m)
-        for (int t = t_lo + tid; t < T; t += LM_THREADS) out[(long long)m * mel_stride + t] = fill;
-    }
+  if (!FZ_DEFER_TILE_END) {
+    half_sync(half);
+    if (H.last && min(T, fill_to) > T_real) do_fill(c, T_real, min(T, fill_to), H.fill_max);
   }
   }   // tiles of this half
+  if (FZ_DEFER_TILE_END && FZ_INLINE_NORM) {         // the count of this half's last tile
+    if (tid == 0) resolve_pending();
+    half_sync(half);
+    if (H.fill_c >= 0) do_fill(H.fill_c, H.pend_T_real, H.pend_T, H.fill_max);
+  }
 #if FZ_TC_MEL
   tc_fence_before();
   __syncthreads();
