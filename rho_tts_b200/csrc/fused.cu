@@ -77,6 +77,9 @@ cudaError_t upload_fused_taps(const float* taps) {
 #ifndef FZ_FFMA2_FIR
 #define FZ_FFMA2_FIR 1     // FIR as packed fp32x2 dot products
 #endif
+#ifndef FZ_FIR_QPT
+#define FZ_FIR_QPT 5       // consecutive output quads per FIR thread (1: one quad per thread and round, strided)
+#endif
 #ifndef FZ_INLINE_NORM
 #define FZ_INLINE_NORM 1   // the half that finishes a clip last writes the constant fill of its zero-padding frames at once: k_logmel_norm 0.249 -> 0.113 ms, this kernel 0.866 -> 0.975 ms, step -2 % (0: k_logmel_norm writes the fill; sliced / dedicated-warp variants: profiles/ncu_r01_v7_summary.md)
 #endif
@@ -96,7 +99,10 @@ cudaError_t upload_fused_taps(const float* taps) {
                               // padding constant then happens; two barriers and the atomic round trip leave every tile end
 #endif
 bool fused_inline_norm() { return FZ_INLINE_NORM != 0; }
-constexpr int FZ_HALVES = 2;
+#ifndef FZ_HALVES_N
+#define FZ_HALVES_N 2              // independent 320-thread instruction streams per SM (1: A/B experiment)
+#endif
+constexpr int FZ_HALVES = FZ_HALVES_N;
 constexpr int FZ_THREADS = LM_THREADS * FZ_HALVES;          // 640
 constexpr int FZ_LEAD = 312;                                // span starts 312 samples before the batch's own range
 constexpr int FZ_SPAN = 8068;                               // 24 kHz samples staged per batch (multiple of 4)
@@ -562,6 +568,45 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       // interior batches read the raw x: start the accumulators at -dc * sum(taps)
       const float i0 = fast ? -dc * c_fsum[0] : 0.f, i1 = fast ? -dc * c_fsum[1] : 0.f;
 #if FZ_FFMA2_FIR
+#if FZ_FIR_QPT > 1
+      // FZ_FIR_QPT consecutive quads (4 outputs each) per thread from ONE window of the span held in registers: a quad on
+      // its own reads 26 floats for 4 outputs, five in a row read 48 for 20 -- the FIR's loads were 22 % of the kernel's
+      // shared-memory traffic, the resource both halves of the SM queue on.  1340 quads = 268 threads x 5: one balanced
+      // pass (the strided loop gave the first two warps five rounds and the others four).
+      static_assert(FZ_DPAIRS % FZ_FIR_QPT == 0, "quads per thread must divide the quads per batch");
+      if (tid < FZ_DPAIRS / FZ_FIR_QPT) {
+        const int d0 = FZ_FIR_QPT * tid;
+        const float2* sp = reinterpret_cast<const float2*>(H.span + 2 + 6 * d0);
+        float2 V[3 * FZ_FIR_QPT + 9];
+#pragma unroll
+        for (int k = 0; k < 3 * FZ_FIR_QPT + 9; ++k) V[k] = sp[k];
+#pragma unroll
+        for (int j = 0; j < FZ_FIR_QPT; ++j) {
+          const int d = d0 + j;
+          float2 o00 = make_float2(i0, 0.f), o10 = o00, o01 = make_float2(i1, 0.f), o11 = o01;
+#ifdef FZ_PROBE_HALF_FIR        // timing probe only (WRONG results): every other tap pair skipped
+#define FZ_KSTEP 2
+#else
+#define FZ_KSTEP 1
+#endif
+#pragma unroll
+          for (int k = 0; k < 10; k += FZ_KSTEP) o00 = __ffma2_rn(V[3 * j + k], c_fA0[k], o00);
+#pragma unroll
+          for (int k = 2; k < 12; k += FZ_KSTEP) o10 = __ffma2_rn(V[3 * j + k], c_fB0[k], o10);
+#pragma unroll
+          for (int k = 1; k < 11; k += FZ_KSTEP) o01 = __ffma2_rn(V[3 * j + k], c_fA1[k], o01);
+#pragma unroll
+          for (int k = 3; k < 12; k += FZ_KSTEP) o11 = __ffma2_rn(V[3 * j + k], c_fB1[k], o11);
+          const int wi = w0 + 4 * d;
+          float4 r;
+          r.x = (wi + 0 < n_valid) ? o00.x + o00.y : 0.f;
+          r.y = (wi + 1 < n_valid) ? o01.x + o01.y : 0.f;
+          r.z = (wi + 2 < n_valid) ? o10.x + o10.y : 0.f;
+          r.w = (wi + 3 < n_valid) ? o11.x + o11.y : 0.f;
+          *reinterpret_cast<float4*>(slab + 4 * d + 20 * (d / (LM_SLAB_BLK / 4))) = r;
+        }
+      }
+#else
       for (int d = tid; d < FZ_DPAIRS; d += LM_THREADS) {
         const float2* sp = reinterpret_cast<const float2*>(H.span + 2 + 6 * d);
         float2 V[13];
@@ -584,6 +629,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
         r.w = (wi + 3 < n_valid) ? o11.x + o11.y : 0.f;
         *reinterpret_cast<float4*>(slab + 4 * d + 20 * (d / (LM_SLAB_BLK / 4))) = r;
       }
+#endif
 #else
       for (int d = tid; d < FZ_DPAIRS; d += LM_THREADS) {
         const float2* sp = reinterpret_cast<const float2*>(H.span + 2 + 6 * d);

@@ -68,6 +68,11 @@ __device__ __forceinline__ void dft4(float2& x0, float2& x1, float2& x2, float2&
 // forward 20-point DFT, in place, Good-Thomas 4x5 (no internal twiddles):
 //   input index n = (5a + 4b) mod 20, output index k = (5*k1 + 16*k2) mod 20.
 __device__ __forceinline__ void dft20(float2 (&v)[20]) {
+#ifdef FZ_PROBE_CHEAP_DFT       // timing probe only (WRONG results): four 5-point DFTs instead of the 20-point one
+  dft5(v[0], v[4], v[8], v[12], v[16]); dft5(v[1], v[5], v[9], v[13], v[17]);
+  dft5(v[2], v[6], v[10], v[14], v[18]); dft5(v[3], v[7], v[11], v[15], v[19]);
+  return;
+#endif
   float2 T[4][5];
 #pragma unroll
   for (int a = 0; a < 4; ++a) {

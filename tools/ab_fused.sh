@@ -10,10 +10,10 @@ NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c+
 while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
   b=build_$name; mkdir -p $b
-  for f in api join resample logmel cosine fused mel_gemm qwen pitch mfcc; do $NV $flags -c $f.cu -o $b/$f.o & done
+  for f in api host_api exchange join resample logmel cosine fused mel_gemm stft_tc qwen pitch mfcc; do $NV $flags -c $f.cu -o $b/$f.o & done
   $NV $flags -x cu -c tables.cpp -o $b/tables.o &
   wait
-  $NV -shared -o ../variants/lib_$name.so $b/*.o -cudart static
+  $NV -shared -o ../variants/lib_$name.so $b/*.o -cudart static -ldl
   rm -rf $b
   echo "built variants/lib_$name.so  [$flags]"
 done
