@@ -17,14 +17,13 @@
 #include <cstring>
 #include <thread>
 #include <vector>
-#if defined(__SSE2__)
-#include <emmintrin.h>
-#endif
 #include "handle.h"
 
 using namespace rho;
 
 namespace rho {
+
+void host_fill_f32(float* p, int64_t n, float v);     // hostfill.cpp: non-temporal fill, widest vectors the CPU has
 
 constexpr int HC_SLOTS = 3;
 
@@ -102,29 +101,15 @@ struct Chunk {
   int t_dev;                          // frames per feature row on the device (compact), 0: no features
 };
 
-void fill_f32(float* p, int64_t n, float v) {
-#if defined(__SSE2__)
-  // streaming stores: the rows are written once and read by somebody else later; keep them out of the cache
-  while (n > 0 && (((uintptr_t)p) & 15u)) { *p++ = v; --n; }
-  const __m128 vv = _mm_set1_ps(v);
-  int64_t q = n >> 2;
-  for (int64_t i = 0; i < q; ++i) _mm_stream_ps(p + 4 * i, vv);
-  p += 4 * q; n -= 4 * q;
-  while (n > 0) { *p++ = v; --n; }
-#else
-  std::fill(p, p + n, v);
-#endif
-}
-
 // developer switches for tools/e2e_sweep.py (timing experiments only)
 bool debug_skip_fill() { static const bool v = getenv("RHO_HOST_DEBUG_SKIP_FILL") != nullptr; return v; }
 
 int fill_threads() {
   static const int n = [] {
     if (const char* v = getenv("RHO_HOST_FILL_THREADS")) return std::max(1, atoi(v));
-    // measured on a 16-core B200 host (tools/e2e_sweep.py, profiles/e2e_sweep_r02.log): 2 threads keep up with the
-    // link (0.64 GB of constants per 1.28 GB of copy-out) and disturb the DMA traffic least; 4 and 8 are slower
-    return 2;
+    // 0.64 GB of constants per 1.28 GB of copy-out: about 26 GB/s of fill to keep up with a gen-5 link
+    // (tools/e2e_sweep.py, profiles/e2e_sweep_r02*.log)
+    return 3;
   }();
   return n;
 }
@@ -309,7 +294,7 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
       if (t1 <= t0 || debug_skip_fill()) continue;
       for (int64_t r = w; r < rows; r += W) {
         const int64_t it = c.i0 + r / n_mels;
-        fill_f32(mel + ((int64_t)c.i0 * n_mels + r) * mel_stride_frames + t0, t1 - t0, h_pad[it]);
+        host_fill_f32(mel + ((int64_t)c.i0 * n_mels + r) * mel_stride_frames + t0, t1 - t0, h_pad[it]);
       }
     }
   };

@@ -12,6 +12,7 @@ while [ $# -ge 2 ]; do
   b=build_$name; mkdir -p $b
   for f in api host_api exchange join resample logmel cosine fused mel_gemm stft_tc qwen pitch mfcc; do $NV $flags -c $f.cu -o $b/$f.o & done
   $NV $flags -x cu -c tables.cpp -o $b/tables.o &
+  g++ -O3 -std=c++17 -fPIC -c hostfill.cpp -o $b/hostfill.o &
   wait
   $NV -shared -o ../variants/lib_$name.so $b/*.o -cudart static -ldl
   rm -rf $b

@@ -54,8 +54,8 @@ if __name__ == "__main__":
         child()
     else:
         for mode in ("full", "full_nofill", "compact", "nomel"):
-            for chunk in (32, 64, 128, 256):
-                for ft in ((2, 4, 8) if mode == "full" and chunk == 128 else (4,)):
+            for chunk in ((64, 128) if mode == "full" else (128,)):
+                for ft in ((1, 2, 3, 4, 6, 2, 3, 4) if mode == "full" and chunk == 128 else (3,)):
                     env = dict(os.environ, SWEEP_CHILD="1", SWEEP_MODE=mode, SWEEP_CHUNK=str(chunk),
                                RHO_HOST_CHUNK_SAMPLES=str(chunk * 240000), RHO_HOST_FILL_THREADS=str(ft))
                     if mode == "full_nofill":           # timing experiment only: the rows' constant tails stay unwritten
