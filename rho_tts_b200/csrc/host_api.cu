@@ -25,7 +25,7 @@ namespace rho {
 
 void host_fill_f32(float* p, int64_t n, float v);     // hostfill.cpp: non-temporal fill, widest vectors the CPU has
 
-constexpr int HC_SLOTS = 3;
+constexpr int HC_MAX_SLOTS = 8;    // chunk slots in the device arena (RHO_HOST_SLOTS, default 4: copy-in may run two chunks ahead)
 
 struct HostCtx {
   cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
@@ -34,7 +34,7 @@ struct HostCtx {
   std::vector<cudaEvent_t> ev_out;                          // one per chunk: everything of the chunk is in host memory
   std::vector<cudaEvent_t> ev_small;                        // one per chunk: its records and pad values are (blocking-sync:
                                                             // the fill threads sleep on them)
-  cudaEvent_t ev_in[HC_SLOTS] = {}, ev_done[HC_SLOTS] = {};
+  cudaEvent_t ev_in[HC_MAX_SLOTS] = {}, ev_done[HC_MAX_SLOTS] = {};
   bool ok = false;
 };
 
@@ -47,7 +47,7 @@ void host_ctx_destroy(HostCtx* c) {
   if (c->pinned) cudaFreeHost(c->pinned);
   for (cudaEvent_t e : c->ev_out) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_small) cudaEventDestroy(e);
-  for (int s = 0; s < HC_SLOTS; ++s) {
+  for (int s = 0; s < HC_MAX_SLOTS; ++s) {
     if (c->ev_in[s]) cudaEventDestroy(c->ev_in[s]);
     if (c->ev_done[s]) cudaEventDestroy(c->ev_done[s]);
   }
@@ -61,7 +61,7 @@ cudaError_t host_ctx_init(HostCtx* c) {
   if ((e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)) != cudaSuccess) return e;
   if ((e = cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking)) != cudaSuccess) return e;
   if ((e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking)) != cudaSuccess) return e;
-  for (int s = 0; s < HC_SLOTS; ++s) {
+  for (int s = 0; s < HC_MAX_SLOTS; ++s) {
     if ((e = cudaEventCreateWithFlags(&c->ev_in[s], cudaEventDisableTiming)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&c->ev_done[s], cudaEventDisableTiming)) != cudaSuccess) return e;
   }
@@ -110,6 +110,15 @@ int fill_threads() {
     // 0.64 GB of constants per 1.28 GB of copy-out: about 26 GB/s of fill to keep up with a gen-5 link
     // (tools/e2e_sweep.py, profiles/e2e_sweep_r02*.log)
     return 3;
+  }();
+  return n;
+}
+
+int host_slots() {
+  static const int n = [] {
+    const char* v = getenv("RHO_HOST_SLOTS");
+    const int k = v ? atoi(v) : 4;
+    return std::min(HC_MAX_SLOTS, std::max(2, k));
   }();
   return n;
 }
@@ -236,7 +245,8 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
   }
   const size_t b_ref = align_up(sizeof(float) * (size_t)std::max(1, emb_dim), 256);
   const size_t per_slot = b_x + b_y + b_mel + b_rec + b_emb + b_meta + b_ws + b_pad;
-  const size_t total = HC_SLOTS * per_slot + b_ref;
+  const int HC_SLOTS = host_slots();
+  const size_t total = (size_t)HC_SLOTS * per_slot + b_ref;
 
   CtxLease lease(h);
   if (!lease.c) return cuda_fail(lease.err, "host context");

@@ -61,9 +61,10 @@ def transcribe_tensor(audio: torch.Tensor, sample_rate: int, model, tokenizer, *
     """Transcription of one clip from its tensor.  `model` is a transformers Whisper model (or anything with
     `.generate(input_features=...)` and, optionally, `.config.num_mel_bins` / `.dtype`) already on the B200;
     `tokenizer` has `batch_decode`.  Returns None when transcription fails, like stt_validator.py:116-148."""
+    # the B200 part is outside the try: a missing library / GPU is a loud RuntimeError, not a skipped validation
+    n_mels = int(getattr(getattr(model, "config", None), "num_mel_bins", 80) or 80)
+    feats = whisper_features(audio, sample_rate, n_mels=n_mels, device=device)
     try:
-        n_mels = int(getattr(getattr(model, "config", None), "num_mel_bins", 80) or 80)
-        feats = whisper_features(audio, sample_rate, n_mels=n_mels, device=device)
         dtype = getattr(model, "dtype", torch.float32)
         with torch.no_grad():
             ids = model.generate(input_features=feats.to(dtype), **(generate_kwargs or {}))

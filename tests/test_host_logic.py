@@ -164,3 +164,39 @@ def test_bind_to_gpu_numa_is_harmless_without_nvml():
     assert R.dist.bind_to_gpu_numa(0) is None or isinstance(R.dist.bind_to_gpu_numa(0), list)
     if not __import__("torch").cuda.is_available():
         assert os.sched_getaffinity(0) == before
+
+
+def test_host_item_layout_matches_join_capacity_rule():
+    """Output offsets / capacities of the ragged host entry point: sum of the item's segment lengths + max(0, n - 2) pauses
+    (SURVEY App. A.5), every offset a multiple of 32 samples."""
+    import numpy as np
+    import rho_tts_b200 as R
+    p = R.make_params()                       # pause 0.1 s -> 2400 samples
+    seg = np.array([1000, 24000, 5, 0, 48017, 300, 301], np.int32)
+    first = np.array([0, 1, 4, 4, 7], np.int32)      # items of 1, 3, 0 and 3 segments
+    off, cap, total = R.host_item_layout(seg, first, p)
+    assert cap.tolist() == [1000, 24000 + 5 + 0 + 2400, 0, 48017 + 300 + 301 + 2400]
+    assert np.all(off % 32 == 0) and np.all(np.diff(off) >= cap[:-1]) and total >= off[-1] + cap[-1]
+    off0, cap0, _ = R.host_item_layout(seg, first, R.make_params(inter_sentence_pause_sec=0.0))
+    assert cap0.tolist() == [1000, 24005, 0, 48618]
+
+
+def test_tensor_validation_sibling_has_no_cpu_fallback():
+    """validate_audio_text_match_tensor needs the STT model and a B200: both are loud errors (RuntimeError, never
+    ValueError: base_tts.py:786-787), a failing transcription is (True, 0.0, None) like stt_validator.py:251-253."""
+    import pytest
+    import torch
+    import rho_tts_b200 as R
+    x = torch.zeros(24000)
+    with pytest.raises(RuntimeError, match="STT model"):
+        R.validate_audio_text_match_tensor(x, 24000, "hello")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            R.whisper_features(x, 24000)
+
+        class M:
+            def generate(self, **kw):
+                return [[1]]
+        # ... also through the validation entry: only the STT model's own failures are "validation skipped"
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            R.validate_audio_text_match_tensor(x, 24000, "hello", model=M(), tokenizer=object(), similarity_fn=lambda a, b: 1.0)

@@ -45,7 +45,7 @@ def child():
         fn()
         ts.append(time.perf_counter() - t0)
     ts.sort()
-    print(json.dumps({"mode": mode, "chunk_clips": os.environ.get("SWEEP_CHUNK"), "fill_threads": os.environ.get("RHO_HOST_FILL_THREADS"),
+    print(json.dumps({"mode": mode, "chunk_clips": os.environ.get("SWEEP_CHUNK"), "fill_threads": os.environ.get("RHO_HOST_FILL_THREADS"), "slots": os.environ.get("RHO_HOST_SLOTS"),
                       "ms_median": 1e3 * ts[len(ts) // 2], "ms_best": 1e3 * ts[0], "audio_s_per_s_median": n * 10.0 / ts[len(ts) // 2]}))
 
 
@@ -53,10 +53,12 @@ if __name__ == "__main__":
     if os.environ.get("SWEEP_CHILD"):
         child()
     else:
-        for mode in ("full", "full_nofill", "compact", "nomel"):
-            for chunk in ((64, 128) if mode == "full" else (128,)):
-                for ft in ((1, 2, 3, 4, 6, 2, 3, 4) if mode == "full" and chunk == 128 else (3,)):
-                    env = dict(os.environ, SWEEP_CHILD="1", SWEEP_MODE=mode, SWEEP_CHUNK=str(chunk),
+        settings = [(m, c, 3, sl) for m in ("full", "compact", "nomel") for c in (32, 64, 128) for sl in (3, 4, 6)]
+        settings += [("full", 128, ft, 4) for ft in (1, 2, 4, 6)] + [("full_nofill", 128, 3, 4)]
+        if True:
+            for mode, chunk, ft, slots in settings:
+                if True:
+                    env = dict(os.environ, SWEEP_CHILD="1", SWEEP_MODE=mode, SWEEP_CHUNK=str(chunk), RHO_HOST_SLOTS=str(slots),
                                RHO_HOST_CHUNK_SAMPLES=str(chunk * 240000), RHO_HOST_FILL_THREADS=str(ft))
                     if mode == "full_nofill":           # timing experiment only: the rows' constant tails stay unwritten
                         env["RHO_HOST_DEBUG_SKIP_FILL"] = "1"
