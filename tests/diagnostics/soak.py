@@ -42,6 +42,23 @@ for r in range(rounds):
         worst["ratio"] = max(worst["ratio"], abs(ratio - rec["decay_ratio"][i]) / max(1.0, abs(ratio)))
         if bool(rec["ok"][i]) != ok and abs(ratio - 0.3) > 1e-4:
             bad += 1; print("round", r, "item", i, "decision", rec["ok"][i], ok, ratio)
+    # (a2) the same joined items through the whole front end (join -> features read from the joined audio -> cosine)
+    nmj = 128 if r % 2 == 0 else 80
+    padj = (r % 3 != 1)
+    vj = R.validate_batch(rb, p, n_mels=nmj, pad_to_30s=padj, item_first_seg=first)
+    vjr = vj.records_host()
+    for i in range(len(first) - 1):
+        o = oracle.smooth_segment_join(clips[first[i]:first[i + 1]], c)
+        if o.audio is None:
+            continue
+        if int(vjr["out_len"][i]) != o.audio.size or int(vjr["out_len"][i]) != int(rec["out_len"][i]):
+            bad += 1; print("round", r, "item", i, "joined-features length", vjr["out_len"][i], o.audio.size); continue
+        w = oracle.resample(o.audio.reshape(-1)) if o.audio.size else np.zeros(0, np.float32)
+        if not padj and w.size <= 200:
+            continue
+        m = oracle.log_mel(w, nmj, padj)
+        g = vj.mel[i, :, :m.shape[1]].cpu().numpy()
+        worst["mel"] = max(worst["mel"], float(np.abs(g - m).max()))
     # (b) one-segment items through the fused path, both feature sizes
     nm = 80 if r % 2 == 0 else 128
     v = R.validate_batch(rb, p, n_mels=nm, pad_to_30s=(r % 3 != 0))
