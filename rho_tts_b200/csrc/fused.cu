@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <vector>
 #include <cstdlib>
+#include <type_traits>
 #include "logmel_dev.cuh"
 
 namespace rho {
@@ -80,6 +81,9 @@ cudaError_t upload_fused_taps(const float* taps) {
 #ifndef FZ_FIR_QPT
 #define FZ_FIR_QPT 5       // consecutive output quads per FIR thread (1: one quad per thread and round, strided)
 #endif
+#ifndef FZ_SPLIT_APPLY
+#define FZ_SPLIT_APPLY 1   // interior batches: warps 8-9 write y while warps 0-7 run the FIR (instead of every thread doing both in turn)
+#endif
 #ifndef FZ_INLINE_NORM
 #define FZ_INLINE_NORM 1   // the half that finishes a clip last writes the constant fill of its zero-padding frames at once: k_logmel_norm 0.249 -> 0.113 ms, this kernel 0.866 -> 0.975 ms, step -2 % (0: k_logmel_norm writes the fill; sliced / dedicated-warp variants: profiles/ncu_r01_v7_summary.md)
 #endif
@@ -109,6 +113,7 @@ constexpr int FZ_SPAN = 8068;                               // 24 kHz samples st
 constexpr int FZ_OWN = 240 * LM_BF;                         // 7680 output samples owned by a batch
 constexpr int FZ_DPAIRS = LM_SLAB / 4;                      // 1340 groups of 4 consecutive 16 kHz samples
 
+constexpr int FZ_FIR_MAIN = 256;                            // split mode: threads (8 warps) that run the FIR five quads at a time
 constexpr int FZ_TWS = 22;                                  // float2 per twiddle row (conflict-free 128-bit reads)
 
 // How the frames of a clip are cut into tiles: tile k covers the 32-frame batches [start[k], start[k+1])
@@ -508,19 +513,36 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     const bool in_first = own_hi <= third, in_last = own_lo >= n - third;
     const bool fast = FROM_Y || (FZ_FAST_APPLY && j0 >= edge_lo && j0 + FZ_SPAN <= edge_hi &&
                                  (in_first || own_lo >= third) && (in_last || own_hi <= n - third));
+    const bool split = FZ_SPLIT_APPLY && !FROM_Y && fast && t0 < T_real;
     if (FROM_Y) {
       // finished audio: nothing to apply, nothing to write back; samples outside the item were zero-filled by the staging
     } else if (fast) {
-      // ---- apply, interior: 6 pieces per thread, registers -> HBM; the span keeps the raw x
+      // ---- apply, interior: registers -> HBM; the span keeps the raw x.  Split mode (a batch that also runs the FIR):
+      // the interior apply and the FIR do not depend on each other, so warps 8-9 write all of y (30 pieces per thread) while
+      // warps 0-7 start the FIR at once (5 quads per thread; the last 60 quads go to warps 8-9 as well) -- the two kinds of
+      // work sit side by side on the SM instead of one after the other in every thread
       float ss = 0.f;
       const float2 ndc = make_float2(-dc, -dc);
+      if (!split) {
 #pragma unroll
-      for (int k = 0; k < FZ_OWN / 4 / LM_THREADS; ++k) {
-        const int q = FZ_LEAD / 4 + tid + k * LM_THREADS;
-        const float4 v = *reinterpret_cast<const float4*>(H.span + 4 * q);
-        const float2 lo = __fadd2_rn(make_float2(v.x, v.y), ndc), hi = __fadd2_rn(make_float2(v.z, v.w), ndc);
-        stg_stream4(ys + own_lo + 4 * (tid + k * LM_THREADS), make_float4(lo.x, lo.y, hi.x, hi.y));
-        ss = fmaf(lo.x, lo.x, ss); ss = fmaf(lo.y, lo.y, ss); ss = fmaf(hi.x, hi.x, ss); ss = fmaf(hi.y, hi.y, ss);
+        for (int k = 0; k < FZ_OWN / 4 / LM_THREADS; ++k) {
+          const int q = FZ_LEAD / 4 + tid + k * LM_THREADS;
+          const float4 v = *reinterpret_cast<const float4*>(H.span + 4 * q);
+          const float2 lo = __fadd2_rn(make_float2(v.x, v.y), ndc), hi = __fadd2_rn(make_float2(v.z, v.w), ndc);
+          stg_stream4(ys + own_lo + 4 * (tid + k * LM_THREADS), make_float4(lo.x, lo.y, hi.x, hi.y));
+          ss = fmaf(lo.x, lo.x, ss); ss = fmaf(lo.y, lo.y, ss); ss = fmaf(hi.x, hi.x, ss); ss = fmaf(hi.y, hi.y, ss);
+        }
+      } else if (tid >= FZ_FIR_MAIN) {
+        constexpr int AT = LM_THREADS - FZ_FIR_MAIN;         // 64 apply threads
+        static_assert((FZ_OWN / 4) % AT == 0, "apply pieces per thread");
+#pragma unroll 6
+        for (int k = 0; k < FZ_OWN / 4 / AT; ++k) {
+          const int i = (tid - FZ_FIR_MAIN) + k * AT;
+          const float4 v = *reinterpret_cast<const float4*>(H.span + FZ_LEAD + 4 * i);
+          const float2 lo = __fadd2_rn(make_float2(v.x, v.y), ndc), hi = __fadd2_rn(make_float2(v.z, v.w), ndc);
+          stg_stream4(ys + own_lo + 4 * i, make_float4(lo.x, lo.y, hi.x, hi.y));
+          ss = fmaf(lo.x, lo.x, ss); ss = fmaf(lo.y, lo.y, ss); ss = fmaf(hi.x, hi.x, ss); ss = fmaf(hi.y, hi.y, ss);
+        }
       }
       if (in_first) a_first += ss;
       if (in_last) a_last += ss;
@@ -571,17 +593,17 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
 #if FZ_FIR_QPT > 1
       // FZ_FIR_QPT consecutive quads (4 outputs each) per thread from ONE window of the span held in registers: a quad on
       // its own reads 26 floats for 4 outputs, five in a row read 48 for 20 -- the FIR's loads were 22 % of the kernel's
-      // shared-memory traffic, the resource both halves of the SM queue on.  1340 quads = 268 threads x 5: one balanced
-      // pass (the strided loop gave the first two warps five rounds and the others four).
+      // shared-memory traffic.  1340 quads = 268 threads x 5: one balanced pass (the strided loop gave the first two warps
+      // five rounds and the others four); in split mode 256 threads x 5 + 60 x 1.
       static_assert(FZ_DPAIRS % FZ_FIR_QPT == 0, "quads per thread must divide the quads per batch");
-      if (tid < FZ_DPAIRS / FZ_FIR_QPT) {
-        const int d0 = FZ_FIR_QPT * tid;
+      auto fir_quads = [&](auto qpt_tag, int d0) {
+        constexpr int QPT = decltype(qpt_tag)::value;
         const float2* sp = reinterpret_cast<const float2*>(H.span + 2 + 6 * d0);
-        float2 V[3 * FZ_FIR_QPT + 9];
+        float2 V[3 * QPT + 9];
 #pragma unroll
-        for (int k = 0; k < 3 * FZ_FIR_QPT + 9; ++k) V[k] = sp[k];
+        for (int k = 0; k < 3 * QPT + 9; ++k) V[k] = sp[k];
 #pragma unroll
-        for (int j = 0; j < FZ_FIR_QPT; ++j) {
+        for (int j = 0; j < QPT; ++j) {
           const int d = d0 + j;
           float2 o00 = make_float2(i0, 0.f), o10 = o00, o01 = make_float2(i1, 0.f), o11 = o01;
 #ifdef FZ_PROBE_HALF_FIR        // timing probe only (WRONG results): every other tap pair skipped
@@ -605,6 +627,13 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
           r.w = (wi + 3 < n_valid) ? o11.x + o11.y : 0.f;
           *reinterpret_cast<float4*>(slab + 4 * d + 20 * (d / (LM_SLAB_BLK / 4))) = r;
         }
+      };
+      if (split) {
+        if (tid < FZ_FIR_MAIN) fir_quads(std::integral_constant<int, FZ_FIR_QPT>{}, FZ_FIR_QPT * tid);
+        else if (FZ_FIR_MAIN * FZ_FIR_QPT + (tid - FZ_FIR_MAIN) < FZ_DPAIRS)
+          fir_quads(std::integral_constant<int, 1>{}, FZ_FIR_MAIN * FZ_FIR_QPT + (tid - FZ_FIR_MAIN));
+      } else if (tid < FZ_DPAIRS / FZ_FIR_QPT) {
+        fir_quads(std::integral_constant<int, FZ_FIR_QPT>{}, FZ_FIR_QPT * tid);
       }
 #else
       for (int d = tid; d < FZ_DPAIRS; d += LM_THREADS) {
