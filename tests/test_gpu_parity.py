@@ -745,3 +745,46 @@ def test_log_mel_on_tensor_cores_only(R, cuda_device):
         e_pr = float(np.abs(got[:, :T] - prod[i, :, :T].cpu().numpy()).max())
         print(f"tensor-core-only log-mel, clip {i}: {e_or:.2e} from the numpy oracle, {e_pr:.2e} from the product path")
         assert e_or < 5e-4 and e_pr < 5e-4
+
+
+# ----------------------------------------------------------------------------- error behaviour of the new entry points
+def test_new_entry_points_fail_loudly(R, cuda_device):
+    """Bad layouts / sizes are refused with a message (RuntimeError through the shim, never a silent fallback)."""
+    import ctypes
+    from rho_tts_b200 import synth, _lib
+    x = synth.make_clip_block(4, 48000, 9)
+    rb = R.RaggedBatch.from_dense(x.to(cuda_device))
+    p = R.make_params()
+    # compact rows shorter than the frames that can see signal
+    plan = R.ValidatePlan(rb, np.arange(5, dtype=np.int32), p, 80, True, compact=True)
+    plan.T_alloc = 100
+    with pytest.raises(RuntimeError, match="compact rows need"):
+        plan.run(rb, None, None)
+    # host entry point: overlapping segments, outputs without room, mel rows too short
+    xh = x.reshape(-1).pin_memory()
+    off = np.array([0, 40000, 96000, 144000], np.int64)                     # segment 1 starts inside segment 0
+    ln = np.full(4, 48000, np.int32)
+    with pytest.raises(RuntimeError, match="non-overlapping"):
+        R.validate_host_ragged(xh, off, ln, np.arange(5, dtype=np.int32), p, features=False)
+    with pytest.raises(RuntimeError, match="item_first_seg"):
+        R.validate_host_ragged(xh, np.arange(4, dtype=np.int64) * 48000, ln, np.array([0, 2, 3], np.int32), p, features=False)
+    h = _lib.Handle.get(0)
+    rec = torch.zeros((4, 48), dtype=torch.uint8).pin_memory()
+    y = torch.empty(4 * 48000).pin_memory()
+    mel = torch.empty((4, 80, 64)).pin_memory()
+    seg_off = (np.arange(4, dtype=np.int64) * 48000)
+    first = np.arange(5, dtype=np.int32)
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)     # noqa: E731
+    rc = h.lib.rho_b200_validate_host_ragged(h.ptr, ctypes.c_void_p(xh.data_ptr()), vp(seg_off), vp(ln), 4, vp(first), 4,
+                                             ctypes.byref(p), ctypes.c_void_p(y.data_ptr()), vp(seg_off), 80, 3000,
+                                             ctypes.c_void_p(mel.data_ptr()), 64, None, None, None, 0,
+                                             ctypes.c_void_p(rec.data_ptr()))
+    assert rc == -1 and "mel_stride_frames" in _lib.last_error()
+    # the tensor-core DFT refuses a misaligned tile list and short rows
+    pw = torch.empty((8, 208), device=cuda_device)
+    tl = torch.zeros((2, 4), dtype=torch.int32, device=cuda_device)
+    assert h.lib.rho_b200_stft_power_tc(h.ptr, ctypes.c_void_p(rb.data.data_ptr()), ctypes.c_void_p(rb.offsets.data_ptr()),
+                                        ctypes.c_void_p(rb.lengths.data_ptr()), 0, ctypes.c_void_p(tl.data_ptr()), 1,
+                                        ctypes.c_void_p(pw.data_ptr()), 100, None) == -1
+    # the exchange cannot be waited on / read before it exists
+    assert h.lib.rho_b200_exchange_wait(h.ptr, 1, None) == -1 and "not connected" in _lib.last_error()
