@@ -287,6 +287,33 @@ __device__ __noinline__ void fz_apply_edge(float* e, int o, int n, int fade, boo
 //                 never leaves shared memory -- the path of base_tts.py:912-926 items that have several segments.
 // fill_to: the constant of the zero-padding frames is written for frames < fill_to only (3000, or the row length of a
 //          compact feature tensor, RHO_V_COMPACT_PAD).
+// The constant of the frames that only see zero padding (2/3 of a 10 s clip's features): pure stores by the 320 threads of
+// a half.  Out of line: three call sites, none of them on the per-batch path.
+template <int NM>
+__device__ __noinline__ void fz_fill_padding(float* __restrict__ fout, long long mel_stride, int fT_real, int fT,
+                                             int fmax_ordered, int tid) {
+  const float mx = ordered_to_float(fmax_ordered);
+  const float fill = __fmul_rn(__fadd_rn(fmaxf(-10.0f, __fsub_rn(mx, 8.0f)), 4.0f), 0.25f);
+  const int t_lo = (fT_real + 3) & ~3;               // whole 128-bit pieces from here; [T_real, t_lo) is k_logmel_norm's
+  const bool vec = (mel_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(fout) & 15u) == 0);
+  if (vec) {
+    const int T4 = (fT - t_lo) >> 2;
+    const float4 f4 = make_float4(fill, fill, fill, fill);
+    for (int cp = tid; cp < T4; cp += LM_THREADS) {
+      float* col = fout + t_lo + 4 * cp;
+#pragma unroll 8
+      for (int m = 0; m < NM; ++m) stg_stream4(col + (long long)m * mel_stride, f4);
+    }
+    for (int i = tid; i < NM * ((fT - t_lo) & 3); i += LM_THREADS) {
+      const int rem = (fT - t_lo) & 3, m = i / rem;
+      fout[(long long)m * mel_stride + t_lo + 4 * T4 + (i - m * rem)] = fill;
+    }
+  } else {
+    for (int m = 0; m < NM; ++m)
+      for (int t = t_lo + tid; t < fT; t += LM_THREADS) fout[(long long)m * mel_stride + t] = fill;
+  }
+}
+
 template <int NM, bool FROM_Y>
 __global__ void __launch_bounds__(FZ_THREADS, 1)
 k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const SegState* __restrict__ seg,
@@ -396,29 +423,8 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     bulk_g2s(H.span, xsn + j0, FZ_SPAN * 4, &H.bar);
     H.nd.prefetched = 1;
   };
-  // The constant of the frames that only see zero padding, for clip fc (2/3 of a 10 s clip's features): pure stores.
   auto do_fill = [&](int fc, int fT_real, int fT, int fmax_ordered) {
-    float* __restrict__ fout = mel + (long long)fc * NM * mel_stride;
-    const float mx = ordered_to_float(fmax_ordered);
-    const float fill = __fmul_rn(__fadd_rn(fmaxf(-10.0f, __fsub_rn(mx, 8.0f)), 4.0f), 0.25f);
-    const int t_lo = (fT_real + 3) & ~3;             // whole 128-bit pieces from here; [T_real, t_lo) is k_logmel_norm's
-    const bool vec = (mel_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(fout) & 15u) == 0);
-    if (vec) {
-      const int T4 = (fT - t_lo) >> 2;
-      const float4 f4 = make_float4(fill, fill, fill, fill);
-      for (int cp = tid; cp < T4; cp += LM_THREADS) {
-        float* col = fout + t_lo + 4 * cp;
-#pragma unroll 8
-        for (int m = 0; m < NM; ++m) stg_stream4(col + (long long)m * mel_stride, f4);
-      }
-      for (int i = tid; i < NM * ((fT - t_lo) & 3); i += LM_THREADS) {
-        const int rem = (fT - t_lo) & 3, m = i / rem;
-        fout[(long long)m * mel_stride + t_lo + 4 * T4 + (i - m * rem)] = fill;
-      }
-    } else {
-      for (int m = 0; m < NM; ++m)
-        for (int t = t_lo + tid; t < fT; t += LM_THREADS) fout[(long long)m * mel_stride + t] = fill;
-    }
+    fz_fill_padding<NM>(mel + (long long)fc * NM * mel_stride, mel_stride, fT_real, fT, fmax_ordered, tid);
   };
   int pend_before = 0;                               // thread 0: the in-flight result of the tile-end count (FZ_DEFER_TILE_END)
   bool pend = false;
@@ -628,13 +634,11 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
           *reinterpret_cast<float4*>(slab + 4 * d + 20 * (d / (LM_SLAB_BLK / 4))) = r;
         }
       };
-      if (split) {
-        if (tid < FZ_FIR_MAIN) fir_quads(std::integral_constant<int, FZ_FIR_QPT>{}, FZ_FIR_QPT * tid);
-        else if (FZ_FIR_MAIN * FZ_FIR_QPT + (tid - FZ_FIR_MAIN) < FZ_DPAIRS)
-          fir_quads(std::integral_constant<int, 1>{}, FZ_FIR_MAIN * FZ_FIR_QPT + (tid - FZ_FIR_MAIN));
-      } else if (tid < FZ_DPAIRS / FZ_FIR_QPT) {
-        fir_quads(std::integral_constant<int, FZ_FIR_QPT>{}, FZ_FIR_QPT * tid);
-      }
+      // one call site for the five-quad pass (the code is 450 instructions): split batches give it the first 256 threads
+      // and the last 60 quads to warps 8-9 one at a time, the others the first 268 threads
+      if (tid < (split ? FZ_FIR_MAIN : FZ_DPAIRS / FZ_FIR_QPT)) fir_quads(std::integral_constant<int, FZ_FIR_QPT>{}, FZ_FIR_QPT * tid);
+      else if (split && FZ_FIR_MAIN * FZ_FIR_QPT + (tid - FZ_FIR_MAIN) < FZ_DPAIRS)
+        fir_quads(std::integral_constant<int, 1>{}, FZ_FIR_MAIN * FZ_FIR_QPT + (tid - FZ_FIR_MAIN));
 #else
       for (int d = tid; d < FZ_DPAIRS; d += LM_THREADS) {
         const float2* sp = reinterpret_cast<const float2*>(H.span + 2 + 6 * d);
