@@ -97,7 +97,7 @@ const char* rho_b200_last_error(void);
  * the library's constants with torchaudio / transformers):
  *   kind 0: resample taps 24k->16k, out[2*23]      (torchaudio functional.py:1305-1405)
  *   kind 1: periodic Hann(400), out[400]           (feature_extraction_whisper.py:141)
- *   kind 2: mel filterbank, arg = n_mels, out[n_mels*201] row-major [mel][bin]
+ *   kind 2: mel filterbank, arg = n_mels (80, 128: Whisper; 40: speaker encoder), out[n_mels*201] row-major [mel][bin]
  *                                                   (transformers audio_utils.py:453-544)
  *   kind 3: pitch shift phase_advance = torch.linspace(0, pi*128, 257) as torch's fp32 kernel makes it, out[257]
  *   kind 4: MFCC DCT-II rows (orthonormal), out[13*128]
@@ -228,6 +228,47 @@ int rho_b200_pitch_shift(rho_handle* h, const float* x, const int64_t* off, cons
 size_t rho_b200_mfcc_workspace_bytes(int n, int64_t max_len);
 int rho_b200_mfcc_stats(rho_handle* h, const float* x16, const int64_t* off, const int32_t* len, int len_stride_bytes,
                         int n, int64_t max_len, float* out, void* workspace, size_t ws_bytes, void* stream);
+
+/* --------------------------------------------------------------- speaker-encoder front end (NEXT-3, resemblyzer) */
+/* What resemblyzer runs on the CPU between a 16 kHz waveform and its LSTM, reached from BaseTTS._compute_speaker_similarity
+ * (base_tts.py:326-347: preprocess_wav -> voice_encoder.embed_utterance -> cosine with the reference embedding),
+ * QwenTTS._initialize_reference_embedding (providers/qwen.py:199-216) and validation/classifier/trainer.py:41-47.
+ * resemblyzer (pyproject.toml: `resemblyzer>=0.1.4`) is not vendored by the reference: oracle/speaker.py restates
+ * audio.py / voice_encoder.py of 0.1.4 and is pinned on transformers' port of librosa's spectrogram.  Not replaced:
+ * librosa.resample (the 16 kHz signal is the input; rho_b200_resample3to2 is this library's 24 -> 16 kHz), webrtcvad
+ * (trim_long_silences: run it on the host between the two calls if wanted) and the LSTM itself. */
+
+/* compute_partial_slices (voice_encoder.py): number of partial utterances of a clip of n_samples -- partial j is mel frames
+ * [frame_step*j, frame_step*j + 160) -- and, in *padded_len, the sample the last partial ends at (embed_utterance
+ * zero-pads the clip to it when it lies past the end).  frame_step = round(16000 / rate / 160) = 77 for the default rate
+ * 1.3; min_coverage 0.75.  Host only, no GPU. */
+int rho_b200_spk_slices(int64_t n_samples, int frame_step, double min_coverage, int64_t* padded_len);
+
+/* normalize_volume (audio.py): gain[s] = 10^((target_dbfs - dBFS(clip s)) / 20) in float32 like numpy's, or 1 where the
+ * mode forbids the change (mode 0 = always, 1 = increase only -- what preprocess_wav uses with -30 dBFS --, 2 = decrease
+ * only).  y (may be NULL: gains only; may alias x) receives the scaled clips.  workspace: 8 bytes per clip, 8-byte
+ * aligned. */
+int rho_b200_normalize_volume(rho_handle* h, const float* x, const int64_t* off, const int32_t* len, int len_stride_bytes,
+                              int n, int64_t max_len, float target_dbfs, int mode, float* y, const int64_t* y_off,
+                              float* gain, void* workspace, size_t ws_bytes, void* stream);
+
+#define RHO_SPK_PAD_TO_SLICES 1u   /* zero-pad every clip to the end of its last partial first, as embed_utterance does */
+/* wav_to_mel_spectrogram (audio.py: librosa.feature.melspectrogram(sr 16000, n_fft 400, hop 160, n_mels 40), transposed):
+ * periodic hann, centred with zero padding, |X|^2, 40 slaney bands, no log.  Clip s gives T_s = 1 + len_s / 160 rows
+ * (len_s after the padding of RHO_SPK_PAD_TO_SLICES) of 40 floats.
+ *   mel      (may be NULL) [frame_off[s] + t][40]
+ *   partials (may be NULL) [part_off[s] + j][160][40] = rows [frame_step*j, frame_step*j + 160) of the padded clip's
+ *            spectrogram, j < rho_b200_spk_slices(len_s): the LSTM's input batch (voice_encoder.py embed_utterance);
+ *            implies the padding
+ *   gain     (may be NULL) per-clip factor applied to the samples first (rho_b200_normalize_volume with y = NULL) */
+int rho_b200_spk_mel(rho_handle* h, const float* x16, const int64_t* off, const int32_t* len, int len_stride_bytes, int n,
+                     int64_t max_len, int frame_step, double min_coverage, unsigned flags, const float* gain, float* mel,
+                     const int64_t* frame_off, float* partials, const int32_t* part_off, void* stream);
+
+/* The tail of embed_utterance: out[s] = mean of partial_embeds[part_off[s] .. part_off[s+1]) (rows of `dim` floats, the
+ * LSTM's output), divided by its L2 norm.  part_off has n + 1 entries. */
+int rho_b200_spk_pool(rho_handle* h, const float* partial_embeds, const int32_t* part_off, int n, int dim, float* out,
+                      void* stream);
 
 /* --------------------------------------------------------------- batched decay check on finished audio (a5) */
 /* _validate_sound_decay (base_tts.py:297-323) for n clips that are already final, e.g. after the Qwen loudness hook,

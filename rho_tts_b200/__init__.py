@@ -13,6 +13,7 @@ from .batch import (make_params, params_from_tts, trim_scan_batch, join_batch, p
 from .mixin import B200AudioMixin, B200QwenAudioMixin, make_b200_provider, register_b200_providers   # noqa: F401
 from . import _lib                                                         # noqa: F401
 from .validation import whisper_features, transcribe_tensor, validate_audio_text_match_tensor   # noqa: F401
+from . import speaker                                                      # noqa: F401  (resemblyzer's front end, NEXT-3)
 from . import dist                                                         # noqa: F401  (sharding, record gather, NUMA binding)
 
 __version__ = "0.1.0"

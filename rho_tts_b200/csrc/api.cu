@@ -52,7 +52,7 @@ const char* const kKernelNames[KID_COUNT] = {
   "k_resample3to2", "k_logmel_init", "k_logmel_frames", "k_logmel_norm", "k_cosine", "k_single_clip_helpers",
   "k_fused_features", "k_mel_gemm", "k_qwen_moments", "k_qwen_plan", "k_qwen_apply", "k_resample_general",
   "k_pv_stft", "k_pv_phase", "k_pv_cumsum", "k_pv_istft", "k_resample_windowed", "k_mfcc_frames", "k_mfcc_stats",
-  "k_wait_flags", "k_stft_tc"};
+  "k_wait_flags", "k_stft_tc", "k_spk_sumsq", "k_spk_scale", "k_spk_mel", "k_spk_pool"};
 }
 
 namespace {
@@ -149,7 +149,7 @@ int rho_b200_host_table(int kind, int arg, float* out, size_t cap) {
       if (cap < N_FFT) return fail(RHO_ERR_INVALID, "capacity");
       host_hann(out); return N_FFT;
     case 2:
-      if (arg != 80 && arg != 128) return fail(RHO_ERR_INVALID, "n_mels must be 80 or 128");
+      if (arg != 80 && arg != 128 && arg != SPK_MELS) return fail(RHO_ERR_INVALID, "n_mels must be 80, 128 or 40");
       if (cap < (size_t)arg * N_BINS) return fail(RHO_ERR_INVALID, "capacity");
       host_mel_filterbank(arg, out); return arg * N_BINS;
     case 3: {                                          // pitch shift: phase_advance = torch.linspace(0, pi * 128, 257)
@@ -523,6 +523,58 @@ int rho_b200_mfcc_stats(rho_handle* h, const float* x16, const int64_t* off, con
   cudaError_t e = launch_mfcc_stats(h->mfcc_tb, x16, off, len, len_stride_bytes, n, max_len, out, workspace,
                                     (cudaStream_t)stream, &h->lc);
   return e == cudaSuccess ? RHO_OK : cuda_fail(e, "mfcc_stats");
+}
+
+// ---- resemblyzer front end (spk.cu)
+int rho_b200_spk_slices(int64_t n_samples, int frame_step, double min_coverage, int64_t* padded_len) {
+  if (n_samples < 0 || frame_step <= 0 || frame_step > SPK_PART_FRAMES || !(min_coverage > 0.0 && min_coverage <= 1.0))
+    return fail(RHO_ERR_INVALID, "spk_slices: n_samples >= 0, 0 < frame_step <= 160, 0 < min_coverage <= 1");
+  long long padded = 0;
+  const int count = spk_slices(n_samples, frame_step, min_coverage, &padded);
+  if (padded_len) *padded_len = padded;
+  return count;
+}
+
+int rho_b200_normalize_volume(rho_handle* h, const float* x, const int64_t* off, const int32_t* len, int len_stride_bytes,
+                              int n, int64_t max_len, float target_dbfs, int mode, float* y, const int64_t* y_off,
+                              float* gain, void* workspace, size_t ws_bytes, void* stream) {
+  RHO_ON_DEVICE(h);
+  if (n < 0 || max_len < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (mode < 0 || mode > 2) return fail(RHO_ERR_INVALID, "mode: 0 = always, 1 = increase only, 2 = decrease only");
+  if (n == 0) return RHO_OK;
+  if (!x || !off || !len || !gain || (y && !y_off)) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  if (!workspace || ws_bytes < sizeof(double) * (size_t)n) return fail(RHO_ERR_WORKSPACE, "workspace too small: have %zu, need %zu", ws_bytes, sizeof(double) * (size_t)n);
+  if (((uintptr_t)workspace) & 7u) return fail(RHO_ERR_INVALID, "workspace must be 8-byte aligned");
+  cudaError_t e = launch_spk_normalize(x, off, len, len_stride_bytes, n, max_len, target_dbfs, mode, y, y_off, gain,
+                                       (double*)workspace, (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "normalize_volume");
+}
+
+int rho_b200_spk_mel(rho_handle* h, const float* x16, const int64_t* off, const int32_t* len, int len_stride_bytes, int n,
+                     int64_t max_len, int frame_step, double min_coverage, unsigned flags, const float* gain, float* mel,
+                     const int64_t* frame_off, float* partials, const int32_t* part_off, void* stream) {
+  RHO_ON_DEVICE(h);
+  if (n < 0 || max_len < 0) return fail(RHO_ERR_INVALID, "negative size");
+  if (frame_step <= 0 || frame_step > SPK_PART_FRAMES || !(min_coverage > 0.0 && min_coverage <= 1.0))
+    return fail(RHO_ERR_INVALID, "spk_mel: 0 < frame_step <= 160, 0 < min_coverage <= 1");
+  if (n == 0) return RHO_OK;
+  if (!x16 || !off || !len) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  if (!mel && !partials) return fail(RHO_ERR_INVALID, "neither mel nor partials asked for");
+  if ((mel && !frame_off) || (partials && !part_off)) return fail(RHO_ERR_INVALID, "an output without its offsets");
+  cudaError_t e = launch_spk_mel(h->tb, x16, off, len, len_stride_bytes, n, max_len, frame_step, min_coverage,
+                                 (flags & RHO_SPK_PAD_TO_SLICES) != 0, gain, mel, frame_off, partials, part_off,
+                                 (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "spk_mel");
+}
+
+int rho_b200_spk_pool(rho_handle* h, const float* partial_embeds, const int32_t* part_off, int n, int dim, float* out,
+                      void* stream) {
+  RHO_ON_DEVICE(h);
+  if (n < 0 || dim <= 0) return fail(RHO_ERR_INVALID, "bad size");
+  if (n == 0) return RHO_OK;
+  if (!partial_embeds || !part_off || !out) return fail(RHO_ERR_INVALID, "NULL device pointer");
+  cudaError_t e = launch_spk_pool(partial_embeds, part_off, n, dim, out, (cudaStream_t)stream, &h->lc);
+  return e == cudaSuccess ? RHO_OK : cuda_fail(e, "spk_pool");
 }
 
 int rho_b200_logmel(rho_handle* h, const float* x16, const int64_t* off, const int32_t* len16, int n,

@@ -48,7 +48,7 @@ struct Tables {
 enum KernelId {
   KID_INIT = 0, KID_SCAN, KID_FINALIZE_SEGS, KID_PLAN, KID_GATHER, KID_FINALIZE_ITEMS,
   KID_RESAMPLE, KID_LOGMEL_INIT, KID_LOGMEL_FRAMES, KID_LOGMEL_NORM, KID_COSINE, KID_SINGLE, KID_FUSED, KID_MEL_GEMM, KID_QWEN_MOMENTS, KID_QWEN_PLAN, KID_QWEN_APPLY, KID_RESAMPLE_GENERAL,
-  KID_PV_STFT, KID_PV_PHASE, KID_PV_CUMSUM, KID_PV_ISTFT, KID_PV_RESAMPLE, KID_MFCC_FRAMES, KID_MFCC_STATS, KID_XCH_WAIT, KID_STFT_TC, KID_COUNT
+  KID_PV_STFT, KID_PV_PHASE, KID_PV_CUMSUM, KID_PV_ISTFT, KID_PV_RESAMPLE, KID_MFCC_FRAMES, KID_MFCC_STATS, KID_XCH_WAIT, KID_STFT_TC, KID_SPK_SUMSQ, KID_SPK_SCALE, KID_SPK_MEL, KID_SPK_POOL, KID_COUNT
 };
 extern const char* const kKernelNames[KID_COUNT];
 
@@ -207,6 +207,34 @@ size_t mfcc_workspace_bytes(int n, int64_t max_len);
 cudaError_t launch_mfcc_stats(const MfccTables& tb, const float* x, const int64_t* off, const int32_t* len,
                               int len_stride_bytes, int n, int64_t max_len, float* out, void* workspace,
                               cudaStream_t st, LaunchCtx* lc);
+
+// spk.cu: resemblyzer's front end (volume normalisation, 40-band mel spectrogram, partial utterances, embedding pooling)
+constexpr int SPK_MELS = 40;
+constexpr int SPK_PART_FRAMES = 160;          // partials_n_frames
+constexpr int SPK_SUM_CHUNK = 65536;          // samples per CTA of the sum-of-squares / scaling kernels
+// resemblyzer/voice_encoder.py compute_partial_slices: how many partial utterances a clip of n_samples gives (partial j =
+// mel frames [frame_step j, frame_step j + 160)), and the length embed_utterance zero-pads the clip to when the last
+// partial sticks out (*padded_len = end of the last partial in samples; smaller than n_samples if nothing sticks out)
+__host__ __device__ inline int spk_slices(long long n_samples, int frame_step, double min_coverage, long long* padded_len) {
+  const long long n_frames = (n_samples + 1 + HOP16 - 1) / HOP16;                 // ceil((n + 1) / 160)
+  long long steps = n_frames - SPK_PART_FRAMES + frame_step + 1;
+  if (steps < 1) steps = 1;
+  long long count = (steps + frame_step - 1) / frame_step;                        // len(range(0, steps, frame_step))
+  const long long last = (count - 1) * frame_step * HOP16;                        // first sample of the last partial
+  const double coverage = (double)(n_samples - last) / (double)(SPK_PART_FRAMES * HOP16);
+  if (coverage < min_coverage && count > 1) --count;
+  if (padded_len) *padded_len = ((count - 1) * frame_step + SPK_PART_FRAMES) * HOP16;
+  return (int)count;
+}
+cudaError_t launch_spk_normalize(const float* x, const int64_t* off, const int32_t* len, int len_stride_bytes, int n,
+                                 int64_t max_len, float target_dbfs, int mode, float* y, const int64_t* y_off,
+                                 float* gain, double* sums, cudaStream_t st, LaunchCtx* lc);
+cudaError_t launch_spk_mel(const Tables& tb, const float* x16, const int64_t* off, const int32_t* len,
+                           int len_stride_bytes, int n, int64_t max_len, int frame_step, double min_coverage,
+                           bool pad_to_slices, const float* gain, float* mel, const int64_t* frame_off, float* partials,
+                           const int32_t* part_off, cudaStream_t st, LaunchCtx* lc);
+cudaError_t launch_spk_pool(const float* partial_embeds, const int32_t* part_off, int n, int dim, float* out,
+                            cudaStream_t st, LaunchCtx* lc);
 
 // cosine.cu
 cudaError_t launch_cosine(const float* emb, const float* ref, int n, int dim, float* out, int out_stride_bytes,

@@ -29,6 +29,11 @@ from .ragged import RaggedBatch
 class B200AudioMixin:
     #: CUDA device index used for the DSP (tensors living elsewhere are staged through it)
     b200_device: int = 0
+    #: True: what resemblyzer does on the CPU around its LSTM (volume normalisation, 40-band spectrogram, partial
+    #: utterances, pooling; rho_tts_b200.speaker) runs on the B200 as well.  Opt-in: the resampler is this library's 3:2
+    #: polyphase filter instead of librosa's soxr and webrtcvad's silence trimming is skipped, so the similarity is close
+    #: to, not identical with, the reference's.
+    b200_speaker_front_end: bool = False
 
     # ------------------------------------------------------------------ helpers
     def _b200_dev(self) -> torch.device:
@@ -152,6 +157,16 @@ class B200AudioMixin:
     def _compute_speaker_similarity(self, wav_tensor: torch.Tensor) -> float:
         # The speaker encoder is third-party (resemblyzer) and out of scope; only the
         # cosine moves to the GPU.
+        if self.b200_speaker_front_end:
+            from .speaker import speaker_similarity
+            enc = self.voice_encoder                         # resemblyzer's VoiceEncoder: forward([P, 160, 40]) -> [P, 256]
+            dev = self._b200_dev()
+
+            def encode(mels: torch.Tensor) -> torch.Tensor:
+                return enc(mels.to(getattr(enc, "device", mels.device))).to(mels.device)
+            rb = RaggedBatch.from_list([self._b200_stage(self._b200_mono(wav_tensor, "_compute_speaker_similarity"))], dev)
+            ref = torch.as_tensor(np.asarray(self.reference_embedding, dtype=np.float32))
+            return np.float32(speaker_similarity(rb, ref, encode, sample_rate=int(self.sample_rate)).item())
         from resemblyzer import preprocess_wav
         wav_np = wav_tensor.cpu().numpy().flatten()
         generated = self.voice_encoder.embed_utterance(preprocess_wav(wav_np, source_sr=self.sample_rate))

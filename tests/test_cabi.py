@@ -127,7 +127,7 @@ def test_create_fails_loudly_without_gpu(lib):
 def test_baked_mel_weights_match_runtime_table(lib):
     """mel_sparse_gen.inc bakes the filterbank into FFMA immediates; they must be the table, bit for bit."""
     text = open(os.path.join(ROOT, "rho_tts_b200", "csrc", "mel_sparse_gen.inc")).read()
-    for nm in (80, 128):
+    for nm in (80, 128, 40):
         body = text[text.index(f"void mel_sparse_{nm}("):]
         body = body[:body.index("static const unsigned int")]
         table = _table(lib, 2, nm, nm * 201).reshape(nm, 201)

@@ -5,6 +5,7 @@
   c3v : the same items through the whole front end (join -> resample -> log-mel 80 -> cosine), unfused path
   c4  : one GPU's shard of C4: 8000 x 10 s clips, 128-bin log-mel (30 s pad), records
   qwen: the Qwen loudness hook (providers/qwen.py:268-378) on 1000 x 10 s post-processed clips
+  pitch / mfcc / spk : the NEXT rows (pitch shift, MFCC statistics, resemblyzer's front end) on 1000 x 10 s clips
 
 One JSON line per configuration: device-timed step (CUDA events, inputs resident, larger than L2), audio-s/s and
 the per-kernel times with algorithmic bytes.  Results are copied to profiles/.
@@ -139,6 +140,22 @@ for cfg in args:
         alg = {"k_mfcc_frames": 4.0 * n * 160000 + 4.0 * 128 * T * n, "k_mfcc_stats": 4.0 * 128 * T * n}
         line(cfg, f"{n} x 10 s clips at 16 kHz, mean / std of librosa.feature.mfcc(n_mfcc=13) (stft 2048/512 -> mel 128 -> dB -> DCT)",
              n * 10.0, ms, prof, alg)
+        del x, rb, out
+    elif cfg == "spk":
+        from rho_tts_b200 import speaker as SP
+        n = 1000
+        x = synth.make_clip_block(n, 160000, 0xB200, device=dev) * 0.05    # 10 s at 16 kHz, quiet: every clip is raised
+        rb = R.RaggedBatch.from_dense(x)
+
+        def run():
+            gain = SP.volume_gains(rb, -30.0, increase_only=True)
+            return SP.partial_mels(rb, gain=gain)
+        out, ms, prof = timed(run, steps)
+        P = int(out[1][-1])
+        s_in = 4.0 * n * 160000
+        alg = {"k_spk_sumsq": s_in, "k_spk_mel": s_in + 4.0 * 160 * 40 * P}
+        line(cfg, f"{n} x 10 s clips at 16 kHz, resemblyzer front end: -30 dBFS gains + 40-band mel spectrogram -> "
+             f"{P} partial utterances [160, 40]", n * 10.0, ms, prof, alg)
         del x, rb, out
     elif cfg in ("c3", "c3v"):
         rb, first = ragged_c3()
