@@ -506,6 +506,7 @@ int rho_b200_mfcc_stats(rho_handle* h, const float* x16, const int64_t* off, con
       }
       if (w.empty()) w.push_back(0.f);
       MfccTables& t = h->mfcc_tb;
+      t.mel_nnz = (int)w.size();
       cudaError_t e;
       if ((e = dev_upload(h, (float**)&t.w256, w256.data(), w256.size())) != cudaSuccess ||
           (e = dev_upload(h, (float**)&t.w1024, w1.data(), w1.size())) != cudaSuccess ||

@@ -201,6 +201,7 @@ struct MfccTables {
   int* mel_cnt;
   int* mel_wofs;
   float* mel_w;
+  int mel_nnz;     // floats in mel_w
   float* dct;      // [13][128]
 };
 size_t mfcc_workspace_bytes(int n, int64_t max_len);

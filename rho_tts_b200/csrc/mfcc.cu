@@ -19,11 +19,14 @@ constexpr int MF_HOP = 512;
 constexpr int MF_BINS = 1025;
 constexpr int MF_MELS = 128;
 constexpr int MF_NCOEF = 13;
-constexpr int MF_WARPS = 4;
+#ifndef RHO_MF_WARPS
+#define RHO_MF_WARPS 8
+#endif
+constexpr int MF_WARPS = RHO_MF_WARPS;
 constexpr int MF_FPW = 2;                                 // frames per warp
 constexpr int MF_Z = 4 * PV_E_SIZE;                       // four natural-order (padded) 256-point spectra
-constexpr int MF_WARP_FLOATS = 2 * (PV_E_SIZE + MF_Z) + 1028;   // exchange buffer, spectra, power
-constexpr int MF_SMEM = (int)(sizeof(float2) * PV_TW_SIZE + sizeof(float) * MF_WARPS * MF_WARP_FLOATS);
+constexpr int MF_WARP_FLOATS = 2 * (PV_E_SIZE + MF_Z) + 4;      // exchange buffer, spectra (the power values replace them in place), P[1024]
+constexpr int MF_SMEM = (int)(sizeof(float2) * PV_TW_SIZE + sizeof(float) * MF_WARPS * MF_WARP_FLOATS);   // + the filterbank's non-zeros
 
 __device__ __forceinline__ int mf_frames(long long n) { return (int)(1 + n / MF_HOP); }
 
@@ -39,6 +42,10 @@ k_mfcc_frames(const float* __restrict__ x, const int64_t* __restrict__ off, cons
   const int f0 = blockIdx.x * (MF_WARPS * MF_FPW);
   if (f0 >= T) return;
   pv_fill_twiddles<false>(tb.w256, tw);
+  // the filterbank's non-zero weights, once per CTA: every lane walks a different band, from global memory that was
+  // one 32-byte sector per lane and step (half of the kernel's L1 traffic)
+  float* __restrict__ s_melw = warp_base + (size_t)MF_WARPS * MF_WARP_FLOATS;
+  for (int i = threadIdx.x; i < tb.mel_nnz; i += 32 * MF_WARPS) s_melw[i] = __ldg(tb.mel_w + i);
   __syncthreads();
   const float2* __restrict__ tw1 = tw;
   const float2* __restrict__ tw2 = tw + 256;
@@ -47,27 +54,40 @@ k_mfcc_frames(const float* __restrict__ x, const int64_t* __restrict__ off, cons
   float2* __restrict__ Z = E + PV_E_SIZE;                 // Z[r * PV_E_SIZE + pv_nat(k)]
   float* __restrict__ P = reinterpret_cast<float*>(Z + MF_Z);
   const float* __restrict__ xs = x + off[c];
+  const bool al16 = (((uintptr_t)xs) & 15u) == 0;
   const int k1 = lane >> 2, q = lane & 3, bq = ((q & 1) << 1) | (q >> 1);
   float lmax = -INFINITY;
   for (int it = 0; it < MF_FPW; ++it) {
     const int f = f0 + it * MF_WARPS + w;
     if (f >= T) break;                                    // warp-uniform
-    const long long base = (long long)f * MF_HOP - MF_NFFT / 2;
-    // ---- four 256-point FFTs of z_r[m] = z[4 m + r], z[j] = (x[2 j], x[2 j + 1]) * hann
+    const long long base = (long long)f * MF_HOP - MF_NFFT / 2;     // a multiple of 4
+    // ---- the windowed frame, read once in 128-bit pieces: z[j] = (x[2 j], x[2 j + 1]) * hann goes to the slot of the
+    // decimated sequence it belongs to, Z[(j & 3)][j >> 2] -- pass r below reads its 256 inputs from the region it later
+    // writes its spectrum to (all reads of a pass are in registers before its first write)
+#pragma unroll 4
+    for (int t = 0; t < MF_NFFT / 128; ++t) {
+      const int s0 = 4 * (lane + 32 * t);
+      const long long i0 = base + s0;
+      float4 xv;
+      if (al16 && i0 >= 0 && i0 + 3 < n) {
+        xv = *reinterpret_cast<const float4*>(xs + i0);
+      } else {
+        xv.x = (i0 >= 0 && i0 < n) ? xs[i0] : 0.f;             xv.y = (i0 + 1 >= 0 && i0 + 1 < n) ? xs[i0 + 1] : 0.f;
+        xv.z = (i0 + 2 >= 0 && i0 + 2 < n) ? xs[i0 + 2] : 0.f; xv.w = (i0 + 3 >= 0 && i0 + 3 < n) ? xs[i0 + 3] : 0.f;
+      }
+      const float4 h = __ldg(reinterpret_cast<const float4*>(tb.hann) + (lane + 32 * t));
+      const int j = s0 >> 1;                                  // even: slots j & 3 in {0, 2} and {1, 3}, same j >> 2
+      Z[(j & 3) * PV_E_SIZE + (j >> 2)] = make_float2(xv.x * h.x, xv.y * h.y);
+      Z[((j + 1) & 3) * PV_E_SIZE + (j >> 2)] = make_float2(xv.z * h.z, xv.w * h.w);
+    }
+    __syncwarp();
+    // ---- four 256-point FFTs of z_r[m] = z[4 m + r]
     for (int r = 0; r < 4; ++r) {
+      float2* __restrict__ Zr = Z + r * PV_E_SIZE;
       float2 v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int m = lane + 32 * j;
-        const int s0 = 2 * (4 * m + r);
-        const long long i0 = base + s0;
-        const float2 h = __ldg(reinterpret_cast<const float2*>(tb.hann) + (4 * m + r));
-        const float a = (i0 >= 0 && i0 < n) ? xs[i0] : 0.f;
-        const float b = (i0 + 1 >= 0 && i0 + 1 < n) ? xs[i0 + 1] : 0.f;
-        v[j] = make_float2(a * h.x, b * h.y);
-      }
+      for (int j = 0; j < 8; ++j) v[j] = Zr[lane + 32 * j];
       warp_fft256<false>(v, E, tw1, tw2, lane);
-      float2* __restrict__ Zr = Z + r * PV_E_SIZE;
 #pragma unroll
       for (int a = 0; a < 8; ++a) Zr[k1 + 8 * a + 72 * bq] = v[a];      // pv_nat(k1 + 8 a + 64 b)
       __syncwarp();
@@ -84,7 +104,11 @@ k_mfcc_frames(const float* __restrict__ x, const int64_t* __restrict__ off, cons
     }
     __syncwarp();
     // ---- real spectrum from the packed one, as powers:  X[K] = E + W2048^K O,  X[1024 - K] = conj(E - W2048^K O)
-    auto zat = [&](int K) { return Z[(K >> 8) * PV_E_SIZE + pv_nat(K & 255)]; };
+    // The power of bin K replaces the real part of the slot Z[K] lived in: a lane reads the pair (K, 1024 - K) and writes
+    // the same two slots, so no second buffer is needed; only P[1024] has no slot of its own.
+    auto zat = [&](int K) { return Z[K + 8 * (K >> 6)]; };            // (K >> 8) * PV_E_SIZE + pv_nat(K & 255)
+    float* __restrict__ Pf = reinterpret_cast<float*>(Z);
+    auto pslot = [&](int K) -> float& { return K == 1024 ? P[0] : Pf[2 * (K + 8 * (K >> 6))]; };
 #pragma unroll 4
     for (int t = 0; t < 16; ++t) {
       const int K = lane + 32 * t;                        // 0..511, partner 1024 - K
@@ -94,14 +118,14 @@ k_mfcc_frames(const float* __restrict__ x, const int64_t* __restrict__ off, cons
       const float2 wo = cmul(__ldg(tb.w2048 + K), o);
       const float ar = e.x + wo.x, ai = K ? e.y + wo.y : 0.f;
       const float br = e.x - wo.x, bi = K ? e.y - wo.y : 0.f;
-      P[K] = ar * ar + ai * ai;
-      P[1024 - K] = br * br + bi * bi;
+      pslot(K) = ar * ar + ai * ai;
+      pslot(1024 - K) = br * br + bi * bi;
     }
     if (lane == 0) {                                      // K = 512 is its own partner: X = Re z - i Im z ... |X|^2 = |z|^2
       const float2 z = zat(512);
       const float2 wo = cmul(__ldg(tb.w2048 + 512), make_float2(z.y, 0.f));
       const float ar = z.x + wo.x, ai = wo.y;
-      P[512] = ar * ar + ai * ai;
+      pslot(512) = ar * ar + ai * ai;
     }
     __syncwarp();
     // ---- 128 mel bands (sparse triangles), dB
@@ -110,9 +134,9 @@ k_mfcc_frames(const float* __restrict__ x, const int64_t* __restrict__ off, cons
     for (int j = 0; j < 4; ++j) {
       const int m = lane + 32 * j;
       const int lo = tb.mel_lo[m], cnt = tb.mel_cnt[m];
-      const float* __restrict__ wv = tb.mel_w + tb.mel_wofs[m];
+      const float* __restrict__ wv = s_melw + tb.mel_wofs[m];
       float acc = 0.f;
-      for (int i = 0; i < cnt; ++i) acc = fmaf(__ldg(wv + i), P[lo + i], acc);
+      for (int i = 0; i < cnt; ++i) acc = fmaf(wv[i], pslot(lo + i), acc);
       const float d = 10.0f * log10f(fmaxf(1e-10f, acc));
       row[m] = d;
       lmax = fmaxf(lmax, d);
@@ -186,12 +210,13 @@ cudaError_t launch_mfcc_stats(const MfccTables& tb, const float* x, const int64_
   int* clip_max = (int*)((char*)workspace + align_up((size_t)n * (size_t)T * MF_MELS * sizeof(float), 256));
   const char* lb = reinterpret_cast<const char*>(len);
   const int ls = len_stride_bytes ? len_stride_bytes : (int)sizeof(int32_t);
-  cudaError_t e = cudaFuncSetAttribute(k_mfcc_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM);
+  const int smem = MF_SMEM + (int)align_up((size_t)tb.mel_nnz * sizeof(float), 16);
+  cudaError_t e = cudaFuncSetAttribute(k_mfcc_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   lc->begin(KID_MFCC_FRAMES, st);
   k_mfcc_init<<<(n + 255) / 256, 256, 0, st>>>(clip_max, n);
   const unsigned gx = (unsigned)((T + MF_WARPS * MF_FPW - 1) / (MF_WARPS * MF_FPW));
-  k_mfcc_frames<<<dim3(gx, (unsigned)n), 32 * MF_WARPS, MF_SMEM, st>>>(x, off, lb, ls, tb, db, (long long)T * MF_MELS,
+  k_mfcc_frames<<<dim3(gx, (unsigned)n), 32 * MF_WARPS, smem, st>>>(x, off, lb, ls, tb, db, (long long)T * MF_MELS,
                                                                      clip_max);
   lc->end(st);
   lc->begin(KID_MFCC_STATS, st);
