@@ -1,8 +1,9 @@
 // HOST entry points of librho_b200 (include/rho_b200.h): the calls an embedder without torch makes.
 //   rho_b200_validate_host_ragged   ragged segments / items in host memory -> join, decay check, features
 //   rho_b200_validate_host          fixed-length clips, one clip per item (a wrapper of the above)
-// The batch is cut into chunks of whole items (~64 MB of samples); three chunk slots in a device arena keep the
-// copy-in of chunk k+1, the kernels of chunk k and the copy-out of chunk k-1 in flight at once, each on its own stream.
+// The batch is cut into chunks of whole items (up to ~123 MB of samples, smaller while the pipeline fills and drains); four
+// chunk slots in a device arena keep the copy-in of chunks k+1 / k+2, the kernels of chunk k and the copy-out of chunk k-1
+// in flight at once, each on its own stream.
 //
 // What crosses PCIe: every input sample once, every processed sample once, one 48-byte record per item and, of the
 // Whisper features, only the frames that can see signal.  The 30 s Whisper window of a 10 s clip is 2/3 zero padding,
@@ -267,10 +268,12 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
     C.pinned_bytes = pin_total;
   }
   while ((int)C.ev_out.size() < n_chunks) {
-    cudaEvent_t ev, ev2;
+    cudaEvent_t ev = nullptr, ev2 = nullptr;
     if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess)
+        (e = cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) {
+      if (ev) cudaEventDestroy(ev);
       return cuda_fail(e, "cudaEventCreate");
+    }
     C.ev_out.push_back(ev);
     C.ev_small.push_back(ev2);
   }
