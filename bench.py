@@ -539,6 +539,12 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
         melc = torch.empty((n, N_MELS, T_c), dtype=torch.float32).pin_memory()
         dt_comp = host_timed(lambda: R.validate_host_ragged(xh.reshape(-1), seg_off, seg_len, first, p, embh, refh, N_MELS,
                                                             compact=True, y=yh.reshape(-1), mel=melc, device=local_rank))
+        # features left in HBM (mel is device memory): what the call costs when the Whisper encoder runs on the same GPU
+        # (SURVEY 8f NEXT-2); audio and records still come back to the host
+        mel_dev = torch.empty((n, N_MELS, PAD_FRAMES), dtype=torch.float32, device=dev)
+        dt_hbm = host_timed(lambda: R.validate_host(xh, p, embh, refh, N_MELS, y=yh, mel=mel_dev, rec=rech, device=local_rank))
+        assert torch.equal(mel_dev[::97], out.mel[::97]), "device-resident feature rows differ from the device path"
+        del mel_dev
         h2d = xh.numel() * 4 + embh.numel() * 4 + refh.numel() * 4
         d2h_link = yh.numel() * 4 + rech.numel() + melc.numel() * 4 + 4 * n     # what crosses the link
         link = link_measure(dev, h2d, d2h_link, reps=3, dist=dist)
@@ -552,6 +558,10 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
                "result_bytes_in_host_memory_per_step": yh.numel() * 4 + rech.numel() + melh.numel() * 4,
                "timer": "host perf_counter around the synchronous C call, max over ranks",
                "value_compact_rows": world * audio_s_per_rank_step * e2e_steps / dt_comp,
+               "value_features_in_hbm": world * audio_s_per_rank_step * e2e_steps / dt_hbm,
+               "value_features_in_hbm_note": "same call with `mel` a device buffer: complete feature rows stay in HBM for a "
+                                             "consumer on the GPU, audio and records come back (not the headline: the "
+                                             "reference arm leaves its features in host memory)",
                "link_ceiling_gbs": {"h2d": link["h2d_gbs_concurrent"], "d2h": link["d2h_gbs_concurrent"],
                                     "h2d_alone": link["h2d_gbs_alone"], "d2h_alone": link["d2h_gbs_alone"]},
                "link_ceiling_value": ceiling, "frac_of_link_ceiling": e2e_value / ceiling,

@@ -381,7 +381,10 @@ int rho_b200_exchange_destroy(rho_handle* h);
  *   mel (may be NULL), mel_stride_frames, pad_value (may be NULL): as rho_b200_validate with the layouts
  *     mel_stride_frames >= 3000 (complete rows) or < 3000 (compact rows + pad_value).  Only the frames that can see
  *     signal cross PCIe in either case: complete rows get their constant tail written by host threads from pad_value
- *     (RHO_HOST_FILL_THREADS, default 2), overlapped with the copies of the following chunks.
+ *     (RHO_HOST_FILL_THREADS, default 3), overlapped with the copies of the following chunks.
+ *     mel may also be DEVICE memory of the handle's GPU (found out with cudaPointerGetAttributes): the rows are then
+ *     written in place in HBM -- complete ones including their constant tail -- and nothing of the features crosses
+ *     PCIe: the hand-off to a consumer on the device (the Whisper encoder, SURVEY.md 8f NEXT-2).
  *   emb [n_items][emb_dim], ref_emb [emb_dim] (may be NULL): speaker cosine into rec[i].cosine. */
 int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* seg_off, const int32_t* seg_len,
                                   int n_segments, const int32_t* item_first_seg, int n_items, const rho_params* p,

@@ -439,7 +439,9 @@ def validate_host(x: torch.Tensor, p: RhoParams, emb: Optional[torch.Tensor], re
                   n_mels: int = 80, y: Optional[torch.Tensor] = None, mel: Optional[torch.Tensor] = None,
                   rec: Optional[torch.Tensor] = None, device: int = 0):
     """HOST buffers in, HOST buffers out (rho_b200_validate_host): x is a pinned CPU tensor (n, L);
-    the library stages chunks through HBM with copy/compute overlap.  Returns (y, mel, rec) CPU tensors."""
+    the library stages chunks through HBM with copy/compute overlap.  Returns (y, mel, rec) CPU tensors.  `mel` may be
+    a CUDA tensor [n, n_mels, 3000] on `device`: the features are then written there and stay in HBM (only audio and
+    records come back), for a consumer on the device such as the Whisper encoder."""
     assert not x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.is_contiguous()
     h = Handle.get(device)
     n, L = x.shape
@@ -481,7 +483,8 @@ def validate_host_ragged(x: torch.Tensor, seg_offsets: np.ndarray, seg_lengths: 
                          mel: Optional[torch.Tensor] = None, device: int = 0) -> HostRaggedOutput:
     """rho_b200_validate_host_ragged: ragged segments / items in HOST memory (x flat CPU fp32, pinned for full speed)
     -> _smooth_segment_join + _validate_sound_decay per item (base_tts.py:435-536, 297-323) and, with features, the
-    16 kHz resample + Whisper log-mel + cosine.  Everything comes back in host memory."""
+    16 kHz resample + Whisper log-mel + cosine.  Everything comes back in host memory -- except the features when `mel`
+    is given as a CUDA tensor on `device`: they are written there and stay in HBM."""
     assert not x.is_cuda and x.dim() == 1 and x.dtype == torch.float32 and x.is_contiguous()
     h = Handle.get(device)
     seg_off = np.ascontiguousarray(seg_offsets, dtype=np.int64)

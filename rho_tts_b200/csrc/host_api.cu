@@ -159,6 +159,20 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
     return fail(RHO_ERR_LAYOUT, "item_first_seg must run from 0 to n_segments");
   const bool have_emb = emb && ref_emb && emb_dim > 0;
   const Derived d = derive(*p);
+  // `mel` may be DEVICE memory of this handle's GPU: the features then stay in HBM for a consumer on the device (the
+  // Whisper encoder: SURVEY 8f NEXT-2) -- complete rows are written in place, nothing of them crosses the link
+  bool mel_on_device = false;
+  if (features) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, mel) == cudaSuccess) {
+      if (pa.type == cudaMemoryTypeDevice) {
+        if (pa.device != h->device) return fail(RHO_ERR_INVALID, "mel is memory of device %d, the handle runs on device %d", pa.device, h->device);
+        mel_on_device = true;
+      }
+    } else {
+      cudaGetLastError();                                   // plain host memory on drivers that report it as an error
+    }
+  }
 
   // ---- layout checks, item capacities, chunk plan
   bool contig = true;                                     // all offsets 16-byte aligned: one copy per chunk and direction
@@ -222,6 +236,8 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
     if (features) {
       c.t_dev = (int)rho_b200_compact_frames(c.max_item_cap, pad_frames);
       if (pad_frames == 0) c.t_dev = std::max(4, (c.t_dev + 3) / 4 * 4);
+      if (mel_on_device && mel_stride_frames >= (pad_frames > 0 ? std::min<int64_t>(c.t_dev, pad_frames) : c.t_dev))
+        c.t_dev = (int)mel_stride_frames;                  // the caller's rows are the rows the kernels write
       if (mel_stride_frames < (pad_frames > 0 ? std::min<int64_t>(c.t_dev, pad_frames) : rho_b200_compact_frames(c.max_item_cap, 0)))
         return fail(RHO_ERR_INVALID, "mel_stride_frames %lld too small: items of up to %lld samples need %d frames per row",
                     (long long)mel_stride_frames, (long long)c.max_item_cap, c.t_dev);
@@ -237,7 +253,7 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
     const int ni = c.i1 - c.i0, ns = c.s1 - c.s0;
     b_x = std::max(b_x, align_up((size_t)(c.dx_samples + 32) * 4, 256));
     b_y = std::max(b_y, align_up((size_t)(c.dy_samples + 32) * 4, 256));
-    if (features) b_mel = std::max(b_mel, align_up((size_t)ni * n_mels * c.t_dev * 4, 256));
+    if (features && !mel_on_device) b_mel = std::max(b_mel, align_up((size_t)ni * n_mels * c.t_dev * 4, 256));
     b_rec = std::max(b_rec, align_up(sizeof(rho_record) * (size_t)ni, 256));
     if (have_emb) b_emb = std::max(b_emb, align_up(sizeof(float) * (size_t)ni * emb_dim, 256));
     b_meta = std::max(b_meta, align_up((size_t)(ns + 1) * 12 + (size_t)(ni + 1) * 12 + 64, 256));
@@ -286,7 +302,7 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
     return cuda_fail(e, "ref upload");
 
   // ---- host fill of the constant tail of every feature row, by helper threads, chunk by chunk as the copies land
-  const bool host_fill = features && pad_frames > 0;
+  const bool host_fill = features && pad_frames > 0 && !mel_on_device;
   std::atomic<int> issued{0};            // chunks whose copy-out has been enqueued (ev_out recorded)
   std::atomic<int> abort_fill{0};
   std::atomic<int> fill_err{0};
@@ -323,7 +339,7 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
     char* sb = slots + (size_t)s * per_slot;
     float* d_x = (float*)sb;
     float* d_y = (float*)(sb + b_x);
-    float* d_mel = (float*)(sb + b_x + b_y);
+    float* d_mel = mel_on_device ? mel + (size_t)c.i0 * n_mels * mel_stride_frames : (float*)(sb + b_x + b_y);
     rho_record* d_rec = (rho_record*)(sb + b_x + b_y + b_mel);
     float* d_emb = (float*)(sb + b_x + b_y + b_mel + b_rec);
     char* d_meta = sb + b_x + b_y + b_mel + b_rec + b_emb;
@@ -407,7 +423,7 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
                                 cudaMemcpyDeviceToHost, C.s_out);
       }
     }
-    if (e == cudaSuccess && features) {
+    if (e == cudaSuccess && features && !mel_on_device) {
       // compact device rows -> the caller's rows: only the frames that can see signal cross the link
       const int64_t wf = std::min<int64_t>(c.t_dev, mel_stride_frames);
       float* dst = mel + (size_t)c.i0 * n_mels * mel_stride_frames;
@@ -423,9 +439,11 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
   if (status != RHO_OK) abort_fill.store(1);
   if (host_fill && status == RHO_OK) fill_worker(0, W);     // the calling thread is worker 0
   for (std::thread& t : helpers) t.join();
+  const bool pad_late = status == RHO_OK && !host_fill && features && pad_frames > 0 && pad_value;
   const cudaError_t e1 = cudaStreamSynchronize(C.s_in);
   const cudaError_t e2 = cudaStreamSynchronize(sc);
   const cudaError_t e3 = cudaStreamSynchronize(C.s_out);
+  if (pad_late && e3 == cudaSuccess) memcpy(pad_value, h_pad, sizeof(float) * (size_t)n_items);
   if (status != RHO_OK) return status;
   if (e1 != cudaSuccess) return cuda_fail(e1, "sync copy-in");
   if (e2 != cudaSuccess) return cuda_fail(e2, "sync compute");

@@ -352,6 +352,43 @@ def test_validate_host_matches_device_path(R, cuda_device):
     assert torch.equal(out.pad_value.cpu(), mel_h[:, 0, 2999])
 
 
+def test_validate_host_features_stay_in_hbm(R, cuda_device):
+    """`mel` of the host entry points may be DEVICE memory: audio and records come back to the host, the features are
+    written in place in HBM for a consumer on the device (SURVEY 8f NEXT-2) -- the same bytes as the all-host call."""
+    from rho_tts_b200 import synth
+    n = 150
+    x = synth.make_clip_block(n, 48000, 78).pin_memory()
+    emb, ref = synth.make_embeddings(n)
+    emb, ref = emb.pin_memory(), ref.pin_memory()
+    p = R.make_params()
+    y_h, mel_h, rec_h = R.validate_host(x, p, emb, ref, 80, mel=torch.empty((n, 80, 3000)).pin_memory())
+    mel_d = torch.full((n, 80, 3000), float("nan"), dtype=torch.float32, device=cuda_device)
+    y_d, mel_d2, rec_d = R.validate_host(x, p, emb, ref, 80, mel=mel_d)
+    assert mel_d2.is_cuda and mel_d2.data_ptr() == mel_d.data_ptr()
+    assert torch.equal(mel_d.cpu(), mel_h) and torch.equal(rec_d, rec_h)
+    rec = rec_h.numpy().view(R.REC_DTYPE).reshape(-1)
+    for i in range(n):
+        L = int(rec["out_len"][i])
+        assert torch.equal(y_d[i, :L], y_h[i, :L])
+    # ragged entry point, compact rows + pad values, joined items; features on the device
+    rng = np.random.default_rng(17)
+    seg_lens = rng.integers(2400, 200000, size=60).astype(np.int32)
+    first = np.asarray([0, 1, 4, 6, 10, 11, 15, 20, 26, 30, 33, 40, 41, 47, 52, 60], np.int32)
+    padded = (seg_lens.astype(np.int64) + 31) // 32 * 32
+    seg_off = np.concatenate([[0], np.cumsum(padded)])[:-1].astype(np.int64)
+    flat = torch.zeros(int(seg_off[-1] + padded[-1]), dtype=torch.float32)
+    for k, L in enumerate(seg_lens):
+        flat[seg_off[k]:seg_off[k] + L] = synth.make_clip_block(1, int(L), 7000 + k)[0]
+    flat = flat.pin_memory()
+    a = R.validate_host_ragged(flat, seg_off, seg_lens, first, p, compact=True)
+    T = a.mel.shape[2]
+    mel_dev = torch.full((len(first) - 1, 80, T), float("nan"), dtype=torch.float32, device=cuda_device)
+    b = R.validate_host_ragged(flat, seg_off, seg_lens, first, p, compact=True, mel=mel_dev)
+    assert b.mel.data_ptr() == mel_dev.data_ptr()
+    assert torch.equal(mel_dev.cpu(), a.mel) and torch.equal(a.pad_value, b.pad_value)
+    assert np.array_equal(a.records.view(np.uint8), b.records.view(np.uint8))
+
+
 @pytest.mark.parametrize("n_mels", [80, 128])
 def test_compact_feature_rows(R, cuda_device, n_mels):
     """RHO_V_COMPACT_PAD: rows of rho_b200_compact_frames(L) frames + pad_value[i] == the head and the constant tail
