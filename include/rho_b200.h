@@ -329,6 +329,7 @@ int rho_b200_cosine(rho_handle* h, const float* emb, const float* ref, int n, in
 #define RHO_V_ONE_SEGMENT_ITEMS 1u
 #define RHO_V_NO_FUSION 2u
 #define RHO_V_COMPACT_PAD 4u
+#define RHO_V_GATHER_FIRST 8u
 int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, const int32_t* seg_len,
                       int n_segments, int64_t max_seg_len,
                       const int32_t* item_first_seg, int n_items, int64_t max_item_len,

@@ -26,6 +26,7 @@ F_UNTOUCHED = 8
 V_ONE_SEGMENT_ITEMS = 1
 V_NO_FUSION = 2
 V_COMPACT_PAD = 4
+V_GATHER_FIRST = 8
 
 EXPORTS = (
     "rho_b200_abi_version", "rho_b200_create", "rho_b200_destroy", "rho_b200_last_error",

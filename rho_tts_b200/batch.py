@@ -381,7 +381,7 @@ class ValidatePlan:
     (the benchmark's steady state: allocation is not part of the hot path)."""
 
     def __init__(self, rb: RaggedBatch, item_first_seg: Sequence[int], p: RhoParams, n_mels: int = 80,
-                 pad_to_30s: bool = True, fuse: bool = True, compact: bool = False):
+                 pad_to_30s: bool = True, fuse: bool = True, compact: bool = False, gather_first: bool = False):
         self.dev = _dev_index(rb.data)
         self.h = Handle.get(self.dev)
         self.p = p
@@ -396,7 +396,7 @@ class ValidatePlan:
         # pad_value[i] (RHO_V_COMPACT_PAD) -- a third of the bytes for 10 s clips
         self.compact = bool(compact and pad_to_30s)
         self.flags = (_lib.V_ONE_SEGMENT_ITEMS if one_seg else 0) | (0 if fuse else _lib.V_NO_FUSION) | \
-            (_lib.V_COMPACT_PAD if self.compact else 0)
+            (_lib.V_COMPACT_PAD if self.compact else 0) | (_lib.V_GATHER_FIRST if gather_first else 0)
         pause = int(p.sr * p.pause_sec) if p.pause_sec > 0 else 0
         seg_tot = np.concatenate([[0], np.cumsum(rb.h_lengths.astype(np.int64))])
         cap = (seg_tot[first[1:]] - seg_tot[first[:-1]]) + np.maximum(0, np.diff(first) - 2) * pause
@@ -429,10 +429,11 @@ class ValidatePlan:
 def validate_batch(rb: RaggedBatch, p: RhoParams, emb: Optional[torch.Tensor] = None,
                    ref: Optional[torch.Tensor] = None, n_mels: int = 80, pad_to_30s: bool = True,
                    item_first_seg: Optional[Sequence[int]] = None, fuse: bool = True,
-                   compact: bool = False) -> ValidateOutput:
-    """post-process/join -> resample 24k->16k -> log-mel -> cosine, all on the device."""
+                   compact: bool = False, gather_first: bool = False) -> ValidateOutput:
+    """post-process/join -> resample 24k->16k -> log-mel -> cosine, all on the device.  gather_first (joined items
+    only): k_gather writes the joined audio and the feature kernel reads it back, instead of one kernel doing both."""
     first = np.arange(rb.n + 1, dtype=np.int32) if item_first_seg is None else item_first_seg
-    return ValidatePlan(rb, first, p, n_mels, pad_to_30s, fuse, compact).run(rb, emb, ref)
+    return ValidatePlan(rb, first, p, n_mels, pad_to_30s, fuse, compact, gather_first).run(rb, emb, ref)
 
 
 def validate_host(x: torch.Tensor, p: RhoParams, emb: Optional[torch.Tensor], ref: Optional[torch.Tensor],

@@ -762,15 +762,19 @@ int rho_b200_validate(rho_handle* h, const float* x, const int64_t* seg_off, con
   if (!(flags & RHO_V_NO_FUSION)) {
     // one-segment items:  init -> scan -> bounds / DC / plan -> ONE kernel for apply + resample + log-mel -> clamp +
     //                     records (decay decision, cosine): five launches per batch
-    // joined items:       init -> scan -> bounds / DC -> plan -> gather (y) -> the same kernel reading the finished y
-    //                     (resample + log-mel; the 16 kHz signal never leaves shared memory) -> clamp + records
+    // joined items:       init -> scan -> bounds / DC -> plan -> the same kernel, which also joins: a batch inside one
+    //                     segment is the one-segment case, the joints are computed sample by sample -> clamp + records
+    //                     (RHO_V_GATHER_FIRST: the round-2 path -- k_gather writes y, the kernel reads it back)
+    const bool gather_first = !one_seg && (flags & RHO_V_GATHER_FIRST);
     e = launch_join(x, seg_off, seg_len, n_segments, max_seg_len, item_first_seg, n_items, max_item_len, d, y, y_off,
                     rec, nullptr, ws, st, &h->lc,
                     one_seg ? (JOIN_PREPARE | JOIN_INIT_FEATURES | JOIN_ONE_SEG_ITEMS)
-                            : (JOIN_PREPARE | JOIN_GATHER | JOIN_INIT_FEATURES));
+                            : gather_first ? (JOIN_PREPARE | JOIN_GATHER | JOIN_INIT_FEATURES)
+                                           : (JOIN_PREPARE | JOIN_INIT_FEATURES));
     if (e != cudaSuccess) return cuda_fail(e, "join prepare");
     e = launch_fused_features(h->tb, x, seg_off, ws, item_first_seg, n_items, max_item_len, d, y, y_off, n_mels,
-                              pad_frames, mel, mel_stride_frames, h->sm_count, st, &h->lc, !one_seg, fill_to);
+                              pad_frames, mel, mel_stride_frames, h->sm_count, st, &h->lc,
+                              one_seg ? 0 : gather_first ? 1 : 2, fill_to);
     if (e != cudaSuccess) return cuda_fail(e, "fused features");
     // the Whisper clamp of the frames with signal (and the constant of the zero-padding frames unless the fused kernel
     // wrote it: fill_done); its first warp per clip assembles the record

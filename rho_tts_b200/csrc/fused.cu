@@ -119,7 +119,7 @@ constexpr int FZ_TWS = 22;                                  // float2 per twiddl
 // How the frames of a clip are cut into tiles: tile k covers the 32-frame batches [start[k], start[k+1])
 // (launch_fused_features picks the sizes per call).  Units are handed out tile-major: the last tiles of the clips,
 // which are the short ones, come at the end and level the halves.
-constexpr int FZ_MAX_TILES = 24;
+constexpr int FZ_MAX_TILES = 64;
 struct FzSched {
   int n_tiles;
   int start[FZ_MAX_TILES + 1];
@@ -134,6 +134,15 @@ struct FzNext {
   float dc;
   int tile;
   int prefetched;                   // the unit's first span is a bulk copy already issued on FzHalf::bar
+  int s0, ns;                       // MODE 2 (joined items): the item's first segment and its number of segments
+};
+
+// MODE 2: what a half keeps of a segment's span record (SegSpan, plan_items) while it works on the item
+constexpr int FZ_MAX_JSEG = 8;      // cached spans per item; longer items read the rest from global memory
+struct JSeg {
+  long long x_base, prev_x;         // offsets in x of the segment's processed sample 0 / of the crossfade tail before it
+  int dst, ov, body, pause;
+  float dc, dcp;
 };
 
 struct alignas(1024) FzHalf {
@@ -150,6 +159,7 @@ struct alignas(1024) FzHalf {
   int pend_c, pend_tiles, pend_T_real, pend_T;   // FZ_DEFER_TILE_END: the clip whose tile-end count is in flight
   int fill_c;                       // ... and the clip whose padding constant this half writes next (-1: none)
   FzNext nd;
+  JSeg js[FZ_MAX_JSEG];
 };
 static_assert(LM_SLAB_SM <= LM_BF * LM_PS, "the slab must fit in the pw region");
 static_assert(LM_GROUPS * 201 * 2 <= LM_BF * LM_PS, "the spectrum exchange must fit in the pw region");
@@ -281,6 +291,63 @@ __device__ __noinline__ void fz_apply_edge(float* e, int o, int n, int fade, boo
   }
 }
 
+__device__ __forceinline__ void fz_cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void fz_cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+__device__ __forceinline__ JSeg fz_jseg(const JSeg* __restrict__ cached, const SegSpan* __restrict__ gs, int k) {
+  if (k < FZ_MAX_JSEG) return cached[k];
+  const SegSpan sp = gs[k];
+  JSeg j;
+  j.x_base = sp.x_base; j.prev_x = sp.prev_x; j.dst = sp.dst; j.ov = sp.ov; j.body = sp.body; j.pause = sp.pause;
+  j.dc = sp.dc; j.dcp = sp.dcp;
+  return j;
+}
+
+// MODE 2, batches that touch a crossfade, a pause, a segment boundary or an end of the item: four samples of the JOINED
+// audio at item positions o .. o + 3, computed from the segments exactly as k_gather does (join.cu: equal-power crossfade
+// of the DC-free tails, body, pause zeros, then the fades of the item), written to y when the batch owns them, with the
+// decay sums.  Out of line: it runs on a few percent of the batches.
+__device__ __noinline__ void fz_join_piece(float* e, int o, int n, const JSeg* __restrict__ cached,
+                                           const SegSpan* __restrict__ gs, int ns, const float* __restrict__ x, int fade,
+                                           bool need_fade, int third, int own_lo, int own_hi, float* __restrict__ ys,
+                                           float* a_first, float* a_last) {
+  int k = 0;
+  JSeg s = fz_jseg(cached, gs, 0);
+  for (int i = 0; i < 4; ++i) {
+    const int oo = o + i;
+    float val = 0.f;
+    if (oo >= 0 && oo < n) {
+      while (k + 1 < ns && oo >= s.dst + s.ov + s.body + s.pause) s = fz_jseg(cached, gs, ++k);
+      const int jj = oo - s.dst;
+      if (jj < s.ov) {
+        const float fo = cosf(linspace32(0.f, RHO_HALF_PI_F, s.ov, jj));
+        const float fi = cosf(linspace32(RHO_HALF_PI_F, 0.f, s.ov, jj));
+        const float a = __fmul_rn(__fsub_rn(x[s.prev_x + jj], s.dcp), fo);
+        const float b = __fmul_rn(__fsub_rn(x[s.x_base + jj], s.dc), fi);
+        val = __fadd_rn(a, b);
+      } else if (jj < s.ov + s.body) {
+        val = __fsub_rn(x[s.x_base + jj], s.dc);
+      }
+      if (need_fade) val = __fmul_rn(val, fz_fade_gain(oo, n, fade));
+      if (oo >= own_lo && oo < own_hi) {
+        ys[oo] = val;
+        if (oo < third) *a_first += val * val;
+        if (oo >= n - third) *a_last += val * val;
+      }
+    }
+    e[i] = val;
+  }
+}
+
+// MODE 0: one-segment items, everything above in one pass over x.
+// MODE 2: items JOINED from several segments (base_tts.py:912-926), in the same single pass: a batch whose window lies
+//         inside one segment's body is the one-segment case with that segment's x and DC; the others (crossfades,
+//         pauses, segment boundaries: a few percent) compute their window of the joined audio sample by sample
+//         (fz_join_piece).  y is written here: no k_gather pass, no second read of the audio.
 // FROM_Y = false: one-segment items, everything above in one pass over x.
 // FROM_Y = true : the features of FINISHED items (the output of k_gather: joined, faded audio at y + y_off[c], length
 //                 item[c].out_len): the span is read from y, nothing is applied or written back, the 16 kHz signal still
@@ -314,7 +381,7 @@ __device__ __noinline__ void fz_fill_padding(float* __restrict__ fout, long long
   }
 }
 
-template <int NM, bool FROM_Y>
+template <int NM, int MODE>
 __global__ void __launch_bounds__(FZ_THREADS, 1)
 k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_off, const SegState* __restrict__ seg,
                  ItemState* __restrict__ item, const int32_t* __restrict__ item_first_seg,
@@ -323,7 +390,9 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
                  float* __restrict__ mel, long long mel_stride, int* __restrict__ clip_max,
                  int32_t* __restrict__ len16_out, int* __restrict__ tiles_done, int* __restrict__ work_counter,
                  const __grid_constant__ FzSched sched, int n_items, const float* __restrict__ mel_dense,
-                 int fill_to) {
+                 int fill_to, const SegSpan* __restrict__ gspan) {
+  constexpr bool FROM_Y = MODE == 1;                 // finished audio in y: features only
+  constexpr bool JOIN = MODE == 2;                   // items joined from several segments, y written here
   extern __shared__ unsigned char smem_raw[];
   FzSmem& S = *reinterpret_cast<FzSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   for (int i = threadIdx.x; i < N_FFT; i += FZ_THREADS) {
@@ -389,6 +458,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   auto fill_desc = [&](int un) {
     FzNext d;
     d.u = un; d.c = 0; d.start = 0; d.end = 0; d.dc = 0.f; d.tile = 0; d.prefetched = 0; d.x_off = 0; d.y_off = 0;
+    d.s0 = 0; d.ns = 0;
     if (un < n_units) {
       d.tile = un / n_items;                             // tile-major: the last (short) tiles of the clips come at the end
       d.c = un - d.tile * n_items;
@@ -396,6 +466,9 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       if (FROM_Y) {
         d.start = 0; d.end = item[d.c].out_len; d.dc = 0.f;
         d.x_off = d.y_off;
+      } else if (JOIN) {
+        d.start = 0; d.end = item[d.c].out_len; d.dc = 0.f;
+        d.s0 = item_first_seg[d.c]; d.ns = item_first_seg[d.c + 1] - d.s0;
       } else {
         const int sn = item_first_seg[d.c];
         const SegState sn_st = seg[sn];
@@ -408,7 +481,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   // thread 0 only, once the span buffer is dead: issue the bulk copy of the next unit's first span
   auto prefetch_next_tile = [&]() {
     const FzNext d = H.nd;
-    if (!FZ_BULK || d.u >= n_units) return;
+    if (!FZ_BULK || JOIN || d.u >= n_units) return;
     const int nn = d.end - d.start;
     const int nn16 = nn > 0 ? (int)((2LL * nn + 2) / 3) : 0;
     int Tn, Tn_real, Nn, nvn;
@@ -441,6 +514,13 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   for (;;) {
   half_sync(half);                                   // the descriptor written by tid 0 is visible
   const FzNext nd = H.nd;
+  if (JOIN && nd.u < n_units && tid < min(nd.ns, FZ_MAX_JSEG)) {     // the item's span records, next to the arithmetic
+    const SegSpan sp = gspan[nd.s0 + tid];
+    JSeg j;
+    j.x_base = sp.x_base; j.prev_x = sp.prev_x; j.dst = sp.dst; j.ov = sp.ov; j.body = sp.body; j.pause = sp.pause;
+    j.dc = sp.dc; j.dcp = sp.dcp;
+    H.js[tid] = j;
+  }
   half_sync(half);                                   // ... and read by everybody before it is replaced
   const int u = nd.u;
   if (u >= n_units) break;
@@ -450,7 +530,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   SegState st;
   st.start = nd.start; st.end = nd.end; st.dc = nd.dc;
   const int n = st.end - st.start;                   // samples of y
-  const float dc = st.dc;
+  float dc = st.dc;                                  // MODE 2: of the segment a batch lies in
   const int n16 = n > 0 ? (int)((2LL * n + 2) / 3) : 0;
   int T, T_real, N, n_valid;
   lm_frame_counts(n16, pad_frames, &T, &T_real, &N, &n_valid);
@@ -475,6 +555,24 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   bool pending = false;                              // a batch's mel projection is in flight on the tensor cores
   int pend_t0 = 0;
 #endif
+  const SegSpan* __restrict__ gs = JOIN ? gspan + nd.s0 : nullptr;
+  const int ns = nd.ns;
+  // MODE 2: does the window of the batch at frame t0 lie inside the body of ONE segment (and clear of the item's fades)?
+  // Then it is staged from that segment's x like a one-segment clip: *xe = pointer to the sample at item position 0.
+  // The windows of a tile move forward only: jk remembers the segment the last one started in.  Evaluated ONCE per
+  // batch, when its span is staged (one batch ahead); the batch itself uses the saved answer (nx_*).
+  int jk = 0;
+  bool nx_staged = false, nx_bulk = false;
+  float nx_dc = 0.f;
+  auto jclass = [&](int t0, const float** xe, float* dce) {
+    const long long j0 = 240LL * t0 - FZ_LEAD;
+    if (j0 < edge_lo || j0 + FZ_SPAN > edge_hi) return false;
+    JSeg s = fz_jseg(H.js, gs, jk);
+    while (jk + 1 < ns && j0 >= (long long)s.dst + s.ov + s.body + s.pause) s = fz_jseg(H.js, gs, ++jk);
+    const long long lo = (long long)s.dst + s.ov;
+    if (j0 >= lo && j0 + FZ_SPAN <= lo + s.body) { *xe = x + (s.x_base - s.dst); *dce = s.dc; return true; }
+    return false;
+  };
 
   // A span that lies inside the clip is ONE bulk copy issued by one thread; spans that stick out
   // (clip edges: zero fill) are staged in 16-byte zero-filling LDGSTS pieces by everybody.
@@ -484,6 +582,32 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
   };
   auto stage_span = [&](int t0) {
     const long long j0 = 240LL * t0 - FZ_LEAD;
+    if (JOIN) {
+      // a window inside one segment: a bulk copy if that segment's samples are 16-byte aligned at the window start
+      // (the position of a segment inside its item is arbitrary), else 8- or 4-byte LDGSTS pieces; any other window is
+      // computed sample by sample when its batch starts (fz_join_piece): nothing to stage
+      const float* xe; float dce = 0.f;
+      nx_staged = jclass(t0, &xe, &dce);
+      nx_dc = dce; nx_bulk = false;
+      if (!nx_staged) return;
+      const float* src = xe + j0;
+      const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+      if (FZ_BULK && (a & 15u) == 0) {
+        nx_bulk = true;
+        if (tid == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive_expect_tx(&H.bar, FZ_SPAN * 4);
+          bulk_g2s(H.span, src, FZ_SPAN * 4, &H.bar);
+        }
+      } else if ((a & 7u) == 0) {
+        for (int q = tid; q < FZ_SPAN / 2; q += LM_THREADS) fz_cp_async8(H.span + 2 * q, src + 2 * q);
+        cp_async_commit();
+      } else {
+        for (int q = tid; q < FZ_SPAN; q += LM_THREADS) fz_cp_async4(H.span + q, src + q);
+        cp_async_commit();
+      }
+      return;
+    }
     if (span_is_bulk(t0)) {
       if (tid == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses to the span
@@ -512,16 +636,27 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
     // Bulk mode needs no barrier here: every thread waits on the mbarrier itself, and nothing this batch writes
     // before its first barrier (the slab, in the pw region) is still read by the previous batch (its power
     // spectra live in the fb region, its partner exchange finished before its last barrier).
-    if (span_is_bulk(t0)) { mbar_wait(&H.bar, parity); parity ^= 1u; } else { cp_async_wait_all(); half_sync(half); }
+    const bool staged = JOIN ? nx_staged : true;             // MODE 2: the span holds the raw samples of ONE segment
+    if (JOIN) dc = nx_dc;
+    if (JOIN ? nx_bulk : span_is_bulk(t0)) { mbar_wait(&H.bar, parity); parity ^= 1u; } else { cp_async_wait_all(); half_sync(half); }
     const int j0 = 240 * t0 - FZ_LEAD;
     const int own_lo = 240 * t0, own_hi = own_lo + FZ_OWN;
     // interior batch: every sample of the span is plain x - dc, and the owned range lies in ONE decay zone
     const bool in_first = own_hi <= third, in_last = own_lo >= n - third;
-    const bool fast = FROM_Y || (FZ_FAST_APPLY && j0 >= edge_lo && j0 + FZ_SPAN <= edge_hi &&
+    const bool fast = FROM_Y || (FZ_FAST_APPLY && staged && j0 >= edge_lo && j0 + FZ_SPAN <= edge_hi &&
                                  (in_first || own_lo >= third) && (in_last || own_hi <= n - third));
     const bool split = FZ_SPLIT_APPLY && !FROM_Y && fast && t0 < T_real;
     if (FROM_Y) {
       // finished audio: nothing to apply, nothing to write back; samples outside the item were zero-filled by the staging
+    } else if (JOIN && !staged) {
+      // ---- apply, a batch at a joint (crossfade, pause, segment boundary, end of the item): the window of the joined
+      // audio sample by sample into the span; the batch's own samples go to HBM; decay sums
+      for (int q = tid; q < FZ_SPAN / 4; q += LM_THREADS) {
+        float e[4];
+        fz_join_piece(e, j0 + 4 * q, n, H.js, gs, ns, x, fade, need_fade, third, own_lo, own_hi, ys, &a_first, &a_last);
+        *reinterpret_cast<float4*>(H.span + 4 * q) = make_float4(e[0], e[1], e[2], e[3]);
+      }
+      half_sync(half);
     } else if (fast) {
       // ---- apply, interior: registers -> HBM; the span keeps the raw x.  Split mode (a batch that also runs the FIR):
       // the interior apply and the FIR do not depend on each other, so warps 8-9 write all of y (30 pieces per thread) while
@@ -957,7 +1092,8 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
                                   const int32_t* item_first_seg, int n_items, int64_t max_len,
                                   const Derived& d, float* y, const int64_t* y_off, int n_mels, int pad_frames,
                                   float* mel, int64_t mel_stride_frames, int sm_count, cudaStream_t st, LaunchCtx* lc,
-                                  bool from_y, int fill_to) {
+                                  int mode, int fill_to) {
+  const bool from_y = mode == 1;
   if (n_items <= 0) return cudaSuccess;
   if (fill_to <= 0) fill_to = pad_frames;
   // frames to cover: the features' frames and, for clips the 30 s window truncates, the rest of y
@@ -997,7 +1133,14 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
     int64_t left = n_b - pos, sz;
     if (!forced_sched.empty()) sz = std::max(1, forced_sched[std::min<size_t>(sched.n_tiles, forced_sched.size() - 1)]);
     else if (forced_bpt > 0) sz = forced_bpt;
-    else sz = std::min<int64_t>(std::max<int64_t>((n_b * 2 + 4) / 5, 1), cap);
+    else {
+      // ... and of at most 26 batches: with items of very different lengths (joined items of 2..6 ragged segments: the
+      // longest is three times the average) a tile of 40 % of the LONGEST item swallows most items whole and the halves
+      // end far apart -- C3, join + features, k_fused_features: 7.35 ms with 300-batch tiles, 6.59 / 6.66 / 6.92 ms with
+      // uniform 26 / 52 / 104 (profiles/ab_r02_join_tiles.log); the table holds 64 tiles, longer items get longer ones
+      sz = std::min<int64_t>(std::min<int64_t>(std::max<int64_t>((n_b * 2 + 4) / 5, 1), cap), 26);
+      sz = std::max<int64_t>(sz, (n_b + FZ_MAX_TILES - 2) / (FZ_MAX_TILES - 1));
+    }
     if (sched.n_tiles == FZ_MAX_TILES - 1) sz = left;                      // table full: the rest in one tile
     sz = std::min(sz, left);
     pos += sz;
@@ -1005,8 +1148,9 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
   }
   const int64_t tiles = sched.n_tiles;
   const size_t smem = sizeof(FzSmem) + 1024;      // slack to align the halves to 1024 bytes (swizzle atoms)
-  auto kern = from_y ? ((n_mels == 80) ? k_fused_features<80, true> : k_fused_features<128, true>)
-                     : ((n_mels == 80) ? k_fused_features<80, false> : k_fused_features<128, false>);
+  auto kern = mode == 1 ? ((n_mels == 80) ? k_fused_features<80, 1> : k_fused_features<128, 1>)
+            : mode == 2 ? ((n_mels == 80) ? k_fused_features<80, 2> : k_fused_features<128, 2>)
+                        : ((n_mels == 80) ? k_fused_features<80, 0> : k_fused_features<128, 0>);
   if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
   const uint64_t n_units = (uint64_t)n_items * (uint64_t)tiles;
   if (n_units > 0x7fffffffull) return cudaErrorInvalidValue;
@@ -1016,7 +1160,7 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
   kern<<<grid, FZ_THREADS, smem, st>>>(x, seg_off, ws.seg, ws.item, item_first_seg, y, y_off, d.fade, tb.hann,
                                        tb.twiddle, pad_frames, mel, mel_stride_frames, ws.clip_max, ws.len16,
                                        ws.tiles_done, ws.work_counter, sched, n_items,
-                                       tb.mel_dense[n_mels == 80 ? 0 : 1], fill_to);
+                                       tb.mel_dense[n_mels == 80 ? 0 : 1], fill_to, ws.span);
   lc->end(st);
   return cudaGetLastError();
 }

@@ -154,7 +154,8 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
                                   const int32_t* item_first_seg, int n_items, int64_t max_len,
                                   const Derived& d, float* y, const int64_t* y_off, int n_mels, int pad_frames,
                                   float* mel, int64_t mel_stride_frames, int sm_count, cudaStream_t st, LaunchCtx* lc,
-                                  bool from_y = false, int fill_to = 0);
+                                  int mode = 0, int fill_to = 0);   // mode 0: one-segment items, 1: features of the
+                                                                    // finished audio in y, 2: joined items (y written here)
 
 // mel_gemm.cu: the mel projection as a tcgen05 / TMEM / TMA GEMM (3xTF32), in isolation
 cudaError_t launch_mel_gemm(const Tables& tb, const float* power, int64_t n_frames, int64_t ld_power, int n_mels,

@@ -460,6 +460,54 @@ def test_validate_joined_items_vs_oracle(R, cuda_device, pad):
         T_i = 3000 if pad else ((2 * int(rec["out_len"][i]) + 2) // 3) // 160
         if T_i > 0 and (pad or (2 * int(rec["out_len"][i]) + 2) // 3 > 200):
             assert float((out.mel[i, :, :T_i] - stage.mel[i, :, :T_i]).abs().max()) < 1e-4, i
+    # the single-kernel join (default) against "k_gather writes y, the feature kernel reads it back": same samples, bit
+    # for bit; the features differ by the rounding of the DC folded into the FIR of interior batches
+    gf = R.validate_batch(rb, p, emb.to(cuda_device), ref.to(cuda_device), n_mels=80, pad_to_30s=pad,
+                          item_first_seg=first, gather_first=True)
+    rg = gf.records_host()
+    for f in ("start", "end", "out_len", "ok", "flags", "cosine", "n_segments"):
+        assert np.array_equal(rec[f], rg[f]), f
+    assert np.allclose(rec["first_rms"], rg["first_rms"], rtol=2e-6, atol=1e-9)
+    assert np.allclose(rec["last_rms"], rg["last_rms"], rtol=2e-6, atol=1e-9)
+    for i in range(len(items)):
+        L = int(rec["out_len"][i])
+        assert torch.equal(out.audio.clip(i, L), gf.audio.clip(i, L)), i
+        T_i = 3000 if pad else ((2 * L + 2) // 3) // 160
+        if T_i > 0 and (pad or (2 * L + 2) // 3 > 200):
+            assert float((out.mel[i, :, :T_i] - gf.mel[i, :, :T_i]).abs().max()) < 6e-5, i
+
+
+def test_validate_joined_many_short_segments(R, cuda_device):
+    """The single-kernel join on items of up to 14 segments (more than a half caches), segments shorter than a batch's
+    window (several joints per window), odd lengths (segments at every alignment inside their item), no pauses, a
+    crossfade longer than some segments: against k_gather's output bit for bit and against the oracle."""
+    from rho_tts_b200 import synth
+    rng = np.random.default_rng(777)
+    for kw in (dict(), dict(inter_sentence_pause_sec=0.0, crossfade_duration_sec=0.11), dict(trim_silence=False)):
+        items = []
+        for k in range(10):
+            n = int(rng.integers(2, 15))
+            items.append([synth.make_clip_block(1, int(rng.integers(700, 30000)) if rng.integers(0, 3) else
+                                                int(rng.integers(30000, 200001)), 9000 + 31 * k + j)[0].numpy()
+                          for j in range(n)])
+        segs = [s for it in items for s in it]
+        first = np.concatenate([[0], np.cumsum([len(it) for it in items])]).astype(np.int32)
+        rb = _rb(R, segs, cuda_device)
+        p = R.make_params(**kw)
+        a = R.validate_batch(rb, p, n_mels=80, pad_to_30s=True, item_first_seg=first)
+        b = R.validate_batch(rb, p, n_mels=80, pad_to_30s=True, item_first_seg=first, gather_first=True)
+        ra, rb_ = a.records_host(), b.records_host()
+        for f in ("start", "end", "out_len", "ok", "flags", "n_segments"):
+            assert np.array_equal(ra[f], rb_[f]), f
+        c = oracle.derive_constants(xfade_sec=kw.get("crossfade_duration_sec", 0.05),
+                                    pause_sec=kw.get("inter_sentence_pause_sec", 0.1))
+        for i, it in enumerate(items):
+            L = int(ra["out_len"][i])
+            assert torch.equal(a.audio.clip(i, L), b.audio.clip(i, L)), (kw, i)
+            o = oracle.smooth_segment_join(it, c, kw.get("trim_silence", True))
+            assert L == o.audio.size
+            assert_close(a.audio.clip(i, L).cpu().numpy(), o.audio, what=f"item {i} audio")
+            assert float((a.mel[i] - b.mel[i]).abs().max()) < 6e-5, (kw, i)
 
 
 def test_validate_host_ragged_joins(R, cuda_device):

@@ -157,7 +157,7 @@ for cfg in args:
         line(cfg, f"{n} x 10 s clips at 16 kHz, resemblyzer front end: -30 dBFS gains + 40-band mel spectrogram -> "
              f"{P} partial utterances [160, 40]", n * 10.0, ms, prof, alg)
         del x, rb, out
-    elif cfg in ("c3", "c3v"):
+    elif cfg in ("c3", "c3v", "c3vg"):
         rb, first = ragged_c3()
         audio_s = rb.total_samples / SR
         if cfg == "c3":
@@ -169,7 +169,7 @@ for cfg in args:
                  f"({rb.total_samples * 4 / 1e9:.2f} GB in)", audio_s, ms, prof, alg)
         else:
             emb, ref = synth.make_embeddings(len(first) - 1, device=dev)
-            plan = R.ValidatePlan(rb, first, p, 80, False)
+            plan = R.ValidatePlan(rb, first, p, 80, False, gather_first=(cfg == "c3vg"))   # c3vg: k_gather, then features from y
             out, ms, prof = timed(lambda: plan.run(rb, emb, ref), steps)
             rec = out.records_host()
             s_in, s_out = 4.0 * rb.total_samples, 4.0 * float(rec["out_len"].astype(np.int64).sum())
