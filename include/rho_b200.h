@@ -315,7 +315,9 @@ int rho_b200_cosine(rho_handle* h, const float* emb, const float* ref, int n, in
  * end, stt_validator.py:78-107 -> feature_extraction_whisper.py:135-164, and the speaker cosine base_tts.py:341-344).
  *   one-segment items (RHO_V_ONE_SEGMENT_ITEMS: the caller asserts item_first_seg = 0,1,2,...): ONE kernel applies
  *     DC / fades, resamples and computes the log-mel frames in one pass over each clip;
- *   joined items: the join writes y, the same kernel then reads the finished y (resample + log-mel).
+ *   joined items: the same kernel also joins -- batches inside one segment are the one-segment case, batches at a
+ *     joint (crossfade, pause, item end) are computed sample by sample -- and writes y; RHO_V_GATHER_FIRST keeps the
+ *     two-kernel path (the join writes y, the kernel reads the finished y back) for A/B measurements.
  *   Either way the 16 kHz signal never leaves shared memory; scratch16 is only used with RHO_V_NO_FUSION (the
  *   kernel-per-stage path kept for A/B measurements: same offsets as y, 2/3 the length) and may be NULL otherwise.
  * Features: mel + i*n_mels*mel_stride_frames, rows of mel_stride_frames floats.

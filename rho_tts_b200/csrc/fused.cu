@@ -298,13 +298,26 @@ __device__ __forceinline__ void fz_cp_async8(void* smem_dst, const void* gmem_sr
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 
-__device__ __forceinline__ JSeg fz_jseg(const JSeg* __restrict__ cached, const SegSpan* __restrict__ gs, int k) {
-  if (k < FZ_MAX_JSEG) return cached[k];
+__device__ __noinline__ JSeg fz_jseg_global(const SegSpan* __restrict__ gs, int k) {
   const SegSpan sp = gs[k];
   JSeg j;
   j.x_base = sp.x_base; j.prev_x = sp.prev_x; j.dst = sp.dst; j.ov = sp.ov; j.body = sp.body; j.pause = sp.pause;
   j.dc = sp.dc; j.dcp = sp.dcp;
   return j;
+}
+__device__ __forceinline__ JSeg fz_jseg(const JSeg* __restrict__ cached, const SegSpan* __restrict__ gs, int k) {
+  return k < FZ_MAX_JSEG ? cached[k] : fz_jseg_global(gs, k);
+}
+
+// MODE 2: a window inside one segment whose samples are not 16-byte aligned at the window start (the position of a
+// segment inside its item is arbitrary): 8- or 4-byte LDGSTS pieces.  Out of line: a fifth of the batches, three call sites.
+__device__ __noinline__ void fz_stage_pieces(float* __restrict__ span, const float* __restrict__ src, int tid) {
+  if ((reinterpret_cast<uintptr_t>(src) & 7u) == 0) {
+    for (int q = tid; q < FZ_SPAN / 2; q += LM_THREADS) fz_cp_async8(span + 2 * q, src + 2 * q);
+  } else {
+    for (int q = tid; q < FZ_SPAN; q += LM_THREADS) fz_cp_async4(span + q, src + q);
+  }
+  cp_async_commit();
 }
 
 // MODE 2, batches that touch a crossfade, a pause, a segment boundary or an end of the item: four samples of the JOINED
@@ -317,6 +330,25 @@ __device__ __noinline__ void fz_join_piece(float* e, int o, int n, const JSeg* _
                                            float* a_first, float* a_last) {
   int k = 0;
   JSeg s = fz_jseg(cached, gs, 0);
+  if (o >= 0 && o + 3 < n) {
+    // most pieces of such a window are still plain body samples of one segment, clear of the fades: no per-sample search
+    while (k + 1 < ns && o >= s.dst + s.ov + s.body + s.pause) s = fz_jseg(cached, gs, ++k);
+    const int jj = o - s.dst;
+    if (jj >= s.ov && jj + 3 < s.ov + s.body && (!need_fade || (o >= fade && o + 3 < n - fade))) {
+      const float* __restrict__ xc = x + s.x_base + jj;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) e[i] = __fsub_rn(xc[i], s.dc);
+      if (o >= own_lo && o < own_hi) {                   // own_lo, own_hi and o are multiples of 4
+        *reinterpret_cast<float4*>(ys + o) = make_float4(e[0], e[1], e[2], e[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (o + i < third) *a_first += e[i] * e[i];
+          if (o + i >= n - third) *a_last += e[i] * e[i];
+        }
+      }
+      return;
+    }
+  }
   for (int i = 0; i < 4; ++i) {
     const int oo = o + i;
     float val = 0.f;
@@ -599,12 +631,8 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
           mbar_arrive_expect_tx(&H.bar, FZ_SPAN * 4);
           bulk_g2s(H.span, src, FZ_SPAN * 4, &H.bar);
         }
-      } else if ((a & 7u) == 0) {
-        for (int q = tid; q < FZ_SPAN / 2; q += LM_THREADS) fz_cp_async8(H.span + 2 * q, src + 2 * q);
-        cp_async_commit();
       } else {
-        for (int q = tid; q < FZ_SPAN; q += LM_THREADS) fz_cp_async4(H.span + q, src + q);
-        cp_async_commit();
+        fz_stage_pieces(H.span, src, tid);
       }
       return;
     }
@@ -1134,11 +1162,12 @@ cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_
     if (!forced_sched.empty()) sz = std::max(1, forced_sched[std::min<size_t>(sched.n_tiles, forced_sched.size() - 1)]);
     else if (forced_bpt > 0) sz = forced_bpt;
     else {
-      // ... and of at most 26 batches: with items of very different lengths (joined items of 2..6 ragged segments: the
+      // ... and of at most 32 batches: with items of very different lengths (joined items of 2..6 ragged segments: the
       // longest is three times the average) a tile of 40 % of the LONGEST item swallows most items whole and the halves
       // end far apart -- C3, join + features, k_fused_features: 7.35 ms with 300-batch tiles, 6.59 / 6.66 / 6.92 ms with
-      // uniform 26 / 52 / 104 (profiles/ab_r02_join_tiles.log); the table holds 64 tiles, longer items get longer ones
-      sz = std::min<int64_t>(std::min<int64_t>(std::max<int64_t>((n_b * 2 + 4) / 5, 1), cap), 26);
+      // uniform 26 / 52 / 104, later 6.40 / 6.36 / 6.33 with 20 / 26 / 32 (profiles/ab_r02_join_tiles.log); the table
+      // holds 64 tiles, longer items get longer ones
+      sz = std::min<int64_t>(std::min<int64_t>(std::max<int64_t>((n_b * 2 + 4) / 5, 1), cap), 32);
       sz = std::max<int64_t>(sz, (n_b + FZ_MAX_TILES - 2) / (FZ_MAX_TILES - 1));
     }
     if (sched.n_tiles == FZ_MAX_TILES - 1) sz = left;                      // table full: the rest in one tile
