@@ -224,6 +224,9 @@ int rho_b200_create(rho_handle** out, int device) {
     }
     if (w.size() > 416) { rho_b200_destroy(h); return fail(RHO_ERR_INVALID, "mel filterbank nnz %zu > 416", w.size()); }
     h->tb.mel_nnz[which] = (int)w.size();
+    if ((e = upload_fused_mel(which, nm, lo.data(), cnt.data(), wofs.data(), w.data(), (int)w.size())) != cudaSuccess) {
+      rho_b200_destroy(h); return cuda_fail(e, "fused mel tables");
+    }
     if ((e = dev_upload(h, &h->tb.mel_lo[which], lo.data(), nm)) != cudaSuccess ||
         (e = dev_upload(h, &h->tb.mel_cnt[which], cnt.data(), nm)) != cudaSuccess ||
         (e = dev_upload(h, &h->tb.mel_wofs[which], wofs.data(), nm)) != cudaSuccess ||

@@ -150,6 +150,7 @@ cudaError_t launch_logmel_norm(const int32_t* len16, int n, int n_mels, int pad_
 // fused.cu
 bool fused_inline_norm();   // the fused kernel writes the constant fill of the zero-padding frames itself
 cudaError_t upload_fused_taps(const float* taps /* [2][23] */);
+cudaError_t upload_fused_mel(int which, int n_mels, const int* lo, const int* cnt, const int* wofs, const float* w, int nnz);
 cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_t* seg_off, const Workspace& ws,
                                   const int32_t* item_first_seg, int n_items, int64_t max_len,
                                   const Derived& d, float* y, const int64_t* y_off, int n_mels, int pad_frames,

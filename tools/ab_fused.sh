@@ -10,7 +10,7 @@ NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c+
 while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
   b=build_$name; mkdir -p $b
-  for f in api host_api exchange join resample logmel cosine fused mel_gemm stft_tc qwen pitch mfcc; do $NV $flags -c $f.cu -o $b/$f.o & done
+  for f in api host_api exchange join resample logmel cosine fused mel_gemm stft_tc qwen pitch mfcc spk; do $NV $flags -c $f.cu -o $b/$f.o & done
   $NV $flags -x cu -c tables.cpp -o $b/tables.o &
   g++ -O3 -std=c++17 -fPIC -c hostfill.cpp -o $b/hostfill.o &
   wait
