@@ -71,44 +71,65 @@ cudaError_t upload_fused_taps(const float* taps) {
 // with immediate weights that each of the ten warps of a half streams a tenth of, once per batch: the immediates are one
 // instruction per weight cheaper, but their code is 30 KB of a ~75 KB loop body against a 32 KB instruction cache.
 // Layout: ONE stream of float4 per bank, walked front to back by the ten warps of a half (warp w starts at part4[w] and
-// owns rows [part[w], part[w + 1])): per row a header {byte offset of its first bin in a power row, bytes of power
-// it covers, -, -} followed by its weights, padded with zeros to a multiple of four (fmaf(0, p, a) == a for the
-// finite, non-negative powers: the sums keep their bits); the padding stays inside the 201 bins.
-constexpr int FZ_MEL_TAB4 = 336;                   // float4 per bank: 128 headers + (394 weights + <= 3 zeros per row) / 4
+// owns rows [part[w], part[w + 1])).  Rows go in bundles of FZ_MEL_ROWS consecutive rows that are walked together -- so
+// many independent fmaf chains per lane instead of one: a header {byte offset of each row's first bin in a power row}
+// + {bytes of power every row of the bundle covers}, then the weights, group of four by group of four, the rows of the
+// bundle interleaved.  Rows are padded with zeros to the bundle's longest row and to a multiple of four
+// (fmaf(0, p, a) == a for the finite, non-negative powers: the sums keep their bits); the padding stays inside the 201
+// bins; a bundle that sticks out of its part is filled with all-zero rows whose results are not stored.
+#ifndef FZ_MEL_ROWS
+#define FZ_MEL_ROWS 2
+#endif
+constexpr int FZ_MEL_HDR4 = (FZ_MEL_ROWS + 1 + 3) / 4;      // float4 per bundle header
+constexpr int FZ_MEL_TAB4 = 640;                   // float4 per bank (checked at upload)
 __constant__ float4 c_mel_tab[2][FZ_MEL_TAB4];
 __constant__ int c_mel_part[2][12];                // rows [part[w], part[w + 1]) belong to warp w of a half
 __constant__ int c_mel_part4[2][12];               // ... and start at this float4 of the stream
 
 cudaError_t upload_fused_mel(int which, int n_mels, const int* lo, const int* cnt, const int* wofs, const float* w, int nnz) {
   if (which < 0 || which > 1 || n_mels > 128 || nnz > 416) return cudaErrorInvalidValue;
-  static float4 tab[FZ_MEL_TAB4];
-  int part[12] = {}, part4[12] = {}, row4[129] = {};
-  memset(tab, 0, sizeof(tab));
-  long long total = 0;
-  int n4 = 0;
-  for (int m = 0; m < n_mels; ++m) {
-    const int groups = (cnt[m] + 3) / 4;
-    int first = lo[m];
-    if (first + 4 * groups > N_BINS) first = N_BINS - 4 * groups;      // leading zeros instead of trailing ones
-    if (first < 0 || n4 + 1 + groups > FZ_MEL_TAB4) return cudaErrorInvalidValue;
-    row4[m] = n4;
-    const unsigned hdr[4] = {4u * (unsigned)first, 16u * (unsigned)groups, 0u, 0u};
-    memcpy(&tab[n4], hdr, sizeof(hdr));
-    float* dst = reinterpret_cast<float*>(tab + n4 + 1);
-    for (int j = 0; j < cnt[m]; ++j) dst[lo[m] - first + j] = w[wofs[m] + j];
-    n4 += 1 + groups;
-    total += groups + 2;
-  }
-  row4[n_mels] = n4;
-  // contiguous groups of rows of about equal cost (float4 groups + a fixed cost per row), one per warp
+  constexpr int R = FZ_MEL_ROWS;
   constexpr int PARTS = LM_THREADS / 32;
-  long long acc = 0; int nxt = 1;
+  static float4 tab[FZ_MEL_TAB4];
+  int part[12] = {}, part4[12] = {};
+  memset(tab, 0, sizeof(tab));
+  // contiguous groups of rows of about equal cost (groups of four weights + a fixed cost per row), one per warp
+  long long total = 0, acc = 0;
+  for (int m = 0; m < n_mels; ++m) total += (cnt[m] + 3) / 4 + 2;
+  int nxt = 1;
   for (int m = 0; m < n_mels; ++m) {
     acc += (cnt[m] + 3) / 4 + 2;
     if (nxt < PARTS && acc * PARTS >= total * nxt) part[nxt++] = m + 1;
   }
   while (nxt <= PARTS) part[nxt++] = n_mels;
-  for (int i = 0; i <= PARTS; ++i) part4[i] = row4[part[i]];
+  int n4 = 0;
+  for (int pt = 0; pt < PARTS; ++pt) {
+    part4[pt] = n4;
+    for (int m0 = part[pt]; m0 < part[pt + 1]; m0 += R) {
+      int groups = 0;
+      for (int r = 0; r < R; ++r) if (m0 + r < part[pt + 1]) groups = std::max(groups, (cnt[m0 + r] + 3) / 4);
+      if (n4 + FZ_MEL_HDR4 + R * groups > FZ_MEL_TAB4 || 4 * groups > N_BINS) return cudaErrorInvalidValue;
+      unsigned hdr[4 * FZ_MEL_HDR4] = {};
+      for (int r = 0; r < R; ++r) {
+        int first = 0;
+        if (m0 + r < part[pt + 1]) {
+          const int m = m0 + r;
+          first = lo[m];
+          if (first + 4 * groups > N_BINS) first = N_BINS - 4 * groups;      // leading zeros instead of trailing ones
+          float* base = reinterpret_cast<float*>(tab + n4 + FZ_MEL_HDR4);
+          for (int j = 0; j < cnt[m]; ++j) {
+            const int k = lo[m] - first + j;                                   // position in the padded row
+            base[((k / 4) * R + r) * 4 + (k % 4)] = w[wofs[m] + j];
+          }
+        }
+        hdr[r] = 4u * (unsigned)first;
+      }
+      hdr[R] = 16u * (unsigned)groups;
+      memcpy(&tab[n4], hdr, sizeof(hdr));
+      n4 += FZ_MEL_HDR4 + R * groups;
+    }
+  }
+  part4[PARTS] = n4;
   cudaError_t e;
   if ((e = cudaMemcpyToSymbol(c_mel_tab, tab, sizeof(tab), sizeof(tab) * which)) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbol(c_mel_part4, part4, sizeof(part4), sizeof(part4) * which)) != cudaSuccess) return e;
@@ -1100,27 +1121,41 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       unsigned pbase = smem_u32(p);
       asm volatile("" : "+r"(pbase));                        // keep the row address in a register (ptxas re-derives it per row)
       const float4* __restrict__ tp = c_mel_tab[which] + c_mel_part4[which][part];
-      for (; m < m1; ++m, orow += mel_stride) {
-        const float4 hd = *tp++;                             // {first bin (bytes), bytes of power covered, -, -}
-        unsigned pa = pbase + __float_as_uint(hd.x);
-        const unsigned pe = pa + __float_as_uint(hd.y);
-        float acc = 0.f;                                     // the same left-to-right fmaf chain as the unrolled form
+      constexpr int R = FZ_MEL_ROWS;
+      for (; m < m1; m += R) {
+        const unsigned* __restrict__ hd = reinterpret_cast<const unsigned*>(tp);   // {first bin of each row (bytes)}, {bytes}
+        unsigned pa[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) pa[r] = pbase + hd[r];
+        const unsigned pe = pa[0] + hd[R];
+        tp += FZ_MEL_HDR4;
+        float acc[R];                                        // per row the same left-to-right fmaf chain as the unrolled form
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.f;
 #pragma unroll 1
-        for (; pa != pe; pa += 16u, ++tp) {
-          const float4 w = *tp;
-          float p0, p1, p2, p3;
-          asm volatile("ld.shared.f32 %0, [%4];\n\tld.shared.f32 %1, [%4+4];\n\tld.shared.f32 %2, [%4+8];\n\tld.shared.f32 %3, [%4+12];"
-                       : "=f"(p0), "=f"(p1), "=f"(p2), "=f"(p3) : "r"(pa));
-          acc = fmaf(w.x, p0, acc); acc = fmaf(w.y, p1, acc);
-          acc = fmaf(w.z, p2, acc); acc = fmaf(w.w, p3, acc);
+        for (; pa[0] != pe; tp += R) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float4 w = tp[r];
+            float p0, p1, p2, p3;
+            asm volatile("ld.shared.f32 %0, [%4];\n\tld.shared.f32 %1, [%4+4];\n\tld.shared.f32 %2, [%4+8];\n\tld.shared.f32 %3, [%4+12];"
+                         : "=f"(p0), "=f"(p1), "=f"(p2), "=f"(p3) : "r"(pa[r]));
+            acc[r] = fmaf(w.x, p0, acc[r]); acc[r] = fmaf(w.y, p1, acc[r]);
+            acc[r] = fmaf(w.z, p2, acc[r]); acc[r] = fmaf(w.w, p3, acc[r]);
+            pa[r] += 16u;
+          }
         }
-        // log2 of a value >= 1e-10: the flush-to-zero form gives the same bits without the denormal pre-scaling
-        float l2;
-        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(0.25f * acc, 1e-10f)));
-        const float ls = l2 * 0.30102999566398120f;
-        if (live) {
-          *orow = lm_scaled(ls);
-          lmax = fmaxf(lmax, ls);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          // log2 of a value >= 1e-10: the flush-to-zero form gives the same bits without the denormal pre-scaling
+          float l2;
+          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(0.25f * acc[r], 1e-10f)));
+          const float ls = l2 * 0.30102999566398120f;
+          if (live && m + r < m1) {
+            *orow = lm_scaled(ls);
+            lmax = fmaxf(lmax, ls);
+          }
+          orow += mel_stride;
         }
       }
 #else
