@@ -510,6 +510,38 @@ def test_validate_joined_many_short_segments(R, cuda_device):
             assert float((a.mel[i] - b.mel[i]).abs().max()) < 6e-5, (kw, i)
 
 
+def test_validate_joined_degenerate_items(R, cuda_device):
+    """The single-kernel join on degenerate items: empty segments, items made of empty segments only, one-sample and
+    all-silent segments, an item whose segments are all shorter than the crossfade -- against k_gather's output."""
+    from rho_tts_b200 import synth
+    rng = np.random.default_rng(31)
+    tone = lambda n, k: synth.make_clip_block(1, n, 8100 + k)[0].numpy()          # noqa: E731
+    z = np.zeros(0, np.float32)
+    items = [[z, z], [z, tone(30000, 0), z], [tone(1, 1), tone(50000, 2)], [tone(700, 3), tone(900, 4), tone(800, 5)],
+             [rng.normal(0, 1e-5, 20000).astype(np.float32), tone(40000, 6)], [tone(90000, 7)], [z],
+             [tone(1199, 8), tone(1201, 9), tone(11, 10), tone(60000, 11)]]
+    segs = [s for it in items for s in it]
+    first = np.concatenate([[0], np.cumsum([len(it) for it in items])]).astype(np.int32)
+    rb = _rb(R, segs, cuda_device)
+    p = R.make_params()
+    for pad in (True, False):
+        a = R.validate_batch(rb, p, n_mels=80, pad_to_30s=pad, item_first_seg=first)
+        b = R.validate_batch(rb, p, n_mels=80, pad_to_30s=pad, item_first_seg=first, gather_first=True)
+        ra, rb_ = a.records_host(), b.records_host()
+        for f in ("start", "end", "out_len", "ok", "flags", "n_segments"):
+            assert np.array_equal(ra[f], rb_[f]), (pad, f)
+        c = oracle.derive_constants()
+        for i, it in enumerate(items):
+            L = int(ra["out_len"][i])
+            assert torch.equal(a.audio.clip(i, L), b.audio.clip(i, L)), (pad, i)
+            o = oracle.smooth_segment_join(it, c)
+            assert L == (0 if o.audio is None else o.audio.size), (pad, i)
+            T_i = 3000 if pad else ((2 * L + 2) // 3) // 160
+            if T_i > 0 and (pad or (2 * L + 2) // 3 > 200):
+                assert torch.isfinite(a.mel[i, :, :T_i]).all()
+                assert float((a.mel[i, :, :T_i] - b.mel[i, :, :T_i]).abs().max()) < 6e-5, (pad, i)
+
+
 def test_validate_host_ragged_joins(R, cuda_device):
     """rho_b200_validate_host_ragged: ragged segments and items in host memory (BASELINE config C3's shape, small), several
     chunks, with and without features, aligned and unaligned offsets -- against the device-resident calls, byte for byte."""
