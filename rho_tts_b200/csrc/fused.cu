@@ -77,10 +77,15 @@ cudaError_t upload_fused_taps(const float* taps) {
 // bundle interleaved.  Rows are padded with zeros to the bundle's longest row and to a multiple of four
 // (fmaf(0, p, a) == a for the finite, non-negative powers: the sums keep their bits); the padding stays inside the 201
 // bins; a bundle that sticks out of its part is filled with all-zero rows whose results are not stored.
-#ifndef FZ_MEL_ROWS
-#define FZ_MEL_ROWS 2
+// Rows per bundle: 2 for the 80-band bank, 4 for the 128-band one (measured: C2 0.883 / 0.888 ms with 2 / 4, C4 7.82 / 7.72)
+#ifndef FZ_MEL_ROWS_80
+#define FZ_MEL_ROWS_80 2
 #endif
-constexpr int FZ_MEL_HDR4 = (FZ_MEL_ROWS + 1 + 3) / 4;      // float4 per bundle header
+#ifndef FZ_MEL_ROWS_128
+#define FZ_MEL_ROWS_128 4
+#endif
+__host__ __device__ constexpr int fz_mel_rows(int which) { return which == 0 ? FZ_MEL_ROWS_80 : FZ_MEL_ROWS_128; }
+__host__ __device__ constexpr int fz_mel_hdr4(int which) { return (fz_mel_rows(which) + 1 + 3) / 4; }   // float4 per bundle header
 constexpr int FZ_MEL_TAB4 = 640;                   // float4 per bank (checked at upload)
 __constant__ float4 c_mel_tab[2][FZ_MEL_TAB4];
 __constant__ int c_mel_part[2][12];                // rows [part[w], part[w + 1]) belong to warp w of a half
@@ -88,7 +93,7 @@ __constant__ int c_mel_part4[2][12];               // ... and start at this floa
 
 cudaError_t upload_fused_mel(int which, int n_mels, const int* lo, const int* cnt, const int* wofs, const float* w, int nnz) {
   if (which < 0 || which > 1 || n_mels > 128 || nnz > 416) return cudaErrorInvalidValue;
-  constexpr int R = FZ_MEL_ROWS;
+  const int R = fz_mel_rows(which), HDR4 = fz_mel_hdr4(which);
   constexpr int PARTS = LM_THREADS / 32;
   static float4 tab[FZ_MEL_TAB4];
   int part[12] = {}, part4[12] = {};
@@ -108,25 +113,25 @@ cudaError_t upload_fused_mel(int which, int n_mels, const int* lo, const int* cn
     for (int m0 = part[pt]; m0 < part[pt + 1]; m0 += R) {
       int groups = 0;
       for (int r = 0; r < R; ++r) if (m0 + r < part[pt + 1]) groups = std::max(groups, (cnt[m0 + r] + 3) / 4);
-      if (n4 + FZ_MEL_HDR4 + R * groups > FZ_MEL_TAB4 || 4 * groups > N_BINS) return cudaErrorInvalidValue;
-      unsigned hdr[4 * FZ_MEL_HDR4] = {};
+      if (n4 + HDR4 + R * groups > FZ_MEL_TAB4 || 4 * groups > N_BINS) return cudaErrorInvalidValue;
+      unsigned hdr[8] = {};
       for (int r = 0; r < R; ++r) {
         int first = 0;
         if (m0 + r < part[pt + 1]) {
           const int m = m0 + r;
           first = lo[m];
           if (first + 4 * groups > N_BINS) first = N_BINS - 4 * groups;      // leading zeros instead of trailing ones
-          float* base = reinterpret_cast<float*>(tab + n4 + FZ_MEL_HDR4);
+          float* base = reinterpret_cast<float*>(tab + n4 + HDR4);
           for (int j = 0; j < cnt[m]; ++j) {
             const int k = lo[m] - first + j;                                   // position in the padded row
-            base[((k / 4) * R + r) * 4 + (k % 4)] = w[wofs[m] + j];
+            base[((k / 4) * R + r) * 4 + (k % 4)] = 0.25f * w[wofs[m] + j];   // the spectra are 4 |.|^2: exact scaling
           }
         }
         hdr[r] = 4u * (unsigned)first;
       }
       hdr[R] = 16u * (unsigned)groups;
-      memcpy(&tab[n4], hdr, sizeof(hdr));
-      n4 += FZ_MEL_HDR4 + R * groups;
+      memcpy(&tab[n4], hdr, sizeof(float4) * (size_t)HDR4);
+      n4 += HDR4 + R * groups;
     }
   }
   part4[PARTS] = n4;
@@ -1121,14 +1126,14 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
       unsigned pbase = smem_u32(p);
       asm volatile("" : "+r"(pbase));                        // keep the row address in a register (ptxas re-derives it per row)
       const float4* __restrict__ tp = c_mel_tab[which] + c_mel_part4[which][part];
-      constexpr int R = FZ_MEL_ROWS;
+      constexpr int R = fz_mel_rows(which);
       for (; m < m1; m += R) {
         const unsigned* __restrict__ hd = reinterpret_cast<const unsigned*>(tp);   // {first bin of each row (bytes)}, {bytes}
         unsigned pa[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) pa[r] = pbase + hd[r];
         const unsigned pe = pa[0] + hd[R];
-        tp += FZ_MEL_HDR4;
+        tp += fz_mel_hdr4(which);
         float acc[R];                                        // per row the same left-to-right fmaf chain as the unrolled form
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = 0.f;
@@ -1149,7 +1154,7 @@ k_fused_features(const float* __restrict__ x, const int64_t* __restrict__ seg_of
         for (int r = 0; r < R; ++r) {
           // log2 of a value >= 1e-10: the flush-to-zero form gives the same bits without the denormal pre-scaling
           float l2;
-          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(0.25f * acc[r], 1e-10f)));
+          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(acc[r], 1e-10f)));   // the 1/4 is in the table
           const float ls = l2 * 0.30102999566398120f;
           if (live && m + r < m1) {
             *orow = lm_scaled(ls);
