@@ -558,6 +558,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
                "result_bytes_in_host_memory_per_step": yh.numel() * 4 + rech.numel() + melh.numel() * 4,
                "timer": "host perf_counter around the synchronous C call, max over ranks",
                "value_compact_rows": world * audio_s_per_rank_step * e2e_steps / dt_comp,
+               "host_fill_threads": int(R._lib.load().rho_b200_host_fill_threads(R._lib.Handle.get(local_rank).ptr)),
                "value_features_in_hbm": world * audio_s_per_rank_step * e2e_steps / dt_hbm,
                "value_features_in_hbm_note": "same call with `mel` a device buffer: complete feature rows stay in HBM for a "
                                              "consumer on the GPU, audio and records come back (not the headline: the "

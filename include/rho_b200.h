@@ -396,6 +396,11 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
                                   const float* ref_emb, int emb_dim, rho_record* rec);
 /* Fixed-length layout: n clips of clip_len samples each, every item is one clip; complete feature rows
  * [n][n_mels][3000] (mel may be NULL).  A wrapper of rho_b200_validate_host_ragged. */
+/* Host threads the next host-entry call on this handle uses to write the constant tails of complete feature rows
+ * (default 3, RHO_HOST_FILL_THREADS pins it; raised by two, up to 9, after a call whose fill ended well behind its last
+ * copy: a host with slower memory). */
+int rho_b200_host_fill_threads(rho_handle* h);
+
 int rho_b200_validate_host(rho_handle* h, const float* x, int n, int32_t clip_len,
                            const rho_params* p, float* y /* n*clip_len */, int n_mels, int pad_frames,
                            float* mel /* n*n_mels*pad_frames or NULL */,

@@ -35,7 +35,7 @@ EXPORTS = (
     "rho_b200_resample_out_len", "rho_b200_resample", "rho_b200_pitch_workspace_bytes", "rho_b200_pitch_shift", "rho_b200_mfcc_workspace_bytes", "rho_b200_mfcc_stats", "rho_b200_spk_slices", "rho_b200_normalize_volume", "rho_b200_spk_mel", "rho_b200_spk_pool", "rho_b200_pcm16", "rho_b200_logmel", "rho_b200_mel_project", "rho_b200_stft_power_tc", "rho_b200_qwen_workspace_bytes", "rho_b200_qwen_postprocess",
     "rho_b200_cosine", "rho_b200_validate", "rho_b200_compact_frames", "rho_b200_exchange_create", "rho_b200_exchange_connect",
     "rho_b200_exchange_wait", "rho_b200_exchange_epoch", "rho_b200_exchange_read", "rho_b200_exchange_destroy",
-    "rho_b200_validate_host", "rho_b200_validate_host_ragged",
+    "rho_b200_validate_host", "rho_b200_validate_host_ragged", "rho_b200_host_fill_threads",
     "rho_b200_build_flags", "rho_b200_launch_count", "rho_b200_profile_begin", "rho_b200_profile_end", "rho_b200_kernel_name",
 )
 
@@ -125,6 +125,7 @@ def load():
             "rho_b200_validate_host_ragged": (c_int, [vp, vp, vp, vp, c_int, vp, c_int, P, vp, vp, c_int, c_int, vp, i64,
                                                       vp, vp, vp, c_int, vp]),
             "rho_b200_validate_host": (c_int, [vp, vp, c_int, c_int32, P, vp, c_int, c_int, vp, vp, vp, c_int, vp]),
+            "rho_b200_host_fill_threads": (c_int, [vp]),
             "rho_b200_build_flags": (c_int, []),
             "rho_b200_launch_count": (c_int64, [vp]),
             "rho_b200_profile_begin": (c_int, [vp]),

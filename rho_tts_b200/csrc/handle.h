@@ -1,5 +1,6 @@
 // The library handle and the helpers shared by the translation units that implement the C ABI (api.cu, host_api.cu).
 #pragma once
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -68,6 +69,8 @@ struct rho_handle {
   // HOST entry points: one context per concurrent caller, recycled (a handle may be shared by concurrent sessions,
   // ui/state.py:85-87 of the reference: callers do not serialise on each other)
   std::vector<rho::HostCtx*> host_ctx_free;
+  // host entry points: fill threads of the next call (0 = default); raised when a call's fill fell behind its copies
+  std::atomic<int> host_fill_threads{0};
   // tap tables of rho_b200_resample, one per reduced ratio seen so far: key = (orig << 32) | new
   std::map<uint64_t, float*> resample_taps;
   // rho_b200_pitch_shift: FFT / window / phase-advance tables (built on first use) and windowed tap tables per ratio

@@ -14,6 +14,7 @@
 // following chunks.  (Round 1 shipped the constants over the link: a third of a saturated link.)
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -104,15 +105,22 @@ struct Chunk {
 
 // developer switches for tools/e2e_sweep.py (timing experiments only)
 bool debug_skip_fill() { static const bool v = getenv("RHO_HOST_DEBUG_SKIP_FILL") != nullptr; return v; }
+// test hook: worker 0 sleeps this long per chunk, as a host with slow memory would (tests/test_gpu_parity.py)
+int debug_fill_delay_us() { static const int v = [] { const char* e = getenv("RHO_HOST_DEBUG_FILL_DELAY_US"); return e ? atoi(e) : 0; }(); return v; }
 
-int fill_threads() {
-  static const int n = [] {
-    if (const char* v = getenv("RHO_HOST_FILL_THREADS")) return std::max(1, atoi(v));
-    // 0.64 GB of constants per 1.28 GB of copy-out: about 26 GB/s of fill to keep up with a gen-5 link
-    // (tools/e2e_sweep.py, profiles/e2e_sweep_r02*.log)
-    return 3;
-  }();
+// 0.64 GB of constants per 1.28 GB of copy-out: about 26 GB/s of fill to keep up with a gen-5 link.  Three threads do
+// that on most hosts of the pool (tools/e2e_sweep.py, profiles/e2e_sweep_r02*.log) -- but not on all: a call whose fill
+// ends well after its last copy (more than 8 % of the call) gives the handle's next calls two more threads, up to 9.
+// RHO_HOST_FILL_THREADS pins the count.
+constexpr int FILL_THREADS_DEFAULT = 3, FILL_THREADS_MAX = 9;
+int fill_threads_env() {
+  static const int n = [] { const char* v = getenv("RHO_HOST_FILL_THREADS"); return v ? std::max(1, atoi(v)) : 0; }();
   return n;
+}
+int fill_threads(rho_handle* h) {
+  if (fill_threads_env() > 0) return fill_threads_env();
+  const int hint = h->host_fill_threads.load(std::memory_order_relaxed);
+  return hint > 0 ? hint : FILL_THREADS_DEFAULT;
 }
 
 int host_slots() {
@@ -285,7 +293,7 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
   }
   while ((int)C.ev_out.size() < n_chunks) {
     cudaEvent_t ev = nullptr, ev2 = nullptr;
-    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess ||
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) {
       if (ev) cudaEventDestroy(ev);
       return cuda_fail(e, "cudaEventCreate");
@@ -306,6 +314,7 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
   std::atomic<int> issued{0};            // chunks whose copy-out has been enqueued (ev_out recorded)
   std::atomic<int> abort_fill{0};
   std::atomic<int> fill_err{0};
+  std::atomic<int> out_recorded{0};      // chunks whose ev_out has been recorded in THIS call
   auto fill_worker = [&](int w, int W) {
     cudaSetDevice(h->device);
     for (int k = 0; k < n_chunks; ++k) {
@@ -320,6 +329,7 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
       const int64_t t0 = std::min<int64_t>(c.t_dev, mel_stride_frames), t1 = std::min<int64_t>(mel_stride_frames, pad_frames);
       const int64_t rows = (int64_t)(c.i1 - c.i0) * n_mels;
       if (pad_value && w == 0) memcpy(pad_value + c.i0, h_pad + c.i0, sizeof(float) * (size_t)(c.i1 - c.i0));
+      if (w == 0 && debug_fill_delay_us() > 0) std::this_thread::sleep_for(std::chrono::microseconds(debug_fill_delay_us()));
       if (t1 <= t0 || debug_skip_fill()) continue;
       for (int64_t r = w; r < rows; r += W) {
         const int64_t it = c.i0 + r / n_mels;
@@ -328,8 +338,22 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
     }
   };
   std::vector<std::thread> helpers;
-  const int W = host_fill ? fill_threads() : 0;
+  const int W = host_fill ? fill_threads(h) : 0;
   for (int w = 1; w < W; ++w) helpers.emplace_back(fill_worker, w, W);
+  // does the fill keep up with the link on this host?  A watcher sleeps on the last chunk's copy-out event and notes
+  // when it completed; the fill's own end is compared with it below.
+  using Clock = std::chrono::steady_clock;
+  const Clock::time_point t_start = Clock::now();
+  Clock::time_point t_copies_done = t_start;
+  const bool adapt = host_fill && fill_threads_env() == 0 && W < FILL_THREADS_MAX;
+  if (adapt) helpers.emplace_back([&] {
+    cudaSetDevice(h->device);
+    while (out_recorded.load(std::memory_order_acquire) < n_chunks) {
+      if (abort_fill.load(std::memory_order_relaxed)) return;
+      std::this_thread::yield();
+    }
+    if (cudaEventSynchronize(C.ev_out[n_chunks - 1]) == cudaSuccess) t_copies_done = Clock::now();
+  });
 
   int status = RHO_OK;
   for (int k = 0; k < n_chunks && status == RHO_OK; ++k) {
@@ -435,10 +459,19 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
     }
     if (e != cudaSuccess) { status = cuda_fail(e, "D2H"); break; }
     cudaEventRecord(C.ev_out[k], C.s_out);
+    out_recorded.store(k + 1, std::memory_order_release);
   }
   if (status != RHO_OK) abort_fill.store(1);
   if (host_fill && status == RHO_OK) fill_worker(0, W);     // the calling thread is worker 0
+  const Clock::time_point t_fill_done = Clock::now();
   for (std::thread& t : helpers) t.join();
+  if (adapt && status == RHO_OK) {
+    // (t_fill_done is worker 0's end; the other workers end within a row of it)
+    const double lag = std::chrono::duration<double>(t_fill_done - t_copies_done).count();
+    const double call = std::chrono::duration<double>(t_fill_done - t_start).count();
+    if (t_copies_done != t_start && lag > 0.08 * call)
+      h->host_fill_threads.store(std::min(FILL_THREADS_MAX, W + 2), std::memory_order_relaxed);
+  }
   const bool pad_late = status == RHO_OK && !host_fill && features && pad_frames > 0 && pad_value;
   const cudaError_t e1 = cudaStreamSynchronize(C.s_in);
   const cudaError_t e2 = cudaStreamSynchronize(sc);
@@ -450,6 +483,11 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
   if (e3 != cudaSuccess) return cuda_fail(e3, "sync copy-out");
   if (fill_err.load()) return fail(RHO_ERR_CUDA, "host fill: waiting for a copy-out event failed");
   return RHO_OK;
+}
+
+int rho_b200_host_fill_threads(rho_handle* h) {
+  if (!h) return fail(RHO_ERR_INVALID, "handle is NULL");
+  return fill_threads(h);
 }
 
 int rho_b200_validate_host(rho_handle* h, const float* x, int n, int32_t clip_len, const rho_params* p,

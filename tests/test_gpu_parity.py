@@ -3,6 +3,8 @@
 Bar (BASELINE.json north_star): trim bounds, join lengths / segment boundaries and accept/reject
 decisions exact; waveforms, RMS, ratio, cosine and log-mel within 1e-4 (abs-or-rel, tests/util.TOL).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -12,6 +14,7 @@ from oracle import dsp as odsp
 from tests.util import TOL, assert_close, tone_clip
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -583,6 +586,45 @@ def test_validate_host_ragged_joins(R, cuda_device):
         for i in range(0, n_items, 3):
             L = int(rdv["out_len"][i])
             assert torch.equal(dv.audio.clip(i, L).cpu(), hv.audio[hv.y_offsets[i]:hv.y_offsets[i] + L]), i
+
+
+def test_host_fill_threads_adapt_to_a_slow_host(cuda_device):
+    """A call whose host fill ends well behind its last copy gives the handle's next calls two more fill threads (a host
+    with slow memory; simulated with RHO_HOST_DEBUG_FILL_DELAY_US, read once per process: subprocess).  The outputs do
+    not depend on the thread count."""
+    import subprocess
+    import sys
+    code = """
+import os, sys, torch
+sys.path.insert(0, os.getcwd())
+import rho_tts_b200 as R
+from rho_tts_b200 import synth, _lib
+h = _lib.Handle.get(0)
+x = synth.make_clip_block(200, 48000, 5).pin_memory()
+p = R.make_params()
+seen = [int(h.lib.rho_b200_host_fill_threads(h.ptr))]
+outs = []
+for _ in range(4):
+    y, mel, rec = R.validate_host(x, p, None, None, 80, mel=torch.full((200, 80, 3000), float("nan")).pin_memory())
+    outs.append((y.clone(), mel.clone(), rec.clone()))
+    seen.append(int(h.lib.rho_b200_host_fill_threads(h.ptr)))
+assert all(torch.equal(outs[0][1], o[1]) and torch.equal(outs[0][2], o[2]) for o in outs[1:])
+assert not torch.isnan(outs[0][1]).any()
+print("THREADS", seen)
+"""
+    env = dict(os.environ, RHO_HOST_DEBUG_FILL_DELAY_US="4000")
+    env.pop("RHO_HOST_FILL_THREADS", None)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    seen = eval(r.stdout.strip().splitlines()[-1].split("THREADS", 1)[1])
+    assert seen[0] == 3 and seen[1] == 5 and seen[-1] == 9 and seen == sorted(seen), seen
+    # a host that keeps up stays at the default; a pinned count is never changed
+    env2 = {k: v for k, v in os.environ.items() if k not in ("RHO_HOST_DEBUG_FILL_DELAY_US",)}
+    env2["RHO_HOST_FILL_THREADS"] = "2"
+    r2 = subprocess.run([sys.executable, "-c", code], env=dict(env2, RHO_HOST_DEBUG_FILL_DELAY_US="4000"), capture_output=True,
+                        text=True, cwd=ROOT, timeout=300)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    assert eval(r2.stdout.strip().splitlines()[-1].split("THREADS", 1)[1]) == [2] * 5
 
 
 def test_validate_host_odd_clip_length_and_unpadded_errors(R, cuda_device):
