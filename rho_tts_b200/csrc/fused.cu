@@ -19,7 +19,9 @@
 //   FIR   : 2 phases x 23 taps as packed fp32x2 dot products (FFMA2, taps in uniform registers) from the
 //           span -> 5360 samples of the 16 kHz slab (reflection fixed up in smem)
 //   FFT   : as k_logmel_frames (two real frames per 400-point complex FFT, 20 x 20, packed fp32x2 butterflies)
-//   mel   : immediate-weight FFMAs, SFU log2, ordered-int atomicMax of the clip maximum
+//   mel   : the sparse filterbank as a table in constant memory walked by a small loop (FZ_MEL_TABLE), SFU log2,
+//           ordered-int atomicMax of the clip maximum
+// MODE 1 / 2 of the template: features of finished audio in y / items joined from several segments (see the kernel)
 #include <algorithm>
 #include <vector>
 #include <cstdlib>
@@ -167,7 +169,7 @@ cudaError_t upload_fused_mel(int which, int n_mels, const int* lo, const int* cn
 #define FZ_INLINE_NORM 1   // the half that finishes a clip last writes the constant fill of its zero-padding frames at once: k_logmel_norm 0.249 -> 0.113 ms, this kernel 0.866 -> 0.975 ms, step -2 % (0: k_logmel_norm writes the fill; sliced / dedicated-warp variants: profiles/ncu_r01_v7_summary.md)
 #endif
 #ifndef FZ_TC_MEL
-// 0: mel projection as immediate-weight FFMAs (the bank is 97.5 % zeros)             -> 0.864 ms   <- product
+// 0: mel projection on the CUDA cores (the bank is 97.5 % zeros; FZ_MEL_TABLE)        -> 0.864 ms   <- product
 // 1: on the tensor cores inside this kernel (tcgen05, 3xTF32, filterbank in TMEM)     -> 1.033 ms
 // 2: same with two products, P rounded to TF32 (accuracy 4.2e-5 -> 6.6e-5 vs float64) -> 0.981 ms
 // Both tensor-core variants pass every parity test; they lose because the power spectra have to be re-laid out
