@@ -150,7 +150,23 @@ def test_c3_every_segment_and_item(cuda_device):
     for i, audio in zip(pick, _pool_map(_w_join_audio, pick)):
         assert_close(out.audio.clip(int(i), audio.size).cpu().numpy(), audio, what=f"item {i}")
     _X = _ITEMS = None
-    print(f"C3: {n} segments and {n_items} items exact in bounds / lengths / fallback / decisions")
+    # the same items through the single-kernel path (join inside the feature kernel): every sample of every item equal to
+    # k_gather's, bit for bit; lengths / flags / decisions equal; finite features
+    v = R.validate_batch(rb, R.make_params(), n_mels=80, pad_to_30s=False, item_first_seg=first)
+    rv = v.records_host()
+    for f in ("start", "end", "out_len", "flags", "ok", "n_segments"):
+        assert np.array_equal(rv[f], rec[f]), f
+    assert np.allclose(rv["decay_ratio"], rec["decay_ratio"], rtol=1e-5, atol=1e-7)
+    bad = 0
+    for i in range(n_items):
+        L = int(rec["out_len"][i])
+        bad += int(not torch.equal(v.audio.clip(i, L), out.audio.clip(i, L)))
+        T_i = ((2 * L + 2) // 3) // 160
+        if T_i > 0 and (2 * L + 2) // 3 > 200 and i % 16 == 0:
+            assert torch.isfinite(v.mel[i, :, :T_i]).all(), i
+    assert bad == 0, f"{bad} items differ between the single-kernel join and k_gather"
+    print(f"C3: {n} segments and {n_items} items exact in bounds / lengths / fallback / decisions; "
+          f"single-kernel join == k_gather on all {n_items} items")
 
 
 def test_randomised_soak_reduced():
