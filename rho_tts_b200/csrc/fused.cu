@@ -143,6 +143,13 @@ cudaError_t upload_fused_mel(int which, int n_mels, const int* lo, const int* cn
     part[PARTS] = n_mels;
     for (int pt = PARTS; pt >= 1; --pt) { i = from[pt][i]; part[pt - 1] = i; }
   }
+  if (const char* ov = getenv(which == 0 ? "RHO_FUSED_MEL_PARTS_80" : "RHO_FUSED_MEL_PARTS_128")) {   // A/B tool: "0,10,20,...,80"
+    std::vector<int> v;
+    for (const char* q = ov; *q;) { v.push_back(atoi(q)); while (*q && *q != ',') ++q; if (*q) ++q; }
+    bool ok = (int)v.size() == PARTS + 1 && v.front() == 0 && v.back() == n_mels;
+    for (size_t i = 1; ok && i < v.size(); ++i) ok = v[i] >= v[i - 1];
+    if (ok) for (int i = 0; i <= PARTS; ++i) part[i] = v[i];
+  }
   int n4 = 0;
   for (int pt = 0; pt < PARTS; ++pt) {
     part4[pt] = n4;
