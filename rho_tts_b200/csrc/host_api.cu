@@ -110,7 +110,7 @@ int debug_fill_delay_us() { static const int v = [] { const char* e = getenv("RH
 
 // 0.64 GB of constants per 1.28 GB of copy-out: about 26 GB/s of fill to keep up with a gen-5 link.  Three threads do
 // that on most hosts of the pool (tools/e2e_sweep.py, profiles/e2e_sweep_r02*.log) -- but not on all: a call whose fill
-// ends well after its last copy (more than 8 % of the call) gives the handle's next calls two more threads, up to 9.
+// ends well after its last copy (more than 5 % of the call) gives the handle's next calls two more threads, up to 9.
 // RHO_HOST_FILL_THREADS pins the count.
 constexpr int FILL_THREADS_DEFAULT = 3, FILL_THREADS_MAX = 9;
 int fill_threads_env() {
@@ -469,7 +469,7 @@ int rho_b200_validate_host_ragged(rho_handle* h, const float* x, const int64_t* 
     // (t_fill_done is worker 0's end; the other workers end within a row of it)
     const double lag = std::chrono::duration<double>(t_fill_done - t_copies_done).count();
     const double call = std::chrono::duration<double>(t_fill_done - t_start).count();
-    if (t_copies_done != t_start && lag > 0.08 * call)
+    if (t_copies_done != t_start && lag > 0.05 * call)
       h->host_fill_threads.store(std::min(FILL_THREADS_MAX, W + 2), std::memory_order_relaxed);
   }
   const bool pad_late = status == RHO_OK && !host_fill && features && pad_frames > 0 && pad_value;
