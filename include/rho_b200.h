@@ -107,6 +107,14 @@ const char* rho_b200_last_error(void);
  * Returns the number of floats written, or a negative status. */
 int rho_b200_host_table(int kind, int arg, float* out, size_t out_capacity);
 
+/* Host only: the mel filterbank (n_mels = 80 or 128) as the fused kernel walks it -- one stream of float4 in constant
+ * memory (csrc/fused.cu): bundles of *rows_per_bundle rows, each a header {byte offset of every row's first bin in a
+ * power row ..., bytes of power each row covers} padded to whole float4, then the rows' weights (x 1/4: the kernel's
+ * spectra are 4 |.|^2) group of four by group of four, the rows of the bundle interleaved, zero-padded.  part[11] /
+ * part4[11]: the rows / the float4 each of the ten warps of a half starts at.  Returns the floats written (capacity at
+ * least 2560), or a negative status.  For tests: the packing is checked against kind 2 of rho_b200_host_table. */
+int rho_b200_host_mel_stream(int n_mels, float* stream, size_t out_capacity, int32_t* part, int32_t* part4, int* rows_per_bundle);
+
 /* Bytes of scratch the calls below need for a batch of `n_segments` segments in
  * `n_items` items whose longest segment has `max_seg_len` samples. */
 size_t rho_b200_workspace_bytes(int n_segments, int n_items, int64_t max_seg_len);

@@ -30,7 +30,7 @@ V_GATHER_FIRST = 8
 
 EXPORTS = (
     "rho_b200_abi_version", "rho_b200_create", "rho_b200_destroy", "rho_b200_last_error",
-    "rho_b200_host_table", "rho_b200_workspace_bytes", "rho_b200_trim_scan", "rho_b200_join",
+    "rho_b200_host_table", "rho_b200_host_mel_stream", "rho_b200_workspace_bytes", "rho_b200_trim_scan", "rho_b200_join",
     "rho_b200_remove_dc", "rho_b200_apply_fades", "rho_b200_sound_decay", "rho_b200_sound_decay_batch", "rho_b200_resample3to2",
     "rho_b200_resample_out_len", "rho_b200_resample", "rho_b200_pitch_workspace_bytes", "rho_b200_pitch_shift", "rho_b200_mfcc_workspace_bytes", "rho_b200_mfcc_stats", "rho_b200_spk_slices", "rho_b200_normalize_volume", "rho_b200_spk_mel", "rho_b200_spk_pool", "rho_b200_pcm16", "rho_b200_logmel", "rho_b200_mel_project", "rho_b200_stft_power_tc", "rho_b200_qwen_workspace_bytes", "rho_b200_qwen_postprocess",
     "rho_b200_cosine", "rho_b200_validate", "rho_b200_compact_frames", "rho_b200_exchange_create", "rho_b200_exchange_connect",
@@ -85,6 +85,7 @@ def load():
             "rho_b200_destroy": (c_int, [vp]),
             "rho_b200_last_error": (c_char_p, []),
             "rho_b200_host_table": (c_int, [c_int, c_int, vp, c_size_t]),
+            "rho_b200_host_mel_stream": (c_int, [c_int, vp, c_size_t, vp, vp, POINTER(c_int)]),
             "rho_b200_workspace_bytes": (c_size_t, [c_int, c_int, i64]),
             "rho_b200_trim_scan": (c_int, [vp, vp, vp, vp, vp, i32, i64, P, vp, vp, c_size_t, vp]),
             "rho_b200_join": (c_int, [vp, vp, vp, vp, i32, i64, vp, i32, i64, P, vp, vp, vp, vp, vp, c_size_t, vp]),

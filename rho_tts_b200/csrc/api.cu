@@ -183,6 +183,37 @@ int rho_b200_host_table(int kind, int arg, float* out, size_t cap) {
   }
 }
 
+// the sparse form of a slaney bank over the 201 bins: per row the first non-zero bin, the span to the last one, and the
+// weights of that span back to back
+static void sparse_mel_bank(int nm, std::vector<float>& dense, std::vector<int>& lo, std::vector<int>& cnt,
+                            std::vector<int>& wofs, std::vector<float>& w) {
+  dense.assign((size_t)nm * N_BINS, 0.f);
+  host_mel_filterbank(nm, dense.data());
+  lo.assign(nm, 0); cnt.assign(nm, 0); wofs.assign(nm, 0); w.clear();
+  for (int m = 0; m < nm; ++m) {
+    int a = -1, b = -1;
+    for (int k = 0; k < N_BINS; ++k) if (dense[(size_t)m * N_BINS + k] != 0.f) { if (a < 0) a = k; b = k; }
+    lo[m] = a < 0 ? 0 : a; cnt[m] = a < 0 ? 0 : b - a + 1; wofs[m] = (int)w.size();
+    for (int k = 0; k < cnt[m]; ++k) w.push_back(dense[(size_t)m * N_BINS + lo[m] + k]);
+  }
+}
+
+int rho_b200_host_mel_stream(int n_mels, float* stream, size_t cap_floats, int32_t* part, int32_t* part4, int* rows_per_bundle) {
+  if (n_mels != 80 && n_mels != 128) return fail(RHO_ERR_INVALID, "n_mels must be 80 or 128");
+  if (!stream || !part || !part4 || cap_floats < (size_t)4 * FUSED_MEL_STREAM_FLOAT4) return fail(RHO_ERR_INVALID, "capacity");
+  std::vector<float> dense, w;
+  std::vector<int> lo, cnt, wofs;
+  sparse_mel_bank(n_mels, dense, lo, cnt, wofs, w);
+  std::vector<float4> tab((size_t)FUSED_MEL_STREAM_FLOAT4);
+  int p[12] = {}, p4[12] = {};
+  const int n4 = build_fused_mel_stream(n_mels == 80 ? 0 : 1, n_mels, lo.data(), cnt.data(), wofs.data(), w.data(), (int)w.size(),
+                                        tab.data(), p, p4, rows_per_bundle);
+  if (n4 < 0) return fail(RHO_ERR_INVALID, "the filterbank does not fit the stream");
+  memcpy(stream, tab.data(), sizeof(float4) * (size_t)n4);
+  for (int i = 0; i < 11; ++i) { part[i] = p[i]; part4[i] = p4[i]; }
+  return 4 * n4;
+}
+
 int rho_b200_create(rho_handle** out, int device) {
   if (!out) return fail(RHO_ERR_INVALID, "handle out pointer is NULL");
   *out = nullptr;
@@ -212,16 +243,9 @@ int rho_b200_create(rho_handle** out, int device) {
   if ((e = dev_upload(h, (float**)&h->tb.twiddle, tw.data(), 2 * N_FFT)) != cudaSuccess) { rho_b200_destroy(h); return cuda_fail(e, "twiddle"); }
   for (int which = 0; which < 2; ++which) {
     const int nm = which == 0 ? 80 : 128;
-    std::vector<float> dense((size_t)nm * N_BINS);
-    host_mel_filterbank(nm, dense.data());
-    std::vector<int> lo(nm), cnt(nm), wofs(nm);
-    std::vector<float> w;
-    for (int m = 0; m < nm; ++m) {
-      int a = -1, b = -1;
-      for (int k = 0; k < N_BINS; ++k) if (dense[(size_t)m * N_BINS + k] != 0.f) { if (a < 0) a = k; b = k; }
-      lo[m] = a < 0 ? 0 : a; cnt[m] = a < 0 ? 0 : b - a + 1; wofs[m] = (int)w.size();
-      for (int k = 0; k < cnt[m]; ++k) w.push_back(dense[(size_t)m * N_BINS + lo[m] + k]);
-    }
+    std::vector<float> dense, w;
+    std::vector<int> lo, cnt, wofs;
+    sparse_mel_bank(nm, dense, lo, cnt, wofs, w);
     if (w.size() > 416) { rho_b200_destroy(h); return fail(RHO_ERR_INVALID, "mel filterbank nnz %zu > 416", w.size()); }
     h->tb.mel_nnz[which] = (int)w.size();
     if ((e = upload_fused_mel(which, nm, lo.data(), cnt.data(), wofs.data(), w.data(), (int)w.size())) != cudaSuccess) {

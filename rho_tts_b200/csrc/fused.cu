@@ -88,18 +88,22 @@ cudaError_t upload_fused_taps(const float* taps) {
 #endif
 __host__ __device__ constexpr int fz_mel_rows(int which) { return which == 0 ? FZ_MEL_ROWS_80 : FZ_MEL_ROWS_128; }
 __host__ __device__ constexpr int fz_mel_hdr4(int which) { return (fz_mel_rows(which) + 1 + 3) / 4; }   // float4 per bundle header
-constexpr int FZ_MEL_TAB4 = 640;                   // float4 per bank (checked at upload)
+constexpr int FZ_MEL_TAB4 = FUSED_MEL_STREAM_FLOAT4; // float4 per bank (checked when the stream is built)
 __constant__ float4 c_mel_tab[2][FZ_MEL_TAB4];
 __constant__ int c_mel_part[2][12];                // rows [part[w], part[w + 1]) belong to warp w of a half
 __constant__ int c_mel_part4[2][12];               // ... and start at this float4 of the stream
 
-cudaError_t upload_fused_mel(int which, int n_mels, const int* lo, const int* cnt, const int* wofs, const float* w, int nnz) {
-  if (which < 0 || which > 1 || n_mels > 128 || nnz > 416) return cudaErrorInvalidValue;
+// Host only: builds the stream of one bank (which = 0: 80 bands, 1: 128) into tab[FZ_MEL_TAB4] and the warps' row / stream
+// starts into part[11] / part4[11]; rows_per_bundle (optional) receives the bundle size.  Returns the float4 used, or -1.
+// Also behind rho_b200_host_mel_stream, so that the packing can be checked without a GPU (tests/test_cabi.py).
+int build_fused_mel_stream(int which, int n_mels, const int* lo, const int* cnt, const int* wofs, const float* w, int nnz,
+                           float4* tab, int* part, int* part4, int* rows_per_bundle) {
+  if (which < 0 || which > 1 || n_mels > 128 || nnz > 416) return -1;
   const int R = fz_mel_rows(which), HDR4 = fz_mel_hdr4(which);
+  if (rows_per_bundle) *rows_per_bundle = R;
   constexpr int PARTS = LM_THREADS / 32;
-  std::vector<float4> tabv((size_t)FZ_MEL_TAB4, make_float4(0.f, 0.f, 0.f, 0.f));   // (local: handles may be created concurrently)
-  float4* tab = tabv.data();
-  int part[12] = {}, part4[12] = {};
+  for (int i = 0; i < FZ_MEL_TAB4; ++i) tab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i <= PARTS; ++i) { part[i] = 0; part4[i] = 0; }
   // Contiguous groups of rows, one per warp, chosen so that the SLOWEST warp is as fast as possible (the mel phase ends
   // at a barrier): a small dynamic program over the cost the loop below has per bundle -- ~14 instructions of set-up,
   // 12.5 per row and group of four weights (every row of a bundle walks the bundle's longest row), 10 per row for the
@@ -156,7 +160,7 @@ cudaError_t upload_fused_mel(int which, int n_mels, const int* lo, const int* cn
     for (int m0 = part[pt]; m0 < part[pt + 1]; m0 += R) {
       int groups = 0;
       for (int r = 0; r < R; ++r) if (m0 + r < part[pt + 1]) groups = std::max(groups, (cnt[m0 + r] + 3) / 4);
-      if (n4 + HDR4 + R * groups > FZ_MEL_TAB4 || 4 * groups > N_BINS) return cudaErrorInvalidValue;
+      if (n4 + HDR4 + R * groups > FZ_MEL_TAB4 || 4 * groups > N_BINS) return -1;
       unsigned hdr[8] = {};
       for (int r = 0; r < R; ++r) {
         int first = 0;
@@ -178,6 +182,14 @@ cudaError_t upload_fused_mel(int which, int n_mels, const int* lo, const int* cn
     }
   }
   part4[PARTS] = n4;
+  return n4;
+}
+
+cudaError_t upload_fused_mel(int which, int n_mels, const int* lo, const int* cnt, const int* wofs, const float* w, int nnz) {
+  std::vector<float4> tabv((size_t)FZ_MEL_TAB4);          // (local: handles may be created concurrently)
+  float4* tab = tabv.data();
+  int part[12] = {}, part4[12] = {};
+  if (build_fused_mel_stream(which, n_mels, lo, cnt, wofs, w, nnz, tab, part, part4, nullptr) < 0) return cudaErrorInvalidValue;
   cudaError_t e;
   if ((e = cudaMemcpyToSymbol(c_mel_tab, tab, sizeof(float4) * FZ_MEL_TAB4, sizeof(float4) * FZ_MEL_TAB4 * which)) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbol(c_mel_part4, part4, sizeof(part4), sizeof(part4) * which)) != cudaSuccess) return e;

@@ -151,6 +151,9 @@ cudaError_t launch_logmel_norm(const int32_t* len16, int n, int n_mels, int pad_
 bool fused_inline_norm();   // the fused kernel writes the constant fill of the zero-padding frames itself
 cudaError_t upload_fused_taps(const float* taps /* [2][23] */);
 cudaError_t upload_fused_mel(int which, int n_mels, const int* lo, const int* cnt, const int* wofs, const float* w, int nnz);
+constexpr int FUSED_MEL_STREAM_FLOAT4 = 640;   // capacity of one bank's stream (fused.cu: FZ_MEL_TAB4)
+int build_fused_mel_stream(int which, int n_mels, const int* lo, const int* cnt, const int* wofs, const float* w, int nnz,
+                           float4* tab, int* part, int* part4, int* rows_per_bundle);
 cudaError_t launch_fused_features(const Tables& tb, const float* x, const int64_t* seg_off, const Workspace& ws,
                                   const int32_t* item_first_seg, int n_items, int64_t max_len,
                                   const Derived& d, float* y, const int64_t* y_off, int n_mels, int pad_frames,

@@ -140,6 +140,48 @@ def test_baked_mel_weights_match_runtime_table(lib):
         assert np.array_equal(seen.view(np.uint32), table.view(np.uint32))
 
 
+def test_fused_mel_stream_is_the_filterbank(lib):
+    """The filterbank as the fused kernel walks it (a stream of float4 in constant memory: bundles of rows, headers,
+    interleaved zero-padded groups of four weights, x 1/4) decodes back to the table of rho_b200_host_table(2), every row
+    exactly once, split over the ten warps of a half; the padding never leaves the 201 bins."""
+    for nm in (80, 128):
+        stream = np.zeros(2560, np.float32)
+        part = np.zeros(11, np.int32)
+        part4 = np.zeros(11, np.int32)
+        rows = ctypes.c_int(0)
+        n = lib.rho_b200_host_mel_stream(nm, stream.ctypes.data, stream.size, part.ctypes.data, part4.ctypes.data,
+                                         ctypes.byref(rows))
+        assert n > 0 and n % 4 == 0 and rows.value in (1, 2, 4)
+        R = rows.value
+        hdr4 = (R + 1 + 3) // 4
+        table = _table(lib, 2, nm, nm * 201).reshape(nm, 201)
+        got = np.zeros_like(table)
+        seen = np.zeros(nm, np.int32)
+        assert part[0] == 0 and part[10] == nm and np.all(np.diff(part) >= 0) and part4[0] == 0 and part4[10] == n // 4
+        words = stream.view(np.uint32)
+        for w in range(10):
+            pos = int(part4[w])
+            for m0 in range(int(part[w]), int(part[w + 1]), R):
+                first = words[4 * pos:4 * pos + R] // 4
+                nbytes = int(words[4 * pos + R])
+                assert nbytes % 16 == 0
+                groups = nbytes // 16
+                body = stream[4 * (pos + hdr4):4 * (pos + hdr4 + R * groups)].reshape(groups, R, 4)
+                for r in range(R):
+                    if m0 + r < part[w + 1]:
+                        f = int(first[r])
+                        assert 0 <= f and f + 4 * groups <= 201
+                        got[m0 + r, f:f + 4 * groups] += body[:, r, :].reshape(-1)
+                        seen[m0 + r] += 1
+                    else:
+                        assert not body[:, r, :].any()                      # filler rows of the last bundle: all zero
+                pos += hdr4 + R * groups
+            assert pos == part4[w + 1]
+        assert np.all(seen == 1)
+        assert np.array_equal(got, (0.25 * table).astype(np.float32))          # exact: a power of two
+    assert lib.rho_b200_host_mel_stream(40, None, 0, None, None, None) < 0
+
+
 def test_pitch_and_mfcc_host_tables(lib):
     """The tables the pitch-shift / MFCC kernels get from the host, against torch / the oracle (no GPU needed)."""
     import math
